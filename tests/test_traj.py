@@ -1,0 +1,36 @@
+import os
+
+import numpy as np
+import pytest
+
+from bluerov2_b200 import traj
+
+REF = "/root/reference/bluerov2_path/config/traj"
+
+
+def test_shapes_and_quirks():
+    c = traj.circle()
+    assert c.shape == (4801, 16)
+    assert np.all(c[:, 6] == 1.5) and np.all(c[:, 7] == 1.498945)     # circle.py:45-46 flatten-index slip
+    assert np.all(c[:, 14] == 57.5)                                    # circle.py:55, outside the +-50 box
+    l = traj.lemniscate()
+    assert l.shape == (1201, 16) and np.all(l[:, 2] == -20.0)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_bit_identical_to_reference_files():
+    assert np.array_equal(traj.circle(), np.loadtxt(os.path.join(REF, "circle.txt")))
+    assert np.array_equal(traj.lemniscate(), np.loadtxt(os.path.join(REF, "lemniscate.txt")))
+
+
+def test_window_clamps_to_last_row():
+    """ref_cb (bluerov2_dob.cpp:218-265): all three branches."""
+    t = np.arange(10 * 16, dtype=float).reshape(10, 16)
+    w = traj.window(t, 2, 4)
+    assert np.array_equal(w, t[2:7])
+    w = traj.window(t, 7, 4)          # partially past the end
+    assert np.array_equal(w[:3], t[7:10]) and np.all(w[3:] == t[9])
+    w = traj.window(t, 40, 4)         # entirely past the end
+    assert np.all(w == t[9])
+    wb = traj.window_batch(t, np.array([2, 7, 40]), 4)
+    assert np.array_equal(wb[0], traj.window(t, 2, 4)) and np.array_equal(wb[1], traj.window(t, 7, 4))
