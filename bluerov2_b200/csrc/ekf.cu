@@ -1,0 +1,315 @@
+// ekf.cu -- batched 18-state disturbance-observer EKF, one warp per instance.
+//
+// Restates BLUEROV2_DOB::EKF and its helpers (bluerov2_dobmpc/src/bluerov2_dob.cpp:495-545, 621-752) with the
+// constants of include/bluerov2_dobmpc/bluerov2_dob.h:170-208 and the constructor (bluerov2_dob.cpp:41-65):
+//   state  [eta(6), nu(6), d(6)];  process model f (:637-695) with rigid-body Coriolis terms and invM(i,i) of the
+//   COUPLED mass matrix;  RK4 with k3 = f(x + k2/3) (sic, :630);  F and H by forward differences, d = 1e-6
+//   (:722-752);  gain through an explicit 18x18 inverse (:535);  Joseph-form covariance update (:537).
+// Lane mapping: the 19 RK4 / 19 h() evaluations of the two finite-difference Jacobians run on lanes 0..18 in
+// parallel (lane 0 = unperturbed); the ten 18x18x18 products and the Gauss-Jordan inverse are row-per-lane with
+// operands in shared memory.  Output: esti_x, esti_P, world-frame disturbance (:540-545) and the OCP parameter
+// vector handed to the solver (bluerov2_dob.cpp:324-355).
+#include "engine.h"
+
+namespace br2 {
+
+#define FULL_MASK 0xffffffffu
+constexpr int EN = 18;
+constexpr int LD = 20;            // leading dimension of the shared-memory matrices (16-byte aligned rows)
+constexpr int EKF_WARPS = 2;
+
+namespace ekfc {
+constexpr double DT = 0.05, M = 11.26, Ix = 0.3, Iy = 0.63, Iz = 0.58, Zg = 0.02, G = 9.81, EBUOY = 0.661618;
+constexpr double COMP = 0.032546960744430276, RCK = 0.026546960744430276;
+constexpr double AM0 = 1.7182, AM1 = 0, AM2 = 5.468, AM3 = 0, AM4 = 1.2481, AM5 = 0.4006;
+// diagonal of M and of M^-1 for M = diag(m+am) with the four ZG couplings (bluerov2_dob.cpp:41-47):
+// the (0,4) and (1,3) 2x2 blocks invert in closed form.
+constexpr double M0 = M + AM0, M1 = M + AM1, M2 = M + AM2, M3 = Ix + AM3, M4 = Iy + AM4, M5 = Iz + AM5;
+constexpr double C = M * Zg;
+constexpr double IM0 = M4 / (M0 * M4 - C * C), IM4 = M0 / (M0 * M4 - C * C);
+constexpr double IM1 = M3 / (M1 * M3 - C * C), IM3 = M1 / (M1 * M3 - C * C);
+constexpr double IM2 = 1.0 / M2, IM5 = 1.0 / M5;
+}  // namespace ekfc
+
+__constant__ double c_K[36] = {
+    0.7071067811847433, 0.7071067811847433, -0.7071067811919605, -0.7071067811919605, 0.0, 0.0,
+    0.7071067811883519, -0.7071067811883519, 0.7071067811811348, -0.7071067811811348, 0.0, 0.0,
+    0, 0, 0, 0, 1, 1,
+    0.051265241636155506, -0.05126524163615552, 0.05126524163563227, -0.05126524163563227, -0.11050000000000001, 0.11050000000000003,
+    -0.05126524163589389, -0.051265241635893896, 0.05126524163641713, 0.05126524163641713, -0.002499999999974481, -0.002499999999974481,
+    0.16652364696949604, -0.16652364696949604, -0.17500892834341342, 0.17500892834341342, 0.0, 0.0};
+__constant__ double c_Dl[6] = {-11.7391, -20, -31.8678, -25, -44.9085, -5};
+__constant__ double c_Dnl[6] = {-18.18, -21.66, -36.99, -1.55, -1.55, -1.55};
+
+// process model, bluerov2_dob.cpp:637-695 (tau = K * thrusts precomputed)
+__device__ void ekf_f(const double* x, const double* tau, double* xd)
+{
+    using namespace ekfc;
+    double s3, c3, s4, c4, s5, c5;
+    sincos(x[3], &s3, &c3); sincos(x[4], &s4, &c4); sincos(x[5], &s5, &c5);
+    xd[0] = (c5 * c4) * x[6] + (-s5 * c3 + c5 * s4 * s3) * x[7] + (s5 * s3 + c5 * c3 * s4) * x[8];
+    xd[1] = (s5 * c4) * x[6] + (c5 * c3 + s3 * s4 * s5) * x[7] + (-c5 * s3 + s4 * s5 * c3) * x[8];
+    xd[2] = (-s4) * x[6] + (c4 * s3) * x[7] + (c4 * c3) * x[8];
+    xd[3] = x[9] + (s5 * s4 / c4) * x[10] + c3 * s4 / c4 * x[11];
+    xd[4] = (c3) * x[10] + (s3) * x[11];
+    xd[5] = (s3 / c4) * x[10] + (c3 / c4) * x[11];
+    xd[6] = IM0 * (tau[0] + M * x[11] * x[7] - M * x[10] * x[8] - EBUOY * s4 + x[12] + c_Dl[0] * x[6] + c_Dnl[0] * fabs(x[6]) * x[6]);
+    xd[7] = IM1 * (tau[1] - M * x[11] * x[6] + M * x[9] * x[8] + EBUOY * c4 * s3 + x[13] + c_Dl[1] * x[7] + c_Dnl[1] * fabs(x[7]) * x[7]);
+    xd[8] = IM2 * (tau[2] + M * x[10] * x[6] - M * x[9] * x[7] + EBUOY * c4 * c3 + x[14] + c_Dl[2] * x[8] + c_Dnl[2] * fabs(x[8]) * x[8]);
+    xd[9] = IM3 * (tau[3] + (Iy - Iz) * x[10] * x[11] - M * Zg * G * c4 * s3 + x[15] + c_Dl[3] * x[9] + c_Dnl[3] * fabs(x[9]) * x[9]);
+    xd[10] = IM4 * (tau[4] + (Iz - Ix) * x[9] * x[11] - M * Zg * G * s4 + x[16] + c_Dl[4] * x[10] + c_Dnl[4] * fabs(x[10]) * x[10]);
+    xd[11] = IM5 * (tau[5] - (Iy - Ix) * x[9] * x[10] + x[17] + c_Dl[5] * x[11] + c_Dnl[5] * fabs(x[11]) * x[11]);
+#pragma unroll
+    for (int i = 12; i < EN; i++) xd[i] = 0.0;
+}
+
+// measurement model, bluerov2_dob.cpp:698-719
+__device__ void ekf_h(const double* x, const double* acc, double* y)
+{
+    using namespace ekfc;
+    double s3, c3, s4, c4;
+    sincos(x[3], &s3, &c3); sincos(x[4], &s4, &c4);
+#pragma unroll
+    for (int i = 0; i < 12; i++) y[i] = x[i];
+    y[12] = M0 * acc[0] - M * x[11] * x[7] + M * x[10] * x[8] + EBUOY * s4 - x[12] - c_Dl[0] * x[6] - c_Dnl[0] * fabs(x[6]) * x[6];
+    y[13] = M1 * acc[1] + M * x[11] * x[6] - M * x[9] * x[8] - EBUOY * c4 * s3 - x[13] - c_Dl[1] * x[7] - c_Dnl[1] * fabs(x[7]) * x[7];
+    y[14] = M2 * acc[2] - M * x[10] * x[6] + M * x[9] * x[7] - EBUOY * c4 * c3 - x[14] - c_Dl[2] * x[8] - c_Dnl[2] * fabs(x[8]) * x[8];
+    y[15] = M3 * acc[3] - (Iy - Iz) * x[10] * x[11] + M * Zg * G * c4 * s3 - x[15] - c_Dl[3] * x[9] - c_Dnl[3] * fabs(x[9]) * x[9];
+    y[16] = M4 * acc[4] - (Iz - Ix) * x[9] * x[11] + M * Zg * G * s4 - x[16] - c_Dl[4] * x[10] - c_Dnl[4] * fabs(x[10]) * x[10];
+    y[17] = M5 * acc[5] + (Iy - Ix) * x[9] * x[10] - x[17] - c_Dl[5] * x[11] - c_Dnl[5] * fabs(x[11]) * x[11];
+}
+
+__device__ void ekf_rk4(const double* x, const double* tau, double* xn)
+{
+    using namespace ekfc;
+    double k1[EN], k2[EN], k3[EN], k4[EN], xs[EN];
+    ekf_f(x, tau, k1);
+#pragma unroll
+    for (int i = 0; i < EN; i++) { k1[i] *= DT; xs[i] = x[i] + k1[i] / 2; }
+    ekf_f(xs, tau, k2);
+#pragma unroll
+    for (int i = 0; i < EN; i++) { k2[i] *= DT; xs[i] = x[i] + k2[i] / 3; }   // sic: /3 (bluerov2_dob.cpp:630)
+    ekf_f(xs, tau, k3);
+#pragma unroll
+    for (int i = 0; i < EN; i++) { k3[i] *= DT; xs[i] = x[i] + k3[i]; }
+    ekf_f(xs, tau, k4);
+#pragma unroll
+    for (int i = 0; i < EN; i++) { k4[i] *= DT; xn[i] = x[i] + (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]) / 6; }
+}
+
+// C = A * B or A * B' (18x18, shared memory, leading dimension LD); lane i < 18 owns row i.
+__device__ __forceinline__ void mm18(const double* A, const double* B, double* C, bool transB, int lane)
+{
+    if (lane < EN) {
+        double a[EN];
+#pragma unroll
+        for (int k = 0; k < EN; k++) a[k] = A[lane * LD + k];
+#pragma unroll 2
+        for (int j = 0; j < EN; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < EN; k++) s = fma(a[k], transB ? B[j * LD + k] : B[k * LD + j], s);
+            C[lane * LD + j] = s;
+        }
+    }
+    __syncwarp();
+}
+
+struct __align__(16) EkfSmem {
+    double Fm[EN * LD], Hm[EN * LD], Pp[EN * LD], Kal[EN * LD], T1[EN * LD], T2[EN * LD];
+    double aug[EN * 2 * LD];     // [S | I] for the Gauss-Jordan inverse
+    double vec[64];
+};
+
+__global__ void __launch_bounds__(EKF_WARPS * 32) ekf_kernel(EkfArgs a)
+{
+    using namespace ekfc;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    EkfSmem& sm = reinterpret_cast<EkfSmem*>(smraw)[wib];
+    const int inst = blockIdx.x * EKF_WARPS + wib;
+    if (inst >= a.B) return;
+    const double d = 1e-6;
+    double* ex = a.esti_x + (size_t)inst * EN;
+    double* eP = a.esti_P + (size_t)inst * EN * EN;
+
+    // meas_y = [pose, body velocity, tau = K * thrusts] (:499-504)
+    double tau[6], acc[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) s += c_K[i * 6 + j] * a.thrusts[(size_t)inst * 6 + j];
+        tau[i] = s;
+        acc[i] = a.body_acc[(size_t)inst * 6 + i];
+    }
+    double x[EN], f1[EN];
+#pragma unroll
+    for (int i = 0; i < EN; i++) x[i] = ex[i];
+    // esti_P -> shared (T2 as staging)
+    for (int idx = lane; idx < EN * EN; idx += 32) sm.T2[(idx / EN) * LD + idx % EN] = eP[idx];
+
+    // ---- F = d RK4 / dx by forward differences: lane 0 unperturbed, lane c+1 perturbs component c ----
+    if (lane >= 1 && lane <= EN) {
+#pragma unroll
+        for (int i = 0; i < EN; i++)
+            if (i == lane - 1) x[i] += d;
+    }
+    ekf_rk4(x, tau, f1);
+    double xp[EN];   // x_pred = RK4(esti_x) on every lane
+#pragma unroll
+    for (int i = 0; i < EN; i++) {
+        xp[i] = __shfl_sync(FULL_MASK, f1[i], 0);
+        if (lane >= 1 && lane <= EN) sm.Fm[i * LD + lane - 1] = (f1[i] - xp[i]) / d;
+    }
+    __syncwarp();
+    // ---- P_pred = F P F' + Q (:529) ----
+    mm18(sm.Fm, sm.T2, sm.T1, false, lane);
+    mm18(sm.T1, sm.Fm, sm.Pp, true, lane);
+    if (lane < EN) sm.Pp[lane * LD + lane] += (lane < 6) ? (DT * DT * DT * DT) / 4 : DT * DT;
+    __syncwarp();
+    // ---- H = dh/dx at x_pred by forward differences (:738-752) ----
+#pragma unroll
+    for (int i = 0; i < EN; i++) {
+        x[i] = xp[i];
+        if (lane >= 1 && lane <= EN && i == lane - 1) x[i] += d;
+    }
+    double y1[EN], yp[EN];
+    ekf_h(x, acc, y1);
+#pragma unroll
+    for (int i = 0; i < EN; i++) {
+        yp[i] = __shfl_sync(FULL_MASK, y1[i], 0);
+        if (lane >= 1 && lane <= EN) sm.Hm[i * LD + lane - 1] = (y1[i] - yp[i]) / d;
+    }
+    __syncwarp();
+    // ---- S = H Pp H' + R ; explicit inverse by Gauss-Jordan with partial pivoting (:535) ----
+    mm18(sm.Hm, sm.Pp, sm.T1, false, lane);
+    mm18(sm.T1, sm.Hm, sm.T2, true, lane);
+    const int AL = 2 * LD;
+    if (lane < EN) {
+        for (int j = 0; j < EN; j++) {
+            sm.aug[lane * AL + j] = sm.T2[lane * LD + j] + (j == lane ? (DT * DT * DT * DT) / 4 : 0.0);
+            sm.aug[lane * AL + LD + j] = (j == lane) ? 1.0 : 0.0;
+        }
+    }
+    __syncwarp();
+    for (int c = 0; c < EN; c++) {
+        // pivot: largest |a[i][c]| over i >= c, first index on ties
+        double v = (lane >= c && lane < EN) ? fabs(sm.aug[lane * AL + c]) : -1.0;
+        int piv = lane;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double vo = __shfl_xor_sync(FULL_MASK, v, o);
+            const int po = __shfl_xor_sync(FULL_MASK, piv, o);
+            if (vo > v || (vo == v && po < piv)) { v = vo; piv = po; }
+        }
+        if (piv != c) {
+            // swap rows c and piv: lanes 0..2*LD-1 each move one column (2*LD = 40 > 32: two rounds)
+            for (int j = lane; j < AL; j += 32) {
+                const double t = sm.aug[c * AL + j];
+                sm.aug[c * AL + j] = sm.aug[piv * AL + j];
+                sm.aug[piv * AL + j] = t;
+            }
+        }
+        __syncwarp();
+        const double dinv = 1.0 / sm.aug[c * AL + c];
+        __syncwarp();
+        for (int j = lane; j < AL; j += 32) sm.aug[c * AL + j] *= dinv;
+        __syncwarp();
+        if (lane < EN && lane != c) {
+            const double f = sm.aug[lane * AL + c];
+            if (f != 0.0) {
+                for (int j = 0; j < EN; j++) sm.aug[lane * AL + j] -= f * sm.aug[c * AL + j];
+                for (int j = 0; j < EN; j++) sm.aug[lane * AL + LD + j] -= f * sm.aug[c * AL + LD + j];
+            }
+        }
+        __syncwarp();
+    }
+    // Si -> T2
+    if (lane < EN)
+        for (int j = 0; j < EN; j++) sm.T2[lane * LD + j] = sm.aug[lane * AL + LD + j];
+    __syncwarp();
+    // ---- Kal = Pp H' Si ----
+    mm18(sm.Pp, sm.Hm, sm.T1, true, lane);
+    mm18(sm.T1, sm.T2, sm.Kal, false, lane);
+    // ---- esti_x = x_pred + Kal (y - y_pred) (:536) ----
+    if (lane < EN) {
+        double ym;
+        if (lane < 12) ym = a.meas[(size_t)inst * 12 + lane];
+        else {
+            ym = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+                if (i == lane - 12) ym = tau[i];
+        }
+        double ypl = 0.0;
+#pragma unroll
+        for (int i = 0; i < EN; i++)
+            if (i == lane) ypl = yp[i];
+        sm.vec[lane] = ym - ypl;
+        sm.vec[32 + lane] = ym;
+    }
+    __syncwarp();
+    double exn = 0.0;
+    if (lane < EN) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < EN; i++)
+            if (i == lane) s = xp[i];
+        for (int j = 0; j < EN; j++) s += sm.Kal[lane * LD + j] * sm.vec[j];
+        exn = s;
+        ex[lane] = s;
+    }
+    // ---- Joseph form (:537): P = (I - K H) Pp (I - K H)' + K R K' ----
+    mm18(sm.Kal, sm.Hm, sm.T1, false, lane);
+    if (lane < EN)
+        for (int j = 0; j < EN; j++) sm.T1[lane * LD + j] = (j == lane ? 1.0 : 0.0) - sm.T1[lane * LD + j];
+    __syncwarp();
+    mm18(sm.T1, sm.Pp, sm.T2, false, lane);
+    mm18(sm.T2, sm.T1, sm.Fm, true, lane);          // Fm reused: (I-KH) Pp (I-KH)'
+    mm18(sm.Kal, sm.Kal, sm.T2, true, lane);        // K K'
+    for (int idx = lane; idx < EN * EN; idx += 32) {
+        const int i = idx / EN, j = idx % EN;
+        eP[idx] = sm.Fm[i * LD + j] + sm.T2[i * LD + j] * ((DT * DT * DT * DT) / 4);
+    }
+    // ---- world-frame disturbance (:540-545) and OCP parameters (:324-355) ----
+    const double e12 = __shfl_sync(FULL_MASK, exn, 12), e13 = __shfl_sync(FULL_MASK, exn, 13), e14 = __shfl_sync(FULL_MASK, exn, 14);
+    const double e15 = __shfl_sync(FULL_MASK, exn, 15), e16 = __shfl_sync(FULL_MASK, exn, 16), e17 = __shfl_sync(FULL_MASK, exn, 17);
+    if (lane == 0) {
+        if (a.wf_dist) {
+            double s3, c3, s4, c4, s5, c5;
+            sincos(sm.vec[32 + 3], &s3, &c3); sincos(sm.vec[32 + 4], &s4, &c4); sincos(sm.vec[32 + 5], &s5, &c5);
+            double* wf = a.wf_dist + (size_t)inst * 6;
+            wf[0] = (c5 * c4) * e12 + (-s5 * c3 + c5 * s4 * s3) * e13 + (s5 * s3 + c5 * c3 * s4) * e14;
+            wf[1] = (s5 * c4) * e12 + (c5 * c3 + s3 * s4 * s5) * e13 + (-c5 * s3 + s4 * s5 * c3) * e14;
+            wf[2] = (-s4) * e12 + (c4 * s3) * e13 + (c4 * c3) * e14;
+            wf[3] = e15 + (s5 * s4 / c4) * e16 + c3 * s4 / c4 * e17;
+            wf[4] = (c3) * e16 + (s3) * e17;
+            wf[5] = (s3 / c4) * e16 + (c3 / c4) * e17;
+        }
+        if (a.p_out) {
+            double* p = a.p_out + (size_t)inst * NP;
+            p[0] = a.compensate ? e12 / COMP : 0.0;
+            p[1] = a.compensate ? e13 / COMP : 0.0;
+            p[2] = a.compensate ? e14 / RCK : 0.0;
+            p[3] = a.compensate ? e17 / RCK : 0.0;
+            p[4] = 1.7182; p[5] = 0; p[6] = 5.468; p[7] = 0.4006;
+            p[8] = -11.7391; p[9] = -20; p[10] = -31.8678; p[11] = -5;
+            p[12] = -18.18; p[13] = -21.66; p[14] = -36.99; p[15] = -1.55;
+        }
+    }
+}
+
+void launch_ekf(const EkfArgs& a, cudaStream_t s)
+{
+    static bool configured = false;
+    const size_t smem = sizeof(EkfSmem) * EKF_WARPS;
+    if (!configured) {
+        cudaFuncSetAttribute(ekf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    const int grid = (a.B + EKF_WARPS - 1) / EKF_WARPS;
+    ekf_kernel<<<grid, EKF_WARPS * 32, smem, s>>>(a);
+}
+
+}  // namespace br2

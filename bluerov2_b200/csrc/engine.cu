@@ -1,0 +1,434 @@
+// engine.cu -- host side of the batched SQP-RTI engine and its C-ABI (include/bluerov2_b200.h).
+//
+// Owns the HBM-resident state of B OCP instances (iterate, stage records, IPM workspaces, EKF state) and
+// enqueues the kernels of kernels.cu / ekf.cu.  No CPU fallback exists: creation fails without a CUDA device.
+#include "engine.h"
+#include "../../include/bluerov2_b200.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+using namespace br2;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(BR2_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct br2_batch_solver {
+    int B, N, device, sm_count;
+    double Ts[NMAX];
+    double W[16], We[12], lbu[4], ubu[4];
+    int max_iter;
+    double tol;
+    // device state
+    double *d_Ts, *d_X, *d_U, *d_G, *d_F, *d_V, *d_u0, *d_thrust, *d_info;
+    int *d_status, *d_iters, *d_counter;
+    double *d_x0, *d_yref, *d_p;              // staging for the host API
+    double *d_ex, *d_eP, *d_thr, *d_meas, *d_acc, *d_wf, *d_pout;   // EKF state + staging
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1, ev_mid;   // solve start / end / between linearisation and IPM
+    unsigned long long* d_iter_total;   // IPM iterations executed, summed over instances and solves
+    bool timed;
+};
+
+// generated-C defaults: acados_solver_bluerov2.c:424-459 (W), :468-479 (W_e), :547-571 (bounds)
+static const double kW[16] = {300, 480, 200, 10, 10, 200, 40, 40, 10, 10, 10, 10, 1, 1, 0.1, 0.05};
+
+extern "C" const char* br2_last_error(void) { return g_err; }
+extern "C" const char* br2_version(void) { return "bluerov2_b200 0.1 (sm_100a)"; }
+extern "C" int br2_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+template <class T>
+static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+extern "C" int br2_batch_free(br2_batch_solver* s)
+{
+    if (!s) return BR2_OK;
+    cudaSetDevice(s->device);
+    void* ptrs[] = {s->d_Ts, s->d_X, s->d_U, s->d_G, s->d_F, s->d_V, s->d_u0, s->d_thrust, s->d_info, s->d_status,
+                    s->d_iters, s->d_counter, s->d_x0, s->d_yref, s->d_p, s->d_ex, s->d_eP, s->d_thr, s->d_meas,
+                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_mid) cudaEventDestroy(s->ev_mid);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    free(s);
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const double* time_steps, int device)
+{
+    if (!out) return fail(BR2_EINVAL, "br2_batch_create: out is NULL");
+    *out = nullptr;
+    if (batch < 1) return fail(BR2_EINVAL, "br2_batch_create: batch = %d", batch);
+    if (N < 1 || N > NMAX) return fail(BR2_EINVAL, "br2_batch_create: N = %d outside [1, %d]", N, NMAX);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BR2_ECUDA, "br2_batch_create: no CUDA device (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= ndev) return fail(BR2_EINVAL, "br2_batch_create: device %d of %d", device, ndev);
+    CK(cudaSetDevice(device));
+    br2_batch_solver* s = (br2_batch_solver*)calloc(1, sizeof(br2_batch_solver));
+    if (!s) return fail(BR2_ENOMEM, "br2_batch_create: out of host memory");
+    s->B = batch; s->N = N; s->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    for (int k = 0; k < N; k++) s->Ts[k] = time_steps ? time_steps[k] : 1.0 / N;
+    memcpy(s->W, kW, sizeof kW);
+    memcpy(s->We, kW, sizeof(double) * 12);
+    for (int i = 0; i < 4; i++) { s->lbu[i] = -50.0; s->ubu[i] = 50.0; }
+    s->max_iter = 50;
+    s->tol = 1e-11;
+    const size_t B = batch;
+#define DA(p, n)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = dalloc(&s->p, (n));                                                              \
+        if (e_ != cudaSuccess) {                                                                          \
+            br2_batch_free(s);                                                                            \
+            return fail(BR2_ENOMEM, "cudaMalloc(%s, %zu elements) failed: %s", #p, (size_t)(n), cudaGetErrorString(e_)); \
+        }                                                                                                 \
+    } while (0)
+    DA(d_Ts, N); DA(d_X, B * (N + 1) * NX); DA(d_U, B * N * NU);
+    DA(d_G, B * N * GREC); DA(d_F, B * N * FREC); DA(d_V, B * (N + 1) * VREC);
+    DA(d_u0, B * 4); DA(d_thrust, B * 6); DA(d_info, B * 4); DA(d_status, B); DA(d_iters, B); DA(d_counter, 1);
+    DA(d_x0, B * NX); DA(d_yref, B * (N + 1) * NY); DA(d_p, B * (N + 1) * NP);
+    DA(d_ex, B * 18); DA(d_eP, B * 324); DA(d_thr, B * 6); DA(d_meas, B * 12); DA(d_acc, B * 6); DA(d_wf, B * 6);
+    DA(d_pout, B * NP);
+    DA(d_iter_total, 1);
+#undef DA
+    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&s->ev0));
+    CK(cudaEventCreate(&s->ev1));
+    CK(cudaEventCreate(&s->ev_mid));
+    CK(cudaMemset(s->d_iter_total, 0, sizeof(unsigned long long)));
+    CK(cudaMemcpy(s->d_Ts, s->Ts, sizeof(double) * N, cudaMemcpyHostToDevice));
+    CK(cudaMemset(s->d_status, 0, sizeof(int) * B));
+    CK(cudaMemset(s->d_iters, 0, sizeof(int) * B));
+    CK(cudaMemset(s->d_info, 0, sizeof(double) * B * 4));
+    CK(cudaMemset(s->d_V, 0, sizeof(double) * B * (N + 1) * VREC));
+    *out = s;
+    int rc = br2_batch_reset(s, 0);
+    if (rc == BR2_OK) rc = br2_batch_ekf_reset(s);
+    if (rc != BR2_OK) { br2_batch_free(s); *out = nullptr; }
+    return rc;
+}
+
+extern "C" int br2_batch_size(const br2_batch_solver* s) { return s ? s->B : 0; }
+extern "C" int br2_batch_horizon(const br2_batch_solver* s) { return s ? s->N : 0; }
+
+extern "C" int br2_batch_set_weights(br2_batch_solver* s, const double* W16, const double* We12)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    if (W16) {
+        for (int i = 0; i < 16; i++)
+            if (!(W16[i] >= 0) || (i >= 12 && !(W16[i] > 0))) return fail(BR2_EINVAL, "W[%d] = %g: need W >= 0 and R > 0", i, W16[i]);
+        memcpy(s->W, W16, sizeof(double) * 16);
+    }
+    if (We12) {
+        for (int i = 0; i < 12; i++)
+            if (!(We12[i] >= 0)) return fail(BR2_EINVAL, "We[%d] = %g: need >= 0", i, We12[i]);
+        memcpy(s->We, We12, sizeof(double) * 12);
+    }
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_set_bounds(br2_batch_solver* s, const double* lbu4, const double* ubu4)
+{
+    if (!s || !lbu4 || !ubu4) return fail(BR2_EINVAL, "null argument");
+    for (int i = 0; i < 4; i++)
+        if (!(lbu4[i] < ubu4[i])) return fail(BR2_EINVAL, "bounds %d: lbu %g >= ubu %g", i, lbu4[i], ubu4[i]);
+    memcpy(s->lbu, lbu4, sizeof(double) * 4);
+    memcpy(s->ubu, ubu4, sizeof(double) * 4);
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_set_time_steps(br2_batch_solver* s, const double* ts)
+{
+    if (!s || !ts) return fail(BR2_EINVAL, "null argument");
+    for (int k = 0; k < s->N; k++)
+        if (!(ts[k] > 0)) return fail(BR2_EINVAL, "time_steps[%d] = %g", k, ts[k]);
+    memcpy(s->Ts, ts, sizeof(double) * s->N);
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemcpy(s->d_Ts, s->Ts, sizeof(double) * s->N, cudaMemcpyHostToDevice));
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_set_option_int(br2_batch_solver* s, const char* name, int v)
+{
+    if (!s || !name) return fail(BR2_EINVAL, "null argument");
+    if (!strcmp(name, "qp_iter_max")) {
+        if (v < 1) return fail(BR2_EINVAL, "qp_iter_max = %d", v);
+        s->max_iter = v;
+        return BR2_OK;
+    }
+    return fail(BR2_EINVAL, "unknown int option '%s'", name);
+}
+extern "C" int br2_batch_set_option_double(br2_batch_solver* s, const char* name, double v)
+{
+    if (!s || !name) return fail(BR2_EINVAL, "null argument");
+    if (!strcmp(name, "qp_tol")) {
+        if (!(v > 0)) return fail(BR2_EINVAL, "qp_tol = %g", v);
+        s->tol = v;
+        return BR2_OK;
+    }
+    return fail(BR2_EINVAL, "unknown double option '%s'", name);
+}
+
+extern "C" int br2_batch_reset(br2_batch_solver* s, int mode)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    const size_t nX = (size_t)s->B * (s->N + 1) * NX, nU = (size_t)s->B * s->N * NU;
+    CK(cudaMemset(s->d_U, 0, sizeof(double) * nU));
+    CK(cudaMemset(s->d_X, 0, sizeof(double) * nX));
+    if (mode == 0) {
+        // x_k = (0, 0, -20, 0, ...) for every stage: acados_solver_bluerov2.c:681-708
+        double* h = (double*)calloc(nX, sizeof(double));
+        if (!h) return fail(BR2_ENOMEM, "out of host memory");
+        for (size_t i = 0; i < nX / NX; i++) h[i * NX + 2] = -20.0;
+        cudaError_t e = cudaMemcpy(s->d_X, h, sizeof(double) * nX, cudaMemcpyHostToDevice);
+        free(h);
+        CK(e);
+    }
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_set_iterate_host(br2_batch_solver* s, const double* X, const double* U)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    if (X) CK(cudaMemcpy(s->d_X, X, sizeof(double) * s->B * (s->N + 1) * NX, cudaMemcpyHostToDevice));
+    if (U) CK(cudaMemcpy(s->d_U, U, sizeof(double) * s->B * s->N * NU, cudaMemcpyHostToDevice));
+    return BR2_OK;
+}
+extern "C" int br2_batch_get_iterate_host(br2_batch_solver* s, double* X, double* U)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    if (X) CK(cudaMemcpy(X, s->d_X, sizeof(double) * s->B * (s->N + 1) * NX, cudaMemcpyDeviceToHost));
+    if (U) CK(cudaMemcpy(U, s->d_U, sizeof(double) * s->B * s->N * NU, cudaMemcpyDeviceToHost));
+    return BR2_OK;
+}
+extern "C" int br2_batch_iterate_device(br2_batch_solver* s, double** X, double** U)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    if (X) *X = s->d_X;
+    if (U) *U = s->d_U;
+    return BR2_OK;
+}
+
+static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, const double* d_yref, const double* d_p,
+                      int p_per_stage, double* d_u0, double* d_thrust, int* d_status)
+{
+    a.B = s->B; a.N = s->N;
+    a.x0 = d_x0; a.yref = d_yref; a.p = d_p;
+    a.p_inst_stride = p_per_stage ? (s->N + 1) * NP : NP;
+    a.p_stage_stride = p_per_stage ? NP : 0;
+    a.Ts = s->d_Ts;
+    memcpy(a.W, s->W, sizeof a.W); memcpy(a.We, s->We, sizeof a.We);
+    memcpy(a.lbu, s->lbu, sizeof a.lbu); memcpy(a.ubu, s->ubu, sizeof a.ubu);
+    a.X = s->d_X; a.U = s->d_U; a.G = s->d_G; a.F = s->d_F; a.V = s->d_V;
+    a.u0 = d_u0 ? d_u0 : s->d_u0;
+    a.thrust = d_thrust ? d_thrust : s->d_thrust;
+    a.status = d_status ? d_status : s->d_status;
+    a.iters = s->d_iters; a.info = s->d_info; a.work_counter = s->d_counter; a.iter_total = s->d_iter_total;
+    a.max_iter = s->max_iter; a.tol = s->tol;
+}
+
+extern "C" int br2_batch_solve_device(br2_batch_solver* s, const double* d_x0, const double* d_yref, const double* d_p,
+                                      int p_per_stage, double* d_u0, double* d_thrust, int* d_status, void* stream)
+{
+    if (!s || !d_x0 || !d_yref || !d_p) return fail(BR2_EINVAL, "br2_batch_solve_device: null argument");
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SolveArgs a;
+    fill_args(s, a, d_x0, d_yref, d_p, p_per_stage, d_u0, d_thrust, d_status);
+    CK(cudaEventRecord(s->ev0, st));
+    launch_linearize(a, st);
+    CK(cudaEventRecord(s->ev_mid, st));
+    launch_ipm(a, s->sm_count, st);
+    CK(cudaEventRecord(s->ev1, st));
+    s->timed = true;
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_solve_host(br2_batch_solver* s, const double* x0, const double* yref, const double* p,
+                                    int p_per_stage, double* u0, double* thrust, int* status)
+{
+    if (!s || !x0 || !yref || !p) return fail(BR2_EINVAL, "br2_batch_solve_host: null argument");
+    CK(cudaSetDevice(s->device));
+    const size_t B = s->B, N = s->N;
+    cudaStream_t st = s->stream;
+    CK(cudaMemcpyAsync(s->d_x0, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_yref, yref, sizeof(double) * B * (N + 1) * NY, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_p, p, sizeof(double) * B * (p_per_stage ? (N + 1) * NP : NP), cudaMemcpyHostToDevice, st));
+    int rc = br2_batch_solve_device(s, s->d_x0, s->d_yref, s->d_p, p_per_stage, nullptr, nullptr, nullptr, st);
+    if (rc != BR2_OK) return rc;
+    if (u0) CK(cudaMemcpyAsync(u0, s->d_u0, sizeof(double) * B * 4, cudaMemcpyDeviceToHost, st));
+    if (thrust) CK(cudaMemcpyAsync(thrust, s->d_thrust, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, s->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_get_stats_host(br2_batch_solver* s, int* iters, double* info)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    if (iters) CK(cudaMemcpy(iters, s->d_iters, sizeof(int) * s->B, cudaMemcpyDeviceToHost));
+    if (info) CK(cudaMemcpy(info, s->d_info, sizeof(double) * s->B * 4, cudaMemcpyDeviceToHost));
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_get_linearization_host(br2_batch_solver* s, double* AB, double* b)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    const size_t n = (size_t)s->B * s->N;
+    double* h = (double*)malloc(sizeof(double) * n * GREC);
+    if (!h) return fail(BR2_ENOMEM, "out of host memory");
+    cudaError_t e = cudaMemcpy(h, s->d_G, sizeof(double) * n * GREC, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        for (size_t i = 0; i < n; i++) {
+            if (AB) memcpy(AB + i * 192, h + i * GREC, sizeof(double) * 192);
+            if (b) memcpy(b + i * 12, h + i * GREC + G_B_OFF, sizeof(double) * 12);
+        }
+    free(h);
+    CK(e);
+    return BR2_OK;
+}
+
+extern "C" double br2_batch_last_solve_time(br2_batch_solver* s)
+{
+    if (!s || !s->timed) return 0.0;
+    cudaSetDevice(s->device);
+    if (cudaEventSynchronize(s->ev1) != cudaSuccess) return 0.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) != cudaSuccess) return 0.0;
+    return ms * 1e-3;
+}
+
+extern "C" int br2_batch_last_kernel_times(br2_batch_solver* s, double* t_linearize, double* t_ipm)
+{
+    if (!s || !s->timed) return fail(BR2_EINVAL, "no solve recorded");
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventSynchronize(s->ev1));
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, s->ev0, s->ev_mid));
+    CK(cudaEventElapsedTime(&b, s->ev_mid, s->ev1));
+    if (t_linearize) *t_linearize = a * 1e-3;
+    if (t_ipm) *t_ipm = b * 1e-3;
+    return BR2_OK;
+}
+
+extern "C" long long br2_batch_ipm_iterations_total(br2_batch_solver* s, int reset)
+{
+    if (!s) return -1;
+    cudaSetDevice(s->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, s->d_iter_total, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset) cudaMemset(s->d_iter_total, 0, sizeof v);
+    return (long long)v;
+}
+
+// ---- EKF ------------------------------------------------------------------------------------------------
+extern "C" int br2_batch_ekf_reset(br2_batch_solver* s)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    const size_t B = s->B;
+    double* hx = (double*)calloc(B * 18, sizeof(double));
+    double* hP = (double*)calloc(B * 324, sizeof(double));
+    if (!hx || !hP) { free(hx); free(hP); return fail(BR2_ENOMEM, "out of host memory"); }
+    for (size_t i = 0; i < B; i++) {
+        hx[i * 18 + 2] = -20.0;                                  // esti_x, bluerov2_dob.cpp:64
+        hx[i * 18 + 12] = hx[i * 18 + 13] = hx[i * 18 + 14] = 6.0;
+        for (int j = 0; j < 18; j++) hP[i * 324 + j * 19] = 1.0;  // P0 = I, bluerov2_dob.h:203
+    }
+    cudaError_t e1 = cudaMemcpy(s->d_ex, hx, sizeof(double) * B * 18, cudaMemcpyHostToDevice);
+    cudaError_t e2 = cudaMemcpy(s->d_eP, hP, sizeof(double) * B * 324, cudaMemcpyHostToDevice);
+    free(hx); free(hP);
+    CK(e1); CK(e2);
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_ekf_device(br2_batch_solver* s, const double* d_thrusts, const double* d_meas,
+                                    const double* d_body_acc, double* d_wf_dist, double* d_p_out, int compensate, void* stream)
+{
+    if (!s || !d_thrusts || !d_meas || !d_body_acc) return fail(BR2_EINVAL, "br2_batch_ekf_device: null argument");
+    CK(cudaSetDevice(s->device));
+    EkfArgs a;
+    a.B = s->B; a.esti_x = s->d_ex; a.esti_P = s->d_eP;
+    a.thrusts = d_thrusts; a.meas = d_meas; a.body_acc = d_body_acc;
+    a.wf_dist = d_wf_dist; a.p_out = d_p_out; a.compensate = compensate;
+    launch_ekf(a, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_ekf_host(br2_batch_solver* s, const double* thrusts, const double* meas, const double* body_acc,
+                                  double* wf_dist, double* p_out, int compensate)
+{
+    if (!s || !thrusts || !meas || !body_acc) return fail(BR2_EINVAL, "br2_batch_ekf_host: null argument");
+    CK(cudaSetDevice(s->device));
+    const size_t B = s->B;
+    cudaStream_t st = s->stream;
+    CK(cudaMemcpyAsync(s->d_thr, thrusts, sizeof(double) * B * 6, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_meas, meas, sizeof(double) * B * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_acc, body_acc, sizeof(double) * B * 6, cudaMemcpyHostToDevice, st));
+    int rc = br2_batch_ekf_device(s, s->d_thr, s->d_meas, s->d_acc, s->d_wf, s->d_pout, compensate, st);
+    if (rc != BR2_OK) return rc;
+    if (wf_dist) CK(cudaMemcpyAsync(wf_dist, s->d_wf, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
+    if (p_out) CK(cudaMemcpyAsync(p_out, s->d_pout, sizeof(double) * B * NP, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_ekf_get_state_host(br2_batch_solver* s, double* esti_x, double* esti_P)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    if (esti_x) CK(cudaMemcpy(esti_x, s->d_ex, sizeof(double) * s->B * 18, cudaMemcpyDeviceToHost));
+    if (esti_P) CK(cudaMemcpy(esti_P, s->d_eP, sizeof(double) * s->B * 324, cudaMemcpyDeviceToHost));
+    return BR2_OK;
+}
+extern "C" int br2_batch_ekf_set_state_host(br2_batch_solver* s, const double* esti_x, const double* esti_P)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    if (esti_x) CK(cudaMemcpy(s->d_ex, esti_x, sizeof(double) * s->B * 18, cudaMemcpyHostToDevice));
+    if (esti_P) CK(cudaMemcpy(s->d_eP, esti_P, sizeof(double) * s->B * 324, cudaMemcpyHostToDevice));
+    return BR2_OK;
+}

@@ -1,0 +1,59 @@
+// engine.h -- internal interface between the host engine (engine.cu) and the kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "layout.h"
+#include "model.cuh"
+
+namespace br2 {
+
+constexpr int NMAX = 256;   // maximum horizon supported by the engine
+
+// Everything a launch needs; passed by value (fits the 4 KB kernel parameter space).
+struct SolveArgs {
+    int B, N;
+    // problem data (device)
+    const double* x0;      // [B][12]
+    const double* yref;    // [B][N+1][16]
+    const double* p;       // [B][p_inst_stride]: stage k reads p + k*p_stage_stride
+    int p_inst_stride;     // 16 (one vector per instance) or (N+1)*16
+    int p_stage_stride;    // 0 or 16
+    const double* Ts;      // [N] (device)
+    double W[16], We[12], lbu[4], ubu[4];
+    // iterate (device, in/out)
+    double* X;             // [B][N+1][12]
+    double* U;             // [B][N][4]
+    // workspaces (device)
+    double* G;             // [B][N][GREC]
+    double* F;             // [B][N][FREC]
+    double* V;             // [B][N+1][VREC]
+    // outputs (device)
+    double* u0;            // [B][4]
+    double* thrust;        // [B][6]  (may alias an NCCL / symmetric send buffer)
+    int* status;           // [B]
+    int* iters;            // [B]
+    double* info;          // [B][4]: mu, res_stat, max|b| (dynamics gap at the linearisation point), max step
+    int* work_counter;     // [1] persistent-kernel instance queue
+    unsigned long long* iter_total;   // [1] IPM iterations executed, accumulated over instances and solves
+    // options
+    int max_iter;          // qp_solver_iter_max (50)
+    double tol;            // IPM tolerance on mu and on the scaled stationarity residual
+};
+
+void launch_linearize(const SolveArgs& a, cudaStream_t s);
+void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s);
+
+// EKF (bluerov2_dob.cpp:495-545), one warp per instance
+struct EkfArgs {
+    int B;
+    double* esti_x;          // [B][18] in/out
+    double* esti_P;          // [B][18][18] in/out
+    const double* thrusts;   // [B][6]  measured thruster forces (meas_u)
+    const double* meas;      // [B][12] pose + body velocities
+    const double* body_acc;  // [B][6]
+    double* wf_dist;         // [B][6] out (may be null)
+    double* p_out;           // [B][16] out (may be null): OCP parameter vector per bluerov2_dob.cpp:324-355
+    int compensate;          // COMPENSATE_D
+};
+void launch_ekf(const EkfArgs& a, cudaStream_t s);
+
+}  // namespace br2

@@ -1,0 +1,266 @@
+"""Host-side mirror of the batched C-ABI (include/bluerov2_b200.h), via ctypes.
+
+``BatchSolver`` is to B instances what the capsule of the acados-generated solver is to one
+(bluerov2_dobmpc/scripts/c_generated_code/acados_solver_bluerov2.h:79-167): create once, then per control tick
+set (x0, yref, p) and solve, exactly the call sequence of ``BLUEROV2_DOB::solve`` (bluerov2_dob.cpp:307-395).
+The arithmetic is entirely in the CUDA library; this file only marshals pointers.  There is NO CPU path: the
+constructor raises if the library is missing or no CUDA device is visible.
+
+Inputs may be
+
+* numpy arrays (host): ``solve`` goes through ``br2_batch_solve_host`` (H2D, kernels, D2H, synchronise);
+* torch CUDA tensors (float64, contiguous, on the solver's device): ``solve`` only enqueues on torch's current
+  stream through ``br2_batch_solve_device`` and returns torch tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+NX, NU, NP, NY, NTHRUST, NEKF = 12, 4, 16, 16, 6, 18
+
+_D = C.POINTER(C.c_double)
+_I = C.POINTER(C.c_int)
+_lib = None
+
+
+class SolverError(RuntimeError):
+    pass
+
+
+def load_library(path: str | None = None):
+    """dlopen the product library (built in-tree by bluerov2_b200.build).  Raises if it does not exist."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _build.LIB
+    if not os.path.exists(path):
+        raise SolverError(f"{path} not built: run `python -m bluerov2_b200.build` (needs nvcc); there is no CPU fallback")
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    V = C.c_void_p
+    sig = {
+        "br2_last_error": (C.c_char_p, []),
+        "br2_version": (C.c_char_p, []),
+        "br2_device_count": (C.c_int, []),
+        "br2_batch_create": (C.c_int, [C.POINTER(V), C.c_int, C.c_int, V, C.c_int]),
+        "br2_batch_free": (C.c_int, [V]),
+        "br2_batch_size": (C.c_int, [V]),
+        "br2_batch_horizon": (C.c_int, [V]),
+        "br2_batch_set_weights": (C.c_int, [V, V, V]),
+        "br2_batch_set_bounds": (C.c_int, [V, V, V]),
+        "br2_batch_set_time_steps": (C.c_int, [V, V]),
+        "br2_batch_set_option_int": (C.c_int, [V, C.c_char_p, C.c_int]),
+        "br2_batch_set_option_double": (C.c_int, [V, C.c_char_p, C.c_double]),
+        "br2_batch_reset": (C.c_int, [V, C.c_int]),
+        "br2_batch_set_iterate_host": (C.c_int, [V, V, V]),
+        "br2_batch_get_iterate_host": (C.c_int, [V, V, V]),
+        "br2_batch_iterate_device": (C.c_int, [V, C.POINTER(V), C.POINTER(V)]),
+        "br2_batch_solve_device": (C.c_int, [V, V, V, V, C.c_int, V, V, V, V]),
+        "br2_batch_solve_host": (C.c_int, [V, V, V, V, C.c_int, V, V, V]),
+        "br2_batch_get_stats_host": (C.c_int, [V, V, V]),
+        "br2_batch_get_linearization_host": (C.c_int, [V, V, V]),
+        "br2_batch_last_solve_time": (C.c_double, [V]),
+        "br2_batch_last_kernel_times": (C.c_int, [V, _D, _D]),
+        "br2_batch_ipm_iterations_total": (C.c_longlong, [V, C.c_int]),
+        "br2_batch_ekf_reset": (C.c_int, [V]),
+        "br2_batch_ekf_device": (C.c_int, [V, V, V, V, V, V, C.c_int, V]),
+        "br2_batch_ekf_host": (C.c_int, [V, V, V, V, V, V, C.c_int]),
+        "br2_batch_ekf_get_state_host": (C.c_int, [V, V, V]),
+        "br2_batch_ekf_set_state_host": (C.c_int, [V, V, V]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _is_torch(a) -> bool:
+    return type(a).__module__.startswith("torch")
+
+
+def _np(a, shape, dtype=np.float64):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if a.shape != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+class BatchSolver:
+    """B independent BlueROV2 OCP instances advanced by one SQP-RTI step per ``solve`` call."""
+
+    def __init__(self, batch: int, N: int = 40, time_steps=None, device: int = 0, lib_path: str | None = None):
+        self._L = load_library(lib_path)
+        self._h = C.c_void_p()
+        ts = None if time_steps is None else _np(time_steps, (N,))
+        self._check(self._L.br2_batch_create(C.byref(self._h), int(batch), int(N), _ptr(ts), int(device)))
+        self.B, self.N, self.device = int(batch), int(N), int(device)
+
+    # -- plumbing --------------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SolverError(f"bluerov2_b200 error {rc}: {self._L.br2_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.br2_batch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev_check(self, t, shape, dtype=None):
+        import torch
+        dtype = dtype or torch.float64
+        if not t.is_cuda or t.device.index != self.device:
+            raise ValueError(f"tensor must live on cuda:{self.device}")
+        if t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected contiguous {dtype} tensor of shape {tuple(shape)}, got {t.dtype} {tuple(t.shape)}")
+        return t
+
+    # -- configuration (== the options baked by generate_c_code.py / settable through ocp_nlp_*_set) ----
+    def set_weights(self, W=None, We=None):
+        W = None if W is None else _np(W, (16,))
+        We = None if We is None else _np(We, (12,))
+        self._check(self._L.br2_batch_set_weights(self._h, _ptr(W), _ptr(We)))
+
+    def set_bounds(self, lbu, ubu):
+        lbu, ubu = _np(lbu, (4,)), _np(ubu, (4,))
+        self._check(self._L.br2_batch_set_bounds(self._h, _ptr(lbu), _ptr(ubu)))
+
+    def set_time_steps(self, ts):
+        ts = _np(ts, (self.N,))
+        self._check(self._L.br2_batch_set_time_steps(self._h, _ptr(ts)))
+
+    def set_option(self, name: str, value):
+        if isinstance(value, (int, np.integer)) and not isinstance(value, bool):
+            self._check(self._L.br2_batch_set_option_int(self._h, name.encode(), int(value)))
+        else:
+            self._check(self._L.br2_batch_set_option_double(self._h, name.encode(), float(value)))
+
+    # -- iterate (nlp_out) -----------------------------------------------------------------------------
+    def reset(self, mode: int = 0):
+        self._check(self._L.br2_batch_reset(self._h, int(mode)))
+
+    def set_iterate(self, X=None, U=None):
+        X = None if X is None else _np(X, (self.B, self.N + 1, NX))
+        U = None if U is None else _np(U, (self.B, self.N, NU))
+        self._check(self._L.br2_batch_set_iterate_host(self._h, _ptr(X), _ptr(U)))
+
+    def get_iterate(self):
+        X = np.empty((self.B, self.N + 1, NX))
+        U = np.empty((self.B, self.N, NU))
+        self._check(self._L.br2_batch_get_iterate_host(self._h, _ptr(X), _ptr(U)))
+        return X, U
+
+    # -- the RTI step ----------------------------------------------------------------------------------
+    def solve(self, x0, yref, p, out=None):
+        """One SQP-RTI step for all instances.  Returns (u0[B,4], thrust[B,6], status[B]).
+
+        ``p`` is [B,16] (one parameter vector per instance, what the nodes do: bluerov2_dob.cpp:324-355) or
+        [B,N+1,16] (per stage, acados_solver_bluerov2.c:835-883).  ``out`` = (u0, thrust, status) buffers to reuse.
+        """
+        per_stage = int(len(p.shape) == 3)
+        pshape = (self.B, self.N + 1, NP) if per_stage else (self.B, NP)
+        if _is_torch(x0):
+            import torch
+            self._dev_check(x0, (self.B, NX)); self._dev_check(yref, (self.B, self.N + 1, NY)); self._dev_check(p, pshape)
+            if out is None:
+                dev = x0.device
+                out = (torch.empty((self.B, NU), dtype=torch.float64, device=dev),
+                       torch.empty((self.B, NTHRUST), dtype=torch.float64, device=dev),
+                       torch.empty((self.B,), dtype=torch.int32, device=dev))
+            u0, th, st = out
+            self._dev_check(u0, (self.B, NU)); self._dev_check(th, (self.B, NTHRUST)); self._dev_check(st, (self.B,), torch.int32)
+            stream = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)
+            self._check(self._L.br2_batch_solve_device(self._h, _ptr(x0), _ptr(yref), _ptr(p), per_stage,
+                                                       _ptr(u0), _ptr(th), _ptr(st), stream))
+            return u0, th, st
+        x0, yref, p = _np(x0, (self.B, NX)), _np(yref, (self.B, self.N + 1, NY)), _np(p, pshape)
+        if out is None:
+            out = (np.empty((self.B, NU)), np.empty((self.B, NTHRUST)), np.empty((self.B,), dtype=np.int32))
+        u0, th, st = out
+        self._check(self._L.br2_batch_solve_host(self._h, _ptr(x0), _ptr(yref), _ptr(p), per_stage,
+                                                 _ptr(u0), _ptr(th), _ptr(st)))
+        return u0, th, st
+
+    def stats(self):
+        """(ipm_iterations[B], info[B,4] = (mu, stationarity residual, max |dynamics gap|, stationarity scale))."""
+        it = np.empty((self.B,), dtype=np.int32)
+        info = np.empty((self.B, 4))
+        self._check(self._L.br2_batch_get_stats_host(self._h, _ptr(it), _ptr(info)))
+        return it, info
+
+    def linearization(self):
+        """(A[B,N,12,12], B[B,N,12,4], b[B,N,12]) of the last solve."""
+        AB = np.empty((self.B, self.N, 12, 16))
+        b = np.empty((self.B, self.N, 12))
+        self._check(self._L.br2_batch_get_linearization_host(self._h, _ptr(AB), _ptr(b)))
+        return np.ascontiguousarray(AB[..., :12]), np.ascontiguousarray(AB[..., 12:]), b
+
+    def last_solve_time(self) -> float:
+        return float(self._L.br2_batch_last_solve_time(self._h))
+
+    def last_kernel_times(self):
+        """(linearisation seconds, Riccati-IPM seconds) of the last solve, CUDA events on the launching stream."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self._L.br2_batch_last_kernel_times(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def ipm_iterations_total(self, reset: bool = False) -> int:
+        return int(self._L.br2_batch_ipm_iterations_total(self._h, int(reset)))
+
+    # -- EKF (BLUEROV2_DOB::EKF) -----------------------------------------------------------------------
+    def ekf_reset(self):
+        self._check(self._L.br2_batch_ekf_reset(self._h))
+
+    def ekf(self, thrusts, meas, body_acc, compensate: bool = True, out=None):
+        """One EKF step for all instances.  Returns (wf_dist[B,6], p[B,16])."""
+        if _is_torch(thrusts):
+            import torch
+            self._dev_check(thrusts, (self.B, 6)); self._dev_check(meas, (self.B, 12)); self._dev_check(body_acc, (self.B, 6))
+            if out is None:
+                out = (torch.empty((self.B, 6), dtype=torch.float64, device=thrusts.device),
+                       torch.empty((self.B, NP), dtype=torch.float64, device=thrusts.device))
+            wf, pp = out
+            stream = C.c_void_p(torch.cuda.current_stream(thrusts.device).cuda_stream)
+            self._check(self._L.br2_batch_ekf_device(self._h, _ptr(thrusts), _ptr(meas), _ptr(body_acc), _ptr(wf), _ptr(pp),
+                                                     int(bool(compensate)), stream))
+            return wf, pp
+        thrusts, meas, body_acc = _np(thrusts, (self.B, 6)), _np(meas, (self.B, 12)), _np(body_acc, (self.B, 6))
+        if out is None:
+            out = (np.empty((self.B, 6)), np.empty((self.B, NP)))
+        wf, pp = out
+        self._check(self._L.br2_batch_ekf_host(self._h, _ptr(thrusts), _ptr(meas), _ptr(body_acc), _ptr(wf), _ptr(pp),
+                                               int(bool(compensate))))
+        return wf, pp
+
+    def ekf_state(self):
+        x = np.empty((self.B, NEKF)); P = np.empty((self.B, NEKF, NEKF))
+        self._check(self._L.br2_batch_ekf_get_state_host(self._h, _ptr(x), _ptr(P)))
+        return x, P
+
+    def set_ekf_state(self, x=None, P=None):
+        x = None if x is None else _np(x, (self.B, NEKF))
+        P = None if P is None else _np(P, (self.B, NEKF, NEKF))
+        self._check(self._L.br2_batch_ekf_set_state_host(self._h, _ptr(x), _ptr(P)))
+
+
+def device_count() -> int:
+    return int(load_library().br2_device_count())

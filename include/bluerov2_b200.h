@@ -1,0 +1,119 @@
+/* bluerov2_b200.h -- batched C-ABI of the B200 SQP-RTI engine (extension; not in the reference).
+ *
+ * The reference solves ONE OCP instance per process through the acados-generated ABI
+ * (include/acados_solver_bluerov2.h, mirroring bluerov2_dobmpc/scripts/c_generated_code/acados_solver_bluerov2.h).
+ * This header is the batched view of the same engine: B independent instances of the BlueROV2 OCP
+ * (nx = 12, nu = 4, np = 16, horizon N) advanced by one SQP-RTI step per call.  Each entry point names the
+ * reference call sequence it batches.  Plain C types only: pointers and sizes, no torch / C++ types.
+ *
+ * Conventions
+ *   - all arrays are dense, row-major, double, instance-major: x0[B][12], yref[B][N+1][16] (terminal row: first
+ *     12 entries used, like double yref[N+1][NY] in bluerov2_dob.h:68-71), p[B][16] (or [B][N+1][16] when
+ *     p_per_stage != 0), u0[B][4], thrust[B][6], status[B] (acados codes: 0 success, 1 NaN, 2 max iter, 4 QP failure).
+ *   - "_device" entry points take device pointers valid on the solver's GPU and a cudaStream_t passed as void*;
+ *     they only enqueue work.  "_host" entry points copy in, solve, copy out and synchronise.
+ *   - every function returns 0 on success, a negative BR2_E* code on misuse / CUDA failure (message via
+ *     br2_last_error()).  There is no CPU fallback: without a CUDA device br2_batch_create fails.
+ */
+#ifndef BLUEROV2_B200_H_
+#define BLUEROV2_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32) || defined(__CYGWIN__)
+#define BR2_API __declspec(dllexport)
+#else
+#define BR2_API __attribute__((visibility("default")))
+#endif
+
+#define BR2_NX 12
+#define BR2_NU 4
+#define BR2_NP 16
+#define BR2_NY 16
+#define BR2_NTHRUST 6
+#define BR2_NEKF 18
+
+#define BR2_OK 0
+#define BR2_EINVAL (-1)
+#define BR2_ECUDA (-2)
+#define BR2_ENOMEM (-3)
+
+typedef struct br2_batch_solver br2_batch_solver;
+
+BR2_API const char *br2_last_error(void);
+BR2_API const char *br2_version(void);
+/* number of CUDA devices visible (0 when none / no driver) */
+BR2_API int br2_device_count(void);
+
+/* == bluerov2_acados_create_with_discretization (acados_solver_bluerov2.c:734-783) for `batch` instances on CUDA
+ * device `device`.  time_steps[N] may be NULL: N equal steps over Tf = 1 s (generate_c_code.py:17,24).
+ * Defaults baked exactly as the generated C: W, W_e (:424-479), |u| <= 50 (:547-571), qp_iter_max 50 (:668),
+ * initial guess x_k = (0,0,-20,0..), u_k = 0 (:681-708). */
+BR2_API int br2_batch_create(br2_batch_solver **out, int batch, int N, const double *time_steps, int device);
+BR2_API int br2_batch_free(br2_batch_solver *s);
+
+BR2_API int br2_batch_size(const br2_batch_solver *s);
+BR2_API int br2_batch_horizon(const br2_batch_solver *s);
+
+/* == ocp_nlp_cost_model_set(..., "W", ...) for all stages: diagonal stage weights W[16] and terminal We[12] */
+BR2_API int br2_batch_set_weights(br2_batch_solver *s, const double *W16, const double *We12);
+/* == ocp_nlp_constraints_model_set(..., "lbu"/"ubu", ...) for all stages */
+BR2_API int br2_batch_set_bounds(br2_batch_solver *s, const double *lbu4, const double *ubu4);
+/* == bluerov2_acados_update_time_steps (acados_solver_bluerov2.c:111-132): Ts and cost scaling per stage */
+BR2_API int br2_batch_set_time_steps(br2_batch_solver *s, const double *time_steps);
+/* options: "qp_iter_max" (int, default 50), "qp_tol" (double, default 1e-11) */
+BR2_API int br2_batch_set_option_int(br2_batch_solver *s, const char *name, int v);
+BR2_API int br2_batch_set_option_double(br2_batch_solver *s, const char *name, double v);
+
+/* iterate (X[B][N+1][12], U[B][N][4]) -- the linearisation point carried from tick to tick (nlp_out).
+ * mode 0: the create-time initial guess (:681-708); mode 1: all zeros like bluerov2_acados_reset (:797-830). */
+BR2_API int br2_batch_reset(br2_batch_solver *s, int mode);
+BR2_API int br2_batch_set_iterate_host(br2_batch_solver *s, const double *X, const double *U);
+BR2_API int br2_batch_get_iterate_host(br2_batch_solver *s, double *X, double *U);
+/* device pointers of the iterate (owned by the solver) */
+BR2_API int br2_batch_iterate_device(br2_batch_solver *s, double **X, double **U);
+
+/* One SQP-RTI step for every instance == per instance the sequence of BLUEROV2_DOB::solve
+ * (bluerov2_dob.cpp:320-321 lbx/ubx = x0, :324-355 update_params, :370-372 yref, :375 bluerov2_acados_solve,
+ * :388 ocp_nlp_out_get "u", :390-395 thrust allocation).  Device-resident inputs/outputs; enqueues on `stream`.
+ * Any of d_u0 / d_thrust / d_status may be NULL (internal buffers are used). */
+BR2_API int br2_batch_solve_device(br2_batch_solver *s, const double *d_x0, const double *d_yref, const double *d_p,
+                           int p_per_stage, double *d_u0, double *d_thrust, int *d_status, void *stream);
+/* Same with HOST buffers: H2D of x0/yref/p, solve, D2H of u0/thrust/status, synchronise.  Pinned host memory
+ * makes the copies asynchronous; pageable memory works too. */
+BR2_API int br2_batch_solve_host(br2_batch_solver *s, const double *x0, const double *yref, const double *p,
+                         int p_per_stage, double *u0, double *thrust, int *status);
+
+/* statistics of the last solve: iters[B] (IPM iterations), info[B][4] = (mu, stationarity residual,
+ * max |dynamics gap| at the linearisation point, stationarity scale) */
+BR2_API int br2_batch_get_stats_host(br2_batch_solver *s, int *iters, double *info);
+/* linearisation of the last solve (debug / tests): G[B][N][12][16] = [A|B] row-major, b[B][N][12] */
+BR2_API int br2_batch_get_linearization_host(br2_batch_solver *s, double *AB, double *b);
+/* device time of the last br2_batch_solve_* in seconds (CUDA events) == ocp_nlp_get(..., "time_tot", ...) */
+BR2_API double br2_batch_last_solve_time(br2_batch_solver *s);
+/* device time of the two kernels of the last solve (linearisation, Riccati IPM), seconds, CUDA events on the
+ * launching stream */
+BR2_API int br2_batch_last_kernel_times(br2_batch_solver *s, double *t_linearize, double *t_ipm);
+/* IPM iterations executed, summed over all instances and all solves since creation / the last reset (the n_it of
+ * the roofline formula bytes_sweep = 4384 * N * n_it) */
+BR2_API long long br2_batch_ipm_iterations_total(br2_batch_solver *s, int reset);
+
+/* == BLUEROV2_DOB::EKF (bluerov2_dob.cpp:495-545) for every instance, on the solver's stream order.
+ * esti_x[B][18], esti_P[B][18][18] live in the solver (br2_batch_ekf_reset sets x = (0,0,-20,0..,6,6,6,0,0,0),
+ * P = I: bluerov2_dob.cpp:64-65).  thrusts[B][6] = measured thruster forces, meas[B][12] = pose + body velocities,
+ * body_acc[B][6].  d_p_out[B][16] (may be NULL) receives the OCP parameter vector of bluerov2_dob.cpp:324-355
+ * (disturbance estimates scaled by compensate_coef / rotor_constant when `compensate`, nominal hydrodynamics). */
+BR2_API int br2_batch_ekf_reset(br2_batch_solver *s);
+BR2_API int br2_batch_ekf_device(br2_batch_solver *s, const double *d_thrusts, const double *d_meas, const double *d_body_acc,
+                         double *d_wf_dist, double *d_p_out, int compensate, void *stream);
+BR2_API int br2_batch_ekf_host(br2_batch_solver *s, const double *thrusts, const double *meas, const double *body_acc,
+                       double *wf_dist, double *p_out, int compensate);
+BR2_API int br2_batch_ekf_get_state_host(br2_batch_solver *s, double *esti_x, double *esti_P);
+BR2_API int br2_batch_ekf_set_state_host(br2_batch_solver *s, const double *esti_x, const double *esti_P);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

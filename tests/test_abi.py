@@ -1,0 +1,218 @@
+"""The drop-in boundary: include/*.h vs the built library, and the reference's own harness linked against it."""
+import ctypes as C
+import os
+import re
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT, REFERENCE
+
+INCLUDE = os.path.join(ROOT, "include")
+ABI_BIN = os.path.join(ROOT, "tests", "abi", "_bin")
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from bluerov2_b200 import build
+    return build.build_library()
+
+
+def _declared_functions():
+    """every function prototype in include/**/*.h (name followed by '(' at prototype level, not a macro/typedef)"""
+    names = set()
+    proto = re.compile(r"^\s*(?:ACADOS_SYMBOL_EXPORT|BR2_API|__attribute__\(\(visibility\(\"default\"\)\)\))?\s*"
+                       r"(?:const\s+)?(?:unsigned\s+)?[A-Za-z_][A-Za-z0-9_]*\s*\**\s*\**\s*([A-Za-z_][A-Za-z0-9_]*)\s*\(", re.M)
+    for r, _, fs in os.walk(INCLUDE):
+        for f in fs:
+            if not f.endswith(".h"):
+                continue
+            src = open(os.path.join(r, f)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            src = re.sub(r"//.*", "", src)
+            src = re.sub(r"typedef\s+struct[^{;]*\{.*?\}\s*[A-Za-z_0-9]*\s*;", "", src, flags=re.S)   # drop struct bodies
+            for m in proto.finditer(src):
+                n = m.group(1)
+                if n not in ("defined", "sizeof", "if", "visibility", "__attribute__", "__declspec"):
+                    names.add(n)
+    return names
+
+
+def test_every_declared_symbol_is_exported(lib_path):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    declared = _declared_functions()
+    assert len(declared) >= 60, sorted(declared)
+    must = {"bluerov2_acados_create_capsule", "bluerov2_acados_free_capsule", "bluerov2_acados_create", "bluerov2_acados_reset",
+            "bluerov2_acados_create_with_discretization", "bluerov2_acados_update_time_steps",
+            "bluerov2_acados_update_qp_solver_cond_N", "bluerov2_acados_update_params", "bluerov2_acados_update_params_sparse",
+            "bluerov2_acados_solve", "bluerov2_acados_free", "bluerov2_acados_print_stats", "bluerov2_acados_custom_update",
+            "bluerov2_acados_get_nlp_in", "bluerov2_acados_get_nlp_out", "bluerov2_acados_get_sens_out",
+            "bluerov2_acados_get_nlp_solver", "bluerov2_acados_get_nlp_config", "bluerov2_acados_get_nlp_opts",
+            "bluerov2_acados_get_nlp_dims", "bluerov2_acados_get_nlp_plan",
+            "ocp_nlp_constraints_model_set", "ocp_nlp_cost_model_set", "ocp_nlp_out_get", "ocp_nlp_out_set", "ocp_nlp_get",
+            "ocp_nlp_solver_opts_set", "d_print_exp_tran_mat", "br2_batch_create", "br2_batch_solve_device",
+            "br2_batch_solve_host", "br2_batch_ekf_device"}
+    assert must <= declared, must - declared
+    missing = declared - exported
+    assert not missing, f"declared in include/ but not exported by {os.path.basename(lib_path)}: {sorted(missing)}"
+
+
+def test_library_loads_and_reports_version(lib_path):
+    from bluerov2_b200 import solver
+    L = solver.load_library()
+    assert b"sm_100a" in L.br2_version()
+    assert L.br2_device_count() >= 0
+
+
+def test_link_shims_exist(lib_path):
+    d = os.path.dirname(lib_path)
+    for s in ("libacados.so", "libhpipm.so", "libblasfeo.so"):
+        out = subprocess.run(["readelf", "-d", os.path.join(d, s)], capture_output=True, text=True, check=True).stdout
+        assert "libacados_ocp_solver_bluerov2.so" in out
+
+
+def test_capsule_layout_and_macros(lib_path, tmp_path):
+    """macros and capsule members the callers use (bluerov2_dob.h:68-77,166; bluerov2_dob.cpp:320,371,384-388)"""
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "acados_solver_bluerov2.h"
+int main(void) {
+    printf("%d %d %d %d %d %d %d\n", BLUEROV2_NX, BLUEROV2_NU, BLUEROV2_NP, BLUEROV2_NY, BLUEROV2_NYN, BLUEROV2_N, BLUEROV2_NBX0);
+    printf("%d\n", (int)ACADOS_SUCCESS);
+    printf("%zu %zu %zu\n", offsetof(bluerov2_solver_capsule, nlp_in), offsetof(bluerov2_solver_capsule, nlp_out),
+           offsetof(bluerov2_solver_capsule, nlp_solver));
+    ocp_nlp_out o; o.inf_norm_res = 1.5; ocp_nlp_dims d; d.N = 3;
+    printf("%g %d\n", o.inf_norm_res, d.N);
+    bluerov2_solver_capsule *c = bluerov2_acados_create_capsule();   /* must not need CUDA (bluerov2_dob.h:168) */
+    printf("%d\n", c != NULL);
+    return bluerov2_acados_free_capsule(c);
+}''')
+    exe = tmp_path / "t"
+    d = os.path.dirname(lib_path)
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", INCLUDE, str(src), "-o", str(exe), "-L", d, "-lacados_ocp_solver_bluerov2",
+                    "-Wl,-rpath," + d], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert out[0] == "12 4 16 16 12 80 12"
+    assert out[1] == "0"
+    assert out[2] == "0 8 24"
+    assert out[3] == "1.5 3"
+    assert out[4] == "1"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="needs /root/reference")
+def test_reference_main_compiles_and_links_unmodified(lib_path):
+    """c_generated_code/main_bluerov2.c, compiled where it lies, against our headers and libraries only"""
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "abi"), "all"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert os.path.exists(os.path.join(ABI_BIN, "main_bluerov2"))
+    nm = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(ABI_BIN, "main_bluerov2")], capture_output=True, text=True).stdout
+    for sym in ("bluerov2_acados_create_with_discretization", "ocp_nlp_out_get", "d_print_exp_tran_mat", "bluerov2_acados_solve"):
+        assert sym in nm
+
+
+def test_model_functions_match_casadi_golden(lib_path, golden):
+    """bluerov2_expl_ode_fun / _vde_forw / _vde_adj exported by the product library (csrc/model.cuh evaluated on the
+    host: the same source the CUDA kernels compile for the device) against the reference's CasADi outputs."""
+    L = C.CDLL(lib_path)
+    g = golden["casadi_vde"]
+    DP = C.POINTER(C.c_double)
+    sig = [C.POINTER(DP), C.POINTER(DP), C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def call(name, ins, shapes):
+        fn = getattr(L, name); fn.argtypes = sig; fn.restype = C.c_int
+        ins = [np.ascontiguousarray(a, dtype=np.float64) for a in ins]
+        outs = [np.zeros(s) for s in shapes]
+        arg = (DP * len(ins))(*[a.ctypes.data_as(DP) for a in ins])
+        res = (DP * len(outs))(*[a.ctypes.data_as(DP) for a in outs])
+        assert fn(arg, res, None, None, None) == 0
+        return outs
+
+    for i in range(g["x"].shape[0]):
+        f, dSx, dSu = call("bluerov2_expl_vde_forw", [g["x"][i], g["Sx_cm"][i], g["Su_cm"][i], g["u"][i], g["p"][i]], [(12,), (144,), (48,)])
+        sc = max(1.0, np.abs(g["f"][i]).max())
+        assert np.abs(f - g["f"][i]).max() < 1e-12 * sc
+        assert np.abs(dSx - g["dSx_cm"][i]).max() < 1e-11 * max(1.0, np.abs(g["dSx_cm"][i]).max())
+        assert np.abs(dSu - g["dSu_cm"][i]).max() < 1e-11 * max(1.0, np.abs(g["dSu_cm"][i]).max())
+        (fo,) = call("bluerov2_expl_ode_fun", [g["x"][i], g["u"][i], g["p"][i]], [(12,)])
+        assert np.abs(fo - g["f_ode"][i]).max() < 1e-12 * sc
+        (adj,) = call("bluerov2_expl_vde_adj", [g["x"][i], g["lam"][i], g["u"][i], g["p"][i]], [(16,)])
+        assert np.abs(adj - g["adj"][i]).max() < 1e-11 * max(1.0, np.abs(g["adj"][i]).max())
+
+
+def test_create_without_gpu_fails_loudly(lib_path):
+    """no CPU fallback: on a box without a CUDA device, create prints the reason and exits 1 (like a failed
+    ocp_nlp_precompute, acados_solver_bluerov2.c:725-728)"""
+    from bluerov2_b200 import solver
+    if solver.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    exe = os.path.join(ABI_BIN, "dob_tick")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "abi"), os.path.join(ABI_BIN, "dob_tick")], check=True)
+    inp = os.path.join(ROOT, "tests", "abi", "_bin", "empty.bin")
+    with open(inp, "wb") as f:
+        f.write(struct.pack("ii", 10, 0))
+    out = subprocess.run([exe, inp, inp + ".out"], capture_output=True, text=True)
+    assert out.returncode == 1
+    assert "no CUDA device" in out.stderr and "no CPU path" in out.stderr
+    with pytest.raises(solver.SolverError):
+        solver.BatchSolver(4, 10)
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_reference_main_runs(lib_path):
+    exe = os.path.join(ABI_BIN, "main_bluerov2")
+    if not os.path.exists(exe):
+        pytest.skip("tests/abi/_bin/main_bluerov2 not prebuilt (needs /root/reference at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "bluerov2_acados_solve(): SUCCESS!" in out.stdout
+    assert "--- utraj ---" in out.stdout and "SQP iterations  1" in out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [80, 20])
+def test_node_call_sequence_matches_oracle(lib_path, oracle, N, tmp_path):
+    """BLUEROV2_DOB::solve's call sequence from C (tests/abi/dob_tick.c), 6 closed-loop ticks, against the oracle.
+    N = 80 is the generated default (bluerov2_acados_create); N = 20 goes through create_with_discretization."""
+    from bluerov2_b200 import traj, workloads as wl
+    exe = os.path.join(ABI_BIN, "dob_tick")
+    assert os.path.exists(exe), "run `make -C tests/abi` (done by __graft_entry__.build())"
+    T = 6
+    w = wl.tracking_batch(1, N, seed=3, pos_spread=2.5)
+    p = w["p"][0].copy(); p[:4] = [4.0, -3.0, 2.0, 0.3]
+    Ts = wl.time_steps(N)
+    X, U = w["X"][0].copy(), w["U"][0].copy()
+    x0, line = w["x0"][0].copy(), int(w["lines"][0])
+    ticks, want = [], []
+    for t in range(T):
+        yref = traj.window(w["traj"], line + t, N)
+        ticks.append((x0.copy(), yref))
+        st, _ = oracle.rti_step(Ts, x0, yref, p, X, U)
+        assert st == 0
+        want.append(U[0].copy())
+        x0 = oracle.erk4(x0, U[0], p, 0.05)
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(struct.pack("ii", N, T))
+        for x0t, yref in ticks:
+            f.write(x0t.tobytes()); f.write(p.tobytes()); f.write(np.ascontiguousarray(yref).tobytes())
+    out = subprocess.run([exe, str(fin), str(fout)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = open(fout, "rb").read()
+    rec = 8 + 8 * 6
+    for t in range(T):
+        st = struct.unpack_from("i", raw, t * rec)[0]
+        vals = np.frombuffer(raw, dtype=np.float64, count=6, offset=t * rec + 8)
+        assert st == 0
+        assert np.abs(vals[:4] - want[t]).max() < 1e-5, (t, vals[:4], want[t])
+        assert 0 < vals[4] < 5.0 and np.isfinite(vals[5])
+    tail = np.frombuffer(raw, dtype=np.float64, offset=T * rec)
+    Xg, Ug = tail[:(N + 1) * 12].reshape(N + 1, 12), tail[(N + 1) * 12:].reshape(N, 4)
+    assert np.abs(Ug - U).max() < 1e-5 and np.abs(Xg - X).max() < 1e-5

@@ -1,0 +1,246 @@
+"""GPU parity: the CUDA path, called through the C-ABI (bluerov2_b200.solver -> include/bluerov2_b200.h), against the
+CPU oracle and the committed golden fixtures.  Run on the B200 box: ``pytest -m gpu``.
+
+Tolerances (fp64 everywhere; the north star asks for |u_gpu - u_ref|_inf < 1e-4):
+  * linearisation (A, B, b):   1e-11 absolute   (same arithmetic, different summation order / libm vs CUDA sincos)
+  * RTI step (X, U, u0):       1e-6  absolute   (two IPMs stopped at 1e-11 / 1e-12 on a QP with cond ~1e5)
+  * EKF (x, P):                1e-6  relative   (forward differences with d = 1e-6 amplify 1-ulp sincos differences by 1e6)
+"""
+import numpy as np
+import pytest
+
+from bluerov2_b200 import traj, workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+TOL_LIN = 1e-11
+TOL_U = 1e-6
+NORTH_STAR_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def solver_mod():
+    from bluerov2_b200 import solver
+    if solver.device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu-marked tests must run on the B200 box")
+    return solver
+
+
+def _replay(solver_mod, g, tag, use_torch=False):
+    N = int(g[tag + "_N"])
+    B = g[tag + "_X0"].shape[0]
+    tr = traj.circle() if str(g[tag + "_ref"]) == "circle" else traj.lemniscate()
+    s = solver_mod.BatchSolver(B, N)
+    s.set_iterate(g[tag + "_X0"], g[tag + "_U0"])
+    worst = 0.0
+    for t in range(g[tag + "_x0"].shape[0]):
+        yref = traj.window_batch(tr, g[tag + "_lines"][t], N)
+        if use_torch:
+            import torch
+            dev = torch.device("cuda", 0)
+            u0, th, st = s.solve(torch.from_numpy(g[tag + "_x0"][t]).to(dev), torch.from_numpy(yref).to(dev),
+                                 torch.from_numpy(g[tag + "_p"]).to(dev))
+            torch.cuda.synchronize()
+            u0, th, st = u0.cpu().numpy(), th.cpu().numpy(), st.cpu().numpy()
+        else:
+            u0, th, st = s.solve(g[tag + "_x0"][t], yref, g[tag + "_p"])
+        assert (st == 0).all(), (tag, t, st)
+        X, U = s.get_iterate()
+        eu = np.abs(U - g[tag + "_Uout"][t]).max()
+        ex = np.abs(X - g[tag + "_Xout"][t]).max()
+        worst = max(worst, eu)
+        assert eu < TOL_U and ex < TOL_U, (tag, t, eu, ex)
+        assert np.array_equal(u0, U[:, 0, :])
+        # thrust allocation, bluerov2_dob.cpp:390-395
+        rc = 0.026546960744430276
+        want = np.stack([-u0[:, 0] + u0[:, 1] + u0[:, 3], -u0[:, 0] - u0[:, 1] - u0[:, 3], u0[:, 0] + u0[:, 1] - u0[:, 3],
+                         u0[:, 0] - u0[:, 1] + u0[:, 3], -u0[:, 2], -u0[:, 2]], axis=1) / rc
+        assert np.allclose(th, want, rtol=1e-14, atol=1e-12)
+        # the golden iterate is carried (both sides then linearise at the same point)
+        s.set_iterate(g[tag + "_Xout"][t], g[tag + "_Uout"][t])
+    s.close()
+    return worst
+
+
+@pytest.mark.parametrize("tag", ["nom40", "act40", "lem40", "act20", "act80"])
+def test_golden_rti_cases(solver_mod, golden, tag):
+    worst = _replay(solver_mod, golden["rti_cases"], tag)
+    assert worst < NORTH_STAR_TOL
+
+
+def test_golden_rti_cases_device_pointers(solver_mod, golden):
+    """same through br2_batch_solve_device with torch CUDA tensors on torch's current stream"""
+    _replay(solver_mod, golden["rti_cases"], "act40", use_torch=True)
+
+
+@pytest.mark.parametrize("N", [80, 40, 20, 10])
+def test_cold_start_known_answer(solver_mod, golden, N):
+    """main_bluerov2.c-style cold solve from the generated initial guess (acados_solver_bluerov2.c:681-708)."""
+    from oracle import NOMINAL_P
+    g = golden["rti_cases"]
+    s = solver_mod.BatchSolver(3, N)       # three identical instances: also checks instance independence
+    x0 = np.tile(g["cold_x0"], (3, 1))
+    yref = np.tile(traj.circle()[:N + 1][None], (3, 1, 1))
+    u0, th, st = s.solve(x0, yref, np.tile(NOMINAL_P, (3, 1)))
+    assert (st == 0).all()
+    X, U = s.get_iterate()
+    assert np.abs(U - g[f"cold_N{N}_U"][None]).max() < TOL_U
+    assert np.abs(X - g[f"cold_N{N}_X"][None]).max() < TOL_U
+    assert np.array_equal(U[0], U[1]) and np.array_equal(U[0], U[2])
+    s.close()
+
+
+def test_linearization_matches_oracle(solver_mod, oracle):
+    N, B = 40, 64
+    w = wl.tracking_batch(B, N, seed=11, pos_spread=1.0)
+    rng = np.random.default_rng(5)
+    X = w["X"] + rng.uniform(-0.3, 0.3, w["X"].shape)
+    U = rng.uniform(-50, 50, w["U"].shape)
+    X[:4, :, 6:9] = 0.0       # sign(0) branch of d|v|v/dv
+    p = w["p"].copy()
+    p[:, :4] = rng.uniform(-10, 10, (B, 4))
+    s = solver_mod.BatchSolver(B, N)
+    s.set_iterate(X, U)
+    s.set_option("qp_iter_max", 1)
+    s.solve(w["x0"], w["yref"], p)
+    A, Bm, b = s.linearization()
+    Ts = wl.time_steps(N)
+    for i in range(B):
+        Ao, Bo, bo = oracle.linearize(Ts, p[i], X[i], U[i])
+        assert np.abs(A[i] - Ao).max() < TOL_LIN
+        assert np.abs(Bm[i] - Bo).max() < TOL_LIN
+        assert np.abs(b[i] - bo).max() < TOL_LIN
+    s.close()
+
+
+def test_per_stage_parameters(solver_mod, oracle):
+    N, B = 20, 4
+    w = wl.tracking_batch(B, N, seed=9)
+    rng = np.random.default_rng(1)
+    pp = np.tile(w["p"][:, None, :], (1, N + 1, 1))
+    pp[:, :, :4] = rng.uniform(-8, 8, (B, N + 1, 4))
+    s = solver_mod.BatchSolver(B, N)
+    s.set_iterate(w["X"], w["U"])
+    u0, th, st = s.solve(w["x0"], w["yref"], pp)
+    assert (st == 0).all()
+    Ts = wl.time_steps(N)
+    for i in range(B):
+        X, U = w["X"][i].copy(), w["U"][i].copy()
+        sto, _ = oracle.rti_step(Ts, w["x0"][i], w["yref"][i], pp[i], X, U)
+        assert sto == 0 and np.abs(U[0] - u0[i]).max() < TOL_U
+    s.close()
+
+
+def test_weights_bounds_and_ragged_batch(solver_mod, oracle):
+    """non-default W / bounds (runtime-settable, SURVEY finding 5) and a batch that is not a multiple of anything"""
+    N, B = 10, 37
+    w = wl.tracking_batch(B, N, seed=21, pos_spread=2.0)
+    W = np.array([300, 480, 200, 10, 10, 200, 10, 10, 10, 10, 10, 10, 1, 1, 0.1, 0.05])   # generate_c_code.py:34
+    We = W[:12] * 2.0
+    lbu, ubu = np.array([-3.0, -4, -5, -0.5]), np.array([2.0, 4, 5, 0.5])
+    s = solver_mod.BatchSolver(B, N)
+    s.set_weights(W, We)
+    s.set_bounds(lbu, ubu)
+    s.set_iterate(w["X"], w["U"])
+    u0, th, st = s.solve(w["x0"], w["yref"], w["p"])
+    assert (st == 0).all()
+    Ts = wl.time_steps(N)
+    X, U = w["X"].copy(), w["U"].copy()
+    sto, _, _ = oracle.rti_step_batch(Ts, w["x0"], w["yref"], w["p"], X, U, W=W, We=We, lbu=lbu, ubu=ubu)
+    assert (sto == 0).all()
+    assert np.abs(U[:, 0] - u0).max() < TOL_U
+    Xg, Ug = s.get_iterate()
+    assert np.abs(Ug - U).max() < TOL_U
+    assert (Ug <= ubu + 1e-9).all() and (Ug >= lbu - 1e-9).all()
+    assert (np.abs(Ug - ubu) < 1e-6).any() or (np.abs(Ug - lbu) < 1e-6).any(), "no bound active in the active-bound case"
+    s.close()
+
+
+@pytest.mark.parametrize("spread", [0.5, 3.0])
+def test_full_size_batch_properties(solver_mod, oracle, spread):
+    """BASELINE config 2 at full size (B = 4096, N = 40): a sample of instances against the oracle, the rest through
+    size-independent properties: bounds respected, states = exact roll-out of the inputs (dynamics residual of the QP),
+    instance independence (a permuted batch gives the permuted answer bit for bit)."""
+    N, B = 40, 4096
+    w = wl.tracking_batch(B, N, seed=0, pos_spread=spread)
+    s = solver_mod.BatchSolver(B, N)
+    s.set_iterate(w["X"], w["U"])
+    u0, th, st = s.solve(w["x0"], w["yref"], w["p"])
+    assert (st == 0).all(), np.unique(st, return_counts=True)
+    it, info = s.stats()
+    assert it.max() < 50 and it.min() >= 1
+    X, U = s.get_iterate()
+    assert (np.abs(U) <= 50 + 1e-9).all()
+    assert np.abs(X[:, 0] - w["x0"]).max() < 1e-12                 # stage-0 state pinned to x0 (lbx = ubx)
+    A, Bm, b = s.linearization()
+    dX, dU = X - w["X"], U - w["U"]
+    roll = np.einsum("bkij,bkj->bki", A, dX[:, :-1]) + np.einsum("bkij,bkj->bki", Bm, dU) + b
+    assert np.abs(roll - dX[:, 1:]).max() < 1e-9
+    Ts = wl.time_steps(N)
+    idx = np.arange(0, B, 64)
+    Xo, Uo = w["X"][idx].copy(), w["U"][idx].copy()
+    sto, _, _ = oracle.rti_step_batch(Ts, w["x0"][idx], w["yref"][idx], w["p"][idx], Xo, Uo)
+    assert (sto == 0).all()
+    assert np.abs(Uo - U[idx]).max() < TOL_U
+    if spread >= 3.0:
+        assert (np.abs(U) > 50 - 1e-6).any()
+    # permutation invariance
+    perm = np.random.default_rng(3).permutation(B)
+    s.set_iterate(w["X"][perm], w["U"][perm])
+    u0p, _, _ = s.solve(w["x0"][perm], w["yref"][perm], w["p"][perm])
+    assert np.array_equal(u0p, u0[perm])
+    s.close()
+
+
+def test_closed_loop_ticks_match_oracle(solver_mod, oracle):
+    """20 closed-loop ticks (plant = nominal ERK4 at 0.05 s), iterate carried on the device, parity on every tick."""
+    N, B, T = 40, 32, 20
+    w = wl.tracking_batch(B, N, seed=4, pos_spread=1.5)
+    Ts = wl.time_steps(N)
+    s = solver_mod.BatchSolver(B, N)
+    s.set_iterate(w["X"], w["U"])
+    Xo, Uo = w["X"].copy(), w["U"].copy()
+    x0, lines = w["x0"].copy(), w["lines"].copy()
+    for t in range(T):
+        yref = traj.window_batch(w["traj"], lines, N)
+        u0, th, st = s.solve(x0, yref, w["p"])
+        sto, _, _ = oracle.rti_step_batch(Ts, x0, yref, w["p"], Xo, Uo)
+        assert (st == 0).all() and (sto == 0).all()
+        assert np.abs(u0 - Uo[:, 0]).max() < 1e-5, (t, np.abs(u0 - Uo[:, 0]).max())
+        for i in range(B):
+            x0[i] = oracle.erk4(x0[i], Uo[i, 0], w["p"][i], 0.05)
+        lines = lines + 1
+        # keep both sides on the same linearisation point so that differences do not compound through the loop
+        s.set_iterate(Xo, Uo)
+    s.close()
+
+
+def test_ekf_golden(solver_mod, golden):
+    g = golden["ekf_cases"]
+    T, B = g["thr"].shape[:2]
+    s = solver_mod.BatchSolver(B, 10)
+    s.ekf_reset()
+    for t in range(T):
+        wf, p = s.ekf(g["thr"][t], g["meas"][t], g["acc"][t], compensate=True)
+        x, P = s.ekf_state()
+        sx = np.maximum(1.0, np.abs(g["ex"][t]))
+        assert (np.abs(x - g["ex"][t]) / sx).max() < 1e-6, (t, (np.abs(x - g["ex"][t]) / sx).max())
+        assert np.abs(P - g["eP"][t]).max() < 1e-6 * max(1.0, np.abs(g["eP"][t]).max()), t
+        assert np.abs(wf - g["wf"][t]).max() < 1e-6 * max(1.0, np.abs(g["wf"][t]).max())
+        assert np.allclose(p, wl.dob_params(x, True), rtol=1e-12, atol=1e-12)
+        # carry the golden state: differences must not compound through the filter
+        s.set_ekf_state(g["ex"][t], g["eP"][t])
+    s.close()
+
+
+def test_errors_are_loud(solver_mod):
+    with pytest.raises(solver_mod.SolverError):
+        solver_mod.BatchSolver(0, 40)
+    with pytest.raises(solver_mod.SolverError):
+        solver_mod.BatchSolver(4, 100000)
+    s = solver_mod.BatchSolver(2, 10)
+    with pytest.raises(solver_mod.SolverError):
+        s.set_bounds(np.ones(4), -np.ones(4))
+    with pytest.raises(ValueError):
+        s.solve(np.zeros((3, 12)), np.zeros((2, 11, 16)), np.zeros((2, 16)))
+    s.close()
