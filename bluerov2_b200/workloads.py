@@ -75,3 +75,46 @@ def dob_params(esti_x: np.ndarray, compensate: bool = True) -> np.ndarray:
         p[:, 2] = esti_x[:, 14] / ROTOR_CONSTANT
         p[:, 3] = esti_x[:, 17] / ROTOR_CONSTANT
     return p
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Nominal plant for closed-loop input generation (numpy, vectorised over the batch).  Same equations as the
+# OCP model (bluerov2.py:103-137) -- this is workload synthesis on the host, not a solver path.
+# ---------------------------------------------------------------------------------------------------------
+_M, _IX, _IY, _IZ, _ZG, _G, _BUOY = 11.26, 0.3, 0.63, 0.58, 0.02, 9.81, 0.66
+
+
+def plant_ode(x: np.ndarray, u: np.ndarray, p: np.ndarray, dist: np.ndarray | None = None) -> np.ndarray:
+    """x[B,12], u[B,4], p[B,16] -> xdot[B,12]; ``dist`` [B,4] adds a true disturbance (X, Y, Z, N) on top of p[:, :4]."""
+    rc = ROTOR_CONSTANT
+    phi, th, psi = x[:, 3], x[:, 4], x[:, 5]
+    uu, v, w, pp, q, r = (x[:, i] for i in range(6, 12))
+    sphi, cphi, sth, cth, spsi, cpsi = np.sin(phi), np.cos(phi), np.sin(th), np.cos(th), np.sin(psi), np.cos(psi)
+    kt0 = -4 * 0.707 * u[:, 0] / rc
+    kt1 = 4 * 0.707 * u[:, 1] / rc
+    kt2 = -2 * u[:, 2] / rc
+    kt5 = ((2 * 0.167 - 2 * 0.175) * u[:, 1] + (2 * 0.167 + 2 * 0.175) * u[:, 3]) / rc
+    d = p[:, :4] if dist is None else p[:, :4] + dist
+    f = np.empty_like(x)
+    f[:, 0] = cpsi * cth * uu + (-spsi * cphi + cpsi * sth * sphi) * v + (spsi * sphi + cpsi * cphi * sth) * w
+    f[:, 1] = spsi * cth * uu + (cpsi * cphi + sphi * sth * spsi) * v + (-cpsi * sphi + sth * spsi * cphi) * w
+    f[:, 2] = -sth * uu + cth * sphi * v + cth * cphi * w
+    f[:, 3] = pp + spsi * sth / cth * q + cphi * sth / cth * r
+    f[:, 4] = cphi * q + sphi * r
+    f[:, 5] = sphi / cth * q + cphi / cth * r
+    f[:, 6] = (kt0 - _BUOY * sth + d[:, 0] + p[:, 8] * uu + p[:, 12] * np.abs(uu) * uu) / (_M + p[:, 4])
+    f[:, 7] = (kt1 + _BUOY * cth * sphi + d[:, 1] + p[:, 9] * v + p[:, 13] * np.abs(v) * v) / (_M + p[:, 5])
+    f[:, 8] = (kt2 + _BUOY * cth * cphi + d[:, 2] + p[:, 10] * w + p[:, 14] * np.abs(w) * w) / (_M + p[:, 6])
+    f[:, 9] = ((_IY - _IZ) * q * r - _M * _ZG * _G * cth * sphi) / _IX
+    f[:, 10] = ((_IZ - _IX) * pp * r - _M * _ZG * _G * sth) / _IY
+    f[:, 11] = (kt5 - (_IY - _IX) * pp * q + d[:, 3] + p[:, 11] * r + p[:, 15] * np.abs(r) * r) / (_IZ + p[:, 7])
+    return f
+
+
+def plant_step(x: np.ndarray, u: np.ndarray, p: np.ndarray, h: float = 0.05, dist: np.ndarray | None = None) -> np.ndarray:
+    """one classical RK4 step of the nominal plant (20 Hz node rate, bluerov2_dob_node.cpp:7)"""
+    k1 = plant_ode(x, u, p, dist)
+    k2 = plant_ode(x + 0.5 * h * k1, u, p, dist)
+    k3 = plant_ode(x + 0.5 * h * k2, u, p, dist)
+    k4 = plant_ode(x + h * k3, u, p, dist)
+    return x + h * (k1 / 6 + k2 / 3 + k3 / 3 + k4 / 6)

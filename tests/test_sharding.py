@@ -1,0 +1,60 @@
+"""world_size-2 gloo test of the multi-GPU host logic (shard bounds + the single all-gather of the thrust vectors)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from bluerov2_b200.sharding import ThrustGather, shard_bounds
+
+RC = 0.026546960744430276
+
+
+def _alloc(u):
+    return np.stack([-u[:, 0] + u[:, 1] + u[:, 3], -u[:, 0] - u[:, 1] - u[:, 3], u[:, 0] + u[:, 1] - u[:, 3],
+                     u[:, 0] - u[:, 1] + u[:, 3], -u[:, 2], -u[:, 2]], axis=1) / RC
+
+
+def test_shard_bounds_cover_the_batch():
+    for total in (0, 1, 7, 4096, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(total, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == total
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def _worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        u = np.random.default_rng(0).uniform(-50, 50, (total, 4))       # every rank can regenerate the global inputs
+        g = ThrustGather(total, "cpu")
+        lo, hi = g.bounds[rank]
+        g.slot.copy_(torch.from_numpy(_alloc(u[lo:hi])))               # stands in for the solver epilogue writing its block
+        full = g.all_gather().numpy()
+        q.put((rank, bool(np.array_equal(full, _alloc(u))), (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [10, 11])
+def test_two_rank_all_gather_gloo(total):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert sorted(b for _, _, b in res) == [shard_bounds(total, 2, 0), shard_bounds(total, 2, 1)]
