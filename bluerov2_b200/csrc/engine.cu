@@ -319,7 +319,9 @@ extern "C" int br2_batch_get_linearization_host(br2_batch_solver* s, double* AB,
     cudaError_t e = cudaMemcpy(h, s->d_G, sizeof(double) * n * GREC, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess)
         for (size_t i = 0; i < n; i++) {
-            if (AB) memcpy(AB + i * 192, h + i * GREC, sizeof(double) * 192);
+            if (AB)   // un-permute the fragment order (layout.h) into row-major 12 x 16
+                for (int r = 0; r < 12; r++)
+                    for (int c = 0; c < 16; c++) AB[i * 192 + r * 16 + c] = h[i * GREC + g_off(r, c)];
             if (b) memcpy(b + i * 12, h + i * GREC + G_B_OFF, sizeof(double) * 12);
         }
     free(h);

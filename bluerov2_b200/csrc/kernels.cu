@@ -6,8 +6,11 @@
 //   ipm_kernel       : one warp per OCP instance, persistent over the batch.  Mehrotra predictor-corrector
 //                      primal-dual IPM on the box-constrained OCP-QP of the RTI step; every Newton system is an
 //                      LQR solved by a Riccati recursion over the horizon (replaces acados full condensing + HPIPM
-//                      dense IPM, acados_solver_bluerov2.c:146,664-668).  Epilogue: full SQP step on (X,U),
-//                      u0 and the 4->6 thrust allocation (bluerov2_dob.cpp:388-395).
+//                      dense IPM, acados_solver_bluerov2.c:146,664-668).  The two 12x16 stage products of the
+//                      factorisation run on the fp64 tensor-core instruction (DMMA, mma.sync.m8n8k4.f64): on B200 it
+//                      has the same 64 FMA/clk/SM as DFMA but reaches it from 4 warps/SM with 8x fewer issue slots,
+//                      no redundant lanes and fragment-resident operands (profiles/r01_fp64_probe.txt).
+//                      Epilogue: full SQP step on (X,U), u0 and the 4->6 thrust allocation (bluerov2_dob.cpp:388-395).
 //
 // Arithmetic: fp64 throughout (casadi_real = double in the reference).  The algorithm is the one restated
 // in oracle/bluerov2_oracle.c (feasible-start, residual-form Newton steps, split primal/dual step lengths);
@@ -100,14 +103,15 @@ __global__ void __launch_bounds__(128) linearize_kernel(SolveArgs a)
 #pragma unroll
         for (int i = 0; i < NX; i++) Gk[G_B_OFF + i] = cur[i] - __ldg(Xn + i);
 #pragma unroll
-        for (int l = 0; l < NX; l++) Gk[l * 16 + 2] = (l == 2) ? 1.0 : 0.0;
+        for (int l = 0; l < NX; l++) Gk[g_off(l, 2)] = (l == 2) ? 1.0 : 0.0;
     } else if (c <= 13) {
+        // column c + 2 of Z = [A|B]; in fragment order rows 4ki..4ki+3 of a column are contiguous (32 B)
 #pragma unroll
-        for (int l = 0; l < NX; l++) Gk[l * 16 + c + 2] = cur[l];
+        for (int l = 0; l < NX; l++) Gk[g_off(l, c + 2)] = cur[l];
     } else {
         const int j = c - 14;
 #pragma unroll
-        for (int l = 0; l < NX; l++) Gk[l * 16 + j] = (l == j) ? 1.0 : 0.0;
+        for (int l = 0; l < NX; l++) Gk[g_off(l, j)] = (l == j) ? 1.0 : 0.0;
         if (c == 14) {
 #pragma unroll
             for (int i = 204; i < GREC; i++) Gk[i] = 0.0;
@@ -126,17 +130,21 @@ void launch_linearize(const SolveArgs& a, cudaStream_t s)
 // ------------------------------------------------------------------------------------------------------
 // Riccati interior-point kernel
 // ------------------------------------------------------------------------------------------------------
+// Lane coordinates (q, t) = (lane >> 2, lane & 3) are the DMMA thread coordinates (layout.h).  Recurring layouts of
+// a 12- or 16-vector v over the warp:
+//   "row layout"   lane (q,t) holds v[4 ki + t], ki = 0..3   (what a B fragment column / a dot over t needs)
+//   "quad layout"  lane (q,*) holds v[q] and v[8 + q]        (what falls out of a reduction over t / a C fragment row)
 constexpr int IPM_WARPS = 4;
 
-struct __align__(16) WarpSmem {
-    double Gs[12 * 16];   // stage matrix [A|B]
-    double Ws[12 * 16];   // W = P+ [A|B]; reused for the symmetrisation of the new P
-    double Hu[4 * 16];    // rows 12..15 of H = [A|B]' W  (B'PA | B'PB)
-    double Ks[4 * 16];    // feedback gain rows
-    double vec[32];       // broadcast vectors (pi+, p+ / z)
-    double gs[4];         // g = gh + B'p+
-    double rt[4];         // barrier-augmented input Hessian diagonal
-};
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL_MASK, v, src); }
+__device__ __forceinline__ double shfl_x(double v, int m) { return __shfl_xor_sync(FULL_MASK, v, m); }
+
+// D(8x8) += A(8x4) B(4x8), fp64 tensor-core instruction
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 
 __device__ __forceinline__ double warp_min(double v)
 {
@@ -176,13 +184,17 @@ __device__ __forceinline__ bool chol4(const double* m, Chol4& L)
     ok &= d > 0.0; L.i3 = rsqrt(d);
     return ok;
 }
-// v <- (L L')^-1 v
-__device__ __forceinline__ void chol4_solve(const Chol4& L, double* v)
+// v <- L^-1 v
+__device__ __forceinline__ void chol4_fwd(const Chol4& L, double* v)
 {
     v[0] = v[0] * L.i0;
     v[1] = (v[1] - L.l10 * v[0]) * L.i1;
     v[2] = (v[2] - L.l20 * v[0] - L.l21 * v[1]) * L.i2;
     v[3] = (v[3] - L.l30 * v[0] - L.l31 * v[1] - L.l32 * v[2]) * L.i3;
+}
+// v <- L^-T v
+__device__ __forceinline__ void chol4_bwd(const Chol4& L, double* v)
+{
     v[3] = v[3] * L.i3;
     v[2] = (v[2] - L.l32 * v[3]) * L.i2;
     v[1] = (v[1] - L.l21 * v[2] - L.l31 * v[3]) * L.i1;
@@ -195,21 +207,18 @@ __device__ __forceinline__ void load_chol(const double* Fk, Chol4& L)
     L.i0 = Fk[F_ID_OFF + 0]; L.i1 = Fk[F_ID_OFF + 1]; L.i2 = Fk[F_ID_OFF + 2]; L.i3 = Fk[F_ID_OFF + 3];
 }
 
-// Lane roles inside the warp that owns one instance: r = lane & 15 is a row of the 16x16 stage matrix
-// H = [A|B]' P+ [A|B] (+ diag(Q, R~)): r < 12 state rows, r >= 12 input rows; h = lane >> 4 selects the
-// column half [8h, 8h+8) the lane accumulates.
+// Per-instance pointers
 struct Inst {
     const SolveArgs& a;
-    int inst, lane, r, h, N;
-    WarpSmem& sm;
+    int inst, lane, q, t, N;
     const double* G;
     double* F;
     double* V;
     const double* Xlin;
     const double* Ulin;
     const double* yref;
-    __device__ Inst(const SolveArgs& a_, int inst_, int lane_, WarpSmem& sm_)
-        : a(a_), inst(inst_), lane(lane_), r(lane_ & 15), h(lane_ >> 4), N(a_.N), sm(sm_)
+    __device__ Inst(const SolveArgs& a_, int inst_, int lane_)
+        : a(a_), inst(inst_), lane(lane_), q(lane_ >> 2), t(lane_ & 3), N(a_.N)
     {
         G = a.G + (size_t)inst * N * GREC;
         F = a.F + (size_t)inst * N * FREC;
@@ -240,241 +249,282 @@ __device__ void ipm_init(Inst& I)
 }
 
 // Forward sweep.  mode 0: roll-out of the iterate  x+ = A x + B v + b, x_0 = x0 - X_0 (writes V_X);
-// mode 1: Newton step  ddu = -K ddx - Lam^-1 g,  ddx+ = A ddx + B ddu, ddx_0 = 0 (writes V_DX, V_DV).
-// Returns max |b| in mode 0.
+// mode 1: Newton step  ddu = -kff - K ddx,  ddx+ = A ddx + B ddu, ddx_0 = 0 (writes V_DX, V_DV).
+// Z = [A|B] is read row-per-quad: lane (q,t) holds Z[q][4ki+t] and Z[8+q][4ki+t]; every product is 4 (3) local
+// FMAs and a reduction over the 4 lanes of a quad.  Returns max |b| in mode 0.
 __device__ double forward_sweep(Inst& I, int mode)
 {
-    const int r = I.r, h = I.h, N = I.N;
-    WarpSmem& sm = I.sm;
-    double xr = 0.0;          // component r of the propagated vector (r < 12), replicated in both halves
+    const int q = I.q, t = I.t, N = I.N, lane = I.lane;
+    const bool lo = q < 4;                      // quad owns a second state row 8 + q (else: no row 12..15)
+    double zr[3];                               // propagated vector, row layout: x[4ki + t]
     double bmax = 0.0;
-    if (mode == 0 && r < 12) xr = I.a.x0[(size_t)I.inst * NX + r] - I.Xlin[r];
+#pragma unroll
+    for (int ki = 0; ki < 3; ki++)
+        zr[ki] = (mode == 0) ? I.a.x0[(size_t)I.inst * NX + 4 * ki + t] - I.Xlin[4 * ki + t] : 0.0;
+    const int xoff = mode ? V_DX : V_X;
     for (int k = 0; k < N; k++) {
         const double* Gk = I.G + (size_t)k * GREC;
+        const double* Fk = I.F + (size_t)k * FREC;
         double* Vk = I.V + (size_t)k * VREC;
-        // row r of [A|B], my half
-        double g[8];
-        if (r < 12) {
-            const double2* g2 = reinterpret_cast<const double2*>(Gk + r * 16 + 8 * h);
+        double z0[4], z1[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { double2 t = g2[j]; g[2 * j] = t.x; g[2 * j + 1] = t.y; }
+        for (int ki = 0; ki < 4; ki++) {
+            z0[ki] = Gk[g_off(q, 4 * ki + t)];
+            z1[ki] = lo ? Gk[g_off(8 + q, 4 * ki + t)] : 0.0;
         }
-        if (r < 12 && h == 0) {
-            sm.vec[r] = xr;
-            Vk[mode ? V_DX + r : V_X + r] = xr;
-        }
-        __syncwarp();
-        // input part z[12..15]
-        if (r >= 12) {
-            const int e = r - 12;
-            double dv;
-            if (mode == 0) {
-                dv = Vk[V_V + e];
-            } else {
-                // ddu_e = -kff_e - sum_j K[e][j] ddx_j ; halves split j
-                const double* Fk = I.F + (size_t)k * FREC;
-                double s = 0.0;
+        if (q == 0) {
 #pragma unroll
-                for (int j = 0; j < 6; j++) s = fma(Fk[(6 * h + j) * 4 + e], sm.vec[6 * h + j], s);
-                s += __shfl_xor_sync(0xf000f000u, s, 16);
-                Chol4 L;
-                load_chol(Fk, L);
-                double gg[4] = {Vk[V_G + 0], Vk[V_G + 1], Vk[V_G + 2], Vk[V_G + 3]};
-                chol4_solve(L, gg);
-                dv = -gg[e] - s;
-                if (h == 0) Vk[V_DV + e] = dv;
-            }
-            if (h == 0) sm.vec[12 + e] = dv;
+            for (int ki = 0; ki < 3; ki++) Vk[xoff + 4 * ki + t] = zr[ki];
         }
-        __syncwarp();
-        double s = 0.0;
-        if (r < 12) {
-            const double2* z2 = reinterpret_cast<const double2*>(sm.vec + 8 * h);
+        double ut;                              // u[t]
+        if (mode == 0) {
+            ut = Vk[V_V + t];
+        } else {
+            // (K x)[q] for q < 4: K[q][4ki+t] = Kt[4ki+t][q]
+            double part = 0.0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) { double2 z = z2[j]; s = fma(g[2 * j], z.x, s); s = fma(g[2 * j + 1], z.y, s); }
+            for (int ki = 0; ki < 3; ki++) part = fma(lo ? Fk[(4 * ki + t) * 4 + q] : 0.0, zr[ki], part);
+            part += shfl_x(part, 1);
+            part += shfl_x(part, 2);
+            const double uq = -Vk[V_KFF + (q & 3)] - part;
+            if (lo && t == 0) Vk[V_DV + q] = uq;
+            ut = shfl(uq, 4 * t);
         }
-        s += __shfl_xor_sync(FULL_MASK, s, 16);
-        if (mode == 0 && r < 12) {
-            const double b = Gk[G_B_OFF + r];
-            s += b;
-            bmax = fmax(bmax, fabs(b));
+        double o0 = z0[3] * ut, o1 = z1[3] * ut;
+#pragma unroll
+        for (int ki = 0; ki < 3; ki++) { o0 = fma(z0[ki], zr[ki], o0); o1 = fma(z1[ki], zr[ki], o1); }
+        o0 += shfl_x(o0, 1); o1 += shfl_x(o1, 1);
+        o0 += shfl_x(o0, 2); o1 += shfl_x(o1, 2);
+        if (mode == 0) {
+            const double b0 = Gk[G_B_OFF + q], b1 = lo ? Gk[G_B_OFF + 8 + q] : 0.0;
+            o0 += b0; o1 += b1;
+            bmax = fmax(bmax, fmax(fabs(b0), fabs(b1)));
         }
-        xr = s;
-        __syncwarp();
+        // quad layout -> row layout
+        zr[0] = shfl(o0, 4 * t);
+        zr[1] = shfl(o0, 4 * (4 + t));
+        zr[2] = shfl(o1, 4 * t);
     }
-    if (r < 12 && h == 0) I.V[(size_t)N * VREC + (mode ? V_DX + r : V_X + r)] = xr;
+    if (q == 0) {
+#pragma unroll
+        for (int ki = 0; ki < 3; ki++) I.V[(size_t)N * VREC + xoff + 4 * ki + t] = zr[ki];
+    }
     __syncwarp();
+    (void)lane;
     return mode == 0 ? warp_max(bmax) : 0.0;
 }
 
-// Backward sweep.  factor = true: costate recursion of the iterate (pi), reduced gradient gu, Riccati
-// factorisation with the current barrier diagonal, and the vector recursion for the predictor rhs (gh = gu).
-// factor = false: vector recursion only, rhs gh = gu - cl/tl + cu/tu (corrector).
-// Returns false if a Cholesky pivot failed.
-__device__ bool backward_sweep(Inst& I, bool factor)
+// C-fragment row block (tiles ni = 0, 1 of one 8-row block) -> A/B-style fragments: out[ki] = element (row q, col 4ki+t)
+__device__ __forceinline__ void c_to_rowfrag(const double (&c0)[2], const double (&c1)[2], int lane, double* out)
 {
-    const int r = I.r, h = I.h, N = I.N, lane = I.lane;
-    WarpSmem& sm = I.sm;
+    const int t = lane & 3;
+    const int s0 = (lane & ~3) | (t >> 1), s1 = s0 | 2;
+    const bool odd = t & 1;
+    double x0, x1;
+    x0 = shfl(c0[0], s0); x1 = shfl(c0[1], s0); out[0] = odd ? x1 : x0;
+    x0 = shfl(c0[0], s1); x1 = shfl(c0[1], s1); out[1] = odd ? x1 : x0;
+    x0 = shfl(c1[0], s0); x1 = shfl(c1[1], s0); out[2] = odd ? x1 : x0;
+}
+
+// Backward factor sweep: costate recursion of the iterate (pi), reduced gradient gu, Riccati factorisation with the
+// current barrier diagonal, and the vector recursion for the predictor rhs (gh = gu), all in one pass.
+//   W' = Z' [P+ | pi+ | p+]   (16 x 14, DMMA: A = Z' fragments, B = P+ fragments with the two vectors riding in the
+//                              otherwise padded columns 12, 13)
+//   H  = W'[:, 0:12] Z        (16 x 16, DMMA)  = [A|B]' P+ [A|B]
+//   Lam = H_uu + R~ = L L',  Y = L^-1 H_ux,  K = L^-T Y,  P = Q + H_xx - Y'Y (DMMA, k = 4)
+// Returns false if a Cholesky pivot failed.
+__device__ bool factor_sweep(Inst& I)
+{
+    const int q = I.q, t = I.t, N = I.N, lane = I.lane;
     const SolveArgs& a = I.a;
-    double Prow[12];
-    double pi_r = 0.0, pv_r = 0.0;
+    const bool lo = q < 4;
+    const int e = q & 3;                        // input index owned by quads 4..7
+    const int qb = lane & ~3;                   // first lane of my quad
     bool ok = true;
-    if (factor) {
-        // terminal: P_N = diag(We), pi_N = We (x_N + X_N - yref_N)
+
+    // P+ as B fragments: pB[ki][ni] = P[4ki+t][8ni+q]; column 12 (ni=1,q=4) carries pi+, column 13 (q=5) carries p+
+    double pB[3][2];
+    {
+        const double* VN = I.V + (size_t)N * VREC;
 #pragma unroll
-        for (int l = 0; l < 12; l++) Prow[l] = (r < 12 && l == r) ? a.We[r < 12 ? r : 0] : 0.0;
-        if (r < 12) pi_r = a.We[r] * (I.V[(size_t)N * VREC + V_X + r] + I.Xlin[N * NX + r] - I.yref[N * NY + r]);
+        for (int ki = 0; ki < 3; ki++) {
+            const int row = 4 * ki + t;
+            pB[ki][0] = (row == q) ? a.We[row] : 0.0;
+            pB[ki][1] = (lo && row == 8 + q) ? a.We[row] : 0.0;
+            if (q == 4) pB[ki][1] = a.We[row] * (VN[V_X + row] + I.Xlin[N * NX + row] - I.yref[N * NY + row]);
+        }
     }
     for (int k = N - 1; k >= 0; k--) {
         const double* Gk = I.G + (size_t)k * GREC;
         double* Fk = I.F + (size_t)k * FREC;
         double* Vk = I.V + (size_t)k * VREC;
+        double g[3][2];
+#pragma unroll
+        for (int ki = 0; ki < 3; ki++) {
+            g[ki][0] = Gk[((ki * 2 + 0) << 5) + lane];
+            g[ki][1] = Gk[((ki * 2 + 1) << 5) + lane];
+        }
         const double tsk = a.Ts[k];
-        // ---- stage scalars ----
-        double qd = 0.0, qx = 0.0;          // state rows: Q_rr and  Q_rr x_r + q_r
-        double rt = 0.0, gu = 0.0, gh = 0.0;  // input rows
-        if (r < 12) {
-            if (factor) {
-                qd = tsk * a.W[r];
-                qx = qd * (Vk[V_X + r] + I.Xlin[k * NX + r] - I.yref[k * NY + r]);
+        // state rows q and 8+q
+        const double qd0 = tsk * a.W[q];
+        const double qx0 = qd0 * (Vk[V_X + q] + I.Xlin[k * NX + q] - I.yref[k * NY + q]);
+        const double qd1 = lo ? tsk * a.W[8 + e] : 0.0;
+        const double qx1 = lo ? qd1 * (Vk[V_X + 8 + e] + I.Xlin[k * NX + 8 + e] - I.yref[k * NY + 8 + e]) : 0.0;
+        // input row e (meaningful in quads 4..7)
+        const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e];
+        const double rd = tsk * a.W[12 + e];
+        const double rt = rd + ll / tl + lu / tu;
+        const double gu_loc = rd * (Vk[V_V + e] + I.Ulin[k * NU + e] - I.yref[k * NY + 12 + e]);
+
+        // ---- W' = Z' [P+ | pi+ | p+] ----
+        double w[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+        for (int ki = 0; ki < 3; ki++)
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 2; ni++) dmma(w[mi][ni], g[ki][mi], pB[ki][ni]);
+        // ---- H = W' Z ----
+        double wA[2][3];
+        c_to_rowfrag(w[0][0], w[0][1], lane, wA[0]);
+        c_to_rowfrag(w[1][0], w[1][1], lane, wA[1]);
+        double h[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+        for (int ki = 0; ki < 3; ki++)
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 2; ni++) dmma(h[mi][ni], wA[mi][ki], g[ki][ni]);
+        // ---- the two vector products sit in columns 12, 13 of W': lane (q,2) holds ([A|B]'pi+)[8mi+q], ([A|B]'p+)[8mi+q] ----
+        const double at0 = shfl(w[0][1][0], qb | 2), bt0 = shfl(w[0][1][1], qb | 2);
+        const double at1 = shfl(w[1][1][0], qb | 2), bt1 = shfl(w[1][1][1], qb | 2);
+        const double gu = gu_loc + at1;          // quads 4..7: R du + r + B'pi+
+        const double gval = gu + bt1;            // predictor rhs: gh = gu
+        // ---- Lam = B'P+B + R~ : add the barrier diagonal where the diagonal element lives, then broadcast ----
+        if (!lo && t == 2 + (e >> 1)) {
+            if (e & 1) h[1][1][1] += rt; else h[1][1][0] += rt;
+        }
+        double m[10];
+        m[0] = shfl(h[1][1][0], 4 * 4 + 2);
+        m[1] = shfl(h[1][1][0], 4 * 5 + 2); m[2] = shfl(h[1][1][1], 4 * 5 + 2);
+        m[3] = shfl(h[1][1][0], 4 * 6 + 2); m[4] = shfl(h[1][1][1], 4 * 6 + 2); m[5] = shfl(h[1][1][0], 4 * 6 + 3);
+        m[6] = shfl(h[1][1][0], 4 * 7 + 2); m[7] = shfl(h[1][1][1], 4 * 7 + 2); m[8] = shfl(h[1][1][0], 4 * 7 + 3);
+        m[9] = shfl(h[1][1][1], 4 * 7 + 3);
+        Chol4 L;
+        ok &= chol4(m, L);
+        // ---- rows q and 8+q of H_xu (columns 12..15 live in lanes t = 2, 3 of the quad) ----
+        double y0[4], y1[4];
+        y0[0] = shfl(h[0][1][0], qb | 2); y0[1] = shfl(h[0][1][1], qb | 2);
+        y0[2] = shfl(h[0][1][0], qb | 3); y0[3] = shfl(h[0][1][1], qb | 3);
+        y1[0] = shfl(h[1][1][0], qb | 2); y1[1] = shfl(h[1][1][1], qb | 2);
+        y1[2] = shfl(h[1][1][0], qb | 3); y1[3] = shfl(h[1][1][1], qb | 3);
+        chol4_fwd(L, y0);                        // Y[:, q]
+        chol4_fwd(L, y1);                        // Y[:, 8+q]   (garbage in quads 4..7, masked below)
+        // ---- feedback gain columns K[:, q], K[:, 8+q] -> F record ----
+        {
+            double kc[4] = {y0[0], y0[1], y0[2], y0[3]};
+            chol4_bwd(L, kc);
+            if (t == 0) {
+                *reinterpret_cast<double2*>(Fk + q * 4) = make_double2(kc[0], kc[1]);
+                *reinterpret_cast<double2*>(Fk + q * 4 + 2) = make_double2(kc[2], kc[3]);
             }
-        } else {
-            const int e = r - 12;
-            const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e];
-            if (factor) {
-                const double rd = tsk * a.W[12 + e];
-                rt = rd + ll / tl + lu / tu;
-                gu = rd * (Vk[V_V + e] + I.Ulin[k * NU + e] - I.yref[k * NY + 12 + e]);   // + B'pi+ below
-            } else {
-                gh = Vk[V_GU + e] - Vk[V_CL + e] / tl + Vk[V_CU + e] / tu;
+            double kd[4] = {y1[0], y1[1], y1[2], y1[3]};
+            chol4_bwd(L, kd);
+            if (t == 1 && lo) {
+                *reinterpret_cast<double2*>(Fk + (8 + q) * 4) = make_double2(kd[0], kd[1]);
+                *reinterpret_cast<double2*>(Fk + (8 + q) * 4 + 2) = make_double2(kd[2], kd[3]);
             }
         }
-        double gc[12];                       // column r of [A|B]
-        double s4[4], kc[4];
-        double at = 0.0, bt = 0.0;
-        if (factor) {
-            // ---- stage matrix to shared memory ----
-            {
-                const double2* src = reinterpret_cast<const double2*>(Gk);
-                double2* dst = reinterpret_cast<double2*>(sm.Gs);
+        if (lane == 2) {
+            Fk[F_L_OFF + 0] = L.l10; Fk[F_L_OFF + 1] = L.l20; Fk[F_L_OFF + 2] = L.l21;
+            Fk[F_L_OFF + 3] = L.l30; Fk[F_L_OFF + 4] = L.l31; Fk[F_L_OFF + 5] = L.l32;
+            Fk[F_ID_OFF + 0] = L.i0; Fk[F_ID_OFF + 1] = L.i1; Fk[F_ID_OFF + 2] = L.i2; Fk[F_ID_OFF + 3] = L.i3;
+        }
+        // ---- g = gh + B'p+ to every lane; kff = Lam^-1 g ----
+        double gt[4];
 #pragma unroll
-                for (int c = 0; c < 3; c++) dst[lane + 32 * c] = src[lane + 32 * c];
+        for (int c = 0; c < 4; c++) gt[c] = shfl(gval, 4 * (4 + c) + 2);
+        if (!lo && t == 2) Vk[V_GU + e] = gu;
+        chol4_fwd(L, gt);                        // L^-1 g
+        const double pv0 = bt0 - (y0[0] * gt[0] + y0[1] * gt[1] + y0[2] * gt[2] + y0[3] * gt[3]);
+        const double pv1 = bt1 - (y1[0] * gt[0] + y1[1] * gt[1] + y1[2] * gt[2] + y1[3] * gt[3]);
+        const double pi0 = qx0 + at0, pi1 = qx1 + at1;
+        {
+            double kf[4] = {gt[0], gt[1], gt[2], gt[3]};
+            chol4_bwd(L, kf);
+            if (lane == 1) {
+                *reinterpret_cast<double2*>(Vk + V_KFF) = make_double2(kf[0], kf[1]);
+                *reinterpret_cast<double2*>(Vk + V_KFF + 2) = make_double2(kf[2], kf[3]);
             }
-            if (r < 12 && h == 0) { sm.vec[r] = pi_r; sm.vec[16 + r] = pv_r; }
-            __syncwarp();
-            // ---- W = P+ [A|B], row r, my column half ----
-            double w[8];
+        }
+        // ---- P = Q + H_xx - Y'Y  (A fragment of Y' and B fragment of Y are the same register: Y[t][8mi+q]) ----
+        const double ys0 = (t == 0) ? y0[0] : (t == 1) ? y0[1] : (t == 2) ? y0[2] : y0[3];
+        double ys1 = (t == 0) ? y1[0] : (t == 1) ? y1[1] : (t == 2) ? y1[2] : y1[3];
+        if (!lo) ys1 = 0.0;
+        dmma(h[0][0], -ys0, ys0); dmma(h[0][1], -ys0, ys1);
+        dmma(h[1][0], -ys1, ys0); dmma(h[1][1], -ys1, ys1);
+        if (t == (q >> 1)) {                     // diagonal element (8mi+q, 8mi+q) is C register q&1 of lane (q, q>>1)
+            if (q & 1) { h[0][0][1] += qd0; h[1][1][1] += qd1; } else { h[0][0][0] += qd0; h[1][1][0] += qd1; }
+        }
+        // ---- next stage's B fragments, read through the symmetry P[4ki+t][8ni+q] = P[8ni+q][4ki+t] ----
+        double f0[3], f1[3];
+        c_to_rowfrag(h[0][0], h[0][1], lane, f0);
+        c_to_rowfrag(h[1][0], h[1][1], lane, f1);
+        const double vs0 = (t == 0) ? pi0 : pv0, vs1 = (t == 0) ? pi1 : pv1;
+        const double i0 = shfl(vs0, 4 * t + (q & 1)), i1 = shfl(vs0, 4 * (4 + t) + (q & 1)), i2 = shfl(vs1, 4 * t + (q & 1));
+        pB[0][0] = f0[0]; pB[1][0] = f0[1]; pB[2][0] = f0[2];
+        pB[0][1] = lo ? f1[0] : 0.0; pB[1][1] = lo ? f1[1] : 0.0; pB[2][1] = lo ? f1[2] : 0.0;
+        if (q == 4 || q == 5) { pB[0][1] = i0; pB[1][1] = i1; pB[2][1] = i2; }
+    }
+    __syncwarp();
+    return __all_sync(FULL_MASK, ok);
+}
+
+// Backward vector sweep (corrector): rhs gh = gu - cl/tl + cu/tu;  g = gh + B'p+,  kff = Lam^-1 g,  p = A'p+ - K'g.
+// Z is read in fragment order; lane (q,t) forms its part of column q and column 8+q of Z'p and the quad reduces over t.
+__device__ void backward_vec_sweep(Inst& I)
+{
+    const int q = I.q, t = I.t, N = I.N, lane = I.lane;
+    const bool lo = q < 4;
+    const int e = q & 3;
+    double pr[3] = {0.0, 0.0, 0.0};             // p+ in row layout
+    for (int k = N - 1; k >= 0; k--) {
+        const double* Gk = I.G + (size_t)k * GREC;
+        const double* Fk = I.F + (size_t)k * FREC;
+        double* Vk = I.V + (size_t)k * VREC;
+        double o0 = 0.0, o1 = 0.0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) w[j] = 0.0;
-            if (r < 12) {
+        for (int ki = 0; ki < 3; ki++) {
+            o0 = fma(Gk[((ki * 2 + 0) << 5) + lane], pr[ki], o0);
+            o1 = fma(Gk[((ki * 2 + 1) << 5) + lane], pr[ki], o1);
+        }
+        const double tl = Vk[V_TL + e], tu = Vk[V_TU + e];
+        const double gh = Vk[V_GU + e] - Vk[V_CL + e] / tl + Vk[V_CU + e] / tu;
+        const double2 ka = *reinterpret_cast<const double2*>(Fk + q * 4), kb = *reinterpret_cast<const double2*>(Fk + q * 4 + 2);
+        double2 kc = make_double2(0.0, 0.0), kd = make_double2(0.0, 0.0);
+        if (lo) { kc = *reinterpret_cast<const double2*>(Fk + (8 + q) * 4); kd = *reinterpret_cast<const double2*>(Fk + (8 + q) * 4 + 2); }
+        Chol4 L;
+        load_chol(Fk, L);
+        o0 += shfl_x(o0, 1); o1 += shfl_x(o1, 1);
+        o0 += shfl_x(o0, 2); o1 += shfl_x(o1, 2);          // (Z'p+)[q], (Z'p+)[8+q]
+        const double gval = gh + o1;                          // quads 4..7
+        double gt[4];
 #pragma unroll
-                for (int l = 0; l < 12; l++) {
-                    const double2* g2 = reinterpret_cast<const double2*>(sm.Gs + l * 16 + 8 * h);
-                    const double pl = Prow[l];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) { double2 t = g2[j]; w[2 * j] = fma(pl, t.x, w[2 * j]); w[2 * j + 1] = fma(pl, t.y, w[2 * j + 1]); }
-                }
-                double2* w2 = reinterpret_cast<double2*>(sm.Ws + r * 16 + 8 * h);
-#pragma unroll
-                for (int j = 0; j < 4; j++) w2[j] = make_double2(w[2 * j], w[2 * j + 1]);
-            }
-#pragma unroll
-            for (int l = 0; l < 12; l++) gc[l] = sm.Gs[l * 16 + r];
-            __syncwarp();
-            // ---- H row r = sum_l G[l][r] W[l][:], my half; [A|B]'pi+, [A|B]'p+ ----
-            double hr[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) hr[j] = 0.0;
-#pragma unroll
-            for (int l = 0; l < 12; l++) {
-                const double2* w2 = reinterpret_cast<const double2*>(sm.Ws + l * 16 + 8 * h);
-                const double gl = gc[l];
-#pragma unroll
-                for (int j = 0; j < 4; j++) { double2 t = w2[j]; hr[2 * j] = fma(gl, t.x, hr[2 * j]); hr[2 * j + 1] = fma(gl, t.y, hr[2 * j + 1]); }
-                at = fma(gl, sm.vec[l], at);
-                bt = fma(gl, sm.vec[16 + l], bt);
-            }
-            if (r >= 12) {
-                const int e = r - 12;
-                double2* h2 = reinterpret_cast<double2*>(sm.Hu + e * 16 + 8 * h);
-#pragma unroll
-                for (int j = 0; j < 4; j++) h2[j] = make_double2(hr[2 * j], hr[2 * j + 1]);
-                gu += at;
-                if (h == 0) { sm.gs[e] = gu + bt; sm.rt[e] = rt; Vk[V_GU + e] = gu; Vk[V_G + e] = gu + bt; }
-            }
-            __syncwarp();
-            // ---- Lam = B'PB + R~, Cholesky (every lane, redundantly) ----
-            double m[10];
-            m[0] = sm.Hu[0 * 16 + 12] + sm.rt[0];
-            m[1] = sm.Hu[1 * 16 + 12]; m[2] = sm.Hu[1 * 16 + 13] + sm.rt[1];
-            m[3] = sm.Hu[2 * 16 + 12]; m[4] = sm.Hu[2 * 16 + 13]; m[5] = sm.Hu[2 * 16 + 14] + sm.rt[2];
-            m[6] = sm.Hu[3 * 16 + 12]; m[7] = sm.Hu[3 * 16 + 13]; m[8] = sm.Hu[3 * 16 + 14]; m[9] = sm.Hu[3 * 16 + 15] + sm.rt[3];
-            Chol4 L;
-            ok &= chol4(m, L);
-            if (lane == 0) {
-                Fk[F_L_OFF + 0] = L.l10; Fk[F_L_OFF + 1] = L.l20; Fk[F_L_OFF + 2] = L.l21;
-                Fk[F_L_OFF + 3] = L.l30; Fk[F_L_OFF + 4] = L.l31; Fk[F_L_OFF + 5] = L.l32;
-                Fk[F_ID_OFF + 0] = L.i0; Fk[F_ID_OFF + 1] = L.i1; Fk[F_ID_OFF + 2] = L.i2; Fk[F_ID_OFF + 3] = L.i3;
-            }
-            // ---- K column r = Lam^-1 (B'PA)[:, r] ----
-            const int rc = r < 12 ? r : 0;
-#pragma unroll
-            for (int e = 0; e < 4; e++) { s4[e] = sm.Hu[e * 16 + rc]; kc[e] = s4[e]; }
-            chol4_solve(L, kc);
-            double g0 = sm.gs[0], g1 = sm.gs[1], g2v = sm.gs[2], g3 = sm.gs[3];
-            if (r < 12) {
-                pv_r = bt - (kc[0] * g0 + kc[1] * g1 + kc[2] * g2v + kc[3] * g3);
-                pi_r = qx + at;
-                if (h == 0) {
-#pragma unroll
-                    for (int e = 0; e < 4; e++) sm.Ks[e * 16 + r] = kc[e];
-                    *reinterpret_cast<double2*>(Fk + r * 4) = make_double2(kc[0], kc[1]);
-                    *reinterpret_cast<double2*>(Fk + r * 4 + 2) = make_double2(kc[2], kc[3]);
-                }
-            }
-            __syncwarp();
-            // ---- P = Q + A'PA - (B'PA)' K ----
-            if (r < 12) {
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const double2* k2 = reinterpret_cast<const double2*>(sm.Ks + e * 16 + 8 * h);
-                    const double se = s4[e];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) { double2 t = k2[j]; hr[2 * j] = fma(-se, t.x, hr[2 * j]); hr[2 * j + 1] = fma(-se, t.y, hr[2 * j + 1]); }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (8 * h + j == r) hr[j] += qd;
-                double2* p2 = reinterpret_cast<double2*>(sm.Ws + r * 16 + 8 * h);
-#pragma unroll
-                for (int j = 0; j < 4; j++) p2[j] = make_double2(hr[2 * j], hr[2 * j + 1]);
-            }
-            __syncwarp();
-            if (r < 12) {
-#pragma unroll
-                for (int l = 0; l < 12; l++) Prow[l] = 0.5 * (sm.Ws[r * 16 + l] + sm.Ws[l * 16 + r]);
-            }
-            __syncwarp();
-        } else {
-            // ---- vector recursion only: g = gh + B'p+,  p = A'p+ - K'g ----
-            if (r < 12 && h == 0) sm.vec[r] = pv_r;
-            __syncwarp();
-            // column r of [A|B], halves split the 12 rows
-            double sacc = 0.0;
-#pragma unroll
-            for (int l = 0; l < 6; l++) sacc = fma(Gk[(6 * h + l) * 16 + r], sm.vec[6 * h + l], sacc);
-            bt = sacc + __shfl_xor_sync(FULL_MASK, sacc, 16);
-            if (r >= 12 && h == 0) { const int e = r - 12; sm.gs[e] = gh + bt; Vk[V_G + e] = gh + bt; }
-            __syncwarp();
-            if (r < 12) {
-                const double2 k01 = *reinterpret_cast<const double2*>(Fk + r * 4);
-                const double2 k23 = *reinterpret_cast<const double2*>(Fk + r * 4 + 2);
-                pv_r = bt - (k01.x * sm.gs[0] + k01.y * sm.gs[1] + k23.x * sm.gs[2] + k23.y * sm.gs[3]);
-            }
-            __syncwarp();
+        for (int c = 0; c < 4; c++) gt[c] = shfl(gval, 4 * (4 + c));
+        const double pv0 = o0 - (ka.x * gt[0] + ka.y * gt[1] + kb.x * gt[2] + kb.y * gt[3]);
+        const double pv1 = o1 - (kc.x * gt[0] + kc.y * gt[1] + kd.x * gt[2] + kd.y * gt[3]);
+        pr[0] = shfl(pv0, 4 * t);
+        pr[1] = shfl(pv0, 4 * (4 + t));
+        pr[2] = shfl(pv1, 4 * t);
+        // feed-forward for the forward sweep (off the recursion's critical path)
+        chol4_fwd(L, gt);
+        chol4_bwd(L, gt);
+        if (lane == 0) {
+            *reinterpret_cast<double2*>(Vk + V_KFF) = make_double2(gt[0], gt[1]);
+            *reinterpret_cast<double2*>(Vk + V_KFF + 2) = make_double2(gt[2], gt[3]);
         }
     }
-    return __all_sync(FULL_MASK, ok);
+    __syncwarp();
 }
 
 __device__ __forceinline__ double step_to_boundary(double v, double dv)
@@ -482,11 +532,9 @@ __device__ __forceinline__ double step_to_boundary(double v, double dv)
     return dv < 0.0 ? -v / dv : 2.0;   // 2 = "not blocking" (callers clamp at 1)
 }
 
-__global__ void __launch_bounds__(IPM_WARPS * 32) ipm_kernel(SolveArgs a)
+__global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
 {
-    __shared__ WarpSmem smem[IPM_WARPS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpSmem& sm = smem[wib];
+    const int lane = threadIdx.x & 31;
     const int N = a.N, nb = 4 * N;
 
     for (;;) {
@@ -494,17 +542,16 @@ __global__ void __launch_bounds__(IPM_WARPS * 32) ipm_kernel(SolveArgs a)
         if (lane == 0) inst = atomicAdd(a.work_counter, 1);
         inst = __shfl_sync(FULL_MASK, inst, 0);
         if (inst >= a.B) break;
-        Inst I(a, inst, lane, sm);
+        Inst I(a, inst, lane);
 
         ipm_init(I);
         const double bmax = forward_sweep(I, 0);
 
         int status = 2, it = 0;
         double mu = 0.0, res_stat = 0.0, stat_scale = 1.0;
-        // mu and stationarity of the starting point are produced by the first factor sweep's by-products
         for (it = 0; it < a.max_iter; it++) {
             // ---------- B1: factorisation + predictor rhs ----------
-            if (!backward_sweep(I, true)) { status = 4; break; }
+            if (!factor_sweep(I)) { status = 4; break; }
             if (it == 0) {
                 // mu and stationarity residual of the starting point (later iterations get them from E2)
                 double s = 0.0, rs = 0.0;
@@ -554,7 +601,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32) ipm_kernel(SolveArgs a)
             }
             __syncwarp();
             // ---------- B2 / F2: corrector ----------
-            backward_sweep(I, false);
+            backward_vec_sweep(I);
             forward_sweep(I, 1);
             // ---------- E2: step lengths and update ----------
             double ap = 2.0, ad = 2.0;

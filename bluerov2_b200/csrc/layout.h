@@ -1,20 +1,29 @@
 // layout.h -- HBM data layout of the batched SQP-RTI engine (see DESIGN.md "Data layout").
 //
-// One OCP instance is solved by one warp, so "coalesced" means: every per-stage record is a contiguous,
-// 128-byte-aligned block that the 32 lanes (or one bulk copy) fetch with 16-byte accesses.
+// One OCP instance is solved by one warp.  Lane l = 4 q + t  (q = l >> 2 in 0..7, t = l & 3), the thread
+// coordinates of the fp64 tensor-core instruction mma.sync.m8n8k4 (DMMA): an A fragment holds element
+// (row q, col t), a B fragment (row t, col q), a C fragment (row q, cols 2t, 2t+1).
 #pragma once
 
 namespace br2 {
 
-// Stage record G_k written by the linearisation kernel, read by every sweep of the IPM:
-//   [0..191]   G = [A_k | B_k], 12 x 16 row-major  (row l: A[l][0..11], B[l][0..3])
-//   [192..203] b_k = Phi(X_k,U_k) - X_{k+1}
-//   [204..207] pad (record = 1664 B = 13 x 128 B)
+// Stage record G_k written by the linearisation kernel, read by every sweep of the IPM.
+//   Z = [A_k | B_k] is 12 x 16.  It is stored in FRAGMENT ORDER: six blocks of 32 doubles,
+//   block (ki, mi), ki = 0..2, mi = 0..1, lane l holds Z[4 ki + t][8 mi + q].
+//   -> the backward sweeps load block (ki, mi) as one fully coalesced 256-byte access and use it directly as the
+//      DMMA A fragment of Z' (tile mi, ki) and as the B fragment of Z (tile ki, mi);
+//   -> the forward sweeps read Z[8 mi + q][4 ki + t] (row-per-quad), which in this order is two full 128-byte lines.
+//   [192..203] b_k = Phi(X_k,U_k) - X_{k+1};  [204..207] pad  (record = 1664 B = 13 x 128 B)
 constexpr int GREC = 208;
 constexpr int G_B_OFF = 192;
+// offset of Z[row][col] inside a record
+__host__ __device__ constexpr int g_off(int row, int col)
+{
+    return (((row >> 2) * 2 + (col >> 3)) << 5) + ((col & 7) << 2) + (row & 3);
+}
 
 // Factor record F_k written by the backward factorisation, read by the vector sweeps:
-//   [0..47]  Kt[j][a] = K[a][j]  (feedback gain, transposed so lane j owns 4 contiguous doubles)
+//   [0..47]  Kt[j][a] = K[a][j]  (feedback gain transposed: column j of K is 4 contiguous doubles)
 //   [48..53] strictly-lower Cholesky entries of Lam = R~ + B'PB: l10 l20 l21 l30 l31 l32
 //   [54..57] reciprocal diagonal 1/l00 .. 1/l33
 //   [58..63] pad (record = 512 B)
@@ -35,6 +44,6 @@ constexpr int V_GU = 44;   // reduced input gradient R du + r + B'pi+
 constexpr int V_DV = 48;   // step in du_k
 constexpr int V_CL = 52;   // complementarity rhs lower: sigma*mu - dt_aff*dlam_aff
 constexpr int V_CU = 56;   // complementarity rhs upper
-constexpr int V_G = 60;    // g = gh + B'p+   (kff = Lam^-1 g)
+constexpr int V_KFF = 60;  // feed-forward  kff = Lam^-1 (gh + B'p+)
 
 }  // namespace br2

@@ -40,6 +40,13 @@ class ThrustGather:
         if self.equal:
             dist.all_gather_into_tensor(self.buf, self.slot, group=self.group)
         else:
-            parts = [self.buf[lo:hi] for lo, hi in self.bounds]
-            dist.all_gather(parts, self.slot, group=self.group)
+            # ragged shards: gather fixed-size padded blocks (collectives want equal sizes), then unpack
+            m = max(hi - lo for lo, hi in self.bounds)
+            send = torch.zeros((m, NTHRUST), dtype=self.buf.dtype, device=self.buf.device)
+            send[: self.slot.shape[0]] = self.slot
+            recv = torch.empty((self.world, m, NTHRUST), dtype=self.buf.dtype, device=self.buf.device)
+            dist.all_gather_into_tensor(recv.view(self.world * m, NTHRUST), send, group=self.group)
+            for r, (lo, hi) in enumerate(self.bounds):
+                if r != self.rank:
+                    self.buf[lo:hi] = recv[r, : hi - lo]
         return self.buf
