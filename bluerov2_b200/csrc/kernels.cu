@@ -98,10 +98,13 @@ __global__ void __launch_bounds__(128) linearize_kernel(SolveArgs a)
 
     if (!live) return;
     double* Gk = a.G + ((size_t)inst * a.N + k) * GREC;
+    const double* yr = a.yref + ((size_t)inst * (a.N + 1) + k) * NY;
     if (c == 0) {
         const double* Xn = Xk + NX;
 #pragma unroll
         for (int i = 0; i < NX; i++) Gk[G_B_OFF + i] = cur[i] - __ldg(Xn + i);
+#pragma unroll
+        for (int i = 0; i < NX; i++) Gk[G_QLIN + i] = h * a.W[i] * (col0[i] - __ldg(yr + i));
 #pragma unroll
         for (int l = 0; l < NX; l++) Gk[g_off(l, 2)] = (l == 2) ? 1.0 : 0.0;
     } else if (c <= 13) {
@@ -114,7 +117,10 @@ __global__ void __launch_bounds__(128) linearize_kernel(SolveArgs a)
         for (int l = 0; l < NX; l++) Gk[g_off(l, j)] = (l == j) ? 1.0 : 0.0;
         if (c == 14) {
 #pragma unroll
-            for (int i = 204; i < GREC; i++) Gk[i] = 0.0;
+            for (int i = 0; i < NU; i++) Gk[G_RLIN + i] = h * a.W[NX + i] * (u[i] - __ldg(yr + NX + i));
+            Gk[G_TS] = h;
+#pragma unroll
+            for (int i = G_TS + 1; i < GREC; i++) Gk[i] = 0.0;
         }
     }
 }
@@ -165,6 +171,36 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+
+// ---- per-warp TMA bulk-copy pipeline: stage records are prefetched HBM -> shared memory one stage ahead ----
+struct __align__(128) StageBuf { double G[GREC]; double F[FREC]; double V[VREC]; };
+struct __align__(128) WarpSmem { StageBuf st[2]; unsigned long long bar[2]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// generic-proxy global writes of this warp (made visible to the issuing lane by __syncwarp) -> async-proxy reads
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // 4x4 Cholesky of the symmetric matrix with lower entries m (row-major lower: 00 10 11 20 21 22 30 31 32 33).
 // Outputs strictly-lower entries and reciprocal diagonal.  Returns false when a pivot is not positive.
 struct Chol4 { double l10, l20, l21, l30, l31, l32, i0, i1, i2, i3; };
@@ -210,6 +246,8 @@ __device__ __forceinline__ void load_chol(const double* Fk, Chol4& L)
 // Per-instance pointers
 struct Inst {
     const SolveArgs& a;
+    WarpSmem& sm;
+    uint32_t& phase;            // parity of the two slot barriers (bit s = next parity to wait for on slot s)
     int inst, lane, q, t, N;
     const double* G;
     double* F;
@@ -217,8 +255,8 @@ struct Inst {
     const double* Xlin;
     const double* Ulin;
     const double* yref;
-    __device__ Inst(const SolveArgs& a_, int inst_, int lane_)
-        : a(a_), inst(inst_), lane(lane_), q(lane_ >> 2), t(lane_ & 3), N(a_.N)
+    __device__ Inst(const SolveArgs& a_, WarpSmem& sm_, uint32_t& phase_, int inst_, int lane_)
+        : a(a_), sm(sm_), phase(phase_), inst(inst_), lane(lane_), q(lane_ >> 2), t(lane_ & 3), N(a_.N)
     {
         G = a.G + (size_t)inst * N * GREC;
         F = a.F + (size_t)inst * N * FREC;
@@ -226,6 +264,30 @@ struct Inst {
         Xlin = a.X + (size_t)inst * (N + 1) * NX;
         Ulin = a.U + (size_t)inst * N * NU;
         yref = a.yref + (size_t)inst * (N + 1) * NY;
+    }
+    // prefetch the records of stage k into slot s (one lane issues; completion lands on the slot's mbarrier)
+    template <bool NEED_F>
+    __device__ __forceinline__ void issue(int s, int k)
+    {
+        if (lane == 0) {
+            mbar_expect_tx(&sm.bar[s], (uint32_t)((GREC + VREC + (NEED_F ? FREC : 0)) * sizeof(double)));
+            bulk_g2s(sm.st[s].G, G + (size_t)k * GREC, GREC * sizeof(double), &sm.bar[s]);
+            bulk_g2s(sm.st[s].V, V + (size_t)k * VREC, VREC * sizeof(double), &sm.bar[s]);
+            if (NEED_F) bulk_g2s(sm.st[s].F, F + (size_t)k * FREC, FREC * sizeof(double), &sm.bar[s]);
+        }
+    }
+    // first prefetch of a sweep: everything this warp wrote to global so far must be visible to the copy engine
+    template <bool NEED_F>
+    __device__ __forceinline__ void begin(int k)
+    {
+        __syncwarp();
+        if (lane == 0) fence_proxy_async();
+        issue<NEED_F>(0, k);
+    }
+    __device__ __forceinline__ void wait(int s)
+    {
+        mbar_wait(&sm.bar[s], (phase >> s) & 1u);
+        phase ^= 1u << s;
     }
 };
 
@@ -252,41 +314,48 @@ __device__ void ipm_init(Inst& I)
 // mode 1: Newton step  ddu = -kff - K ddx,  ddx+ = A ddx + B ddu, ddx_0 = 0 (writes V_DX, V_DV).
 // Z = [A|B] is read row-per-quad: lane (q,t) holds Z[q][4ki+t] and Z[8+q][4ki+t]; every product is 4 (3) local
 // FMAs and a reduction over the 4 lanes of a quad.  Returns max |b| in mode 0.
-__device__ double forward_sweep(Inst& I, int mode)
+template <int MODE>
+__device__ double forward_sweep(Inst& I)
 {
-    const int q = I.q, t = I.t, N = I.N, lane = I.lane;
+    const int q = I.q, t = I.t, N = I.N;
     const bool lo = q < 4;                      // quad owns a second state row 8 + q (else: no row 12..15)
     double zr[3];                               // propagated vector, row layout: x[4ki + t]
     double bmax = 0.0;
 #pragma unroll
     for (int ki = 0; ki < 3; ki++)
-        zr[ki] = (mode == 0) ? I.a.x0[(size_t)I.inst * NX + 4 * ki + t] - I.Xlin[4 * ki + t] : 0.0;
-    const int xoff = mode ? V_DX : V_X;
+        zr[ki] = (MODE == 0) ? I.a.x0[(size_t)I.inst * NX + 4 * ki + t] - I.Xlin[4 * ki + t] : 0.0;
+    constexpr int xoff = MODE ? V_DX : V_X;
+    I.template begin<MODE == 1>(0);
     for (int k = 0; k < N; k++) {
-        const double* Gk = I.G + (size_t)k * GREC;
-        const double* Fk = I.F + (size_t)k * FREC;
+        const int s = k & 1;
+        __syncwarp();                           // every lane is done with slot s^1 (stage k-1)
+        if (k + 1 < N) I.template issue<MODE == 1>(s ^ 1, k + 1);
+        I.wait(s);
+        const double* Gs = I.sm.st[s].G;
+        const double* Fs = I.sm.st[s].F;
+        const double* Vs = I.sm.st[s].V;
         double* Vk = I.V + (size_t)k * VREC;
         double z0[4], z1[4];
 #pragma unroll
         for (int ki = 0; ki < 4; ki++) {
-            z0[ki] = Gk[g_off(q, 4 * ki + t)];
-            z1[ki] = lo ? Gk[g_off(8 + q, 4 * ki + t)] : 0.0;
+            z0[ki] = Gs[g_off(q, 4 * ki + t)];
+            z1[ki] = lo ? Gs[g_off(8 + q, 4 * ki + t)] : 0.0;
         }
         if (q == 0) {
 #pragma unroll
             for (int ki = 0; ki < 3; ki++) Vk[xoff + 4 * ki + t] = zr[ki];
         }
         double ut;                              // u[t]
-        if (mode == 0) {
-            ut = Vk[V_V + t];
+        if (MODE == 0) {
+            ut = Vs[V_V + t];
         } else {
             // (K x)[q] for q < 4: K[q][4ki+t] = Kt[4ki+t][q]
             double part = 0.0;
 #pragma unroll
-            for (int ki = 0; ki < 3; ki++) part = fma(lo ? Fk[(4 * ki + t) * 4 + q] : 0.0, zr[ki], part);
+            for (int ki = 0; ki < 3; ki++) part = fma(lo ? Fs[(4 * ki + t) * 4 + q] : 0.0, zr[ki], part);
             part += shfl_x(part, 1);
             part += shfl_x(part, 2);
-            const double uq = -Vk[V_KFF + (q & 3)] - part;
+            const double uq = -Vs[V_KFF + (q & 3)] - part;
             if (lo && t == 0) Vk[V_DV + q] = uq;
             ut = shfl(uq, 4 * t);
         }
@@ -295,8 +364,8 @@ __device__ double forward_sweep(Inst& I, int mode)
         for (int ki = 0; ki < 3; ki++) { o0 = fma(z0[ki], zr[ki], o0); o1 = fma(z1[ki], zr[ki], o1); }
         o0 += shfl_x(o0, 1); o1 += shfl_x(o1, 1);
         o0 += shfl_x(o0, 2); o1 += shfl_x(o1, 2);
-        if (mode == 0) {
-            const double b0 = Gk[G_B_OFF + q], b1 = lo ? Gk[G_B_OFF + 8 + q] : 0.0;
+        if (MODE == 0) {
+            const double b0 = Gs[G_B_OFF + q], b1 = lo ? Gs[G_B_OFF + 8 + q] : 0.0;
             o0 += b0; o1 += b1;
             bmax = fmax(bmax, fmax(fabs(b0), fabs(b1)));
         }
@@ -310,8 +379,7 @@ __device__ double forward_sweep(Inst& I, int mode)
         for (int ki = 0; ki < 3; ki++) I.V[(size_t)N * VREC + xoff + 4 * ki + t] = zr[ki];
     }
     __syncwarp();
-    (void)lane;
-    return mode == 0 ? warp_max(bmax) : 0.0;
+    return MODE == 0 ? warp_max(bmax) : 0.0;
 }
 
 // C-fragment row block (tiles ni = 0, 1 of one 8-row block) -> A/B-style fragments: out[ki] = element (row q, col 4ki+t)
@@ -354,27 +422,33 @@ __device__ bool factor_sweep(Inst& I)
             if (q == 4) pB[ki][1] = a.We[row] * (VN[V_X + row] + I.Xlin[N * NX + row] - I.yref[N * NY + row]);
         }
     }
-    for (int k = N - 1; k >= 0; k--) {
-        const double* Gk = I.G + (size_t)k * GREC;
+    I.template begin<false>(N - 1);
+    for (int k = N - 1, it = 0; k >= 0; k--, it++) {
+        const int s = it & 1;
+        __syncwarp();                           // every lane is done with slot s^1 (stage k+1)
+        if (k > 0) I.template issue<false>(s ^ 1, k - 1);
+        I.wait(s);
+        const double* Gs = I.sm.st[s].G;
+        const double* Vs = I.sm.st[s].V;
         double* Fk = I.F + (size_t)k * FREC;
         double* Vk = I.V + (size_t)k * VREC;
         double g[3][2];
 #pragma unroll
         for (int ki = 0; ki < 3; ki++) {
-            g[ki][0] = Gk[((ki * 2 + 0) << 5) + lane];
-            g[ki][1] = Gk[((ki * 2 + 1) << 5) + lane];
+            g[ki][0] = Gs[((ki * 2 + 0) << 5) + lane];
+            g[ki][1] = Gs[((ki * 2 + 1) << 5) + lane];
         }
-        const double tsk = a.Ts[k];
-        // state rows q and 8+q
+        const double tsk = Gs[G_TS];
+        // state rows q and 8+q:  Q (x + X - xref) = Q x + qlin
         const double qd0 = tsk * a.W[q];
-        const double qx0 = qd0 * (Vk[V_X + q] + I.Xlin[k * NX + q] - I.yref[k * NY + q]);
+        const double qx0 = fma(qd0, Vs[V_X + q], Gs[G_QLIN + q]);
         const double qd1 = lo ? tsk * a.W[8 + e] : 0.0;
-        const double qx1 = lo ? qd1 * (Vk[V_X + 8 + e] + I.Xlin[k * NX + 8 + e] - I.yref[k * NY + 8 + e]) : 0.0;
+        const double qx1 = lo ? fma(qd1, Vs[V_X + 8 + e], Gs[G_QLIN + 8 + e]) : 0.0;
         // input row e (meaningful in quads 4..7)
-        const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e];
+        const double tl = Vs[V_TL + e], tu = Vs[V_TU + e], ll = Vs[V_LL + e], lu = Vs[V_LU + e];
         const double rd = tsk * a.W[12 + e];
         const double rt = rd + ll / tl + lu / tu;
-        const double gu_loc = rd * (Vk[V_V + e] + I.Ulin[k * NU + e] - I.yref[k * NY + 12 + e]);
+        const double gu_loc = fma(rd, Vs[V_V + e], Gs[G_RLIN + e]);
 
         // ---- W' = Z' [P+ | pi+ | p+] ----
         double w[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
@@ -488,9 +562,15 @@ __device__ void backward_vec_sweep(Inst& I)
     const bool lo = q < 4;
     const int e = q & 3;
     double pr[3] = {0.0, 0.0, 0.0};             // p+ in row layout
-    for (int k = N - 1; k >= 0; k--) {
-        const double* Gk = I.G + (size_t)k * GREC;
-        const double* Fk = I.F + (size_t)k * FREC;
+    I.template begin<true>(N - 1);
+    for (int k = N - 1, it = 0; k >= 0; k--, it++) {
+        const int s = it & 1;
+        __syncwarp();
+        if (k > 0) I.template issue<true>(s ^ 1, k - 1);
+        I.wait(s);
+        const double* Gk = I.sm.st[s].G;
+        const double* Fk = I.sm.st[s].F;
+        const double* Vs = I.sm.st[s].V;
         double* Vk = I.V + (size_t)k * VREC;
         double o0 = 0.0, o1 = 0.0;
 #pragma unroll
@@ -498,8 +578,8 @@ __device__ void backward_vec_sweep(Inst& I)
             o0 = fma(Gk[((ki * 2 + 0) << 5) + lane], pr[ki], o0);
             o1 = fma(Gk[((ki * 2 + 1) << 5) + lane], pr[ki], o1);
         }
-        const double tl = Vk[V_TL + e], tu = Vk[V_TU + e];
-        const double gh = Vk[V_GU + e] - Vk[V_CL + e] / tl + Vk[V_CU + e] / tu;
+        const double tl = Vs[V_TL + e], tu = Vs[V_TU + e];
+        const double gh = Vs[V_GU + e] - Vs[V_CL + e] / tl + Vs[V_CU + e] / tu;
         const double2 ka = *reinterpret_cast<const double2*>(Fk + q * 4), kb = *reinterpret_cast<const double2*>(Fk + q * 4 + 2);
         double2 kc = make_double2(0.0, 0.0), kd = make_double2(0.0, 0.0);
         if (lo) { kc = *reinterpret_cast<const double2*>(Fk + (8 + q) * 4); kd = *reinterpret_cast<const double2*>(Fk + (8 + q) * 4 + 2); }
@@ -534,18 +614,27 @@ __device__ __forceinline__ double step_to_boundary(double v, double dv)
 
 __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
 {
+    __shared__ WarpSmem smem[IPM_WARPS];
     const int lane = threadIdx.x & 31;
     const int N = a.N, nb = 4 * N;
+    WarpSmem& sm = smem[threadIdx.x >> 5];
+    uint32_t phase = 0;
+    if (lane == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
     for (;;) {
         int inst = 0;
         if (lane == 0) inst = atomicAdd(a.work_counter, 1);
         inst = __shfl_sync(FULL_MASK, inst, 0);
         if (inst >= a.B) break;
-        Inst I(a, inst, lane);
+        Inst I(a, sm, phase, inst, lane);
 
         ipm_init(I);
-        const double bmax = forward_sweep(I, 0);
+        const double bmax = forward_sweep<0>(I);
 
         int status = 2, it = 0;
         double mu = 0.0, res_stat = 0.0, stat_scale = 1.0;
@@ -568,7 +657,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
                 if (mu < a.tol && res_stat < a.tol * stat_scale) { status = 0; break; }
             }
             // ---------- F1: affine step ----------
-            forward_sweep(I, 1);
+            forward_sweep<1>(I);
             // ---------- E1: affine step length, sigma, corrector rhs ----------
             double a_aff = 1.0;
             for (int idx = lane; idx < nb; idx += 32) {
@@ -602,7 +691,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
             __syncwarp();
             // ---------- B2 / F2: corrector ----------
             backward_vec_sweep(I);
-            forward_sweep(I, 1);
+            forward_sweep<1>(I);
             // ---------- E2: step lengths and update ----------
             double ap = 2.0, ad = 2.0;
             for (int idx = lane; idx < nb; idx += 32) {
@@ -688,7 +777,7 @@ void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
     cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
     const int warps_needed = a.B;
     int blocks = (warps_needed + IPM_WARPS - 1) / IPM_WARPS;
-    const int max_blocks = sm_count * 8;
+    const int max_blocks = sm_count * 4;   // 4 blocks x 4 warps resident per SM (128 registers, 22.5 KB of staging buffers each)
     if (blocks > max_blocks) blocks = max_blocks;
     ipm_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
 }

@@ -13,9 +13,17 @@ namespace br2 {
 //   -> the backward sweeps load block (ki, mi) as one fully coalesced 256-byte access and use it directly as the
 //      DMMA A fragment of Z' (tile mi, ki) and as the B fragment of Z (tile ki, mi);
 //   -> the forward sweeps read Z[8 mi + q][4 ki + t] (row-per-quad), which in this order is two full 128-byte lines.
-//   [192..203] b_k = Phi(X_k,U_k) - X_{k+1};  [204..207] pad  (record = 1664 B = 13 x 128 B)
-constexpr int GREC = 208;
+//   [192..203] b_k = Phi(X_k,U_k) - X_{k+1}
+//   [204..215] qlin_k = Ts_k W_x (X_k - xref_k)      gradient of the stage cost at the linearisation point
+//   [216..219] rlin_k = Ts_k W_u (U_k - uref_k)
+//   [220]      Ts_k;  [221..223] pad                  (record = 1792 B = 14 x 128 B)
+// With these the IPM sweeps need nothing but the G, F and V records of a stage: each is one contiguous, 128-byte
+// aligned block that a single lane prefetches into shared memory with cp.async.bulk (TMA bulk copy).
+constexpr int GREC = 224;
 constexpr int G_B_OFF = 192;
+constexpr int G_QLIN = 204;
+constexpr int G_RLIN = 216;
+constexpr int G_TS = 220;
 // offset of Z[row][col] inside a record
 __host__ __device__ constexpr int g_off(int row, int col)
 {
