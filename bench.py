@@ -5,15 +5,17 @@
 
 A "step" is one control tick of the hot path over one batch: for every instance the call sequence of
 BLUEROV2_DOB::solve (bluerov2_dob.cpp:307-395) -- x0, parameters, yref window, one SQP-RTI iteration
-(linearisation + Riccati IPM), u0 and the 4->6 thrust allocation.  Workload = BASELINE config 2 (batch 4096 per GPU,
+(linearisation + Riccati IPM), u0 and the 4->6 thrust allocation.  Like the node, which keeps the trajectory file in
+memory and advances a line counter (bluerov2_dob.cpp:367), the solver holds the trajectory on the device and a tick
+passes one row index per instance (reference windowing on the device, ref_cb).  Workload = BASELINE config 2 (batch 4096 per GPU,
 random x0 around the circle reference, N = 40, fp64): closed loop, plant = nominal ERK4 at 0.05 s, iterate carried
 between ticks.  The closed-loop input sequence (x0_t, yref_t) is generated ONCE before the timed region (untimed
 pass through the same CUDA solver + a numpy plant) and then replayed from the same initial iterate, so the timed
 ticks see exactly the warm-started problems of ticks W..W+K-1.
 
   value : whole-job steps/s, inputs resident in HBM, device time (CUDA events), max over ranks.
-  e2e   : the same ticks through the public host API (BatchSolver.solve -> br2_batch_solve_host) with pinned HOST
-          buffers: H2D of x0/yref/p and D2H of u0/thrust/status inside the timed region.
+  e2e   : the same ticks through the public host API (BatchSolver.solve_windowed -> br2_batch_solve_windowed_host) with
+          pinned HOST buffers: H2D of x0 / row indices / p and D2H of u0/thrust/status inside the timed region.
   roofline / cpu_baseline: see DESIGN.md "Measurement".
 
 --impl reference times the reference's CPU algorithm for the same metric: acados/HPIPM cannot be built here, so it
@@ -53,7 +55,7 @@ def peaks():
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons during the timed region (NVML, 100 ms period)."""
+    """SM clock and throttle reasons during the timed region (NVML, 20 ms period)."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -86,7 +88,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
@@ -105,16 +107,16 @@ def record_closed_loop(solver, w, ticks: int, N: int):
     """untimed: run `ticks` closed-loop ticks through the CUDA solver, return the per-tick inputs (host arrays)"""
     x0, lines = w["x0"].copy(), w["lines"].copy()
     solver.set_iterate(w["X"], w["U"])
-    x0s, yrefs = [], []
+    x0s, lns = [], []
+    solver.set_trajectory(w["traj"])
     for _ in range(ticks):
-        yref = traj.window_batch(w["traj"], lines, N)
-        x0s.append(x0.copy()); yrefs.append(yref)
-        u0, _, st = solver.solve(x0, yref, w["p"])
+        x0s.append(x0.copy()); lns.append(lines.astype(np.int32))
+        u0, _, st = solver.solve_windowed(x0, lns[-1], w["p"])
         if (st != 0).any():
             raise RuntimeError(f"solver status != 0 while recording the workload: {np.unique(st, return_counts=True)}")
         x0 = wl.plant_step(x0, u0, w["p"], 0.05)
         lines = lines + 1
-    return x0s, yrefs
+    return x0s, lns
 
 
 def cpu_leg(N: int, budget_s: float, ticks_wanted: int, threads: int = 0, seed: int = 0, pos_spread: float = 0.5):
@@ -200,18 +202,18 @@ def run_ours(args):
     sampler = ClockSampler(local)
     w = make_workload(B, N, seed=1000 * rank, pos_spread=args.pos_spread)
     sol = S.BatchSolver(B, N, device=local)
-    x0s, yrefs = record_closed_loop(sol, w, W + K, N)
+    x0s, lns = record_closed_loop(sol, w, W + K, N)
 
     # ---- device-resident inputs, one distinct buffer per tick ----
     d_x0 = [torch.from_numpy(a).to(dev) for a in x0s]
-    d_yref = [torch.from_numpy(a).to(dev) for a in yrefs]
+    d_lines = [torch.from_numpy(a).to(dev) for a in lns]
     d_p = torch.from_numpy(w["p"]).to(dev)
     gather = torch.empty((world, B, 6), dtype=torch.float64, device=dev)     # all ranks' thrust vectors
     out = (torch.empty((B, 4), dtype=torch.float64, device=dev), gather[rank], torch.empty((B,), dtype=torch.int32, device=dev))
     stream = torch.cuda.current_stream(dev)
 
     def tick(t):
-        sol.solve(d_x0[t], d_yref[t], d_p, out=out)          # thrusts land directly in this rank's slot of `gather`
+        sol.solve_windowed(d_x0[t], d_lines[t], d_p, out=out)   # thrusts land directly in this rank's slot of `gather`
         if distributed:
             dist.all_gather_into_tensor(gather.view(world * B, 6), gather[rank])
 
@@ -252,20 +254,20 @@ def run_ours(args):
     # ---- e2e: host buffers through the public host API ----
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
     h_x0 = [pin(a) for a in x0s]
-    h_yref = [pin(a) for a in yrefs]
+    h_lines = [torch.from_numpy(a).pin_memory().numpy() for a in lns]
     h_p = pin(w["p"])
     h_out = (pin(np.empty((B, 4))), pin(np.empty((B, 6))), torch.empty((B,), dtype=torch.int32).pin_memory().numpy())
     sol.set_iterate(w["X"], w["U"])
     for t in range(W):
-        sol.solve(h_x0[t], h_yref[t], h_p, out=h_out)
+        sol.solve_windowed(h_x0[t], h_lines[t], h_p, out=h_out)
     barrier()
     t0 = time.perf_counter()
     for t in range(W, W + K):
-        sol.solve(h_x0[t], h_yref[t], h_p, out=h_out)
+        sol.solve_windowed(h_x0[t], h_lines[t], h_p, out=h_out)
     barrier()
     dt_e2e = time.perf_counter() - t0
     e2e_ok = bool((h_out[2] == 0).all()) and bool(np.isfinite(h_out[0]).all())
-    h2d = (B * 12 + B * (N + 1) * 16 + B * 16) * 8
+    h2d = (B * 12 + B * 16) * 8 + B * 4          # x0, p (fp64) and one trajectory row index per instance (int32)
     d2h = (B * 4 + B * 6) * 8 + B * 4
 
     if distributed:
@@ -321,7 +323,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=15)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")

@@ -31,12 +31,15 @@ struct br2_batch_solver {
     int B, N, device, sm_count;
     double Ts[NMAX];
     double W[16], We[12], lbu[4], ubu[4];
-    int max_iter;
+    int max_iter, fast_path;
     double tol;
     // device state
     double *d_Ts, *d_X, *d_U, *d_G, *d_F, *d_V, *d_u0, *d_thrust, *d_info;
-    int *d_status, *d_iters, *d_counter;
+    int *d_status, *d_iters, *d_counter, *d_hint;
     double *d_x0, *d_yref, *d_p;              // staging for the host API
+    double* d_traj;                           // reference trajectory for device-side windowing [traj_rows][16]
+    int* d_lines;                             // staging: first trajectory row per instance
+    int traj_rows;
     double *d_ex, *d_eP, *d_thr, *d_meas, *d_acc, *d_wf, *d_pout;   // EKF state + staging
     cudaStream_t stream;
     cudaEvent_t ev0, ev1, ev_mid;   // solve start / end / between linearisation and IPM
@@ -65,7 +68,7 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
     cudaSetDevice(s->device);
     void* ptrs[] = {s->d_Ts, s->d_X, s->d_U, s->d_G, s->d_F, s->d_V, s->d_u0, s->d_thrust, s->d_info, s->d_status,
                     s->d_iters, s->d_counter, s->d_x0, s->d_yref, s->d_p, s->d_ex, s->d_eP, s->d_thr, s->d_meas,
-                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total};
+                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -102,6 +105,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     memcpy(s->We, kW, sizeof(double) * 12);
     for (int i = 0; i < 4; i++) { s->lbu[i] = -50.0; s->ubu[i] = 50.0; }
     s->max_iter = 50;
+    s->fast_path = 1;
     s->tol = 1e-11;
     const size_t B = batch;
 #define DA(p, n)                                                                                          \
@@ -119,6 +123,8 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     DA(d_ex, B * 18); DA(d_eP, B * 324); DA(d_thr, B * 6); DA(d_meas, B * 12); DA(d_acc, B * 6); DA(d_wf, B * 6);
     DA(d_pout, B * NP);
     DA(d_iter_total, 1);
+    DA(d_hint, B);
+    DA(d_lines, B);
 #undef DA
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s->ev0));
@@ -128,6 +134,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     CK(cudaMemcpy(s->d_Ts, s->Ts, sizeof(double) * N, cudaMemcpyHostToDevice));
     CK(cudaMemset(s->d_status, 0, sizeof(int) * B));
     CK(cudaMemset(s->d_iters, 0, sizeof(int) * B));
+    CK(cudaMemset(s->d_hint, 0, sizeof(int) * B));
     CK(cudaMemset(s->d_info, 0, sizeof(double) * B * 4));
     CK(cudaMemset(s->d_V, 0, sizeof(double) * B * (N + 1) * VREC));
     *out = s;
@@ -185,6 +192,10 @@ extern "C" int br2_batch_set_option_int(br2_batch_solver* s, const char* name, i
         s->max_iter = v;
         return BR2_OK;
     }
+    if (!strcmp(name, "fast_path")) {
+        s->fast_path = v != 0;
+        return BR2_OK;
+    }
     return fail(BR2_EINVAL, "unknown int option '%s'", name);
 }
 extern "C" int br2_batch_set_option_double(br2_batch_solver* s, const char* name, double v)
@@ -205,6 +216,7 @@ extern "C" int br2_batch_reset(br2_batch_solver* s, int mode)
     const size_t nX = (size_t)s->B * (s->N + 1) * NX, nU = (size_t)s->B * s->N * NU;
     CK(cudaMemset(s->d_U, 0, sizeof(double) * nU));
     CK(cudaMemset(s->d_X, 0, sizeof(double) * nX));
+    CK(cudaMemset(s->d_hint, 0, sizeof(int) * s->B));
     if (mode == 0) {
         // x_k = (0, 0, -20, 0, ...) for every stage: acados_solver_bluerov2.c:681-708
         double* h = (double*)calloc(nX, sizeof(double));
@@ -224,6 +236,7 @@ extern "C" int br2_batch_set_iterate_host(br2_batch_solver* s, const double* X, 
     CK(cudaDeviceSynchronize());
     if (X) CK(cudaMemcpy(s->d_X, X, sizeof(double) * s->B * (s->N + 1) * NX, cudaMemcpyHostToDevice));
     if (U) CK(cudaMemcpy(s->d_U, U, sizeof(double) * s->B * s->N * NU, cudaMemcpyHostToDevice));
+    CK(cudaMemset(s->d_hint, 0, sizeof(int) * s->B));   // a new iterate invalidates the active-set history
     return BR2_OK;
 }
 extern "C" int br2_batch_get_iterate_host(br2_batch_solver* s, double* X, double* U)
@@ -243,11 +256,12 @@ extern "C" int br2_batch_iterate_device(br2_batch_solver* s, double** X, double*
     return BR2_OK;
 }
 
-static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, const double* d_yref, const double* d_p,
-                      int p_per_stage, double* d_u0, double* d_thrust, int* d_status)
+static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, const double* d_yref, const int* d_lines,
+                      const double* d_p, int p_per_stage, double* d_u0, double* d_thrust, int* d_status)
 {
     a.B = s->B; a.N = s->N;
     a.x0 = d_x0; a.yref = d_yref; a.p = d_p;
+    a.traj = s->d_traj; a.lines = d_lines; a.traj_rows = s->traj_rows;
     a.p_inst_stride = p_per_stage ? (s->N + 1) * NP : NP;
     a.p_stage_stride = p_per_stage ? NP : 0;
     a.Ts = s->d_Ts;
@@ -257,18 +271,67 @@ static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, con
     a.u0 = d_u0 ? d_u0 : s->d_u0;
     a.thrust = d_thrust ? d_thrust : s->d_thrust;
     a.status = d_status ? d_status : s->d_status;
-    a.iters = s->d_iters; a.info = s->d_info; a.work_counter = s->d_counter; a.iter_total = s->d_iter_total;
+    a.iters = s->d_iters; a.info = s->d_info; a.work_counter = s->d_counter; a.iter_total = s->d_iter_total; a.hint = s->d_hint; a.fast_path = s->fast_path;
     a.max_iter = s->max_iter; a.tol = s->tol;
 }
+
+static int solve_enqueue(br2_batch_solver* s, const double* d_x0, const double* d_yref, const int* d_lines, const double* d_p,
+                         int p_per_stage, double* d_u0, double* d_thrust, int* d_status, cudaStream_t st);
 
 extern "C" int br2_batch_solve_device(br2_batch_solver* s, const double* d_x0, const double* d_yref, const double* d_p,
                                       int p_per_stage, double* d_u0, double* d_thrust, int* d_status, void* stream)
 {
     if (!s || !d_x0 || !d_yref || !d_p) return fail(BR2_EINVAL, "br2_batch_solve_device: null argument");
+    return solve_enqueue(s, d_x0, d_yref, nullptr, d_p, p_per_stage, d_u0, d_thrust, d_status, (cudaStream_t)stream);
+}
+
+extern "C" int br2_batch_set_trajectory(br2_batch_solver* s, const double* traj, int rows)
+{
+    if (!s || !traj || rows < 1) return fail(BR2_EINVAL, "br2_batch_set_trajectory: bad argument");
     CK(cudaSetDevice(s->device));
-    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaDeviceSynchronize());
+    if (s->d_traj) { cudaFree(s->d_traj); s->d_traj = nullptr; }
+    cudaError_t e = dalloc(&s->d_traj, (size_t)rows * NY);
+    if (e != cudaSuccess) return fail(BR2_ENOMEM, "cudaMalloc(trajectory, %d rows) failed: %s", rows, cudaGetErrorString(e));
+    CK(cudaMemcpy(s->d_traj, traj, sizeof(double) * (size_t)rows * NY, cudaMemcpyHostToDevice));
+    s->traj_rows = rows;
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_solve_windowed_device(br2_batch_solver* s, const double* d_x0, const int* d_lines, const double* d_p,
+                                               int p_per_stage, double* d_u0, double* d_thrust, int* d_status, void* stream)
+{
+    if (!s || !d_x0 || !d_lines || !d_p) return fail(BR2_EINVAL, "br2_batch_solve_windowed_device: null argument");
+    if (!s->d_traj) return fail(BR2_EINVAL, "br2_batch_solve_windowed_device: no trajectory set (br2_batch_set_trajectory)");
+    return solve_enqueue(s, d_x0, nullptr, d_lines, d_p, p_per_stage, d_u0, d_thrust, d_status, (cudaStream_t)stream);
+}
+
+extern "C" int br2_batch_solve_windowed_host(br2_batch_solver* s, const double* x0, const int* lines, const double* p,
+                                             int p_per_stage, double* u0, double* thrust, int* status)
+{
+    if (!s || !x0 || !lines || !p) return fail(BR2_EINVAL, "br2_batch_solve_windowed_host: null argument");
+    if (!s->d_traj) return fail(BR2_EINVAL, "br2_batch_solve_windowed_host: no trajectory set (br2_batch_set_trajectory)");
+    CK(cudaSetDevice(s->device));
+    const size_t B = s->B, N = s->N;
+    cudaStream_t st = s->stream;
+    CK(cudaMemcpyAsync(s->d_x0, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_lines, lines, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_p, p, sizeof(double) * B * (p_per_stage ? (N + 1) * NP : NP), cudaMemcpyHostToDevice, st));
+    int rc = solve_enqueue(s, s->d_x0, nullptr, s->d_lines, s->d_p, p_per_stage, nullptr, nullptr, nullptr, st);
+    if (rc != BR2_OK) return rc;
+    if (u0) CK(cudaMemcpyAsync(u0, s->d_u0, sizeof(double) * B * 4, cudaMemcpyDeviceToHost, st));
+    if (thrust) CK(cudaMemcpyAsync(thrust, s->d_thrust, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, s->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BR2_OK;
+}
+
+static int solve_enqueue(br2_batch_solver* s, const double* d_x0, const double* d_yref, const int* d_lines, const double* d_p,
+                         int p_per_stage, double* d_u0, double* d_thrust, int* d_status, cudaStream_t st)
+{
+    CK(cudaSetDevice(s->device));
     SolveArgs a;
-    fill_args(s, a, d_x0, d_yref, d_p, p_per_stage, d_u0, d_thrust, d_status);
+    fill_args(s, a, d_x0, d_yref, d_lines, d_p, p_per_stage, d_u0, d_thrust, d_status);
     CK(cudaEventRecord(s->ev0, st));
     launch_linearize(a, st);
     CK(cudaEventRecord(s->ev_mid, st));

@@ -13,7 +13,10 @@ struct SolveArgs {
     int B, N;
     // problem data (device)
     const double* x0;      // [B][12]
-    const double* yref;    // [B][N+1][16]
+    const double* yref;    // [B][N+1][16], or null when the reference is windowed on the device:
+    const double* traj;    // [traj_rows][16] reference trajectory (device), row = min(lines[b] + k, traj_rows - 1)
+    const int* lines;      // [B] first trajectory row of each instance's horizon (ref_cb, bluerov2_dob.cpp:218-265)
+    int traj_rows;
     const double* p;       // [B][p_inst_stride]: stage k reads p + k*p_stage_stride
     int p_inst_stride;     // 16 (one vector per instance) or (N+1)*16
     int p_stage_stride;    // 0 or 16
@@ -33,11 +36,22 @@ struct SolveArgs {
     int* iters;            // [B]
     double* info;          // [B][4]: mu, res_stat, max|b| (dynamics gap at the linearisation point), max step
     int* work_counter;     // [1] persistent-kernel instance queue
+    int* hint;             // [B] 1 = a bound was active at the previous solution (skip the interior fast path)
+    int fast_path;         // try the interior-solution fast path (option "fast_path", default 1)
     unsigned long long* iter_total;   // [1] IPM iterations executed, accumulated over instances and solves
     // options
     int max_iter;          // qp_solver_iter_max (50)
     double tol;            // IPM tolerance on mu and on the scaled stationarity residual
 };
+
+// reference row of (instance, stage): explicit yref or the windowed trajectory (clamped to the last row)
+__device__ __forceinline__ const double* yref_row(const SolveArgs& a, int inst, int k)
+{
+    if (a.yref) return a.yref + ((size_t)inst * (a.N + 1) + k) * NY;
+    int r = a.lines[inst] + k;
+    r = r < a.traj_rows - 1 ? r : a.traj_rows - 1;
+    return a.traj + (size_t)(r < 0 ? 0 : r) * NY;
+}
 
 void launch_linearize(const SolveArgs& a, cudaStream_t s);
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s);

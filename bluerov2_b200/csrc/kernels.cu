@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128) linearize_kernel(SolveArgs a)
 
     if (!live) return;
     double* Gk = a.G + ((size_t)inst * a.N + k) * GREC;
-    const double* yr = a.yref + ((size_t)inst * (a.N + 1) + k) * NY;
+    const double* yr = yref_row(a, inst, k);
     if (c == 0) {
         const double* Xn = Xk + NX;
 #pragma unroll
@@ -254,7 +254,6 @@ struct Inst {
     double* V;
     const double* Xlin;
     const double* Ulin;
-    const double* yref;
     __device__ Inst(const SolveArgs& a_, WarpSmem& sm_, uint32_t& phase_, int inst_, int lane_)
         : a(a_), sm(sm_), phase(phase_), inst(inst_), lane(lane_), q(lane_ >> 2), t(lane_ & 3), N(a_.N)
     {
@@ -263,7 +262,6 @@ struct Inst {
         V = a.V + (size_t)inst * (N + 1) * VREC;
         Xlin = a.X + (size_t)inst * (N + 1) * NX;
         Ulin = a.U + (size_t)inst * N * NU;
-        yref = a.yref + (size_t)inst * (N + 1) * NY;
     }
     // prefetch the records of stage k into slot s (one lane issues; completion lands on the slot's mbarrier)
     template <bool NEED_F>
@@ -400,7 +398,9 @@ __device__ __forceinline__ void c_to_rowfrag(const double (&c0)[2], const double
 //                              otherwise padded columns 12, 13)
 //   H  = W'[:, 0:12] Z        (16 x 16, DMMA)  = [A|B]' P+ [A|B]
 //   Lam = H_uu + R~ = L L',  Y = L^-1 H_ux,  K = L^-T Y,  P = Q + H_xx - Y'Y (DMMA, k = 4)
-// Returns false if a Cholesky pivot failed.
+// BARRIER = false drops the barrier terms (R~ = R): the factorisation of the unconstrained LQR used by the
+// interior-solution fast path.  Returns false if a Cholesky pivot failed.
+template <bool BARRIER>
 __device__ bool factor_sweep(Inst& I)
 {
     const int q = I.q, t = I.t, N = I.N, lane = I.lane;
@@ -414,12 +414,13 @@ __device__ bool factor_sweep(Inst& I)
     double pB[3][2];
     {
         const double* VN = I.V + (size_t)N * VREC;
+        const double* yN = yref_row(a, I.inst, N);
 #pragma unroll
         for (int ki = 0; ki < 3; ki++) {
             const int row = 4 * ki + t;
             pB[ki][0] = (row == q) ? a.We[row] : 0.0;
             pB[ki][1] = (lo && row == 8 + q) ? a.We[row] : 0.0;
-            if (q == 4) pB[ki][1] = a.We[row] * (VN[V_X + row] + I.Xlin[N * NX + row] - I.yref[N * NY + row]);
+            if (q == 4) pB[ki][1] = a.We[row] * (VN[V_X + row] + I.Xlin[N * NX + row] - yN[row]);
         }
     }
     I.template begin<false>(N - 1);
@@ -445,9 +446,9 @@ __device__ bool factor_sweep(Inst& I)
         const double qd1 = lo ? tsk * a.W[8 + e] : 0.0;
         const double qx1 = lo ? fma(qd1, Vs[V_X + 8 + e], Gs[G_QLIN + 8 + e]) : 0.0;
         // input row e (meaningful in quads 4..7)
-        const double tl = Vs[V_TL + e], tu = Vs[V_TU + e], ll = Vs[V_LL + e], lu = Vs[V_LU + e];
         const double rd = tsk * a.W[12 + e];
-        const double rt = rd + ll / tl + lu / tu;
+        double rt = rd;
+        if (BARRIER) rt += Vs[V_LL + e] / Vs[V_TL + e] + Vs[V_LU + e] / Vs[V_TU + e];
         const double gu_loc = fma(rd, Vs[V_V + e], Gs[G_RLIN + e]);
 
         // ---- W' = Z' [P+ | pi+ | p+] ----
@@ -638,9 +639,42 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
 
         int status = 2, it = 0;
         double mu = 0.0, res_stat = 0.0, stat_scale = 1.0;
-        for (it = 0; it < a.max_iter; it++) {
+        bool solved = false;
+        // ---------- interior-solution fast path ----------
+        // If the minimiser of the QP without its box lies inside the box it IS the minimiser of the QP (convexity), and
+        // it costs one Riccati factorisation + one forward sweep instead of an interior-point iteration sequence.  It is
+        // attempted when no bound was active at this instance's previous solution (hint carried between solves; it only
+        // steers which exact method runs first, never the result).
+        if (a.fast_path && a.hint[inst] == 0) {
+            if (!factor_sweep<false>(I)) { status = 4; }
+            else {
+                forward_sweep<1>(I);
+                bool inside = true;
+                for (int idx = lane; idx < nb; idx += 32) {
+                    const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                    const int e = idx & 3;
+                    const double dv = Vk[V_DV + e];
+                    inside &= (Vk[V_TL + e] + dv >= 0.0) && (Vk[V_TU + e] - dv >= 0.0);
+                }
+                if (__all_sync(FULL_MASK, inside)) {
+                    for (int idx = lane; idx < nb; idx += 32) {
+                        double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                        const int e = idx & 3;
+                        const double dv = Vk[V_DV + e];
+                        Vk[V_V + e] += dv; Vk[V_TL + e] += dv; Vk[V_TU + e] -= dv;
+                    }
+                    for (int idx = lane; idx < 12 * (N + 1); idx += 32) {
+                        double* Vk = I.V + (size_t)(idx / 12) * VREC;
+                        Vk[V_X + idx % 12] += Vk[V_DX + idx % 12];
+                    }
+                    __syncwarp();
+                    solved = true; status = 0; it = 1;
+                }
+            }
+        }
+        for (it = solved ? 1 : 0; !solved && status != 4 && it < a.max_iter; it++) {
             // ---------- B1: factorisation + predictor rhs ----------
-            if (!factor_sweep(I)) { status = 4; break; }
+            if (!factor_sweep<true>(I)) { status = 4; break; }
             if (it == 0) {
                 // mu and stationarity residual of the starting point (later iterations get them from E2)
                 double s = 0.0, rs = 0.0;
@@ -739,6 +773,15 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
         }
 
         // ---------- epilogue: full SQP step, u0, thrust allocation ----------
+        {
+            bool active = false;
+            for (int idx = lane; idx < nb; idx += 32) {
+                const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                active |= fmin(Vk[V_TL + (idx & 3)], Vk[V_TU + (idx & 3)]) < 1e-3;
+            }
+            active = __any_sync(FULL_MASK, active);
+            if (lane == 0) a.hint[inst] = (active || status != 0) ? 1 : 0;
+        }
         bool finite = true;
         for (int idx = lane; idx < nb; idx += 32) finite &= isfinite(I.V[(size_t)(idx >> 2) * VREC + V_V + (idx & 3)]);
         for (int idx = lane; idx < 12 * (N + 1); idx += 32) finite &= isfinite(I.V[(size_t)(idx / 12) * VREC + V_X + idx % 12]);

@@ -61,6 +61,9 @@ def load_library(path: str | None = None):
         "br2_batch_iterate_device": (C.c_int, [V, C.POINTER(V), C.POINTER(V)]),
         "br2_batch_solve_device": (C.c_int, [V, V, V, V, C.c_int, V, V, V, V]),
         "br2_batch_solve_host": (C.c_int, [V, V, V, V, C.c_int, V, V, V]),
+        "br2_batch_set_trajectory": (C.c_int, [V, V, C.c_int]),
+        "br2_batch_solve_windowed_device": (C.c_int, [V, V, V, V, C.c_int, V, V, V, V]),
+        "br2_batch_solve_windowed_host": (C.c_int, [V, V, V, V, C.c_int, V, V, V]),
         "br2_batch_get_stats_host": (C.c_int, [V, V, V]),
         "br2_batch_get_linearization_host": (C.c_int, [V, V, V]),
         "br2_batch_last_solve_time": (C.c_double, [V]),
@@ -198,6 +201,42 @@ class BatchSolver:
         u0, th, st = out
         self._check(self._L.br2_batch_solve_host(self._h, _ptr(x0), _ptr(yref), _ptr(p), per_stage,
                                                  _ptr(u0), _ptr(th), _ptr(st)))
+        return u0, th, st
+
+    def set_trajectory(self, traj):
+        """Upload the reference trajectory (rows x 16) once; ``solve_windowed`` then takes one row index per instance."""
+        traj = np.ascontiguousarray(traj, dtype=np.float64)
+        if traj.ndim != 2 or traj.shape[1] != NY:
+            raise ValueError(f"trajectory must be [rows, {NY}], got {traj.shape}")
+        self._check(self._L.br2_batch_set_trajectory(self._h, _ptr(traj), int(traj.shape[0])))
+        self.traj_rows = int(traj.shape[0])
+
+    def solve_windowed(self, x0, lines, p, out=None):
+        """Like ``solve`` but the horizon reference is windowed on the device from the uploaded trajectory:
+        ``lines[b]`` is instance b's first row (``line_number`` in BLUEROV2_DOB::solve, bluerov2_dob.cpp:367)."""
+        per_stage = int(len(p.shape) == 3)
+        pshape = (self.B, self.N + 1, NP) if per_stage else (self.B, NP)
+        if _is_torch(x0):
+            import torch
+            self._dev_check(x0, (self.B, NX)); self._dev_check(lines, (self.B,), torch.int32); self._dev_check(p, pshape)
+            if out is None:
+                dev = x0.device
+                out = (torch.empty((self.B, NU), dtype=torch.float64, device=dev),
+                       torch.empty((self.B, NTHRUST), dtype=torch.float64, device=dev),
+                       torch.empty((self.B,), dtype=torch.int32, device=dev))
+            u0, th, st = out
+            self._dev_check(u0, (self.B, NU)); self._dev_check(th, (self.B, NTHRUST)); self._dev_check(st, (self.B,), torch.int32)
+            stream = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)
+            self._check(self._L.br2_batch_solve_windowed_device(self._h, _ptr(x0), _ptr(lines), _ptr(p), per_stage,
+                                                                _ptr(u0), _ptr(th), _ptr(st), stream))
+            return u0, th, st
+        x0, p = _np(x0, (self.B, NX)), _np(p, pshape)
+        lines = _np(lines, (self.B,), dtype=np.int32)
+        if out is None:
+            out = (np.empty((self.B, NU)), np.empty((self.B, NTHRUST)), np.empty((self.B,), dtype=np.int32))
+        u0, th, st = out
+        self._check(self._L.br2_batch_solve_windowed_host(self._h, _ptr(x0), _ptr(lines), _ptr(p), per_stage,
+                                                          _ptr(u0), _ptr(th), _ptr(st)))
         return u0, th, st
 
     def stats(self):

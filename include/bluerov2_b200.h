@@ -63,7 +63,9 @@ BR2_API int br2_batch_set_weights(br2_batch_solver *s, const double *W16, const 
 BR2_API int br2_batch_set_bounds(br2_batch_solver *s, const double *lbu4, const double *ubu4);
 /* == bluerov2_acados_update_time_steps (acados_solver_bluerov2.c:111-132): Ts and cost scaling per stage */
 BR2_API int br2_batch_set_time_steps(br2_batch_solver *s, const double *time_steps);
-/* options: "qp_iter_max" (int, default 50), "qp_tol" (double, default 1e-11) */
+/* options: "qp_iter_max" (int, default 50), "qp_tol" (double, default 1e-11), "fast_path" (int, default 1: try the
+ * unconstrained Riccati solution first and accept it when it lies inside the input box -- it is then the exact QP
+ * minimiser; 0 = always run the interior-point iteration) */
 BR2_API int br2_batch_set_option_int(br2_batch_solver *s, const char *name, int v);
 BR2_API int br2_batch_set_option_double(br2_batch_solver *s, const char *name, double v);
 
@@ -85,6 +87,16 @@ BR2_API int br2_batch_solve_device(br2_batch_solver *s, const double *d_x0, cons
  * makes the copies asynchronous; pageable memory works too. */
 BR2_API int br2_batch_solve_host(br2_batch_solver *s, const double *x0, const double *yref, const double *p,
                          int p_per_stage, double *u0, double *thrust, int *status);
+
+/* Reference windowing on the device == BLUEROV2_DOB::ref_cb (bluerov2_dob.cpp:218-265) / BLUEROV2_PATH::read_N_pub
+ * (bluerov2_path/src/bluerov2_path.cpp:79-118): the trajectory file's rows (16 columns each, readDataFromFile
+ * bluerov2_dob.cpp:182-216) are uploaded once; per tick an instance only names its first row `line`
+ * (line_number++ in the node) and stage k reads row min(line + k, rows - 1).  Saves the (N+1) x 16 yref upload per tick. */
+BR2_API int br2_batch_set_trajectory(br2_batch_solver *s, const double *traj, int rows);
+BR2_API int br2_batch_solve_windowed_device(br2_batch_solver *s, const double *d_x0, const int *d_lines, const double *d_p,
+                                            int p_per_stage, double *d_u0, double *d_thrust, int *d_status, void *stream);
+BR2_API int br2_batch_solve_windowed_host(br2_batch_solver *s, const double *x0, const int *lines, const double *p,
+                                          int p_per_stage, double *u0, double *thrust, int *status);
 
 /* statistics of the last solve: iters[B] (IPM iterations), info[B][4] = (mu, stationarity residual,
  * max |dynamics gap| at the linearisation point, stationarity scale) */

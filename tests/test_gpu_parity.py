@@ -244,3 +244,60 @@ def test_errors_are_loud(solver_mod):
     with pytest.raises(ValueError):
         s.solve(np.zeros((3, 12)), np.zeros((2, 11, 16)), np.zeros((2, 16)))
     s.close()
+
+
+def test_interior_fast_path_equals_ipm(solver_mod, oracle):
+    """The interior-solution fast path (unconstrained Riccati solve accepted when it lies inside the box) and the
+    interior-point iteration return the same QP minimiser; instances with active bounds fall through to the IPM."""
+    N, B = 40, 512
+    Ts = wl.time_steps(N)
+    for spread in (0.5, 3.0):
+        w = wl.tracking_batch(B, N, seed=17, pos_spread=spread)
+        res = {}
+        for fp in (0, 1):
+            s = solver_mod.BatchSolver(B, N)
+            s.set_option("fast_path", fp)
+            s.set_iterate(w["X"], w["U"])
+            u0, th, st = s.solve(w["x0"], w["yref"], w["p"])
+            assert (st == 0).all()
+            it, info = s.stats()
+            X, U = s.get_iterate()
+            res[fp] = (U.copy(), it.copy())
+            s.close()
+        assert np.abs(res[0][0] - res[1][0]).max() < TOL_U
+        assert (res[0][1] >= 2).all()                      # the IPM never stops after one iteration from a cold start
+        inside = np.abs(res[0][0]).max(axis=(1, 2)) < 50 - 1e-3
+        assert ((res[1][1] == 1) == inside).mean() > 0.99   # fast path taken exactly where no bound is active
+        if spread == 0.5:
+            assert (res[1][1] == 1).mean() > 0.9
+        else:
+            assert (res[1][1] > 1).any()
+        idx = np.arange(0, B, 16)
+        Xo, Uo = w["X"][idx].copy(), w["U"][idx].copy()
+        sto, _, _ = oracle.rti_step_batch(Ts, w["x0"][idx], w["yref"][idx], w["p"][idx], Xo, Uo)
+        assert (sto == 0).all() and np.abs(Uo - res[1][0][idx]).max() < TOL_U
+
+
+def test_device_windowing_equals_explicit_yref(solver_mod):
+    """ref_cb on the device (bluerov2_dob.cpp:218-265): rows line..line+N clamped to the last row == the explicit window"""
+    N, B = 20, 96
+    tr = traj.lemniscate()
+    rng = np.random.default_rng(8)
+    lines = rng.integers(0, tr.shape[0] - N - 1, size=B).astype(np.int32)
+    lines[:6] = [tr.shape[0] - 1, tr.shape[0] - 2, tr.shape[0] - N, tr.shape[0] - N - 1, 0, tr.shape[0] + 5]   # clamped tails
+    yref = traj.window_batch(tr, lines.astype(np.int64), N)
+    x0 = yref[:, 0, :12] + rng.uniform(-0.4, 0.4, (B, 12))
+    p = np.tile(wl.NOMINAL_P, (B, 1))
+    X = np.repeat(x0[:, None, :], N + 1, axis=1).copy(); U = np.zeros((B, N, 4))
+    a = solver_mod.BatchSolver(B, N); a.set_iterate(X, U)
+    ua, ta, sa = a.solve(x0, yref, p)
+    b = solver_mod.BatchSolver(B, N); b.set_iterate(X, U); b.set_trajectory(tr)
+    ub, tb, sb = b.solve_windowed(x0, lines, p)
+    assert (sa == 0).all() and (sb == 0).all()
+    assert np.array_equal(ua, ub) and np.array_equal(ta, tb)
+    Xa, Ua = a.get_iterate(); Xb, Ub = b.get_iterate()
+    assert np.array_equal(Xa, Xb) and np.array_equal(Ua, Ub)
+    c = solver_mod.BatchSolver(B, N)
+    with pytest.raises(solver_mod.SolverError):
+        c.solve_windowed(x0, lines, p)            # no trajectory uploaded
+    a.close(); b.close(); c.close()
