@@ -14,7 +14,10 @@ for r in rows[2:]:
     if not toks: continue
     op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
     op = op.split(".")[0] + ("." + op.split(".")[1] if op.startswith(("SHFL", "LDG", "STG", "DMMA", "MUFU")) and "." in op else "")
-    n = int(float(r[ix["Instructions Executed"]] or 0)); s = int(float(r[ix["# Samples"]] or 0))
+    try:
+        n = int(float(r[ix["Instructions Executed"]] or 0)); s = int(float(r[ix["# Samples"]] or 0))
+    except ValueError:
+        continue          # repeated header (several launches in one report)
     ops[op] += n; samples[op] += s; tot_i += n; tot_s += s
     for c in stall_cols:
         v = r[ix[c]]
