@@ -129,8 +129,11 @@ def cpu_leg(N: int, budget_s: float, ticks_wanted: int, threads: int = 0, seed: 
         o.use_casadi(CasadiRef())
         kind_note += " with the ERK driven by the reference's CasADi-generated bluerov2_expl_vde_forw (oracle/_ref)"
     Ts = wl.time_steps(N)
+    # all host cores this process may run on (torchrun exports OMP_NUM_THREADS=1: ask for the threads explicitly)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if threads <= 0:
+        threads = cores
     # calibrate on 2 x cores instances, then size the sample to the budget
-    cores = os.cpu_count() or 1
     wcal = wl.tracking_batch(2 * cores, N, seed=seed, pos_spread=pos_spread)
     X, U = wcal["X"].copy(), wcal["U"].copy()
     o.rti_step_batch(Ts, wcal["x0"], wcal["yref"], wcal["p"], X.copy(), U.copy(), nthreads=threads)   # thread-pool warm-up
@@ -208,14 +211,15 @@ def run_ours(args):
     d_x0 = [torch.from_numpy(a).to(dev) for a in x0s]
     d_lines = [torch.from_numpy(a).to(dev) for a in lns]
     d_p = torch.from_numpy(w["p"]).to(dev)
-    gather = torch.empty((world, B, 6), dtype=torch.float64, device=dev)     # all ranks' thrust vectors
-    out = (torch.empty((B, 4), dtype=torch.float64, device=dev), gather[rank], torch.empty((B,), dtype=torch.int32, device=dev))
+    from bluerov2_b200.sharding import ThrustGather
+    gather = ThrustGather(world * B, dev)                                    # all ranks' thrust vectors; .slot = this rank's block
+    out = (torch.empty((B, 4), dtype=torch.float64, device=dev), gather.slot, torch.empty((B,), dtype=torch.int32, device=dev))
     stream = torch.cuda.current_stream(dev)
 
     def tick(t):
         sol.solve_windowed(d_x0[t], d_lines[t], d_p, out=out)   # thrusts land directly in this rank's slot of `gather`
         if distributed:
-            dist.all_gather_into_tensor(gather.view(world * B, 6), gather[rank])
+            gather.all_gather()
 
     def barrier():
         if distributed:
