@@ -205,6 +205,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     w = make_workload(B, N, seed=1000 * rank, pos_spread=args.pos_spread)
     sol = S.BatchSolver(B, N, device=local)
+    if args.no_fast_path:
+        sol.set_option("fast_path", 0)
     x0s, lns = record_closed_loop(sol, w, W + K, N)
 
     # ---- device-resident inputs, one distinct buffer per tick ----
@@ -297,7 +299,7 @@ def run_ours(args):
             "config": {"workload": f"config 2: batch {B} per GPU, random x0 around the circle reference (pos spread "
                                    f"{args.pos_spread} m), N={N}, Ts={1.0 / N:g} s, fp64, closed loop (nominal ERK4 plant at 0.05 s), "
                                    f"iterate carried between ticks", "batch_per_gpu": B, "global_batch": world * B, "horizon": N,
-                       "mean_ipm_iterations": iters_mean, "nonzero_status": n_bad,
+                       "mean_ipm_iterations": iters_mean, "nonzero_status": n_bad, "fast_path": not args.no_fast_path,
                        "l2": "per-tick working set (stage records + factors + iterates) "
                              f"{B * N * (208 + 64 + 64) * 8 / 1e6:.0f} MB > 126 MB L2; distinct input buffers per step",
                        "parallelism": f"{world} x independent shards" + (", one NCCL all-gather of the thrust vectors per tick" if distributed else "")},
@@ -335,6 +337,7 @@ def main():
     ap.add_argument("--pos-spread", type=float, default=0.5)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline / reference arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fast-path", action="store_true", help="always run the interior-point iteration (diagnostic)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -174,7 +174,8 @@ __device__ __forceinline__ double warp_sum(double v)
 
 // ---- per-warp TMA bulk-copy pipeline: stage records are prefetched HBM -> shared memory one stage ahead ----
 struct __align__(128) StageBuf { double G[GREC]; double F[FREC]; double V[VREC]; };
-struct __align__(128) WarpSmem { StageBuf st[2]; unsigned long long bar[2]; };
+constexpr int NSLOT = 4;     // ring depth: records of NSLOT-1 stages are in flight ahead of the one being computed
+struct __align__(128) WarpSmem { StageBuf st[NSLOT]; unsigned long long bar[NSLOT]; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
@@ -274,13 +275,28 @@ struct Inst {
             if (NEED_F) bulk_g2s(sm.st[s].F, F + (size_t)k * FREC, FREC * sizeof(double), &sm.bar[s]);
         }
     }
-    // first prefetch of a sweep: everything this warp wrote to global so far must be visible to the copy engine
-    template <bool NEED_F>
-    __device__ __forceinline__ void begin(int k)
+    // Sweep pipeline.  Stages are visited in sequence i = 0..N-1 (k = i forward, k = N-1-i backward); slot = i % NSLOT.
+    // begin(): everything this warp wrote to global so far must be visible to the copy engine, then fill the ring.
+    template <bool NEED_F, bool BACKWARD>
+    __device__ __forceinline__ void begin()
     {
         __syncwarp();
         if (lane == 0) fence_proxy_async();
-        issue<NEED_F>(0, k);
+#pragma unroll
+        for (int j = 0; j < NSLOT - 1; j++)
+            if (j < N) issue<NEED_F>(j, BACKWARD ? N - 1 - j : j);
+    }
+    // top of iteration i: the slot consumed by iteration i-1 is free (after the warp sync) -> refill it with the
+    // records of stage i + NSLOT - 1, then wait for this iteration's records.  Returns the slot to read.
+    template <bool NEED_F, bool BACKWARD>
+    __device__ __forceinline__ int advance(int i)
+    {
+        const int s = i % NSLOT;
+        __syncwarp();
+        const int j = i + NSLOT - 1;
+        if (j < N) issue<NEED_F>(j % NSLOT, BACKWARD ? N - 1 - j : j);
+        wait(s);
+        return s;
     }
     __device__ __forceinline__ void wait(int s)
     {
@@ -323,12 +339,9 @@ __device__ double forward_sweep(Inst& I)
     for (int ki = 0; ki < 3; ki++)
         zr[ki] = (MODE == 0) ? I.a.x0[(size_t)I.inst * NX + 4 * ki + t] - I.Xlin[4 * ki + t] : 0.0;
     constexpr int xoff = MODE ? V_DX : V_X;
-    I.template begin<MODE == 1>(0);
+    I.template begin<MODE == 1, false>();
     for (int k = 0; k < N; k++) {
-        const int s = k & 1;
-        __syncwarp();                           // every lane is done with slot s^1 (stage k-1)
-        if (k + 1 < N) I.template issue<MODE == 1>(s ^ 1, k + 1);
-        I.wait(s);
+        const int s = I.template advance<MODE == 1, false>(k);
         const double* Gs = I.sm.st[s].G;
         const double* Fs = I.sm.st[s].F;
         const double* Vs = I.sm.st[s].V;
@@ -380,24 +393,18 @@ __device__ double forward_sweep(Inst& I)
     return MODE == 0 ? warp_max(bmax) : 0.0;
 }
 
-// C-fragment row block (tiles ni = 0, 1 of one 8-row block) -> A/B-style fragments: out[ki] = element (row q, col 4ki+t)
-__device__ __forceinline__ void c_to_rowfrag(const double (&c0)[2], const double (&c1)[2], int lane, double* out)
-{
-    const int t = lane & 3;
-    const int s0 = (lane & ~3) | (t >> 1), s1 = s0 | 2;
-    const bool odd = t & 1;
-    double x0, x1;
-    x0 = shfl(c0[0], s0); x1 = shfl(c0[1], s0); out[0] = odd ? x1 : x0;
-    x0 = shfl(c0[0], s1); x1 = shfl(c0[1], s1); out[1] = odd ? x1 : x0;
-    x0 = shfl(c1[0], s0); x1 = shfl(c1[1], s0); out[2] = odd ? x1 : x0;
-}
-
 // Backward factor sweep: costate recursion of the iterate (pi), reduced gradient gu, Riccati factorisation with the
 // current barrier diagonal, and the vector recursion for the predictor rhs (gh = gu), all in one pass.
-//   W' = Z' [P+ | pi+ | p+]   (16 x 14, DMMA: A = Z' fragments, B = P+ fragments with the two vectors riding in the
-//                              otherwise padded columns 12, 13)
+//   W' = Z' [P+ | pi+ | p+]   (16 x 14, DMMA; the two vectors ride in the otherwise padded columns 12, 13)
 //   H  = W'[:, 0:12] Z        (16 x 16, DMMA)  = [A|B]' P+ [A|B]
 //   Lam = H_uu + R~ = L L',  Y = L^-1 H_ux,  K = L^-T Y,  P = Q + H_xx - Y'Y (DMMA, k = 4)
+// No fragment is ever re-laid-out between the products: the contraction index of both products is enumerated in
+// the order a C fragment holds it.  A C fragment gives lane (q,t) the columns 8n+2t+j (n, j in {0,1}) of rows q / 8+q;
+// taking k-tile (n,j) := { k = 8n + 2t + j : t = 0..3 } makes
+//   - the C registers of W' the A fragments of the second product,
+//   - the C registers of P+ (read through its symmetry, P[k][c] = P[c][k]) the B fragments of the first product,
+//   - and ONE gather of Z, z[kt][m] = Z[8n+2t+j][8m+q], the A fragment of Z' (first product) and the B fragment of Z
+//     (second product).  k = 12..15 (tile n = 1, t >= 2) does not exist: z is zero there.
 // BARRIER = false drops the barrier terms (R~ = R): the factorisation of the unconstrained LQR used by the
 // interior-solution fast path.  Returns false if a Cholesky pivot failed.
 template <bool BARRIER>
@@ -409,35 +416,48 @@ __device__ bool factor_sweep(Inst& I)
     const int e = q & 3;                        // input index owned by quads 4..7
     const int qb = lane & ~3;                   // first lane of my quad
     bool ok = true;
-
-    // P+ as B fragments: pB[ki][ni] = P[4ki+t][8ni+q]; column 12 (ni=1,q=4) carries pi+, column 13 (q=5) carries p+
-    double pB[3][2];
+    // row of Z / P held for k-tile kt = 2n + j, and its offset inside a G record (column block m adds 32)
+    int zoff[4];
+    bool zval[4];
+#pragma unroll
+    for (int kt = 0; kt < 4; kt++) {
+        const int r = 8 * (kt >> 1) + 2 * t + (kt & 1);
+        zval[kt] = r < 12;
+        zoff[kt] = zval[kt] ? g_off(r, q) : 0;
+    }
+    // P+ in C layout: h[m][n][j] = P[8m+q][8n+2t+j]; vin[kt] = (q == 4 ? pi+ : q == 5 ? p+ : 0)[8n+2t+j]
+    double h[2][2][2];
+    double vin[4];
     {
         const double* VN = I.V + (size_t)N * VREC;
         const double* yN = yref_row(a, I.inst, N);
 #pragma unroll
-        for (int ki = 0; ki < 3; ki++) {
-            const int row = 4 * ki + t;
-            pB[ki][0] = (row == q) ? a.We[row] : 0.0;
-            pB[ki][1] = (lo && row == 8 + q) ? a.We[row] : 0.0;
-            if (q == 4) pB[ki][1] = a.We[row] * (VN[V_X + row] + I.Xlin[N * NX + row] - yN[row]);
+        for (int m = 0; m < 2; m++)
+#pragma unroll
+            for (int n = 0; n < 2; n++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int r = 8 * m + q, c = 8 * n + 2 * t + j;
+                    h[m][n][j] = (r == c && r < 12) ? a.We[r < 12 ? r : 0] : 0.0;
+                }
+#pragma unroll
+        for (int kt = 0; kt < 4; kt++) {
+            const int r = 8 * (kt >> 1) + 2 * t + (kt & 1);
+            vin[kt] = (q == 4 && r < 12) ? a.We[r < 12 ? r : 0] * (VN[V_X + (r < 12 ? r : 0)] + I.Xlin[N * NX + (r < 12 ? r : 0)] - yN[r < 12 ? r : 0]) : 0.0;
         }
     }
-    I.template begin<false>(N - 1);
+    I.template begin<false, true>();
     for (int k = N - 1, it = 0; k >= 0; k--, it++) {
-        const int s = it & 1;
-        __syncwarp();                           // every lane is done with slot s^1 (stage k+1)
-        if (k > 0) I.template issue<false>(s ^ 1, k - 1);
-        I.wait(s);
+        const int s = I.template advance<false, true>(it);
         const double* Gs = I.sm.st[s].G;
         const double* Vs = I.sm.st[s].V;
         double* Fk = I.F + (size_t)k * FREC;
         double* Vk = I.V + (size_t)k * VREC;
-        double g[3][2];
+        double z[4][2];
 #pragma unroll
-        for (int ki = 0; ki < 3; ki++) {
-            g[ki][0] = Gs[((ki * 2 + 0) << 5) + lane];
-            g[ki][1] = Gs[((ki * 2 + 1) << 5) + lane];
+        for (int kt = 0; kt < 4; kt++) {
+            z[kt][0] = zval[kt] ? Gs[zoff[kt]] : 0.0;
+            z[kt][1] = zval[kt] ? Gs[zoff[kt] + 32] : 0.0;
         }
         const double tsk = Gs[G_TS];
         // state rows q and 8+q:  Q (x + X - xref) = Q x + qlin
@@ -454,23 +474,24 @@ __device__ bool factor_sweep(Inst& I)
         // ---- W' = Z' [P+ | pi+ | p+] ----
         double w[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
 #pragma unroll
-        for (int ki = 0; ki < 3; ki++)
+        for (int kt = 0; kt < 4; kt++) {
+            const double b0 = h[0][kt >> 1][kt & 1];
+            const double b1 = lo ? h[1][kt >> 1][kt & 1] : vin[kt];
 #pragma unroll
-            for (int mi = 0; mi < 2; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 2; ni++) dmma(w[mi][ni], g[ki][mi], pB[ki][ni]);
+            for (int m = 0; m < 2; m++) { dmma(w[m][0], z[kt][m], b0); dmma(w[m][1], z[kt][m], b1); }
+        }
         // ---- H = W' Z ----
-        double wA[2][3];
-        c_to_rowfrag(w[0][0], w[0][1], lane, wA[0]);
-        c_to_rowfrag(w[1][0], w[1][1], lane, wA[1]);
-        double h[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
 #pragma unroll
-        for (int ki = 0; ki < 3; ki++)
+        for (int m = 0; m < 2; m++)
 #pragma unroll
-            for (int mi = 0; mi < 2; mi++)
+            for (int n = 0; n < 2; n++) { h[m][n][0] = 0.0; h[m][n][1] = 0.0; }
 #pragma unroll
-                for (int ni = 0; ni < 2; ni++) dmma(h[mi][ni], wA[mi][ki], g[ki][ni]);
-        // ---- the two vector products sit in columns 12, 13 of W': lane (q,2) holds ([A|B]'pi+)[8mi+q], ([A|B]'p+)[8mi+q] ----
+        for (int kt = 0; kt < 4; kt++)
+#pragma unroll
+            for (int m = 0; m < 2; m++)
+#pragma unroll
+                for (int n = 0; n < 2; n++) dmma(h[m][n], w[m][kt >> 1][kt & 1], z[kt][n]);
+        // ---- the two vector products sit in columns 12, 13 of W': lane (q,2) holds ([A|B]'pi+)[8m+q], ([A|B]'p+)[8m+q] ----
         const double at0 = shfl(w[0][1][0], qb | 2), bt0 = shfl(w[0][1][1], qb | 2);
         const double at1 = shfl(w[1][1][0], qb | 2), bt1 = shfl(w[1][1][1], qb | 2);
         const double gu = gu_loc + at1;          // quads 4..7: R du + r + B'pi+
@@ -479,14 +500,14 @@ __device__ bool factor_sweep(Inst& I)
         if (!lo && t == 2 + (e >> 1)) {
             if (e & 1) h[1][1][1] += rt; else h[1][1][0] += rt;
         }
-        double m[10];
-        m[0] = shfl(h[1][1][0], 4 * 4 + 2);
-        m[1] = shfl(h[1][1][0], 4 * 5 + 2); m[2] = shfl(h[1][1][1], 4 * 5 + 2);
-        m[3] = shfl(h[1][1][0], 4 * 6 + 2); m[4] = shfl(h[1][1][1], 4 * 6 + 2); m[5] = shfl(h[1][1][0], 4 * 6 + 3);
-        m[6] = shfl(h[1][1][0], 4 * 7 + 2); m[7] = shfl(h[1][1][1], 4 * 7 + 2); m[8] = shfl(h[1][1][0], 4 * 7 + 3);
-        m[9] = shfl(h[1][1][1], 4 * 7 + 3);
+        double m10[10];
+        m10[0] = shfl(h[1][1][0], 4 * 4 + 2);
+        m10[1] = shfl(h[1][1][0], 4 * 5 + 2); m10[2] = shfl(h[1][1][1], 4 * 5 + 2);
+        m10[3] = shfl(h[1][1][0], 4 * 6 + 2); m10[4] = shfl(h[1][1][1], 4 * 6 + 2); m10[5] = shfl(h[1][1][0], 4 * 6 + 3);
+        m10[6] = shfl(h[1][1][0], 4 * 7 + 2); m10[7] = shfl(h[1][1][1], 4 * 7 + 2); m10[8] = shfl(h[1][1][0], 4 * 7 + 3);
+        m10[9] = shfl(h[1][1][1], 4 * 7 + 3);
         Chol4 L;
-        ok &= chol4(m, L);
+        ok &= chol4(m10, L);
         // ---- rows q and 8+q of H_xu (columns 12..15 live in lanes t = 2, 3 of the quad) ----
         double y0[4], y1[4];
         y0[0] = shfl(h[0][1][0], qb | 2); y0[1] = shfl(h[0][1][1], qb | 2);
@@ -532,24 +553,22 @@ __device__ bool factor_sweep(Inst& I)
                 *reinterpret_cast<double2*>(Vk + V_KFF + 2) = make_double2(kf[2], kf[3]);
             }
         }
-        // ---- P = Q + H_xx - Y'Y  (A fragment of Y' and B fragment of Y are the same register: Y[t][8mi+q]) ----
+        // ---- P = Q + H_xx - Y'Y  (A fragment of Y' and B fragment of Y are the same register: Y[t][8m+q]) ----
         const double ys0 = (t == 0) ? y0[0] : (t == 1) ? y0[1] : (t == 2) ? y0[2] : y0[3];
         double ys1 = (t == 0) ? y1[0] : (t == 1) ? y1[1] : (t == 2) ? y1[2] : y1[3];
         if (!lo) ys1 = 0.0;
         dmma(h[0][0], -ys0, ys0); dmma(h[0][1], -ys0, ys1);
         dmma(h[1][0], -ys1, ys0); dmma(h[1][1], -ys1, ys1);
-        if (t == (q >> 1)) {                     // diagonal element (8mi+q, 8mi+q) is C register q&1 of lane (q, q>>1)
+        if (t == (q >> 1)) {                     // diagonal element (8m+q, 8m+q) is C register q&1 of lane (q, q>>1)
             if (q & 1) { h[0][0][1] += qd0; h[1][1][1] += qd1; } else { h[0][0][0] += qd0; h[1][1][0] += qd1; }
         }
-        // ---- next stage's B fragments, read through the symmetry P[4ki+t][8ni+q] = P[8ni+q][4ki+t] ----
-        double f0[3], f1[3];
-        c_to_rowfrag(h[0][0], h[0][1], lane, f0);
-        c_to_rowfrag(h[1][0], h[1][1], lane, f1);
-        const double vs0 = (t == 0) ? pi0 : pv0, vs1 = (t == 0) ? pi1 : pv1;
-        const double i0 = shfl(vs0, 4 * t + (q & 1)), i1 = shfl(vs0, 4 * (4 + t) + (q & 1)), i2 = shfl(vs1, 4 * t + (q & 1));
-        pB[0][0] = f0[0]; pB[1][0] = f0[1]; pB[2][0] = f0[2];
-        pB[0][1] = lo ? f1[0] : 0.0; pB[1][1] = lo ? f1[1] : 0.0; pB[2][1] = lo ? f1[2] : 0.0;
-        if (q == 4 || q == 5) { pB[0][1] = i0; pB[1][1] = i1; pB[2][1] = i2; }
+        // ---- pi, p+ for the next stage's vector columns: lane (4,t) needs pi[8n+2t+j], lane (5,t) p[8n+2t+j] ----
+        const double vs0 = (t == 0) ? pi0 : pv0, vs1 = (t == 0) ? pi1 : pv1;    // lanes t = 0 serve pi, t = 1 serve p
+        const int sa = 8 * t + (q & 1), sb = sa + 4;                            // quads 2t and 2t+1
+        const double i0 = shfl(vs0, sa), i1 = shfl(vs0, sb), i2 = shfl(vs1, sa), i3 = shfl(vs1, sb);
+        const bool vq = (q == 4) || (q == 5);
+        vin[0] = vq ? i0 : 0.0; vin[1] = vq ? i1 : 0.0;
+        vin[2] = (vq && t < 2) ? i2 : 0.0; vin[3] = (vq && t < 2) ? i3 : 0.0;
     }
     __syncwarp();
     return __all_sync(FULL_MASK, ok);
@@ -563,12 +582,9 @@ __device__ void backward_vec_sweep(Inst& I)
     const bool lo = q < 4;
     const int e = q & 3;
     double pr[3] = {0.0, 0.0, 0.0};             // p+ in row layout
-    I.template begin<true>(N - 1);
+    I.template begin<true, true>();
     for (int k = N - 1, it = 0; k >= 0; k--, it++) {
-        const int s = it & 1;
-        __syncwarp();
-        if (k > 0) I.template issue<true>(s ^ 1, k - 1);
-        I.wait(s);
+        const int s = I.template advance<true, true>(it);
         const double* Gk = I.sm.st[s].G;
         const double* Fk = I.sm.st[s].F;
         const double* Vs = I.sm.st[s].V;
@@ -621,8 +637,8 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
     WarpSmem& sm = smem[threadIdx.x >> 5];
     uint32_t phase = 0;
     if (lane == 0) {
-        mbar_init(&sm.bar[0], 1);
-        mbar_init(&sm.bar[1], 1);
+#pragma unroll
+        for (int j = 0; j < NSLOT; j++) mbar_init(&sm.bar[j], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -645,6 +661,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
         // it costs one Riccati factorisation + one forward sweep instead of an interior-point iteration sequence.  It is
         // attempted when no bound was active at this instance's previous solution (hint carried between solves; it only
         // steers which exact method runs first, never the result).
+        bool active = false;                    // a bound is (nearly) active at the solution -> hint for the next solve
         if (a.fast_path && a.hint[inst] == 0) {
             if (!factor_sweep<false>(I)) { status = 4; }
             else {
@@ -654,22 +671,11 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
                     const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
                     const int e = idx & 3;
                     const double dv = Vk[V_DV + e];
-                    inside &= (Vk[V_TL + e] + dv >= 0.0) && (Vk[V_TU + e] - dv >= 0.0);
+                    const double tl = Vk[V_TL + e] + dv, tu = Vk[V_TU + e] - dv;
+                    inside &= (tl >= 0.0) && (tu >= 0.0);
+                    active |= fmin(tl, tu) < 1e-3;
                 }
-                if (__all_sync(FULL_MASK, inside)) {
-                    for (int idx = lane; idx < nb; idx += 32) {
-                        double* Vk = I.V + (size_t)(idx >> 2) * VREC;
-                        const int e = idx & 3;
-                        const double dv = Vk[V_DV + e];
-                        Vk[V_V + e] += dv; Vk[V_TL + e] += dv; Vk[V_TU + e] -= dv;
-                    }
-                    for (int idx = lane; idx < 12 * (N + 1); idx += 32) {
-                        double* Vk = I.V + (size_t)(idx / 12) * VREC;
-                        Vk[V_X + idx % 12] += Vk[V_DX + idx % 12];
-                    }
-                    __syncwarp();
-                    solved = true; status = 0; it = 1;
-                }
+                if (__all_sync(FULL_MASK, inside)) { solved = true; status = 0; it = 1; }   // solution = iterate + step
             }
         }
         for (it = solved ? 1 : 0; !solved && status != 4 && it < a.max_iter; it++) {
@@ -773,24 +779,45 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
         }
 
         // ---------- epilogue: full SQP step, u0, thrust allocation ----------
-        {
-            bool active = false;
+        // the fast path leaves its solution as iterate + step (V_V + V_DV, V_X + V_DX); the IPM as the iterate itself
+        if (!solved) {
+            active = false;
             for (int idx = lane; idx < nb; idx += 32) {
                 const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
                 active |= fmin(Vk[V_TL + (idx & 3)], Vk[V_TU + (idx & 3)]) < 1e-3;
             }
-            active = __any_sync(FULL_MASK, active);
-            if (lane == 0) a.hint[inst] = (active || status != 0) ? 1 : 0;
         }
-        bool finite = true;
-        for (int idx = lane; idx < nb; idx += 32) finite &= isfinite(I.V[(size_t)(idx >> 2) * VREC + V_V + (idx & 3)]);
-        for (int idx = lane; idx < 12 * (N + 1); idx += 32) finite &= isfinite(I.V[(size_t)(idx / 12) * VREC + V_X + idx % 12]);
-        finite = __all_sync(FULL_MASK, finite);
+        active = __any_sync(FULL_MASK, active);
+        if (lane == 0) a.hint[inst] = (active || status != 0) ? 1 : 0;
         double* Xo = a.X + (size_t)inst * (N + 1) * NX;
         double* Uo = a.U + (size_t)inst * N * NU;
+        bool finite = true;
+        for (int idx = lane; idx < nb; idx += 32) {
+            const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+            double v = Vk[V_V + (idx & 3)];
+            if (solved) v += Vk[V_DV + (idx & 3)];
+            finite &= isfinite(v);
+        }
+        for (int idx = lane; idx < 12 * (N + 1); idx += 32) {
+            const double* Vk = I.V + (size_t)(idx / 12) * VREC;
+            double v = Vk[V_X + idx % 12];
+            if (solved) v += Vk[V_DX + idx % 12];
+            finite &= isfinite(v);
+        }
+        finite = __all_sync(FULL_MASK, finite);
         if (finite) {
-            for (int idx = lane; idx < nb; idx += 32) Uo[idx] += I.V[(size_t)(idx >> 2) * VREC + V_V + (idx & 3)];
-            for (int idx = lane; idx < 12 * (N + 1); idx += 32) Xo[idx] += I.V[(size_t)(idx / 12) * VREC + V_X + idx % 12];
+            for (int idx = lane; idx < nb; idx += 32) {
+                const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                double v = Vk[V_V + (idx & 3)];
+                if (solved) v += Vk[V_DV + (idx & 3)];
+                Uo[idx] += v;
+            }
+            for (int idx = lane; idx < 12 * (N + 1); idx += 32) {
+                const double* Vk = I.V + (size_t)(idx / 12) * VREC;
+                double v = Vk[V_X + idx % 12];
+                if (solved) v += Vk[V_DX + idx % 12];
+                Xo[idx] += v;
+            }
         } else {
             status = 1;
         }
@@ -817,10 +844,15 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
 
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
 {
+    static bool configured = false;
+    if (!configured) {   // 4 resident blocks need 4 x 45 KB of shared memory: ask for the largest carve-out
+        cudaFuncSetAttribute(ipm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
     cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
     const int warps_needed = a.B;
     int blocks = (warps_needed + IPM_WARPS - 1) / IPM_WARPS;
-    const int max_blocks = sm_count * 4;   // 4 blocks x 4 warps resident per SM (128 registers, 22.5 KB of staging buffers each)
+    const int max_blocks = sm_count * 4;   // 4 blocks x 4 warps resident per SM (<= 128 registers, 45 KB of staging buffers each)
     if (blocks > max_blocks) blocks = max_blocks;
     ipm_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
 }
