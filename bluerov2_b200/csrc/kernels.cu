@@ -194,6 +194,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
 {
     uint32_t done;
+    // non-blocking probe first: with the ring NSLOT-1 stages ahead the phase has normally completed already, and
+    // try_wait costs ~90 cycles even then
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) return;
     do {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -269,10 +274,18 @@ struct Inst {
     __device__ __forceinline__ void issue(int s, int k)
     {
         if (lane == 0) {
-            mbar_expect_tx(&sm.bar[s], (uint32_t)((GREC + VREC + (NEED_F ? FREC : 0)) * sizeof(double)));
-            bulk_g2s(sm.st[s].G, G + (size_t)k * GREC, GREC * sizeof(double), &sm.bar[s]);
-            bulk_g2s(sm.st[s].V, V + (size_t)k * VREC, VREC * sizeof(double), &sm.bar[s]);
-            if (NEED_F) bulk_g2s(sm.st[s].F, F + (size_t)k * FREC, FREC * sizeof(double), &sm.bar[s]);
+            const uint32_t bar = smem_u32(&sm.bar[s]), dst = smem_u32(&sm.st[s]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         ::"r"(bar), "r"((uint32_t)((GREC + VREC + (NEED_F ? FREC : 0)) * sizeof(double))) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(G + (size_t)k * GREC), "r"((uint32_t)(GREC * sizeof(double))), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + (uint32_t)((GREC + FREC) * sizeof(double))), "l"(V + (size_t)k * VREC),
+                           "r"((uint32_t)(VREC * sizeof(double))), "r"(bar) : "memory");
+            if (NEED_F)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + (uint32_t)(GREC * sizeof(double))), "l"(F + (size_t)k * FREC),
+                               "r"((uint32_t)(FREC * sizeof(double))), "r"(bar) : "memory");
         }
     }
     // Sweep pipeline.  Stages are visited in sequence i = 0..N-1 (k = i forward, k = N-1-i backward); slot = i % NSLOT.
@@ -310,6 +323,7 @@ struct Inst {
 __device__ void ipm_init(Inst& I)
 {
     const double thr = 1e-1, mu0 = 1.0;
+#pragma unroll 5
     for (int idx = I.lane; idx < 4 * I.N; idx += 32) {
         const int k = idx >> 2, e = idx & 3;
         const double uk = I.Ulin[k * NU + e];
@@ -324,24 +338,31 @@ __device__ void ipm_init(Inst& I)
     __syncwarp();
 }
 
-// Forward sweep.  mode 0: roll-out of the iterate  x+ = A x + B v + b, x_0 = x0 - X_0 (writes V_X);
-// mode 1: Newton step  ddu = -kff - K ddx,  ddx+ = A ddx + B ddu, ddx_0 = 0 (writes V_DX, V_DV).
+// Forward sweep.
+//   MODE 0: roll-out of the iterate            x+ = A x + B v + b,            x_0 = x0 - X_0   (reads V_V, writes V_X)
+//   MODE 1: Newton step                        ddu = -kff - K ddx, ddx+ = A ddx + B ddu, ddx_0 = 0 (writes V_DX, V_DV)
+//   MODE 2: closed-loop roll-out (fast path)   u = -kff - K x,     x+ = A x + B u + b,   x_0 = x0 - X_0 (writes V_X, V_V)
 // Z = [A|B] is read row-per-quad: lane (q,t) holds Z[q][4ki+t] and Z[8+q][4ki+t]; every product is 4 (3) local
-// FMAs and a reduction over the 4 lanes of a quad.  Returns max |b| in mode 0.
+// FMAs and a reduction over the 4 lanes of a quad.  Returns max |b| in MODE 0 / 2.
 template <int MODE>
 __device__ double forward_sweep(Inst& I)
 {
     const int q = I.q, t = I.t, N = I.N;
     const bool lo = q < 4;                      // quad owns a second state row 8 + q (else: no row 12..15)
+    constexpr bool FEEDBACK = MODE != 0, AFFINE = MODE != 1;
     double zr[3];                               // propagated vector, row layout: x[4ki + t]
     double bmax = 0.0;
 #pragma unroll
     for (int ki = 0; ki < 3; ki++)
-        zr[ki] = (MODE == 0) ? I.a.x0[(size_t)I.inst * NX + 4 * ki + t] - I.Xlin[4 * ki + t] : 0.0;
-    constexpr int xoff = MODE ? V_DX : V_X;
-    I.template begin<MODE == 1, false>();
+        zr[ki] = AFFINE ? I.a.x0[(size_t)I.inst * NX + 4 * ki + t] - I.Xlin[4 * ki + t] : 0.0;
+    constexpr int xoff = (MODE == 1) ? V_DX : V_X;
+    constexpr int uoff = (MODE == 1) ? V_DV : V_V;
+    int o0[4], o1[4];                           // shared-memory offsets of my rows of Z (constant over the sweep)
+#pragma unroll
+    for (int ki = 0; ki < 4; ki++) { o0[ki] = g_off(q, 4 * ki + t); o1[ki] = g_off(8 + (q & 3), 4 * ki + t); }
+    I.template begin<FEEDBACK, false>();
     for (int k = 0; k < N; k++) {
-        const int s = I.template advance<MODE == 1, false>(k);
+        const int s = I.template advance<FEEDBACK, false>(k);
         const double* Gs = I.sm.st[s].G;
         const double* Fs = I.sm.st[s].F;
         const double* Vs = I.sm.st[s].V;
@@ -349,15 +370,15 @@ __device__ double forward_sweep(Inst& I)
         double z0[4], z1[4];
 #pragma unroll
         for (int ki = 0; ki < 4; ki++) {
-            z0[ki] = Gs[g_off(q, 4 * ki + t)];
-            z1[ki] = lo ? Gs[g_off(8 + q, 4 * ki + t)] : 0.0;
+            z0[ki] = Gs[o0[ki]];
+            z1[ki] = lo ? Gs[o1[ki]] : 0.0;
         }
         if (q == 0) {
 #pragma unroll
             for (int ki = 0; ki < 3; ki++) Vk[xoff + 4 * ki + t] = zr[ki];
         }
         double ut;                              // u[t]
-        if (MODE == 0) {
+        if (!FEEDBACK) {
             ut = Vs[V_V + t];
         } else {
             // (K x)[q] for q < 4: K[q][4ki+t] = Kt[4ki+t][q]
@@ -367,47 +388,52 @@ __device__ double forward_sweep(Inst& I)
             part += shfl_x(part, 1);
             part += shfl_x(part, 2);
             const double uq = -Vs[V_KFF + (q & 3)] - part;
-            if (lo && t == 0) Vk[V_DV + q] = uq;
+            if (lo && t == 0) Vk[uoff + q] = uq;
             ut = shfl(uq, 4 * t);
         }
-        double o0 = z0[3] * ut, o1 = z1[3] * ut;
+        double p0 = z0[3] * ut, p1 = z1[3] * ut;
 #pragma unroll
-        for (int ki = 0; ki < 3; ki++) { o0 = fma(z0[ki], zr[ki], o0); o1 = fma(z1[ki], zr[ki], o1); }
-        o0 += shfl_x(o0, 1); o1 += shfl_x(o1, 1);
-        o0 += shfl_x(o0, 2); o1 += shfl_x(o1, 2);
-        if (MODE == 0) {
+        for (int ki = 0; ki < 3; ki++) { p0 = fma(z0[ki], zr[ki], p0); p1 = fma(z1[ki], zr[ki], p1); }
+        p0 += shfl_x(p0, 1); p1 += shfl_x(p1, 1);
+        p0 += shfl_x(p0, 2); p1 += shfl_x(p1, 2);
+        if (AFFINE) {
             const double b0 = Gs[G_B_OFF + q], b1 = lo ? Gs[G_B_OFF + 8 + q] : 0.0;
-            o0 += b0; o1 += b1;
+            p0 += b0; p1 += b1;
             bmax = fmax(bmax, fmax(fabs(b0), fabs(b1)));
         }
         // quad layout -> row layout
-        zr[0] = shfl(o0, 4 * t);
-        zr[1] = shfl(o0, 4 * (4 + t));
-        zr[2] = shfl(o1, 4 * t);
+        zr[0] = shfl(p0, 4 * t);
+        zr[1] = shfl(p0, 4 * (4 + t));
+        zr[2] = shfl(p1, 4 * t);
     }
     if (q == 0) {
 #pragma unroll
         for (int ki = 0; ki < 3; ki++) I.V[(size_t)N * VREC + xoff + 4 * ki + t] = zr[ki];
     }
     __syncwarp();
-    return MODE == 0 ? warp_max(bmax) : 0.0;
+    return AFFINE ? warp_max(bmax) : 0.0;
 }
 
-// Backward factor sweep: costate recursion of the iterate (pi), reduced gradient gu, Riccati factorisation with the
-// current barrier diagonal, and the vector recursion for the predictor rhs (gh = gu), all in one pass.
-//   W' = Z' [P+ | pi+ | p+]   (16 x 14, DMMA; the two vectors ride in the otherwise padded columns 12, 13)
+// Backward factor sweep: Riccati factorisation of the stage LQR plus the vector recursion(s) that share it.
+//   W' = Z' [P+ | v1 | v2]    (16 x 14, DMMA; the vectors ride in the otherwise padded columns 12, 13)
 //   H  = W'[:, 0:12] Z        (16 x 16, DMMA)  = [A|B]' P+ [A|B]
 //   Lam = H_uu + R~ = L L',  Y = L^-1 H_ux,  K = L^-T Y,  P = Q + H_xx - Y'Y (DMMA, k = 4)
-// No fragment is ever re-laid-out between the products: the contraction index of both products is enumerated in
-// the order a C fragment holds it.  A C fragment gives lane (q,t) the columns 8n+2t+j (n, j in {0,1}) of rows q / 8+q;
-// taking k-tile (n,j) := { k = 8n + 2t + j : t = 0..3 } makes
-//   - the C registers of W' the A fragments of the second product,
-//   - the C registers of P+ (read through its symmetry, P[k][c] = P[c][k]) the B fragments of the first product,
-//   - and ONE gather of Z, z[kt][m] = Z[8n+2t+j][8m+q], the A fragment of Z' (first product) and the B fragment of Z
-//     (second product).  k = 12..15 (tile n = 1, t >= 2) does not exist: z is zero there.
-// BARRIER = false drops the barrier terms (R~ = R): the factorisation of the unconstrained LQR used by the
-// interior-solution fast path.  Returns false if a Cholesky pivot failed.
-template <bool BARRIER>
+// KIND = FS_IPM  (interior-point iteration, residual form around the iterate): R~ = R + lam_l/t_l + lam_u/t_u,
+//                 v1 = pi+ (costate of the iterate -> reduced gradient gu), v2 = p+ (predictor rhs gh = gu).
+// KIND = FS_ABS  (interior fast path, absolute form of the unconstrained LQR): R~ = R, v1 = s+ = P+ b_k + p+,
+//                 g = rlin + B's+,  p = qlin + A's+ - K'g;  no roll-out of an iterate is needed beforehand.
+// The contraction index of both products is enumerated in the order a C fragment holds it, so no fragment is re-laid-
+// out between the products.  A C fragment gives lane (q,t) the columns 2t, 2t+1, 8+2t, 9+2t of rows q / 8+q.  The 12
+// valid columns make three k-tiles:  kt0 = {2t},  kt1 = {2t+1},  kt2 = {8, 10, 9, 11}[t]  (lanes t = 2, 3 fetch their
+// kt2 element, register 1 of lane t-2, with one shuffle).  Then
+//   - the C registers of W' are the A fragments of the second product,
+//   - the C registers of P+ (read through its symmetry, P[k][c] = P[c][k]) are the B fragments of the first product,
+//   - and ONE gather of Z, z[kt][m] = Z[row(kt,t)][8m+q], is the A fragment of Z' (first product) and the B fragment
+//     of Z (second product).
+// Returns false if a Cholesky pivot failed.
+enum { FS_IPM = 0, FS_ABS = 1 };
+
+template <int KIND>
 __device__ bool factor_sweep(Inst& I)
 {
     const int q = I.q, t = I.t, N = I.N, lane = I.lane;
@@ -415,19 +441,16 @@ __device__ bool factor_sweep(Inst& I)
     const bool lo = q < 4;
     const int e = q & 3;                        // input index owned by quads 4..7
     const int qb = lane & ~3;                   // first lane of my quad
+    const bool hi2 = t >= 2;
+    const int src2 = hi2 ? lane - 2 : lane;     // where my kt2 element lives
     bool ok = true;
-    // row of Z / P held for k-tile kt = 2n + j, and its offset inside a G record (column block m adds 32)
-    int zoff[4];
-    bool zval[4];
-#pragma unroll
-    for (int kt = 0; kt < 4; kt++) {
-        const int r = 8 * (kt >> 1) + 2 * t + (kt & 1);
-        zval[kt] = r < 12;
-        zoff[kt] = zval[kt] ? g_off(r, q) : 0;
-    }
-    // P+ in C layout: h[m][n][j] = P[8m+q][8n+2t+j]; vin[kt] = (q == 4 ? pi+ : q == 5 ? p+ : 0)[8n+2t+j]
+    // contraction rows held for the three k-tiles, and their offsets inside a G record (column block m adds 32)
+    const int row0 = 2 * t, row1 = 2 * t + 1, row2 = hi2 ? 2 * t + 5 : 8 + 2 * t;
+    const int zo0 = g_off(row0, q), zo1 = g_off(row1, q), zo2 = g_off(row2, q);
+    // P+ in C layout: h[m][n][j] = P[8m+q][8n+2t+j]; vin[kt] = (q == 4 ? v1 : q == 5 ? v2 : 0)[row(kt)]
     double h[2][2][2];
-    double vin[4];
+    double vin[3] = {0.0, 0.0, 0.0};
+    double pq0 = 0.0, pq1 = 0.0;                // FS_ABS: p+ in quad layout (rows q, 8+q)
     {
         const double* VN = I.V + (size_t)N * VREC;
         const double* yN = yref_row(a, I.inst, N);
@@ -440,10 +463,17 @@ __device__ bool factor_sweep(Inst& I)
                     const int r = 8 * m + q, c = 8 * n + 2 * t + j;
                     h[m][n][j] = (r == c && r < 12) ? a.We[r < 12 ? r : 0] : 0.0;
                 }
-#pragma unroll
-        for (int kt = 0; kt < 4; kt++) {
-            const int r = 8 * (kt >> 1) + 2 * t + (kt & 1);
-            vin[kt] = (q == 4 && r < 12) ? a.We[r < 12 ? r : 0] * (VN[V_X + (r < 12 ? r : 0)] + I.Xlin[N * NX + (r < 12 ? r : 0)] - yN[r < 12 ? r : 0]) : 0.0;
+        if (KIND == FS_IPM) {
+            // pi_N = We (x_N + X_N - xref_N) for lanes q == 4; p_N = 0
+            if (q == 4) {
+                vin[0] = a.We[row0] * (VN[V_X + row0] + I.Xlin[N * NX + row0] - yN[row0]);
+                vin[1] = a.We[row1] * (VN[V_X + row1] + I.Xlin[N * NX + row1] - yN[row1]);
+                vin[2] = a.We[row2] * (VN[V_X + row2] + I.Xlin[N * NX + row2] - yN[row2]);
+            }
+        } else {
+            // p_N = We (X_N - xref_N)
+            pq0 = a.We[q] * (I.Xlin[N * NX + q] - yN[q]);
+            pq1 = lo ? a.We[8 + e] * (I.Xlin[N * NX + 8 + e] - yN[8 + e]) : 0.0;
         }
     }
     I.template begin<false, true>();
@@ -453,50 +483,76 @@ __device__ bool factor_sweep(Inst& I)
         const double* Vs = I.sm.st[s].V;
         double* Fk = I.F + (size_t)k * FREC;
         double* Vk = I.V + (size_t)k * VREC;
-        double z[4][2];
-#pragma unroll
-        for (int kt = 0; kt < 4; kt++) {
-            z[kt][0] = zval[kt] ? Gs[zoff[kt]] : 0.0;
-            z[kt][1] = zval[kt] ? Gs[zoff[kt] + 32] : 0.0;
-        }
+        double z[3][2];
+        z[0][0] = Gs[zo0]; z[0][1] = Gs[zo0 + 32];
+        z[1][0] = Gs[zo1]; z[1][1] = Gs[zo1 + 32];
+        z[2][0] = Gs[zo2]; z[2][1] = Gs[zo2 + 32];
         const double tsk = Gs[G_TS];
-        // state rows q and 8+q:  Q (x + X - xref) = Q x + qlin
+        // state rows q and 8+q
         const double qd0 = tsk * a.W[q];
-        const double qx0 = fma(qd0, Vs[V_X + q], Gs[G_QLIN + q]);
         const double qd1 = lo ? tsk * a.W[8 + e] : 0.0;
-        const double qx1 = lo ? fma(qd1, Vs[V_X + 8 + e], Gs[G_QLIN + 8 + e]) : 0.0;
+        double qx0 = Gs[G_QLIN + q], qx1 = lo ? Gs[G_QLIN + 8 + e] : 0.0;
         // input row e (meaningful in quads 4..7)
         const double rd = tsk * a.W[12 + e];
         double rt = rd;
-        if (BARRIER) rt += Vs[V_LL + e] / Vs[V_TL + e] + Vs[V_LU + e] / Vs[V_TU + e];
-        const double gu_loc = fma(rd, Vs[V_V + e], Gs[G_RLIN + e]);
+        double gu_loc = Gs[G_RLIN + e];
+        if (KIND == FS_IPM) {
+            // residual form around the iterate (x, v):  Q (x + X - xref) = Q x + qlin,  R (v + U - uref) = R v + rlin
+            qx0 = fma(qd0, Vs[V_X + q], qx0);
+            if (lo) qx1 = fma(qd1, Vs[V_X + 8 + e], qx1);
+            rt += Vs[V_LL + e] / Vs[V_TL + e] + Vs[V_LU + e] / Vs[V_TU + e];
+            gu_loc = fma(rd, Vs[V_V + e], gu_loc);
+        }
+        // kt2 elements of P+ that live in lane t-2
+        const double hx0 = shfl(h[0][1][1], src2), hx1 = shfl(h[1][1][1], src2);
+        const double b02 = hi2 ? hx0 : h[0][1][0];
+        const double b12 = hi2 ? hx1 : h[1][1][0];
+        if (KIND == FS_ABS) {
+            // s+ = P+ b_k + p+ : row-block dot products against b, reduced over the quad, then handed to lanes q == 4
+            const double bb0 = Gs[G_B_OFF + row0], bb1 = Gs[G_B_OFF + row1];
+            const double bb2 = hi2 ? 0.0 : Gs[G_B_OFF + 8 + 2 * t], bb3 = hi2 ? 0.0 : Gs[G_B_OFF + 9 + 2 * t];
+            double s0 = h[0][0][0] * bb0 + h[0][0][1] * bb1 + h[0][1][0] * bb2 + h[0][1][1] * bb3;
+            double s1 = h[1][0][0] * bb0 + h[1][0][1] * bb1 + h[1][1][0] * bb2 + h[1][1][1] * bb3;
+            s0 += shfl_x(s0, 1); s1 += shfl_x(s1, 1);
+            s0 += shfl_x(s0, 2); s1 += shfl_x(s1, 2);
+            s0 += pq0; s1 += pq1;                       // quad layout: s+[q], s+[8+q]
+            const double i0 = shfl(s0, 8 * t), i1 = shfl(s0, 8 * t + 4), i2 = shfl(s1, hi2 ? 4 * (2 * t - 3) : 8 * t);
+            vin[0] = (q == 4) ? i0 : 0.0; vin[1] = (q == 4) ? i1 : 0.0; vin[2] = (q == 4) ? i2 : 0.0;
+        }
 
-        // ---- W' = Z' [P+ | pi+ | p+] ----
+        // ---- W' = Z' [P+ | v1 | v2] ----
         double w[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+        {
+            const double b00 = h[0][0][0], b01 = h[0][0][1];
+            const double b10 = lo ? h[1][0][0] : vin[0], b11 = lo ? h[1][0][1] : vin[1], b1x = lo ? b12 : vin[2];
 #pragma unroll
-        for (int kt = 0; kt < 4; kt++) {
-            const double b0 = h[0][kt >> 1][kt & 1];
-            const double b1 = lo ? h[1][kt >> 1][kt & 1] : vin[kt];
-#pragma unroll
-            for (int m = 0; m < 2; m++) { dmma(w[m][0], z[kt][m], b0); dmma(w[m][1], z[kt][m], b1); }
+            for (int m = 0; m < 2; m++) {
+                dmma(w[m][0], z[0][m], b00); dmma(w[m][1], z[0][m], b10);
+                dmma(w[m][0], z[1][m], b01); dmma(w[m][1], z[1][m], b11);
+                dmma(w[m][0], z[2][m], b02); dmma(w[m][1], z[2][m], b1x);
+            }
         }
         // ---- H = W' Z ----
+        const double wx0 = shfl(w[0][1][1], src2), wx1 = shfl(w[1][1][1], src2);
+        const double a02 = hi2 ? wx0 : w[0][1][0];
+        const double a12 = hi2 ? wx1 : w[1][1][0];
 #pragma unroll
         for (int m = 0; m < 2; m++)
 #pragma unroll
             for (int n = 0; n < 2; n++) { h[m][n][0] = 0.0; h[m][n][1] = 0.0; }
 #pragma unroll
-        for (int kt = 0; kt < 4; kt++)
-#pragma unroll
-            for (int m = 0; m < 2; m++)
-#pragma unroll
-                for (int n = 0; n < 2; n++) dmma(h[m][n], w[m][kt >> 1][kt & 1], z[kt][n]);
-        // ---- the two vector products sit in columns 12, 13 of W': lane (q,2) holds ([A|B]'pi+)[8m+q], ([A|B]'p+)[8m+q] ----
-        const double at0 = shfl(w[0][1][0], qb | 2), bt0 = shfl(w[0][1][1], qb | 2);
-        const double at1 = shfl(w[1][1][0], qb | 2), bt1 = shfl(w[1][1][1], qb | 2);
-        const double gu = gu_loc + at1;          // quads 4..7: R du + r + B'pi+
-        const double gval = gu + bt1;            // predictor rhs: gh = gu
-        // ---- Lam = B'P+B + R~ : add the barrier diagonal where the diagonal element lives, then broadcast ----
+        for (int n = 0; n < 2; n++) {
+            dmma(h[0][n], w[0][0][0], z[0][n]); dmma(h[1][n], w[1][0][0], z[0][n]);
+            dmma(h[0][n], w[0][0][1], z[1][n]); dmma(h[1][n], w[1][0][1], z[1][n]);
+            dmma(h[0][n], a02, z[2][n]);        dmma(h[1][n], a12, z[2][n]);
+        }
+        // ---- the vector products sit in columns 12, 13 of W': lane (q,2) holds ([A|B]'v1)[8m+q], ([A|B]'v2)[8m+q] ----
+        const double at0 = shfl(w[0][1][0], qb | 2), at1 = shfl(w[1][1][0], qb | 2);
+        double bt0 = 0.0, bt1 = 0.0;
+        if (KIND == FS_IPM) { bt0 = shfl(w[0][1][1], qb | 2); bt1 = shfl(w[1][1][1], qb | 2); }
+        const double gu = gu_loc + at1;          // quads 4..7: IPM: R du + r + B'pi+;  ABS: rlin + B's+ (= g)
+        const double gval = gu + bt1;            // IPM predictor rhs: gh = gu
+        // ---- Lam = B'P+B + R~ : add the diagonal where the diagonal element lives, then broadcast ----
         if (!lo && t == 2 + (e >> 1)) {
             if (e & 1) h[1][1][1] += rt; else h[1][1][0] += rt;
         }
@@ -531,20 +587,19 @@ __device__ bool factor_sweep(Inst& I)
                 *reinterpret_cast<double2*>(Fk + (8 + q) * 4 + 2) = make_double2(kd[2], kd[3]);
             }
         }
-        if (lane == 2) {
+        if (KIND == FS_IPM && lane == 2) {       // the corrector's backward sweep re-solves with Lam
             Fk[F_L_OFF + 0] = L.l10; Fk[F_L_OFF + 1] = L.l20; Fk[F_L_OFF + 2] = L.l21;
             Fk[F_L_OFF + 3] = L.l30; Fk[F_L_OFF + 4] = L.l31; Fk[F_L_OFF + 5] = L.l32;
             Fk[F_ID_OFF + 0] = L.i0; Fk[F_ID_OFF + 1] = L.i1; Fk[F_ID_OFF + 2] = L.i2; Fk[F_ID_OFF + 3] = L.i3;
         }
-        // ---- g = gh + B'p+ to every lane; kff = Lam^-1 g ----
+        // ---- g to every lane; kff = Lam^-1 g ----
         double gt[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) gt[c] = shfl(gval, 4 * (4 + c) + 2);
-        if (!lo && t == 2) Vk[V_GU + e] = gu;
+        if (KIND == FS_IPM && !lo && t == 2) Vk[V_GU + e] = gu;
         chol4_fwd(L, gt);                        // L^-1 g
-        const double pv0 = bt0 - (y0[0] * gt[0] + y0[1] * gt[1] + y0[2] * gt[2] + y0[3] * gt[3]);
-        const double pv1 = bt1 - (y1[0] * gt[0] + y1[1] * gt[1] + y1[2] * gt[2] + y1[3] * gt[3]);
-        const double pi0 = qx0 + at0, pi1 = qx1 + at1;
+        const double yg0 = y0[0] * gt[0] + y0[1] * gt[1] + y0[2] * gt[2] + y0[3] * gt[3];   // (K'g)[q]
+        const double yg1 = y1[0] * gt[0] + y1[1] * gt[1] + y1[2] * gt[2] + y1[3] * gt[3];
         {
             double kf[4] = {gt[0], gt[1], gt[2], gt[3]};
             chol4_bwd(L, kf);
@@ -562,13 +617,20 @@ __device__ bool factor_sweep(Inst& I)
         if (t == (q >> 1)) {                     // diagonal element (8m+q, 8m+q) is C register q&1 of lane (q, q>>1)
             if (q & 1) { h[0][0][1] += qd0; h[1][1][1] += qd1; } else { h[0][0][0] += qd0; h[1][1][0] += qd1; }
         }
-        // ---- pi, p+ for the next stage's vector columns: lane (4,t) needs pi[8n+2t+j], lane (5,t) p[8n+2t+j] ----
-        const double vs0 = (t == 0) ? pi0 : pv0, vs1 = (t == 0) ? pi1 : pv1;    // lanes t = 0 serve pi, t = 1 serve p
-        const int sa = 8 * t + (q & 1), sb = sa + 4;                            // quads 2t and 2t+1
-        const double i0 = shfl(vs0, sa), i1 = shfl(vs0, sb), i2 = shfl(vs1, sa), i3 = shfl(vs1, sb);
-        const bool vq = (q == 4) || (q == 5);
-        vin[0] = vq ? i0 : 0.0; vin[1] = vq ? i1 : 0.0;
-        vin[2] = (vq && t < 2) ? i2 : 0.0; vin[3] = (vq && t < 2) ? i3 : 0.0;
+        if (KIND == FS_IPM) {
+            // ---- pi, p for the next stage's vector columns: lane (4,t) needs pi[row(kt)], lane (5,t) p[row(kt)] ----
+            const double pi0 = qx0 + at0, pi1 = qx1 + at1;
+            const double pv0 = bt0 - yg0, pv1 = bt1 - yg1;
+            const double vs0 = (t == 0) ? pi0 : pv0, vs1 = (t == 0) ? pi1 : pv1;    // lanes t = 0 serve pi, t = 1 serve p
+            const int sel = q & 1;
+            const double i0 = shfl(vs0, 8 * t + sel), i1 = shfl(vs0, 8 * t + 4 + sel);
+            const double i2 = shfl(vs1, (hi2 ? 4 * (2 * t - 3) : 8 * t) + sel);
+            const bool vq = (q == 4) || (q == 5);
+            vin[0] = vq ? i0 : 0.0; vin[1] = vq ? i1 : 0.0; vin[2] = vq ? i2 : 0.0;
+        } else {
+            pq0 = qx0 + at0 - yg0;               // p = qlin + A's+ - K'g
+            pq1 = qx1 + at1 - yg1;
+        }
     }
     __syncwarp();
     return __all_sync(FULL_MASK, ok);
@@ -650,37 +712,37 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
         if (inst >= a.B) break;
         Inst I(a, sm, phase, inst, lane);
 
-        ipm_init(I);
-        const double bmax = forward_sweep<0>(I);
-
         int status = 2, it = 0;
-        double mu = 0.0, res_stat = 0.0, stat_scale = 1.0;
+        double mu = 0.0, res_stat = 0.0, stat_scale = 1.0, bmax = 0.0;
         bool solved = false;
         // ---------- interior-solution fast path ----------
         // If the minimiser of the QP without its box lies inside the box it IS the minimiser of the QP (convexity), and
-        // it costs one Riccati factorisation + one forward sweep instead of an interior-point iteration sequence.  It is
-        // attempted when no bound was active at this instance's previous solution (hint carried between solves; it only
-        // steers which exact method runs first, never the result).
+        // it costs one Riccati factorisation + one closed-loop roll-out instead of an interior-point iteration sequence.
+        // It is attempted when no bound was active at this instance's previous solution (hint carried between solves; it
+        // only steers which exact method runs first, never the result).
         bool active = false;                    // a bound is (nearly) active at the solution -> hint for the next solve
         if (a.fast_path && a.hint[inst] == 0) {
-            if (!factor_sweep<false>(I)) { status = 4; }
-            else {
-                forward_sweep<1>(I);
+            if (factor_sweep<FS_ABS>(I)) {
+                bmax = forward_sweep<2>(I);     // leaves (dx, du) in V_X, V_V
                 bool inside = true;
+#pragma unroll 5
                 for (int idx = lane; idx < nb; idx += 32) {
-                    const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
                     const int e = idx & 3;
-                    const double dv = Vk[V_DV + e];
-                    const double tl = Vk[V_TL + e] + dv, tu = Vk[V_TU + e] - dv;
+                    const double un = I.Ulin[idx] + I.V[(size_t)(idx >> 2) * VREC + V_V + e];
+                    const double tl = un - a.lbu[e], tu = a.ubu[e] - un;
                     inside &= (tl >= 0.0) && (tu >= 0.0);
                     active |= fmin(tl, tu) < 1e-3;
                 }
-                if (__all_sync(FULL_MASK, inside)) { solved = true; status = 0; it = 1; }   // solution = iterate + step
+                if (__all_sync(FULL_MASK, inside)) { solved = true; status = 0; it = 1; }
             }
         }
-        for (it = solved ? 1 : 0; !solved && status != 4 && it < a.max_iter; it++) {
+        if (!solved) {
+            ipm_init(I);
+            bmax = forward_sweep<0>(I);
+        }
+        for (it = solved ? 1 : 0; !solved && it < a.max_iter; it++) {
             // ---------- B1: factorisation + predictor rhs ----------
-            if (!factor_sweep<true>(I)) { status = 4; break; }
+            if (!factor_sweep<FS_IPM>(I)) { status = 4; break; }
             if (it == 0) {
                 // mu and stationarity residual of the starting point (later iterations get them from E2)
                 double s = 0.0, rs = 0.0;
@@ -778,46 +840,28 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
             if (mu < a.tol && res_stat < a.tol * stat_scale) { status = 0; it++; break; }
         }
 
-        // ---------- epilogue: full SQP step, u0, thrust allocation ----------
-        // the fast path leaves its solution as iterate + step (V_V + V_DV, V_X + V_DX); the IPM as the iterate itself
-        if (!solved) {
-            active = false;
-            for (int idx = lane; idx < nb; idx += 32) {
-                const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
-                active |= fmin(Vk[V_TL + (idx & 3)], Vk[V_TU + (idx & 3)]) < 1e-3;
-            }
-        }
-        active = __any_sync(FULL_MASK, active);
-        if (lane == 0) a.hint[inst] = (active || status != 0) ? 1 : 0;
+        // ---------- epilogue: full SQP step, u0, thrust allocation (both paths leave (dx, du) in V_X, V_V) ----------
         double* Xo = a.X + (size_t)inst * (N + 1) * NX;
         double* Uo = a.U + (size_t)inst * N * NU;
         bool finite = true;
+        bool act2 = false;
+#pragma unroll 5
         for (int idx = lane; idx < nb; idx += 32) {
             const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
-            double v = Vk[V_V + (idx & 3)];
-            if (solved) v += Vk[V_DV + (idx & 3)];
-            finite &= isfinite(v);
+            finite &= isfinite(Vk[V_V + (idx & 3)]);
+            if (!solved) act2 |= fmin(Vk[V_TL + (idx & 3)], Vk[V_TU + (idx & 3)]) < 1e-3;
         }
-        for (int idx = lane; idx < 12 * (N + 1); idx += 32) {
-            const double* Vk = I.V + (size_t)(idx / 12) * VREC;
-            double v = Vk[V_X + idx % 12];
-            if (solved) v += Vk[V_DX + idx % 12];
-            finite &= isfinite(v);
-        }
+        // the states are the exact roll-out of the inputs: NaN/Inf anywhere reaches x_N
+        if (lane < 12) finite &= isfinite(I.V[(size_t)N * VREC + V_X + lane]);
         finite = __all_sync(FULL_MASK, finite);
+        if (!solved) active = act2;
+        active = __any_sync(FULL_MASK, active);
+        if (lane == 0) a.hint[inst] = (active || status != 0) ? 1 : 0;
         if (finite) {
-            for (int idx = lane; idx < nb; idx += 32) {
-                const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
-                double v = Vk[V_V + (idx & 3)];
-                if (solved) v += Vk[V_DV + (idx & 3)];
-                Uo[idx] += v;
-            }
-            for (int idx = lane; idx < 12 * (N + 1); idx += 32) {
-                const double* Vk = I.V + (size_t)(idx / 12) * VREC;
-                double v = Vk[V_X + idx % 12];
-                if (solved) v += Vk[V_DX + idx % 12];
-                Xo[idx] += v;
-            }
+#pragma unroll 5
+            for (int idx = lane; idx < nb; idx += 32) Uo[idx] += I.V[(size_t)(idx >> 2) * VREC + V_V + (idx & 3)];
+#pragma unroll 4
+            for (int idx = lane; idx < 12 * (N + 1); idx += 32) Xo[idx] += I.V[(size_t)(idx / 12) * VREC + V_X + idx % 12];
         } else {
             status = 1;
         }
