@@ -25,16 +25,22 @@ namespace br2 {
 // ------------------------------------------------------------------------------------------------------
 // linearisation
 // ------------------------------------------------------------------------------------------------------
-// team lane c: 0 = state column (evolves by f); 1..9 = Sx columns 3..11; 10..13 = Su columns 0..3;
-// 14, 15 = helpers that write the constant [I;0] columns 0, 1 of A (positions do not enter f).
+// One 8-lane team per (instance, stage); a lane carries TWO of the 16 column slots of the augmented state through
+// the RK4 stages, so the stage Jacobian (the 48 non-zeros of df/dx) is formed once per two columns:
+//   slot 0 = state x (evolves by f), slots 1..9 = Sx columns 3..11, slots 10..13 = Su columns 0..3,
+//   slots 14, 15 (lane 7) carry nothing: that lane writes the constant [I;0] columns 0..2 of A (positions do not
+//   enter f) and the cost-gradient tail of the stage record.
+// lane l of the team holds slots 2l and 2l+1.
+constexpr int LIN_TEAM = 8;
+
 __global__ void __launch_bounds__(128) linearize_kernel(SolveArgs a)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int c = lane & 15;
-    const unsigned tmask = 0xffffu << (lane & 16);
+    const int l = lane & (LIN_TEAM - 1);
+    const unsigned tmask = 0xffu << (lane & ~(LIN_TEAM - 1));
     const int total = a.B * a.N;
-    int team = gtid >> 4;
+    int team = gtid / LIN_TEAM;
     const bool live = team < total;
     if (!live) team = total - 1;            // keep the lanes alive for the team shuffles; stores are predicated
     const int inst = team / a.N, k = team - inst * a.N;
@@ -53,81 +59,92 @@ __global__ void __launch_bounds__(128) linearize_kernel(SolveArgs a)
 #pragma unroll
     for (int i = 0; i < NU; i++) u[i] = __ldg(a.U + ((size_t)inst * a.N + k) * NU + i);
 
-    double col0[NX], cur[NX], acc[NX], kk[NX];
+    // slot sa = 2l, sb = 2l+1; the unit / zero seed of a sensitivity slot is implicit (seed_a, seed_b = its row or -1)
+    const int sa = 2 * l, sb = 2 * l + 1;
+    const int seed_a = (sa >= 1 && sa <= 9) ? sa + 2 : -1;
+    const int seed_b = (sb >= 1 && sb <= 9) ? sb + 2 : -1;
+    const int su_a = sa - 10, su_b = sb - 10;            // Su column when in 0..3
+    double x0v[NX];                                      // linearisation state (every lane: stage 1 needs it anyway)
+#pragma unroll
+    for (int i = 0; i < NX; i++) x0v[i] = __ldg(Xk + i);
+    double ca[NX], cb[NX], aa[NX], ab[NX];               // current stage value and weighted sum of the two slots
 #pragma unroll
     for (int i = 0; i < NX; i++) {
-        col0[i] = (c == 0) ? __ldg(Xk + i) : ((c >= 1 && c <= 9 && i == c + 2) ? 1.0 : 0.0);
-        cur[i] = col0[i];
-        acc[i] = 0.0;
+        ca[i] = (sa == 0) ? x0v[i] : (i == seed_a ? 1.0 : 0.0);
+        cb[i] = (i == seed_b) ? 1.0 : 0.0;
+        aa[i] = 0.0; ab[i] = 0.0;
     }
-    const int su_col = c - 10;   // valid for c in 10..13
 
 #pragma unroll 1
     for (int s = 0; s < 4; s++) {
-        // stage state (only components 3..11 enter f and J)
+        // stage state (only components 3..11 enter f and J): slot 0 lives in lane 0 of the team
         double xs[NX];
         xs[0] = xs[1] = xs[2] = 0.0;
 #pragma unroll
-        for (int i = 3; i < NX; i++) xs[i] = __shfl_sync(tmask, cur[i], 0, 16);
+        for (int i = 3; i < NX; i++) xs[i] = __shfl_sync(tmask, ca[i], 0, LIN_TEAM);
         // one sincos per lane: lanes 0,1,2 of the team own phi, theta, psi
         double sn, cs;
-        const int which = c % 3;
+        const int which = l % 3;
         sincos(which == 0 ? xs[3] : (which == 1 ? xs[4] : xs[5]), &sn, &cs);
         Trig t;
-        t.sphi = __shfl_sync(tmask, sn, 0, 16); t.cphi = __shfl_sync(tmask, cs, 0, 16);
-        t.sth = __shfl_sync(tmask, sn, 1, 16);  t.cth = __shfl_sync(tmask, cs, 1, 16);
-        t.spsi = __shfl_sync(tmask, sn, 2, 16); t.cpsi = __shfl_sync(tmask, cs, 2, 16);
-        if (c == 0) {
-            ode(xs, u, mc, t, kk);
-        } else {
-            Jac J;
-            jac_of(xs, mc, t, J);
-            jac_mul(J, cur, kk);
-            if (c >= 10 && c <= 13) ju_add(mc, su_col, kk);
-        }
+        t.sphi = __shfl_sync(tmask, sn, 0, LIN_TEAM); t.cphi = __shfl_sync(tmask, cs, 0, LIN_TEAM);
+        t.sth = __shfl_sync(tmask, sn, 1, LIN_TEAM);  t.cth = __shfl_sync(tmask, cs, 1, LIN_TEAM);
+        t.spsi = __shfl_sync(tmask, sn, 2, LIN_TEAM); t.cpsi = __shfl_sync(tmask, cs, 2, LIN_TEAM);
+        Jac J;
+        jac_of(xs, mc, t, J);
+        double ka[NX], kb[NX];
+        jac_mul(J, ca, ka);
+        jac_mul(J, cb, kb);
+        if (sa == 0) ode_from_jac(xs, u, mc, t, J, ka);
+        if (su_a >= 0 && su_a < NU) ju_add(mc, su_a, ka);
+        if (su_b >= 0 && su_b < NU) ju_add(mc, su_b, kb);
         const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
         const double cn = (s == 2) ? 1.0 : 0.5;     // c_{s+1} of the classical tableau
 #pragma unroll
         for (int i = 0; i < NX; i++) {
-            acc[i] += bw * kk[i];
-            cur[i] = col0[i] + cn * h * kk[i];
+            aa[i] += bw * ka[i];
+            ab[i] += bw * kb[i];
+            ca[i] = ((sa == 0) ? x0v[i] : (i == seed_a ? 1.0 : 0.0)) + cn * h * ka[i];
+            cb[i] = ((i == seed_b) ? 1.0 : 0.0) + cn * h * kb[i];
         }
     }
 #pragma unroll
-    for (int i = 0; i < NX; i++) cur[i] = col0[i] + h * acc[i];
+    for (int i = 0; i < NX; i++) {
+        ca[i] = ((sa == 0) ? x0v[i] : (i == seed_a ? 1.0 : 0.0)) + h * aa[i];
+        cb[i] = ((i == seed_b) ? 1.0 : 0.0) + h * ab[i];
+    }
 
     if (!live) return;
     double* Gk = a.G + ((size_t)inst * a.N + k) * GREC;
     const double* yr = yref_row(a, inst, k);
-    if (c == 0) {
+    // slot c >= 1 is column c + 2 of Z = [A|B]; in fragment order rows 4ki..4ki+3 of a column are contiguous (32 B)
+    if (l == 0) {
         const double* Xn = Xk + NX;
 #pragma unroll
-        for (int i = 0; i < NX; i++) Gk[G_B_OFF + i] = cur[i] - __ldg(Xn + i);
+        for (int i = 0; i < NX; i++) Gk[G_B_OFF + i] = ca[i] - __ldg(Xn + i);
 #pragma unroll
-        for (int i = 0; i < NX; i++) Gk[G_QLIN + i] = h * a.W[i] * (col0[i] - __ldg(yr + i));
+        for (int i = 0; i < NX; i++) Gk[G_QLIN + i] = h * a.W[i] * (x0v[i] - __ldg(yr + i));
 #pragma unroll
-        for (int l = 0; l < NX; l++) Gk[g_off(l, 2)] = (l == 2) ? 1.0 : 0.0;
-    } else if (c <= 13) {
-        // column c + 2 of Z = [A|B]; in fragment order rows 4ki..4ki+3 of a column are contiguous (32 B)
+        for (int r = 0; r < NX; r++) Gk[g_off(r, 3)] = cb[r];
+    } else if (l < LIN_TEAM - 1) {
 #pragma unroll
-        for (int l = 0; l < NX; l++) Gk[g_off(l, c + 2)] = cur[l];
+        for (int r = 0; r < NX; r++) { Gk[g_off(r, sa + 2)] = ca[r]; Gk[g_off(r, sb + 2)] = cb[r]; }
     } else {
-        const int j = c - 14;
 #pragma unroll
-        for (int l = 0; l < NX; l++) Gk[g_off(l, j)] = (l == j) ? 1.0 : 0.0;
-        if (c == 14) {
+        for (int j = 0; j < 3; j++)
 #pragma unroll
-            for (int i = 0; i < NU; i++) Gk[G_RLIN + i] = h * a.W[NX + i] * (u[i] - __ldg(yr + NX + i));
-            Gk[G_TS] = h;
+            for (int r = 0; r < NX; r++) Gk[g_off(r, j)] = (r == j) ? 1.0 : 0.0;
 #pragma unroll
-            for (int i = G_TS + 1; i < GREC; i++) Gk[i] = 0.0;
-        }
+        for (int i = 0; i < NU; i++) Gk[G_RLIN + i] = h * a.W[NX + i] * (u[i] - __ldg(yr + NX + i));
+        Gk[G_TS] = h;
+#pragma unroll
+        for (int i = G_TS + 1; i < GREC; i++) Gk[i] = 0.0;
     }
 }
 
 void launch_linearize(const SolveArgs& a, cudaStream_t s)
 {
-    const long long threads = (long long)a.B * a.N * 16;
+    const long long threads = (long long)a.B * a.N * LIN_TEAM;
     const int block = 128;
     const int grid = (int)((threads + block - 1) / block);
     linearize_kernel<<<grid, block, 0, s>>>(a);
