@@ -45,6 +45,18 @@ UNIT = "steps/s"
 BYTES_PER_STAGE_ITER = 4384          # 548 doubles per instance, stage and IPM iteration
 
 
+def measured_traffic(B, N, fast_path):
+    """DRAM bytes per ipm_kernel launch from the committed ncu capture of the same configuration, else None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ipm_traffic.json")) as f:
+            for e in json.load(f)["entries"]:
+                if e["batch"] == B and e["horizon"] == N and bool(e["fast_path"]) == bool(fast_path):
+                    return float(e["dram_bytes_per_launch"]), e["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -292,6 +304,7 @@ def run_ours(args):
         t_ipm_avg = float(np.mean(t_ipm))
         alg_bytes = B * BYTES_PER_STAGE_ITER * N * iters_mean
         achieved = alg_bytes / t_ipm_avg / 1e9
+        traffic, traffic_src = measured_traffic(B, N, not args.no_fast_path)
         line = {
             "metric": METRIC, "value": world * B * K / dt, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -309,7 +322,8 @@ def run_ours(args):
             "kernels": {"linearize_ms": 1e3 * float(np.mean(t_lin)), "ipm_ms": 1e3 * t_ipm_avg,
                         "ipm_share_of_step": t_ipm_avg / (dt / K)},
             "roofline": {"kernel": "ipm_kernel (Riccati sweeps)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
+                         "peak_source": peak_src,
                          "formula": f"B*{BYTES_PER_STAGE_ITER}*N*mean_ipm_iterations / t_ipm"},
             "clocks": clocks,
         }
