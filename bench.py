@@ -131,6 +131,42 @@ def record_closed_loop(solver, w, ticks: int, N: int):
     return x0s, lns
 
 
+def record_closed_loop_dob(solver, w, ticks: int, N: int, seed: int, settle: int = 60):
+    """untimed, BASELINE config 3: inputs of DOB-MPC ticks (thruster forces, pose/velocity measurement, finite-differenced
+    body acceleration, trajectory row) from a plant driven by sampled wave disturbances (mode 0 of applyBodyWrench,
+    bluerov2_dob.cpp:774-797).  The loop is first settled for `settle` ticks (the filter of the reference is explicit
+    RK4 at 50 ms on roll/pitch dynamics with |lambda dt| > 2.8: it only lives in the gentle regime |u| < 1), and the
+    plant is driven by the UNCOMPENSATED command: the node's compensation gain 1/0.0325 (bluerov2_dob.cpp:326-338) over-
+    compensates ~30x on any plant whose thrust scale is the OCP model's, so the compensated command is computed (timed
+    path) but not fed back.  Returns the per-tick inputs and the state to restart the replay from."""
+    B = w["x0"].shape[0]
+    amp, tau0 = wl.wave_disturbance(B, seed=seed + 1)
+    x, lines = w["x0"].copy(), w["lines"].copy()
+    solver.set_trajectory(w["traj"])
+    solver.set_iterate(w["X"], w["U"])
+    vel_prev, thr = x[:, 6:12].copy(), np.zeros((B, 6))
+    rec = {"thr": [], "meas": [], "acc": [], "lines": []}
+    start = None
+    for t in range(settle + ticks):
+        if t == settle:
+            X0, U0 = solver.get_iterate()
+            solver.ekf_reset()
+            ex, eP = solver.ekf_state()
+            ex[:, :12] = x                  # filter starts at the true pose
+            start = (X0, U0, ex, eP)
+        if t >= settle:
+            rec["thr"].append(thr.copy()); rec["meas"].append(x.copy())
+            rec["acc"].append((x[:, 6:12] - vel_prev) / 0.05); rec["lines"].append(lines.astype(np.int32))
+        vel_prev = x[:, 6:12].copy()
+        u0, th, st = solver.solve_windowed(x, lines.astype(np.int32), w["p"])
+        if (st != 0).any():
+            raise RuntimeError(f"solver status != 0 while recording the DOB workload: {np.unique(st, return_counts=True)}")
+        thr = th.copy()                                   # thrust feedback = previous command
+        x = wl.plant_step(x, u0, w["p"], 0.05, dist=wl.wave_at(amp, tau0, t))
+        lines = lines + 1
+    return rec, start
+
+
 def cpu_leg(N: int, budget_s: float, ticks_wanted: int, threads: int = 0, seed: int = 0, pos_spread: float = 0.5):
     """the oracle port timed on the host cores over a bounded closed-loop sample of the same workload"""
     from oracle import Oracle, CasadiRef
@@ -215,23 +251,43 @@ def run_ours(args):
         raise SystemExit("--warmup must be >= 3")
 
     sampler = ClockSampler(local)
-    w = make_workload(B, N, seed=1000 * rank, pos_spread=args.pos_spread)
+    dob = args.workload == "dob"
+    w = wl.tracking_batch(B, N, seed=1000 * rank, reference="lemniscate" if dob else "circle",
+                          pos_spread=min(args.pos_spread, 0.2) if dob else args.pos_spread, level=dob)
     sol = S.BatchSolver(B, N, device=local)
     if args.no_fast_path:
         sol.set_option("fast_path", 0)
-    x0s, lns = record_closed_loop(sol, w, W + K, N)
+    if dob:
+        rec, dob0 = record_closed_loop_dob(sol, w, W + K, N, seed=1000 * rank)
+        x0s, lns = rec["meas"], rec["lines"]
+        d_thr = [torch.from_numpy(a).to(dev) for a in rec["thr"]]
+        d_acc = [torch.from_numpy(a).to(dev) for a in rec["acc"]]
+        ekf_out = (torch.empty((B, 6), dtype=torch.float64, device=dev), torch.empty((B, 16), dtype=torch.float64, device=dev))
+    else:
+        x0s, lns = record_closed_loop(sol, w, W + K, N)
 
     # ---- device-resident inputs, one distinct buffer per tick ----
     d_x0 = [torch.from_numpy(a).to(dev) for a in x0s]
     d_lines = [torch.from_numpy(a).to(dev) for a in lns]
     d_p = torch.from_numpy(w["p"]).to(dev)
+
+    def restart():
+        if dob:
+            sol.set_iterate(dob0[0], dob0[1])
+            sol.set_ekf_state(dob0[2], dob0[3])
+        else:
+            sol.set_iterate(w["X"], w["U"])
     from bluerov2_b200.sharding import ThrustGather
     gather = ThrustGather(world * B, dev)                                    # all ranks' thrust vectors; .slot = this rank's block
     out = (torch.empty((B, 4), dtype=torch.float64, device=dev), gather.slot, torch.empty((B,), dtype=torch.int32, device=dev))
     stream = torch.cuda.current_stream(dev)
 
     def tick(t):
-        sol.solve_windowed(d_x0[t], d_lines[t], d_p, out=out)   # thrusts land directly in this rank's slot of `gather`
+        if dob:     # EKF writes the OCP parameters on the device; the solve reads them there (same stream, no host hop)
+            sol.ekf(d_thr[t], d_x0[t], d_acc[t], compensate=True, out=ekf_out)
+            sol.solve_windowed(d_x0[t], d_lines[t], ekf_out[1], out=out)
+        else:
+            sol.solve_windowed(d_x0[t], d_lines[t], d_p, out=out)   # thrusts land directly in this rank's slot of `gather`
         if distributed:
             gather.all_gather()
 
@@ -240,7 +296,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sol.set_iterate(w["X"], w["U"])
+    restart()
     for t in range(W):
         tick(t)
     barrier()
@@ -261,7 +317,7 @@ def run_ours(args):
 
     # per-kernel device times (CUDA events recorded by the library on the launching stream around each kernel):
     # replay the timed ticks once more, reading the events after each tick (outside the steps/s measurement)
-    sol.set_iterate(w["X"], w["U"])
+    restart()
     for t in range(W + K):
         tick(t)
         if t >= W:
@@ -275,18 +331,34 @@ def run_ours(args):
     h_lines = [torch.from_numpy(a).pin_memory().numpy() for a in lns]
     h_p = pin(w["p"])
     h_out = (pin(np.empty((B, 4))), pin(np.empty((B, 6))), torch.empty((B,), dtype=torch.int32).pin_memory().numpy())
-    sol.set_iterate(w["X"], w["U"])
+    if dob:
+        h_thr = [pin(a) for a in rec["thr"]]
+        h_acc = [pin(a) for a in rec["acc"]]
+        h_ekf = (pin(np.empty((B, 6))), pin(np.empty((B, 16))))
+
+    def host_tick(t):
+        if dob:     # the two public host calls of a DOB-MPC tick; p makes the round trip through the host like in the node
+            sol.ekf(h_thr[t], h_x0[t], h_acc[t], compensate=True, out=h_ekf)
+            sol.solve_windowed(h_x0[t], h_lines[t], h_ekf[1], out=h_out)
+        else:
+            sol.solve_windowed(h_x0[t], h_lines[t], h_p, out=h_out)
+
+    restart()
     for t in range(W):
-        sol.solve_windowed(h_x0[t], h_lines[t], h_p, out=h_out)
+        host_tick(t)
     barrier()
     t0 = time.perf_counter()
     for t in range(W, W + K):
-        sol.solve_windowed(h_x0[t], h_lines[t], h_p, out=h_out)
+        host_tick(t)
     barrier()
     dt_e2e = time.perf_counter() - t0
     e2e_ok = bool((h_out[2] == 0).all()) and bool(np.isfinite(h_out[0]).all())
-    h2d = (B * 12 + B * 16) * 8 + B * 4          # x0, p (fp64) and one trajectory row index per instance (int32)
-    d2h = (B * 4 + B * 6) * 8 + B * 4
+    if dob:     # thrusts, measurement (= x0), body acceleration, row index up; disturbance, p, u0, thrust, status down; p up again
+        h2d = (B * 6 + B * 12 + B * 6 + B * 16) * 8 + B * 4
+        d2h = (B * 6 + B * 16 + B * 4 + B * 6) * 8 + B * 4
+    else:
+        h2d = (B * 12 + B * 16) * 8 + B * 4      # x0, p (fp64) and one trajectory row index per instance (int32)
+        d2h = (B * 4 + B * 6) * 8 + B * 4
 
     if distributed:
         tt = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=dev)
@@ -309,16 +381,20 @@ def run_ours(args):
             "metric": METRIC, "value": world * B * K / dt, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"config 2: batch {B} per GPU, random x0 around the circle reference (pos spread "
-                                   f"{args.pos_spread} m), N={N}, Ts={1.0 / N:g} s, fp64, closed loop (nominal ERK4 plant at 0.05 s), "
-                                   f"iterate carried between ticks", "batch_per_gpu": B, "global_batch": world * B, "horizon": N,
+            "config": {"workload": (f"config 3: batch {B} per GPU DOB-MPC (18-state EKF -> parameters -> RTI solve, back to back on "
+                                    f"one stream), sampled wave disturbances, lemniscate reference, N={N}, fp64; inputs recorded from the settled "
+                                    f"closed loop driven by the uncompensated command (see record_closed_loop_dob)"
+                                    if dob else
+                                    f"config 2: batch {B} per GPU, random x0 around the circle reference (pos spread "
+                                    f"{args.pos_spread} m), N={N}, Ts={1.0 / N:g} s, fp64, closed loop (nominal ERK4 plant at 0.05 s), "
+                                    f"iterate carried between ticks"), "batch_per_gpu": B, "global_batch": world * B, "horizon": N,
                        "mean_ipm_iterations": iters_mean, "nonzero_status": n_bad, "fast_path": not args.no_fast_path,
                        "l2": "per-tick working set (stage records + factors + iterates) "
                              f"{B * N * (208 + 64 + 64) * 8 / 1e6:.0f} MB > 126 MB L2; distinct input buffers per step",
                        "parallelism": f"{world} x independent shards" + (", one NCCL all-gather of the thrust vectors per tick" if distributed else "")},
             "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ok": e2e_ok,
                     "ms_per_step": 1e3 * dt_e2e / K},
-            "gpu_launches": 2 * K,
+            "gpu_launches": (3 if dob else 2) * K,
             "kernels": {"linearize_ms": 1e3 * float(np.mean(t_lin)), "ipm_ms": 1e3 * t_ipm_avg,
                         "ipm_share_of_step": t_ipm_avg / (dt / K)},
             "roofline": {"kernel": "ipm_kernel (Riccati sweeps)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -328,7 +404,7 @@ def run_ours(args):
             "clocks": clocks,
         }
         # ---- CPU baseline on this box's host cores (bounded sample) ----
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and not dob:
             r = cpu_leg(N, budget_s=args.cpu_budget, ticks_wanted=3 + 2, seed=0, pos_spread=args.pos_spread)
             tcpu = float(np.sum(r["times"][2:]))
             line["cpu_baseline"] = {"value": r["batch"] * 3 / tcpu, "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -349,6 +425,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
     ap.add_argument("--horizon", type=int, default=40)
     ap.add_argument("--pos-spread", type=float, default=0.5)
+    ap.add_argument("--workload", default="tracking", choices=["tracking", "dob"],
+                    help="tracking = BASELINE config 2 (default, the headline); dob = config 3 (EKF + solve per tick)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline / reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fast-path", action="store_true", help="always run the interior-point iteration (diagnostic)")
