@@ -66,7 +66,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for src in sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-Xptxas", "-v",
+        extra = os.environ.get("BR2_NVCC_DEFS", "").split()     # tuning experiments, e.g. "-DBR2_NSLOT=3 -DBR2_IPM_MINB=5"
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *extra, "-Xptxas", "-v",
                "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
         out = subprocess.run(cmd, capture_output=True, text=True)
         if out.returncode != 0:

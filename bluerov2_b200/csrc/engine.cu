@@ -106,7 +106,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     for (int i = 0; i < 4; i++) { s->lbu[i] = -50.0; s->ubu[i] = 50.0; }
     s->max_iter = 50;
     s->fast_path = 1;
-    s->tol = 1e-11;
+    s->tol = 1e-12;
     const size_t B = batch;
 #define DA(p, n)                                                                                          \
     do {                                                                                                  \

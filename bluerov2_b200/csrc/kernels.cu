@@ -18,6 +18,17 @@
 #include "engine.h"
 #include <stdint.h>
 
+// occupancy knobs (defaults = the measured best; scripts/gpu_tune.sh rebuilds with others)
+#ifndef BR2_NSLOT
+#define BR2_NSLOT 4
+#endif
+#ifndef BR2_IPM_MINB
+#define BR2_IPM_MINB 4
+#endif
+#ifndef BR2_LIN_MINB
+#define BR2_LIN_MINB 2
+#endif
+
 namespace br2 {
 
 #define FULL_MASK 0xffffffffu
@@ -33,7 +44,7 @@ namespace br2 {
 // lane l of the team holds slots 2l and 2l+1.
 constexpr int LIN_TEAM = 8;
 
-__global__ void __launch_bounds__(128) linearize_kernel(SolveArgs a)
+__global__ void __launch_bounds__(128, BR2_LIN_MINB) linearize_kernel(SolveArgs a)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -190,8 +201,12 @@ __device__ __forceinline__ double warp_sum(double v)
 
 
 // ---- per-warp TMA bulk-copy pipeline: stage records are prefetched HBM -> shared memory one stage ahead ----
+#ifdef BR2_EXP_EXTRACOPY
+struct __align__(128) StageBuf { double G[GREC]; double F[FREC]; double V[VREC]; double dummy[VREC]; };
+#else
 struct __align__(128) StageBuf { double G[GREC]; double F[FREC]; double V[VREC]; };
-constexpr int NSLOT = 4;     // ring depth: records of NSLOT-1 stages are in flight ahead of the one being computed
+#endif
+constexpr int NSLOT = BR2_NSLOT;     // ring depth: records of NSLOT-1 stages are in flight ahead of the one being computed
 struct __align__(128) WarpSmem { StageBuf st[NSLOT]; unsigned long long bar[NSLOT]; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -292,8 +307,16 @@ struct Inst {
     {
         if (lane == 0) {
             const uint32_t bar = smem_u32(&sm.bar[s]), dst = smem_u32(&sm.st[s]);
+#ifdef BR2_EXP_EXTRACOPY
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         ::"r"(bar), "r"((uint32_t)((GREC + 2 * VREC + (NEED_F ? FREC : 0)) * sizeof(double))) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + (uint32_t)((GREC + FREC + VREC) * sizeof(double))), "l"(V + (size_t)k * VREC),
+                           "r"((uint32_t)(VREC * sizeof(double))), "r"(bar) : "memory");
+#else
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                          ::"r"(bar), "r"((uint32_t)((GREC + VREC + (NEED_F ? FREC : 0)) * sizeof(double))) : "memory");
+#endif
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(G + (size_t)k * GREC), "r"((uint32_t)(GREC * sizeof(double))), "r"(bar) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -708,7 +731,7 @@ __device__ __forceinline__ double step_to_boundary(double v, double dv)
     return dv < 0.0 ? -v / dv : 2.0;   // 2 = "not blocking" (callers clamp at 1)
 }
 
-__global__ void __launch_bounds__(IPM_WARPS * 32, 4) ipm_kernel(SolveArgs a)
+__global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(SolveArgs a)
 {
     __shared__ WarpSmem smem[IPM_WARPS];
     const int lane = threadIdx.x & 31;
@@ -913,7 +936,7 @@ void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
     cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
     const int warps_needed = a.B;
     int blocks = (warps_needed + IPM_WARPS - 1) / IPM_WARPS;
-    const int max_blocks = sm_count * 4;   // 4 blocks x 4 warps resident per SM (<= 128 registers, 45 KB of staging buffers each)
+    const int max_blocks = sm_count * BR2_IPM_MINB;   // 4 blocks x 4 warps resident per SM (<= 128 registers, 45 KB of staging buffers each)
     if (blocks > max_blocks) blocks = max_blocks;
     ipm_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
 }

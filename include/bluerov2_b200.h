@@ -63,7 +63,7 @@ BR2_API int br2_batch_set_weights(br2_batch_solver *s, const double *W16, const 
 BR2_API int br2_batch_set_bounds(br2_batch_solver *s, const double *lbu4, const double *ubu4);
 /* == bluerov2_acados_update_time_steps (acados_solver_bluerov2.c:111-132): Ts and cost scaling per stage */
 BR2_API int br2_batch_set_time_steps(br2_batch_solver *s, const double *time_steps);
-/* options: "qp_iter_max" (int, default 50), "qp_tol" (double, default 1e-11), "fast_path" (int, default 1: try the
+/* options: "qp_iter_max" (int, default 50), "qp_tol" (double, default 1e-12), "fast_path" (int, default 1: try the
  * unconstrained Riccati solution first and accept it when it lies inside the input box -- it is then the exact QP
  * minimiser; 0 = always run the interior-point iteration) */
 BR2_API int br2_batch_set_option_int(br2_batch_solver *s, const char *name, int v);
