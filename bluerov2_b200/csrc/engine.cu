@@ -426,6 +426,21 @@ extern "C" long long br2_batch_ipm_iterations_total(br2_batch_solver* s, int res
     return (long long)v;
 }
 
+// ---- nominal plant (closed-loop studies on the device) ----
+extern "C" int br2_plant_step_device(int batch, double* d_x, const double* d_u, const double* d_p, const double* d_dist,
+                                     const double* d_wave_amp, const double* d_wave_tau0, int tick, double h,
+                                     double* d_body_acc, int* d_lines, void* stream)
+{
+    if (batch < 1 || !d_x || !d_u || !d_p || !(h > 0)) return fail(BR2_EINVAL, "br2_plant_step_device: bad argument");
+    if ((d_wave_amp == nullptr) != (d_wave_tau0 == nullptr)) return fail(BR2_EINVAL, "br2_plant_step_device: wave_amp and wave_tau0 go together");
+    PlantArgs a;
+    a.B = batch; a.x = d_x; a.u = d_u; a.p = d_p; a.dist = d_dist; a.wave_amp = d_wave_amp; a.wave_tau0 = d_wave_tau0;
+    a.body_acc = d_body_acc; a.lines = d_lines; a.h = h; a.tick = tick;
+    launch_plant(a, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+
 // ---- EKF ------------------------------------------------------------------------------------------------
 extern "C" int br2_batch_ekf_reset(br2_batch_solver* s)
 {

@@ -70,4 +70,20 @@ struct EkfArgs {
 };
 void launch_ekf(const EkfArgs& a, cudaStream_t s);
 
+// nominal plant (plant.cu): x <- RK4_h(x, u, p + disturbance); optional wave disturbance, body acceleration, line counter
+struct PlantArgs {
+    int B;
+    double* x;               // [B][12] in/out
+    const double* u;         // [B][4]
+    const double* p;         // [B][16]
+    const double* dist;      // [B][4] extra disturbance on p[0..3], or null
+    const double* wave_amp;  // [B][4] wave amplitudes (A_x, A_y, A_z, A_y/3), or null
+    const double* wave_tau0; // [B]    wave phases
+    double* body_acc;        // [B][6] out, or null
+    int* lines;              // [B] in/out trajectory row counters, or null
+    double h;
+    int tick;
+};
+void launch_plant(const PlantArgs& a, cudaStream_t s);
+
 }  // namespace br2

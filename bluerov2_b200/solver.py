@@ -69,6 +69,7 @@ def load_library(path: str | None = None):
         "br2_batch_last_solve_time": (C.c_double, [V]),
         "br2_batch_last_kernel_times": (C.c_int, [V, _D, _D]),
         "br2_batch_ipm_iterations_total": (C.c_longlong, [V, C.c_int]),
+        "br2_plant_step_device": (C.c_int, [C.c_int, V, V, V, V, V, V, C.c_int, C.c_double, V, V, V]),
         "br2_batch_ekf_reset": (C.c_int, [V]),
         "br2_batch_ekf_device": (C.c_int, [V, V, V, V, V, V, C.c_int, V]),
         "br2_batch_ekf_host": (C.c_int, [V, V, V, V, V, V, C.c_int]),
@@ -299,6 +300,25 @@ class BatchSolver:
         x = None if x is None else _np(x, (self.B, NEKF))
         P = None if P is None else _np(P, (self.B, NEKF, NEKF))
         self._check(self._L.br2_batch_ekf_set_state_host(self._h, _ptr(x), _ptr(P)))
+
+
+def plant_step(x, u, p, h: float = 0.05, dist=None, wave=None, tick: int = 0, body_acc=None, lines=None):
+    """Nominal plant on the device (torch CUDA tensors, in place on ``x``): one RK4 step of the OCP model per instance.
+    ``wave`` = (amp[B,4], tau0[B]) adds the sampled wave wrench at ``tick``; ``body_acc`` [B,6] receives the finite-
+    differenced body velocities; ``lines`` [B] int32 is incremented.  Enqueues on torch's current stream."""
+    import torch
+    L = load_library()
+    B = x.shape[0]
+    for t, shp, dt in ((x, (B, NX), torch.float64), (u, (B, NU), torch.float64), (p, (B, NP), torch.float64)):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous() or tuple(t.shape) != shp:
+            raise ValueError(f"expected contiguous CUDA {dt} tensor of shape {shp}")
+    amp, tau0 = wave if wave is not None else (None, None)
+    stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    rc = L.br2_plant_step_device(int(B), _ptr(x), _ptr(u), _ptr(p), _ptr(dist), _ptr(amp), _ptr(tau0), int(tick), float(h),
+                                 _ptr(body_acc), _ptr(lines), stream)
+    if rc != 0:
+        raise SolverError(f"bluerov2_b200 error {rc}: {L.br2_last_error().decode()}")
+    return x
 
 
 def device_count() -> int:

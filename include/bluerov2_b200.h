@@ -112,6 +112,16 @@ BR2_API int br2_batch_last_kernel_times(br2_batch_solver *s, double *t_linearize
  * the roofline formula bytes_sweep = 4384 * N * n_it) */
 BR2_API long long br2_batch_ipm_iterations_total(br2_batch_solver *s, int reset);
 
+/* Nominal plant for device-resident closed-loop studies: one RK4 step of length h of the OCP model
+ * (bluerov2_dobmpc/scripts/bluerov2.py:103-137) per instance, x[B][12] in place, inputs u[B][4], parameters p[B][16].
+ * Optional (NULL to skip): d_dist[B][4] extra disturbance on p[0..3]; d_wave_amp[B][4] + d_wave_tau0[B] the wave wrench of
+ * applyBodyWrench mode 0 (bluerov2_dob.cpp:774-797) at tick `tick`; d_body_acc[B][6] out = finite-differenced body
+ * velocities (bluerov2_dob.cpp:148-153); d_lines[B] trajectory row counters, incremented (line_number++, :367).
+ * Uses the device of the pointers' current context; only enqueues on `stream`. */
+BR2_API int br2_plant_step_device(int batch, double *d_x, const double *d_u, const double *d_p, const double *d_dist,
+                                  const double *d_wave_amp, const double *d_wave_tau0, int tick, double h,
+                                  double *d_body_acc, int *d_lines, void *stream);
+
 /* == BLUEROV2_DOB::EKF (bluerov2_dob.cpp:495-545) for every instance, on the solver's stream order.
  * esti_x[B][18], esti_P[B][18][18] live in the solver (br2_batch_ekf_reset sets x = (0,0,-20,0..,6,6,6,0,0,0),
  * P = I: bluerov2_dob.cpp:64-65).  thrusts[B][6] = measured thruster forces, meas[B][12] = pose + body velocities,

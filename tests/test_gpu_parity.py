@@ -431,3 +431,45 @@ def test_single_instance_batch(solver_mod, oracle):
         line = line + 1
         s.set_iterate(X, U)
     s.close()
+
+
+def test_device_closed_loop_matches_host_loop(solver_mod, oracle):
+    """Device-resident closed loop (SURVEY 8f): solve -> plant step -> row counter, nothing leaves the GPU between ticks;
+    compared with the same loop stepped on the host (oracle plant), including the wave disturbance and body acceleration."""
+    import torch
+    N, B, T = 20, 64, 12
+    dev = torch.device("cuda", 0)
+    w = wl.tracking_batch(B, N, seed=13, reference="lemniscate", pos_spread=0.4)
+    amp, tau0 = wl.wave_disturbance(B, seed=2)
+    s = solver_mod.BatchSolver(B, N)
+    s.set_trajectory(w["traj"])
+    s.set_iterate(w["X"], w["U"])
+    x = torch.from_numpy(w["x0"].copy()).to(dev)
+    lines = torch.from_numpy(w["lines"].astype(np.int32)).to(dev)
+    p = torch.from_numpy(w["p"]).to(dev)
+    d_amp, d_tau0 = torch.from_numpy(amp).to(dev), torch.from_numpy(tau0).to(dev)
+    acc = torch.zeros((B, 6), dtype=torch.float64, device=dev)
+    out = None
+    xh, lh = w["x0"].copy(), w["lines"].copy()
+    s2 = solver_mod.BatchSolver(B, N); s2.set_trajectory(w["traj"]); s2.set_iterate(w["X"], w["U"])
+    for t in range(T):
+        out = s.solve_windowed(x, lines, p, out=out)
+        solver_mod.plant_step(x, out[0], p, 0.05, wave=(d_amp, d_tau0), tick=t, body_acc=acc, lines=lines)
+        # host-stepped twin
+        u0h, _, sth = s2.solve_windowed(xh, lh.astype(np.int32), w["p"])
+        assert (sth == 0).all()
+        xn = wl.plant_step(xh, u0h, w["p"], 0.05, dist=wl.wave_at(amp, tau0, t))
+        acch = (xn[:, 6:12] - xh[:, 6:12]) / 0.05
+        xh, lh = xn, lh + 1
+    torch.cuda.synchronize()
+    assert (out[2].cpu().numpy() == 0).all()
+    assert np.array_equal(lines.cpu().numpy(), lh.astype(np.int32))
+    assert np.abs(x.cpu().numpy() - xh).max() < 1e-9
+    assert np.abs(acc.cpu().numpy() - acch).max() < 1e-7
+    # one plant step against the oracle's RK4
+    x1 = torch.from_numpy(w["x0"].copy()).to(dev)
+    u1 = torch.from_numpy(np.random.default_rng(0).uniform(-20, 20, (B, 4))).to(dev)
+    solver_mod.plant_step(x1, u1, p, 0.05)
+    want = np.stack([oracle.erk4(w["x0"][i], u1.cpu().numpy()[i], w["p"][i], 0.05) for i in range(B)])
+    assert np.abs(x1.cpu().numpy() - want).max() < 1e-12
+    s.close(); s2.close()
