@@ -473,3 +473,36 @@ def test_device_closed_loop_matches_host_loop(solver_mod, oracle):
     want = np.stack([oracle.erk4(w["x0"][i], u1.cpu().numpy()[i], w["p"][i], 0.05) for i in range(B)])
     assert np.abs(x1.cpu().numpy() - want).max() < 1e-12
     s.close(); s2.close()
+
+
+def test_hint_carried_across_ticks(solver_mod):
+    """closed loop from a large offset: bounds are active for the first ticks, then release.  The hint that steers fast
+    path vs interior-point iteration is carried on the device across ticks; both settings must produce the same
+    controls (each method returns the unique QP minimiser), with the fast path taking over once the bounds release."""
+    N, B, T = 40, 256, 40
+    w = wl.tracking_batch(B, N, seed=23, pos_spread=3.0)
+    sols = []
+    for fp in (0, 1):
+        s = solver_mod.BatchSolver(B, N)
+        s.set_option("fast_path", fp)
+        s.set_trajectory(w["traj"])
+        s.set_iterate(w["X"], w["U"])
+        sols.append(s)
+    x = [w["x0"].copy(), w["x0"].copy()]
+    lines = w["lines"].astype(np.int32)
+    frac_fast = []
+    for t in range(T):
+        us = []
+        for k, s in enumerate(sols):
+            u0, _, st = s.solve_windowed(x[k], lines + t, w["p"])
+            assert (st == 0).all(), (t, k, np.unique(st, return_counts=True))
+            us.append(u0.copy())
+        assert np.abs(us[0] - us[1]).max() < 1e-5, (t, np.abs(us[0] - us[1]).max())
+        it, _ = sols[1].stats()
+        frac_fast.append(float((it == 1).mean()))
+        for k in range(2):
+            x[k] = wl.plant_step(x[k], us[k], w["p"], 0.05)
+    assert np.abs(x[0] - x[1]).max() < 1e-4
+    assert frac_fast[0] < 0.9 and frac_fast[-1] > 0.9, frac_fast      # saturated at first, interior at the end
+    for s in sols:
+        s.close()
