@@ -26,7 +26,11 @@
 #define BR2_IPM_MINB 4
 #endif
 #ifndef BR2_LIN_MINB
+#ifdef BR2_LIN_V1
 #define BR2_LIN_MINB 2
+#else
+#define BR2_LIN_MINB 12
+#endif
 #endif
 
 namespace br2 {
@@ -36,6 +40,253 @@ namespace br2 {
 // ------------------------------------------------------------------------------------------------------
 // linearisation
 // ------------------------------------------------------------------------------------------------------
+#ifndef BR2_LIN_V1
+// v2: one warp per round of LRND (instance, stage) pairs, three phases with three lane mappings so that nothing is
+// computed redundantly:
+//   A   lane per stage: the RK4 STATE trajectory only (x_1..x_4, 3 sincos + f per RK stage; the sensitivities do not
+//       feed back into it) -> RK-stage states and trig values to shared memory, Phi -> b_k, cost gradients -> tail of G_k.
+//   J   lane per (stage, RK stage), LSUB stages at a time: the 48 structural non-zeros of df/dx at x_s -> shared memory.
+//   B   8-lane team per stage, a lane carries two of the 16 column slots of Z = [A|B] through the four RK stages with the
+//       Jacobians read back from shared memory (LDS.128, broadcast inside the team): 48 FMAs per column and RK stage.
+//       slots 0..12 = columns 3..15 of Z (Sx columns 3..11, Su); slots 13..15 = the constant columns 0..2 ([I;0]:
+//       positions do not enter f, so J annihilates them and the same code writes them).
+// (v1 formed the Jacobian, the sincos and f once per lane of the team, 8x redundantly: profiles/r01f_lin_ncu_summary.txt.)
+#ifndef BR2_LIN_RND
+#define BR2_LIN_RND 16
+#endif
+#ifndef BR2_LIN_SUB
+#define BR2_LIN_SUB 4
+#endif
+constexpr int LRND = BR2_LIN_RND;              // stages per warp round (16 or 32)
+constexpr int LSUB = BR2_LIN_SUB;              // stages per Jacobian sub-round (4 or 8)
+constexpr int XT_F = 15;                       // x[3..11], sphi cphi sth cth spsi cpsi
+constexpr int XT_SSTRIDE = XT_F * LRND + 8;    // +8: RK-stage planes land on different banks for the J-phase reads
+constexpr int CS_F = 18;                       // imx imy imz imn | dl[4] | dnl[4] | ju[5] | h
+constexpr int JREC = 50;                       // 48 + 2: 128-bit accesses of consecutive records are conflict-free
+static_assert(LRND % LSUB == 0 && LSUB % 4 == 0 && LSUB * 4 <= 32 && LRND <= 32, "lineariser tiling");
+
+struct __align__(16) LinSmem {
+    double jb[LSUB * 4 * JREC];
+    double xt[4 * XT_SSTRIDE];
+    double cs[CS_F * LRND];
+};
+__device__ __forceinline__ int xt_idx(int s, int f, int slot) { return s * XT_SSTRIDE + f * LRND + slot; }
+
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+#define BR2_JAC_FIELDS(X) \
+    X(j03) X(j04) X(j05) X(j06) X(j07) X(j08) X(j13) X(j14) X(j15) X(j16) X(j17) X(j18) \
+    X(j23) X(j24) X(j26) X(j27) X(j28) X(j33) X(j34) X(j35) X(j3a) X(j3b) X(j43) X(j4a) \
+    X(j4b) X(j53) X(j54) X(j5a) X(j5b) X(j64) X(j66) X(j73) X(j74) X(j77) X(j83) X(j84) \
+    X(j88) X(j93) X(j94) X(j9a) X(j9b) X(ja4) X(ja9) X(jab) X(jb9) X(jba) X(jbb)
+// 47 named fields + one pad = 24 double2
+
+__device__ __forceinline__ void jac_store(const Jac& J, double* dst)
+{
+    double v[48];
+    int n = 0;
+#define X(f) v[n++] = J.f;
+    BR2_JAC_FIELDS(X)
+#undef X
+    v[47] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 24; i++) reinterpret_cast<double2*>(dst)[i] = make_double2(v[2 * i], v[2 * i + 1]);
+}
+__device__ __forceinline__ void jac_load(Jac& J, const double* src)
+{
+    double v[48];
+#pragma unroll
+    for (int i = 0; i < 24; i++) {
+        const double2 d = reinterpret_cast<const double2*>(src)[i];
+        v[2 * i] = d.x; v[2 * i + 1] = d.y;
+    }
+    int n = 0;
+#define X(f) J.f = v[n++];
+    BR2_JAC_FIELDS(X)
+#undef X
+}
+
+// phase A for one stage (lane-private)
+__device__ __forceinline__ void lin_phase_a(const SolveArgs& a, LinSmem& sm, int slot, int gs, bool live)
+{
+    const int inst = gs / a.N, k = gs - inst * a.N;
+    const double* p = a.p + (size_t)inst * a.p_inst_stride + (size_t)k * a.p_stage_stride;
+    ModelConst mc;
+    {
+        double pl[NP];
+#pragma unroll
+        for (int i = 0; i < NP; i++) pl[i] = __ldg(p + i);
+        mc.set(pl);
+    }
+    const double h = __ldg(a.Ts + k);
+    const double* Xk = a.X + ((size_t)inst * (a.N + 1) + k) * NX;
+    double x0v[NX], xs[NX], acc[NX], u[NU];
+#pragma unroll
+    for (int i = 0; i < NX; i++) { x0v[i] = __ldg(Xk + i); xs[i] = x0v[i]; acc[i] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < NU; i++) u[i] = __ldg(a.U + ((size_t)inst * a.N + k) * NU + i);
+#pragma unroll 1
+    for (int s = 0; s < 4; s++) {
+        Trig t;
+        trig_of(xs, t);
+        double f[NX];
+        ode(xs, u, mc, t, f);
+        double* xt = sm.xt + xt_idx(s, 0, slot);
+#pragma unroll
+        for (int i = 0; i < 9; i++) xt[i * LRND] = xs[3 + i];
+        xt[9 * LRND] = t.sphi; xt[10 * LRND] = t.cphi; xt[11 * LRND] = t.sth;
+        xt[12 * LRND] = t.cth; xt[13 * LRND] = t.spsi; xt[14 * LRND] = t.cpsi;
+        const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
+        const double cn = (s == 2) ? 1.0 : 0.5;     // c_{s+1} of the classical tableau
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+            acc[i] = fma(bw, f[i], acc[i]);
+            xs[i] = fma(cn * h, f[i], x0v[i]);
+        }
+    }
+    double* cs = sm.cs + slot;
+    cs[0 * LRND] = mc.imx; cs[1 * LRND] = mc.imy; cs[2 * LRND] = mc.imz; cs[3 * LRND] = mc.imn;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { cs[(4 + i) * LRND] = mc.dl[i]; cs[(8 + i) * LRND] = mc.dnl[i]; }
+    cs[12 * LRND] = mc.ju_surge; cs[13 * LRND] = mc.ju_sway; cs[14 * LRND] = mc.ju_heave;
+    cs[15 * LRND] = mc.ju_yaw2; cs[16 * LRND] = mc.ju_yaw4; cs[17 * LRND] = h;
+    if (!live) return;
+    // tail of the stage record: b_k, qlin_k, rlin_k, Ts_k, pad (32 doubles, 32-byte aligned)
+    double* Gt = a.G + (size_t)gs * GREC + G_B_OFF;
+    const double* yr = yref_row(a, inst, k);
+    const double* Xn = Xk + NX;
+    double tl[32];
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+        tl[i] = fma(h, acc[i], x0v[i]) - __ldg(Xn + i);
+        tl[12 + i] = h * a.W[i] * (x0v[i] - __ldg(yr + i));
+    }
+#pragma unroll
+    for (int i = 0; i < NU; i++) tl[24 + i] = h * a.W[NX + i] * (u[i] - __ldg(yr + NX + i));
+    tl[28] = h; tl[29] = tl[30] = tl[31] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) st256(Gt + 4 * i, tl[4 * i], tl[4 * i + 1], tl[4 * i + 2], tl[4 * i + 3]);
+}
+static_assert(G_B_OFF == 192 && G_QLIN == 204 && G_RLIN == 216 && G_TS == 220 && GREC == 224, "tail layout");
+
+__global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a)
+{
+    __shared__ LinSmem sm;
+    const int lane = threadIdx.x;
+    const int total = a.B * a.N;
+    const int base = blockIdx.x * LRND;
+    if (lane < LRND) {
+        const int gs = base + lane;
+        lin_phase_a(a, sm, lane, gs < total ? gs : total - 1, gs < total);
+    }
+    __syncwarp();
+
+    const int tm = lane >> 3, l = lane & 7;
+    // my two column slots: Z column, unit seed row (or none), Su column (or none)
+    const int sa = 2 * l, sb = 2 * l + 1;
+    const int zca = sa < 13 ? sa + 3 : sa - 13, zcb = sb < 13 ? sb + 3 : sb - 13;
+    const int seed_a = zca < NX ? zca : -1, seed_b = zcb < NX ? zcb : -1;
+    const int su_a = zca - NX, su_b = zcb - NX;
+
+#pragma unroll 1
+    for (int r = 0; r < LRND / LSUB; r++) {
+        // ---- phase J: Jacobians of LSUB stages x 4 RK stages ----
+        if (lane < LSUB * 4) {
+            const int s = lane / LSUB, i = lane % LSUB;
+            const int slot = r * LSUB + i;
+            double xs[NX];
+            xs[0] = xs[1] = xs[2] = 0.0;
+            const double* xt = sm.xt + xt_idx(s, 0, slot);
+#pragma unroll
+            for (int f = 0; f < 9; f++) xs[3 + f] = xt[f * LRND];
+            Trig t;
+            t.sphi = xt[9 * LRND]; t.cphi = xt[10 * LRND]; t.sth = xt[11 * LRND];
+            t.cth = xt[12 * LRND]; t.spsi = xt[13 * LRND]; t.cpsi = xt[14 * LRND];
+            const double* cs = sm.cs + slot;
+            ModelConst mc;
+            mc.imx = cs[0 * LRND]; mc.imy = cs[1 * LRND]; mc.imz = cs[2 * LRND]; mc.imn = cs[3 * LRND];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { mc.dl[j] = cs[(4 + j) * LRND]; mc.dnl[j] = cs[(8 + j) * LRND]; }
+            Jac J;
+            jac_of(xs, mc, t, J);
+            jac_store(J, sm.jb + (i * 4 + s) * JREC);
+        }
+        __syncwarp();
+        // ---- phase B: sensitivities, 4 stages per pass ----
+#pragma unroll 1
+        for (int pp = 0; pp < LSUB / 4; pp++) {
+            const int si = pp * 4 + tm;
+            const int slot = r * LSUB + si;
+            const int gs = base + slot;
+            const double* cs = sm.cs + slot;
+            const double h = cs[17 * LRND];
+            const double ja6 = su_a == 0 ? cs[12 * LRND] : 0.0, jb6 = su_b == 0 ? cs[12 * LRND] : 0.0;
+            const double ja7 = su_a == 1 ? cs[13 * LRND] : 0.0, jb7 = su_b == 1 ? cs[13 * LRND] : 0.0;
+            const double ja8 = su_a == 2 ? cs[14 * LRND] : 0.0, jb8 = su_b == 2 ? cs[14 * LRND] : 0.0;
+            const double jab_ = su_a == 1 ? cs[15 * LRND] : (su_a == 3 ? cs[16 * LRND] : 0.0);
+            const double jbb_ = su_b == 1 ? cs[15 * LRND] : (su_b == 3 ? cs[16 * LRND] : 0.0);
+            double ca[NX], cb[NX], aa[NX], ab[NX];
+#pragma unroll
+            for (int i = 0; i < NX; i++) {
+                ca[i] = (i == seed_a) ? 1.0 : 0.0;
+                cb[i] = (i == seed_b) ? 1.0 : 0.0;
+                aa[i] = 0.0; ab[i] = 0.0;
+            }
+#pragma unroll 1
+            for (int s = 0; s < 4; s++) {
+                Jac J;
+                jac_load(J, sm.jb + (si * 4 + s) * JREC);
+                double ka[NX], kb[NX];
+                jac_mul(J, ca, ka);
+                jac_mul(J, cb, kb);
+                ka[6] += ja6; ka[7] += ja7; ka[8] += ja8; ka[11] += jab_;
+                kb[6] += jb6; kb[7] += jb7; kb[8] += jb8; kb[11] += jbb_;
+                const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
+                const double ch = ((s == 2) ? 1.0 : 0.5) * h;
+#pragma unroll
+                for (int i = 0; i < NX; i++) {
+                    aa[i] = fma(bw, ka[i], aa[i]);
+                    ab[i] = fma(bw, kb[i], ab[i]);
+                }
+#pragma unroll
+                for (int i = 3; i < NX; i++) {      // rows 0..2 never feed back (columns 0..2 of J are zero)
+                    ca[i] = fma(ch, ka[i], (i == seed_a) ? 1.0 : 0.0);
+                    cb[i] = fma(ch, kb[i], (i == seed_b) ? 1.0 : 0.0);
+                }
+            }
+            if (gs < total) {
+                double* Gk = a.G + (size_t)gs * GREC;
+                double* da = Gk + (((zca >> 3)) << 5) + ((zca & 7) << 2);     // g_off(0, zc); row block ki adds 64
+                double* db = Gk + (((zcb >> 3)) << 5) + ((zcb & 7) << 2);
+#pragma unroll
+                for (int ki = 0; ki < 3; ki++) {
+                    double oa[4], ob[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int i = 4 * ki + j;
+                        oa[j] = fma(h, aa[i], (i == seed_a) ? 1.0 : 0.0);
+                        ob[j] = fma(h, ab[i], (i == seed_b) ? 1.0 : 0.0);
+                    }
+                    st256(da + 64 * ki, oa[0], oa[1], oa[2], oa[3]);
+                    st256(db + 64 * ki, ob[0], ob[1], ob[2], ob[3]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+void launch_linearize(const SolveArgs& a, cudaStream_t s)
+{
+    const long long total = (long long)a.B * a.N;
+    const int grid = (int)((total + LRND - 1) / LRND);
+    linearize_kernel<<<grid, 32, 0, s>>>(a);
+}
+
+#else   // BR2_LIN_V1
 // One 8-lane team per (instance, stage); a lane carries TWO of the 16 column slots of the augmented state through
 // the RK4 stages, so the stage Jacobian (the 48 non-zeros of df/dx) is formed once per two columns:
 //   slot 0 = state x (evolves by f), slots 1..9 = Sx columns 3..11, slots 10..13 = Su columns 0..3,
@@ -160,6 +411,8 @@ void launch_linearize(const SolveArgs& a, cudaStream_t s)
     const int grid = (int)((threads + block - 1) / block);
     linearize_kernel<<<grid, block, 0, s>>>(a);
 }
+
+#endif  // BR2_LIN_V1
 
 // ------------------------------------------------------------------------------------------------------
 // Riccati interior-point kernel
