@@ -22,8 +22,11 @@
 #ifndef BR2_NSLOT
 #define BR2_NSLOT 4
 #endif
+#ifndef BR2_IPM_WARPS
+#define BR2_IPM_WARPS 4
+#endif
 #ifndef BR2_IPM_MINB
-#define BR2_IPM_MINB 4
+#define BR2_IPM_MINB (16 / BR2_IPM_WARPS)
 #endif
 #ifndef BR2_LIN_MINB
 #ifdef BR2_LIN_V1
@@ -421,7 +424,7 @@ void launch_linearize(const SolveArgs& a, cudaStream_t s)
 // a 12- or 16-vector v over the warp:
 //   "row layout"   lane (q,t) holds v[4 ki + t], ki = 0..3   (what a B fragment column / a dot over t needs)
 //   "quad layout"  lane (q,*) holds v[q] and v[8 + q]        (what falls out of a reduction over t / a C fragment row)
-constexpr int IPM_WARPS = 4;
+constexpr int IPM_WARPS = BR2_IPM_WARPS;
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL_MASK, v, src); }
 __device__ __forceinline__ double shfl_x(double v, int m) { return __shfl_xor_sync(FULL_MASK, v, m); }
@@ -454,11 +457,7 @@ __device__ __forceinline__ double warp_sum(double v)
 
 
 // ---- per-warp TMA bulk-copy pipeline: stage records are prefetched HBM -> shared memory one stage ahead ----
-#ifdef BR2_EXP_EXTRACOPY
-struct __align__(128) StageBuf { double G[GREC]; double F[FREC]; double V[VREC]; double dummy[VREC]; };
-#else
 struct __align__(128) StageBuf { double G[GREC]; double F[FREC]; double V[VREC]; };
-#endif
 constexpr int NSLOT = BR2_NSLOT;     // ring depth: records of NSLOT-1 stages are in flight ahead of the one being computed
 struct __align__(128) WarpSmem { StageBuf st[NSLOT]; unsigned long long bar[NSLOT]; };
 
@@ -534,6 +533,43 @@ __device__ __forceinline__ void load_chol(const double* Fk, Chol4& L)
     L.i0 = Fk[F_ID_OFF + 0]; L.i1 = Fk[F_ID_OFF + 1]; L.i2 = Fk[F_ID_OFF + 2]; L.i3 = Fk[F_ID_OFF + 3];
 }
 
+// Explicit inverse of the symmetric positive definite 4x4 matrix with lower entries m (same packing as chol4) by
+// 2x2 sub-determinants: no dependent rsqrt/divide chain (one reciprocal), used where Lam is well conditioned (the
+// unconstrained LQR of the fast path: Lam = R + B'PB).  Returns false unless all leading minors are positive.
+struct Inv4 { double b00, b10, b11, b20, b21, b22, b30, b31, b32, b33; };
+__device__ __forceinline__ bool inv4(const double* m, Inv4& B)
+{
+    const double m00 = m[0], m10 = m[1], m11 = m[2], m20 = m[3], m21 = m[4], m22 = m[5], m30 = m[6], m31 = m[7],
+                 m32 = m[8], m33 = m[9];
+    const double s0 = m00 * m11 - m10 * m10, s1 = m00 * m21 - m10 * m20, s2 = m00 * m31 - m10 * m30;
+    const double s3 = m10 * m21 - m11 * m20, s4 = m10 * m31 - m11 * m30, s5 = m20 * m31 - m21 * m30;
+    const double c5 = m22 * m33 - m32 * m32, c4 = m21 * m33 - m31 * m32, c3 = m21 * m32 - m31 * m22;
+    const double c2 = m20 * m33 - m30 * m32, c1 = m20 * m32 - m30 * m22, c0 = m20 * m31 - m30 * m21;
+    const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    const double minor3 = m20 * s3 - m21 * s1 + m22 * s0;
+    const bool ok = (m00 > 0.0) && (s0 > 0.0) && (minor3 > 0.0) && (det > 0.0);
+    const double id = 1.0 / det;
+    B.b00 = (m11 * c5 - m21 * c4 + m31 * c3) * id;
+    B.b10 = (-m10 * c5 + m20 * c4 - m30 * c3) * id;
+    B.b11 = (m00 * c5 - m20 * c2 + m30 * c1) * id;
+    B.b20 = (m31 * s5 - m32 * s4 + m33 * s3) * id;
+    B.b21 = (-m30 * s5 + m32 * s2 - m33 * s1) * id;
+    B.b22 = (m30 * s4 - m31 * s2 + m33 * s0) * id;
+    B.b30 = (-m21 * s5 + m22 * s4 - m32 * s3) * id;
+    B.b31 = (m20 * s5 - m22 * s2 + m32 * s1) * id;
+    B.b32 = (-m20 * s4 + m21 * s2 - m32 * s0) * id;
+    B.b33 = minor3 * id;
+    return ok;
+}
+// v <- B v
+__device__ __forceinline__ void inv4_apply(const Inv4& B, const double* v, double* o)
+{
+    o[0] = B.b00 * v[0] + B.b10 * v[1] + B.b20 * v[2] + B.b30 * v[3];
+    o[1] = B.b10 * v[0] + B.b11 * v[1] + B.b21 * v[2] + B.b31 * v[3];
+    o[2] = B.b20 * v[0] + B.b21 * v[1] + B.b22 * v[2] + B.b32 * v[3];
+    o[3] = B.b30 * v[0] + B.b31 * v[1] + B.b32 * v[2] + B.b33 * v[3];
+}
+
 // Per-instance pointers
 struct Inst {
     const SolveArgs& a;
@@ -555,26 +591,19 @@ struct Inst {
         Ulin = a.U + (size_t)inst * N * NU;
     }
     // prefetch the records of stage k into slot s (one lane issues; completion lands on the slot's mbarrier)
-    template <bool NEED_F>
+    template <bool NEED_F, bool NEED_V>
     __device__ __forceinline__ void issue(int s, int k)
     {
         if (lane == 0) {
             const uint32_t bar = smem_u32(&sm.bar[s]), dst = smem_u32(&sm.st[s]);
-#ifdef BR2_EXP_EXTRACOPY
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                         ::"r"(bar), "r"((uint32_t)((GREC + 2 * VREC + (NEED_F ? FREC : 0)) * sizeof(double))) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + (uint32_t)((GREC + FREC + VREC) * sizeof(double))), "l"(V + (size_t)k * VREC),
-                           "r"((uint32_t)(VREC * sizeof(double))), "r"(bar) : "memory");
-#else
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                         ::"r"(bar), "r"((uint32_t)((GREC + VREC + (NEED_F ? FREC : 0)) * sizeof(double))) : "memory");
-#endif
+                         ::"r"(bar), "r"((uint32_t)((GREC + (NEED_V ? VREC : 0) + (NEED_F ? FREC : 0)) * sizeof(double))) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(G + (size_t)k * GREC), "r"((uint32_t)(GREC * sizeof(double))), "r"(bar) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + (uint32_t)((GREC + FREC) * sizeof(double))), "l"(V + (size_t)k * VREC),
-                           "r"((uint32_t)(VREC * sizeof(double))), "r"(bar) : "memory");
+            if (NEED_V)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + (uint32_t)((GREC + FREC) * sizeof(double))), "l"(V + (size_t)k * VREC),
+                               "r"((uint32_t)(VREC * sizeof(double))), "r"(bar) : "memory");
             if (NEED_F)
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(dst + (uint32_t)(GREC * sizeof(double))), "l"(F + (size_t)k * FREC),
@@ -583,24 +612,24 @@ struct Inst {
     }
     // Sweep pipeline.  Stages are visited in sequence i = 0..N-1 (k = i forward, k = N-1-i backward); slot = i % NSLOT.
     // begin(): everything this warp wrote to global so far must be visible to the copy engine, then fill the ring.
-    template <bool NEED_F, bool BACKWARD>
+    template <bool NEED_F, bool BACKWARD, bool NEED_V>
     __device__ __forceinline__ void begin()
     {
         __syncwarp();
         if (lane == 0) fence_proxy_async();
 #pragma unroll
         for (int j = 0; j < NSLOT - 1; j++)
-            if (j < N) issue<NEED_F>(j, BACKWARD ? N - 1 - j : j);
+            if (j < N) issue<NEED_F, NEED_V>(j, BACKWARD ? N - 1 - j : j);
     }
     // top of iteration i: the slot consumed by iteration i-1 is free (after the warp sync) -> refill it with the
     // records of stage i + NSLOT - 1, then wait for this iteration's records.  Returns the slot to read.
-    template <bool NEED_F, bool BACKWARD>
+    template <bool NEED_F, bool BACKWARD, bool NEED_V>
     __device__ __forceinline__ int advance(int i)
     {
         const int s = i % NSLOT;
         __syncwarp();
         const int j = i + NSLOT - 1;
-        if (j < N) issue<NEED_F>(j % NSLOT, BACKWARD ? N - 1 - j : j);
+        if (j < N) issue<NEED_F, NEED_V>(j % NSLOT, BACKWARD ? N - 1 - j : j);
         wait(s);
         return s;
     }
@@ -653,9 +682,9 @@ __device__ double forward_sweep(Inst& I)
     int o0[4], o1[4];                           // shared-memory offsets of my rows of Z (constant over the sweep)
 #pragma unroll
     for (int ki = 0; ki < 4; ki++) { o0[ki] = g_off(q, 4 * ki + t); o1[ki] = g_off(8 + (q & 3), 4 * ki + t); }
-    I.template begin<FEEDBACK, false>();
+    I.template begin<FEEDBACK, false, !FEEDBACK>();
     for (int k = 0; k < N; k++) {
-        const int s = I.template advance<FEEDBACK, false>(k);
+        const int s = I.template advance<FEEDBACK, false, !FEEDBACK>(k);
         const double* Gs = I.sm.st[s].G;
         const double* Fs = I.sm.st[s].F;
         const double* Vs = I.sm.st[s].V;
@@ -680,7 +709,7 @@ __device__ double forward_sweep(Inst& I)
             for (int ki = 0; ki < 3; ki++) part = fma(lo ? Fs[(4 * ki + t) * 4 + q] : 0.0, zr[ki], part);
             part += shfl_x(part, 1);
             part += shfl_x(part, 2);
-            const double uq = -Vs[V_KFF + (q & 3)] - part;
+            const double uq = -Fs[F_KFF + (q & 3)] - part;
             if (lo && t == 0) Vk[uoff + q] = uq;
             ut = shfl(uq, 4 * t);
         }
@@ -769,9 +798,9 @@ __device__ bool factor_sweep(Inst& I)
             pq1 = lo ? a.We[8 + e] * (I.Xlin[N * NX + 8 + e] - yN[8 + e]) : 0.0;
         }
     }
-    I.template begin<false, true>();
+    I.template begin<false, true, KIND == FS_IPM>();
     for (int k = N - 1, it = 0; k >= 0; k--, it++) {
-        const int s = I.template advance<false, true>(it);
+        const int s = I.template advance<false, true, KIND == FS_IPM>(it);
         const double* Gs = I.sm.st[s].G;
         const double* Vs = I.sm.st[s].V;
         double* Fk = I.F + (size_t)k * FREC;
@@ -855,58 +884,92 @@ __device__ bool factor_sweep(Inst& I)
         m10[3] = shfl(h[1][1][0], 4 * 6 + 2); m10[4] = shfl(h[1][1][1], 4 * 6 + 2); m10[5] = shfl(h[1][1][0], 4 * 6 + 3);
         m10[6] = shfl(h[1][1][0], 4 * 7 + 2); m10[7] = shfl(h[1][1][1], 4 * 7 + 2); m10[8] = shfl(h[1][1][0], 4 * 7 + 3);
         m10[9] = shfl(h[1][1][1], 4 * 7 + 3);
-        Chol4 L;
-        ok &= chol4(m10, L);
         // ---- rows q and 8+q of H_xu (columns 12..15 live in lanes t = 2, 3 of the quad) ----
         double y0[4], y1[4];
         y0[0] = shfl(h[0][1][0], qb | 2); y0[1] = shfl(h[0][1][1], qb | 2);
         y0[2] = shfl(h[0][1][0], qb | 3); y0[3] = shfl(h[0][1][1], qb | 3);
         y1[0] = shfl(h[1][1][0], qb | 2); y1[1] = shfl(h[1][1][1], qb | 2);
         y1[2] = shfl(h[1][1][0], qb | 3); y1[3] = shfl(h[1][1][1], qb | 3);
-        chol4_fwd(L, y0);                        // Y[:, q]
-        chol4_fwd(L, y1);                        // Y[:, 8+q]   (garbage in quads 4..7, masked below)
-        // ---- feedback gain columns K[:, q], K[:, 8+q] -> F record ----
-        {
-            double kc[4] = {y0[0], y0[1], y0[2], y0[3]};
-            chol4_bwd(L, kc);
-            if (t == 0) {
-                *reinterpret_cast<double2*>(Fk + q * 4) = make_double2(kc[0], kc[1]);
-                *reinterpret_cast<double2*>(Fk + q * 4 + 2) = make_double2(kc[2], kc[3]);
-            }
-            double kd[4] = {y1[0], y1[1], y1[2], y1[3]};
-            chol4_bwd(L, kd);
-            if (t == 1 && lo) {
-                *reinterpret_cast<double2*>(Fk + (8 + q) * 4) = make_double2(kd[0], kd[1]);
-                *reinterpret_cast<double2*>(Fk + (8 + q) * 4 + 2) = make_double2(kd[2], kd[3]);
-            }
-        }
-        if (KIND == FS_IPM && lane == 2) {       // the corrector's backward sweep re-solves with Lam
-            Fk[F_L_OFF + 0] = L.l10; Fk[F_L_OFF + 1] = L.l20; Fk[F_L_OFF + 2] = L.l21;
-            Fk[F_L_OFF + 3] = L.l30; Fk[F_L_OFF + 4] = L.l31; Fk[F_L_OFF + 5] = L.l32;
-            Fk[F_ID_OFF + 0] = L.i0; Fk[F_ID_OFF + 1] = L.i1; Fk[F_ID_OFF + 2] = L.i2; Fk[F_ID_OFF + 3] = L.i3;
-        }
-        // ---- g to every lane; kff = Lam^-1 g ----
+        // ---- g to every lane ----
         double gt[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) gt[c] = shfl(gval, 4 * (4 + c) + 2);
         if (KIND == FS_IPM && !lo && t == 2) Vk[V_GU + e] = gu;
-        chol4_fwd(L, gt);                        // L^-1 g
-        const double yg0 = y0[0] * gt[0] + y0[1] * gt[1] + y0[2] * gt[2] + y0[3] * gt[3];   // (K'g)[q]
-        const double yg1 = y1[0] * gt[0] + y1[1] * gt[1] + y1[2] * gt[2] + y1[3] * gt[3];
-        {
-            double kf[4] = {gt[0], gt[1], gt[2], gt[3]};
-            chol4_bwd(L, kf);
-            if (lane == 1) {
-                *reinterpret_cast<double2*>(Vk + V_KFF) = make_double2(kf[0], kf[1]);
-                *reinterpret_cast<double2*>(Vk + V_KFF + 2) = make_double2(kf[2], kf[3]);
+        double yg0, yg1;                         // (K'g)[q], (K'g)[8+q]
+        if (KIND == FS_ABS) {
+            // Lam = R + B'P+B is well conditioned here: explicit inverse, no dependent rsqrt / substitution chains.
+            //   K = Lam^-1 H_ux,  kff = Lam^-1 g,  P = Q + H_xx - H_xu K
+            Inv4 Bi;
+            ok &= inv4(m10, Bi);
+            double kc[4], kd[4], kf[4];
+            inv4_apply(Bi, y0, kc);              // K[:, q]
+            inv4_apply(Bi, y1, kd);              // K[:, 8+q]   (garbage in quads 4..7, masked below)
+            inv4_apply(Bi, gt, kf);
+            if (t == 0) {
+                *reinterpret_cast<double2*>(Fk + q * 4) = make_double2(kc[0], kc[1]);
+                *reinterpret_cast<double2*>(Fk + q * 4 + 2) = make_double2(kc[2], kc[3]);
             }
+            if (t == 1 && lo) {
+                *reinterpret_cast<double2*>(Fk + (8 + q) * 4) = make_double2(kd[0], kd[1]);
+                *reinterpret_cast<double2*>(Fk + (8 + q) * 4 + 2) = make_double2(kd[2], kd[3]);
+            }
+            if (lane == 2) {
+                *reinterpret_cast<double2*>(Fk + F_KFF) = make_double2(kf[0], kf[1]);
+                *reinterpret_cast<double2*>(Fk + F_KFF + 2) = make_double2(kf[2], kf[3]);
+            }
+            yg0 = y0[0] * kf[0] + y0[1] * kf[1] + y0[2] * kf[2] + y0[3] * kf[3];
+            yg1 = y1[0] * kf[0] + y1[1] * kf[1] + y1[2] * kf[2] + y1[3] * kf[3];
+            const double ys0 = (t == 0) ? y0[0] : (t == 1) ? y0[1] : (t == 2) ? y0[2] : y0[3];
+            double ys1 = (t == 0) ? y1[0] : (t == 1) ? y1[1] : (t == 2) ? y1[2] : y1[3];
+            const double ks0 = (t == 0) ? kc[0] : (t == 1) ? kc[1] : (t == 2) ? kc[2] : kc[3];
+            double ks1 = (t == 0) ? kd[0] : (t == 1) ? kd[1] : (t == 2) ? kd[2] : kd[3];
+            if (!lo) { ys1 = 0.0; ks1 = 0.0; }
+            dmma(h[0][0], -ys0, ks0); dmma(h[0][1], -ys0, ks1);
+            dmma(h[1][0], -ys1, ks0); dmma(h[1][1], -ys1, ks1);
+        } else {
+            Chol4 L;
+            ok &= chol4(m10, L);
+            chol4_fwd(L, y0);                    // Y[:, q]
+            chol4_fwd(L, y1);                    // Y[:, 8+q]   (garbage in quads 4..7, masked below)
+            // ---- feedback gain columns K[:, q], K[:, 8+q] -> F record ----
+            {
+                double kc[4] = {y0[0], y0[1], y0[2], y0[3]};
+                chol4_bwd(L, kc);
+                if (t == 0) {
+                    *reinterpret_cast<double2*>(Fk + q * 4) = make_double2(kc[0], kc[1]);
+                    *reinterpret_cast<double2*>(Fk + q * 4 + 2) = make_double2(kc[2], kc[3]);
+                }
+                double kd[4] = {y1[0], y1[1], y1[2], y1[3]};
+                chol4_bwd(L, kd);
+                if (t == 1 && lo) {
+                    *reinterpret_cast<double2*>(Fk + (8 + q) * 4) = make_double2(kd[0], kd[1]);
+                    *reinterpret_cast<double2*>(Fk + (8 + q) * 4 + 2) = make_double2(kd[2], kd[3]);
+                }
+            }
+            if (lane == 2) {                     // the corrector's backward sweep re-solves with Lam
+                Fk[F_L_OFF + 0] = L.l10; Fk[F_L_OFF + 1] = L.l20; Fk[F_L_OFF + 2] = L.l21;
+                Fk[F_L_OFF + 3] = L.l30; Fk[F_L_OFF + 4] = L.l31; Fk[F_L_OFF + 5] = L.l32;
+                Fk[F_ID_OFF + 0] = L.i0; Fk[F_ID_OFF + 1] = L.i1; Fk[F_ID_OFF + 2] = L.i2; Fk[F_ID_OFF + 3] = L.i3;
+            }
+            // ---- kff = Lam^-1 g ----
+            chol4_fwd(L, gt);                    // L^-1 g
+            yg0 = y0[0] * gt[0] + y0[1] * gt[1] + y0[2] * gt[2] + y0[3] * gt[3];
+            yg1 = y1[0] * gt[0] + y1[1] * gt[1] + y1[2] * gt[2] + y1[3] * gt[3];
+            {
+                double kf[4] = {gt[0], gt[1], gt[2], gt[3]};
+                chol4_bwd(L, kf);
+                if (lane == 1) {
+                    *reinterpret_cast<double2*>(Fk + F_KFF) = make_double2(kf[0], kf[1]);
+                    *reinterpret_cast<double2*>(Fk + F_KFF + 2) = make_double2(kf[2], kf[3]);
+                }
+            }
+            // ---- P = Q + H_xx - Y'Y  (A fragment of Y' and B fragment of Y are the same register: Y[t][8m+q]) ----
+            const double ys0 = (t == 0) ? y0[0] : (t == 1) ? y0[1] : (t == 2) ? y0[2] : y0[3];
+            double ys1 = (t == 0) ? y1[0] : (t == 1) ? y1[1] : (t == 2) ? y1[2] : y1[3];
+            if (!lo) ys1 = 0.0;
+            dmma(h[0][0], -ys0, ys0); dmma(h[0][1], -ys0, ys1);
+            dmma(h[1][0], -ys1, ys0); dmma(h[1][1], -ys1, ys1);
         }
-        // ---- P = Q + H_xx - Y'Y  (A fragment of Y' and B fragment of Y are the same register: Y[t][8m+q]) ----
-        const double ys0 = (t == 0) ? y0[0] : (t == 1) ? y0[1] : (t == 2) ? y0[2] : y0[3];
-        double ys1 = (t == 0) ? y1[0] : (t == 1) ? y1[1] : (t == 2) ? y1[2] : y1[3];
-        if (!lo) ys1 = 0.0;
-        dmma(h[0][0], -ys0, ys0); dmma(h[0][1], -ys0, ys1);
-        dmma(h[1][0], -ys1, ys0); dmma(h[1][1], -ys1, ys1);
         if (t == (q >> 1)) {                     // diagonal element (8m+q, 8m+q) is C register q&1 of lane (q, q>>1)
             if (q & 1) { h[0][0][1] += qd0; h[1][1][1] += qd1; } else { h[0][0][0] += qd0; h[1][1][0] += qd1; }
         }
@@ -937,9 +1000,9 @@ __device__ void backward_vec_sweep(Inst& I)
     const bool lo = q < 4;
     const int e = q & 3;
     double pr[3] = {0.0, 0.0, 0.0};             // p+ in row layout
-    I.template begin<true, true>();
+    I.template begin<true, true, true>();
     for (int k = N - 1, it = 0; k >= 0; k--, it++) {
-        const int s = I.template advance<true, true>(it);
+        const int s = I.template advance<true, true, true>(it);
         const double* Gk = I.sm.st[s].G;
         const double* Fk = I.sm.st[s].F;
         const double* Vs = I.sm.st[s].V;
@@ -972,8 +1035,9 @@ __device__ void backward_vec_sweep(Inst& I)
         chol4_fwd(L, gt);
         chol4_bwd(L, gt);
         if (lane == 0) {
-            *reinterpret_cast<double2*>(Vk + V_KFF) = make_double2(gt[0], gt[1]);
-            *reinterpret_cast<double2*>(Vk + V_KFF + 2) = make_double2(gt[2], gt[3]);
+            double* Fo = I.F + (size_t)k * FREC + F_KFF;
+            *reinterpret_cast<double2*>(Fo) = make_double2(gt[0], gt[1]);
+            *reinterpret_cast<double2*>(Fo + 2) = make_double2(gt[2], gt[3]);
         }
     }
     __syncwarp();
@@ -1151,10 +1215,14 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         active = __any_sync(FULL_MASK, active);
         if (lane == 0) a.hint[inst] = (active || status != 0) ? 1 : 0;
         if (finite) {
+            // restrict: X/U never alias the V workspace, so the loads of an unrolled batch may be issued ahead of its stores
+            const double* __restrict__ Vr = I.V;
+            double* __restrict__ Ur = Uo;
+            double* __restrict__ Xr = Xo;
 #pragma unroll 5
-            for (int idx = lane; idx < nb; idx += 32) Uo[idx] += I.V[(size_t)(idx >> 2) * VREC + V_V + (idx & 3)];
+            for (int idx = lane; idx < nb; idx += 32) Ur[idx] += Vr[(size_t)(idx >> 2) * VREC + V_V + (idx & 3)];
 #pragma unroll 4
-            for (int idx = lane; idx < 12 * (N + 1); idx += 32) Xo[idx] += I.V[(size_t)(idx / 12) * VREC + V_X + idx % 12];
+            for (int idx = lane; idx < 12 * (N + 1); idx += 32) Xr[idx] += Vr[(size_t)(idx / 12) * VREC + V_X + idx % 12];
         } else {
             status = 1;
         }
@@ -1182,15 +1250,16 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
 {
     static bool configured = false;
-    if (!configured) {   // 4 resident blocks need 4 x 45 KB of shared memory: ask for the largest carve-out
+    if (!configured) {   // the resident blocks need MINB x WARPS x 11.4 KB of staging buffers: ask for the largest carve-out
         cudaFuncSetAttribute(ipm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
     cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
-    const int warps_needed = a.B;
-    int blocks = (warps_needed + IPM_WARPS - 1) / IPM_WARPS;
-    const int max_blocks = sm_count * BR2_IPM_MINB;   // 4 blocks x 4 warps resident per SM (<= 128 registers, 45 KB of staging buffers each)
-    if (blocks > max_blocks) blocks = max_blocks;
+    // Persistent grid, one warp per instance at a time, instances handed out by an atomic queue.  (Sizing the resident
+    // set for even waves -- 14 instead of 16 warps/SM at B = 4096 -- measured 8 % slower: throughput grows with the
+    // number of resident warps and the queue already evens out the tail; profiles/r01h_ipm_variants.txt.)
+    int blocks = (a.B + IPM_WARPS - 1) / IPM_WARPS;
+    if (blocks > sm_count * BR2_IPM_MINB) blocks = sm_count * BR2_IPM_MINB;
     ipm_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
 }
 

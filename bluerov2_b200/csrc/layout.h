@@ -34,10 +34,12 @@ __host__ __device__ constexpr int g_off(int row, int col)
 //   [0..47]  Kt[j][a] = K[a][j]  (feedback gain transposed: column j of K is 4 contiguous doubles)
 //   [48..53] strictly-lower Cholesky entries of Lam = R~ + B'PB: l10 l20 l21 l30 l31 l32
 //   [54..57] reciprocal diagonal 1/l00 .. 1/l33
-//   [58..63] pad (record = 512 B)
+//   [58..61] feed-forward kff = Lam^-1 g of the most recent backward sweep (16-byte aligned);  [62..63] pad
+//   (record = 512 B)
 constexpr int FREC = 64;
 constexpr int F_L_OFF = 48;
 constexpr int F_ID_OFF = 54;
+constexpr int F_KFF = 58;
 
 // Vector record V_k (IPM iterate + step, per stage; record = 512 B):
 constexpr int VREC = 64;
@@ -52,6 +54,6 @@ constexpr int V_GU = 44;   // reduced input gradient R du + r + B'pi+
 constexpr int V_DV = 48;   // step in du_k
 constexpr int V_CL = 52;   // complementarity rhs lower: sigma*mu - dt_aff*dlam_aff
 constexpr int V_CU = 56;   // complementarity rhs upper
-constexpr int V_KFF = 60;  // feed-forward  kff = Lam^-1 (gh + B'p+)
+// [60..63] pad
 
 }  // namespace br2
