@@ -38,11 +38,13 @@ __constant__ double c_K[36] = {
     0.051265241636155506, -0.05126524163615552, 0.05126524163563227, -0.05126524163563227, -0.11050000000000001, 0.11050000000000003,
     -0.05126524163589389, -0.051265241635893896, 0.05126524163641713, 0.05126524163641713, -0.002499999999974481, -0.002499999999974481,
     0.16652364696949604, -0.16652364696949604, -0.17500892834341342, 0.17500892834341342, 0.0, 0.0};
-__constant__ double c_Dl[6] = {-11.7391, -20, -31.8678, -25, -44.9085, -5};
-__constant__ double c_Dnl[6] = {-18.18, -21.66, -36.99, -1.55, -1.55, -1.55};
+// damping of the filter model, selected per launch (EkfArgs::model): 0 = BLUEROV2_DOB (bluerov2_dob.h:182-183),
+// 1 = BLUEROV2_AMPC (bluerov2_ampc.cpp:41-42: Dl = 0; its f/h :658-696 have no quadratic damping)
+__constant__ double c_DlM[2][6] = {{-11.7391, -20, -31.8678, -25, -44.9085, -5}, {0, 0, 0, 0, 0, 0}};
+__constant__ double c_DnlM[2][6] = {{-18.18, -21.66, -36.99, -1.55, -1.55, -1.55}, {0, 0, 0, 0, 0, 0}};
 
 // process model, bluerov2_dob.cpp:637-695 (tau = K * thrusts precomputed)
-__device__ void ekf_f(const double* x, const double* tau, double* xd)
+__device__ void ekf_f(const double* x, const double* tau, double* xd, const double* c_Dl, const double* c_Dnl)
 {
     using namespace ekfc;
     double s3, c3, s4, c4, s5, c5;
@@ -64,7 +66,7 @@ __device__ void ekf_f(const double* x, const double* tau, double* xd)
 }
 
 // measurement model, bluerov2_dob.cpp:698-719
-__device__ void ekf_h(const double* x, const double* acc, double* y)
+__device__ void ekf_h(const double* x, const double* acc, double* y, const double* c_Dl, const double* c_Dnl)
 {
     using namespace ekfc;
     double s3, c3, s4, c4;
@@ -79,20 +81,20 @@ __device__ void ekf_h(const double* x, const double* acc, double* y)
     y[17] = M5 * acc[5] + (Iy - Ix) * x[9] * x[10] - x[17] - c_Dl[5] * x[11] - c_Dnl[5] * fabs(x[11]) * x[11];
 }
 
-__device__ void ekf_rk4(const double* x, const double* tau, double* xn)
+__device__ void ekf_rk4(const double* x, const double* tau, double* xn, const double* c_Dl, const double* c_Dnl)
 {
     using namespace ekfc;
     double k1[EN], k2[EN], k3[EN], k4[EN], xs[EN];
-    ekf_f(x, tau, k1);
+    ekf_f(x, tau, k1, c_Dl, c_Dnl);
 #pragma unroll
     for (int i = 0; i < EN; i++) { k1[i] *= DT; xs[i] = x[i] + k1[i] / 2; }
-    ekf_f(xs, tau, k2);
+    ekf_f(xs, tau, k2, c_Dl, c_Dnl);
 #pragma unroll
     for (int i = 0; i < EN; i++) { k2[i] *= DT; xs[i] = x[i] + k2[i] / 3; }   // sic: /3 (bluerov2_dob.cpp:630)
-    ekf_f(xs, tau, k3);
+    ekf_f(xs, tau, k3, c_Dl, c_Dnl);
 #pragma unroll
     for (int i = 0; i < EN; i++) { k3[i] *= DT; xs[i] = x[i] + k3[i]; }
-    ekf_f(xs, tau, k4);
+    ekf_f(xs, tau, k4, c_Dl, c_Dnl);
 #pragma unroll
     for (int i = 0; i < EN; i++) { k4[i] *= DT; xn[i] = x[i] + (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]) / 6; }
 }
@@ -130,6 +132,8 @@ __global__ void __launch_bounds__(EKF_WARPS * 32) ekf_kernel(EkfArgs a)
     const int inst = blockIdx.x * EKF_WARPS + wib;
     if (inst >= a.B) return;
     const double d = 1e-6;
+    const double* c_Dl = c_DlM[a.model & 1];
+    const double* c_Dnl = c_DnlM[a.model & 1];
     double* ex = a.esti_x + (size_t)inst * EN;
     double* eP = a.esti_P + (size_t)inst * EN * EN;
 
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(EKF_WARPS * 32) ekf_kernel(EkfArgs a)
         for (int i = 0; i < EN; i++)
             if (i == lane - 1) x[i] += d;
     }
-    ekf_rk4(x, tau, f1);
+    ekf_rk4(x, tau, f1, c_Dl, c_Dnl);
     double xp[EN];   // x_pred = RK4(esti_x) on every lane
 #pragma unroll
     for (int i = 0; i < EN; i++) {
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(EKF_WARPS * 32) ekf_kernel(EkfArgs a)
         if (lane >= 1 && lane <= EN && i == lane - 1) x[i] += d;
     }
     double y1[EN], yp[EN];
-    ekf_h(x, acc, y1);
+    ekf_h(x, acc, y1, c_Dl, c_Dnl);
 #pragma unroll
     for (int i = 0; i < EN; i++) {
         yp[i] = __shfl_sync(FULL_MASK, y1[i], 0);

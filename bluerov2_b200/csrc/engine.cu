@@ -31,7 +31,7 @@ struct br2_batch_solver {
     int B, N, device, sm_count;
     double Ts[NMAX];
     double W[16], We[12], lbu[4], ubu[4];
-    int max_iter, fast_path;
+    int max_iter, fast_path, ekf_model;
     double tol;
     // device state
     double *d_Ts, *d_X, *d_U, *d_G, *d_F, *d_V, *d_u0, *d_thrust, *d_info;
@@ -41,6 +41,7 @@ struct br2_batch_solver {
     int* d_lines;                             // staging: first trajectory row per instance
     int traj_rows;
     double *d_ex, *d_eP, *d_thr, *d_meas, *d_acc, *d_wf, *d_pout;   // EKF state + staging
+    double* d_rls;                            // RLS-VFF state [B][4][RLS_STRIDE] (AMPC)
     cudaStream_t stream;
     cudaEvent_t ev0, ev1, ev_mid;   // solve start / end / between linearisation and IPM
     unsigned long long* d_iter_total;   // IPM iterations executed, summed over instances and solves
@@ -68,7 +69,7 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
     cudaSetDevice(s->device);
     void* ptrs[] = {s->d_Ts, s->d_X, s->d_U, s->d_G, s->d_F, s->d_V, s->d_u0, s->d_thrust, s->d_info, s->d_status,
                     s->d_iters, s->d_counter, s->d_x0, s->d_yref, s->d_p, s->d_ex, s->d_eP, s->d_thr, s->d_meas,
-                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines};
+                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -122,6 +123,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     DA(d_x0, B * NX); DA(d_yref, B * (N + 1) * NY); DA(d_p, B * (N + 1) * NP);
     DA(d_ex, B * 18); DA(d_eP, B * 324); DA(d_thr, B * 6); DA(d_meas, B * 12); DA(d_acc, B * 6); DA(d_wf, B * 6);
     DA(d_pout, B * NP);
+    DA(d_rls, B * 4 * RLS_STRIDE);
     DA(d_iter_total, 1);
     DA(d_hint, B);
     DA(d_lines, B);
@@ -140,6 +142,8 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     *out = s;
     int rc = br2_batch_reset(s, 0);
     if (rc == BR2_OK) rc = br2_batch_ekf_reset(s);
+    if (rc == BR2_OK) rc = br2_batch_rls_reset(s);
+    if (rc == BR2_OK) { cudaError_t e2 = cudaMemset(s->d_pout, 0, sizeof(double) * B * NP); if (e2 != cudaSuccess) rc = fail(BR2_ECUDA, "cudaMemset failed"); }
     if (rc != BR2_OK) { br2_batch_free(s); *out = nullptr; }
     return rc;
 }
@@ -194,6 +198,11 @@ extern "C" int br2_batch_set_option_int(br2_batch_solver* s, const char* name, i
     }
     if (!strcmp(name, "fast_path")) {
         s->fast_path = v != 0;
+        return BR2_OK;
+    }
+    if (!strcmp(name, "ekf_model")) {      // 0 = BLUEROV2_DOB filter, 1 = BLUEROV2_AMPC filter (bluerov2_ampc.cpp:658-696)
+        if (v != 0 && v != 1) return fail(BR2_EINVAL, "ekf_model = %d (0 = dob, 1 = ampc)", v);
+        s->ekf_model = v;
         return BR2_OK;
     }
     return fail(BR2_EINVAL, "unknown int option '%s'", name);
@@ -470,7 +479,7 @@ extern "C" int br2_batch_ekf_device(br2_batch_solver* s, const double* d_thrusts
     EkfArgs a;
     a.B = s->B; a.esti_x = s->d_ex; a.esti_P = s->d_eP;
     a.thrusts = d_thrusts; a.meas = d_meas; a.body_acc = d_body_acc;
-    a.wf_dist = d_wf_dist; a.p_out = d_p_out; a.compensate = compensate;
+    a.wf_dist = d_wf_dist; a.p_out = d_p_out; a.compensate = compensate; a.model = s->ekf_model;
     launch_ekf(a, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return BR2_OK;
@@ -512,3 +521,69 @@ extern "C" int br2_batch_ekf_set_state_host(br2_batch_solver* s, const double* e
     if (esti_P) CK(cudaMemcpy(s->d_eP, esti_P, sizeof(double) * s->B * 324, cudaMemcpyHostToDevice));
     return BR2_OK;
 }
+
+// ---- RLS with variable forgetting factor (AMPC) ---------------------------------------------------------------
+extern "C" int br2_batch_rls_reset(br2_batch_solver* s)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    const size_t n = (size_t)s->B * 4;
+    double* h = (double*)calloc(n * RLS_STRIDE, sizeof(double));
+    if (!h) return fail(BR2_ENOMEM, "out of host memory");
+    for (size_t i = 0; i < n; i++) {
+        for (int j = 0; j < 4; j++) h[i * RLS_STRIDE + RLS_P + j * 5] = 1.0;   // P = I, bluerov2_ampc.cpp:63-68
+        h[i * RLS_STRIDE + RLS_LAMBDA] = 0.9;                                    // :70-73
+    }
+    cudaError_t e = cudaMemcpy(s->d_rls, h, sizeof(double) * n * RLS_STRIDE, cudaMemcpyHostToDevice);
+    free(h);
+    CK(e);
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_rls_device(br2_batch_solver* s, const double* d_meas, const double* d_body_acc, double* d_p_out,
+                                    int compensate, void* stream)
+{
+    if (!s || !d_meas || !d_body_acc) return fail(BR2_EINVAL, "br2_batch_rls_device: null argument");
+    CK(cudaSetDevice(s->device));
+    RlsArgs a;
+    a.B = s->B; a.state = s->d_rls; a.esti_x = s->d_ex; a.body_acc = d_body_acc; a.meas = d_meas; a.p_out = d_p_out;
+    a.compensate = compensate;
+    launch_rls(a, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_rls_host(br2_batch_solver* s, const double* meas, const double* body_acc, double* p_out, int compensate)
+{
+    if (!s || !meas || !body_acc) return fail(BR2_EINVAL, "br2_batch_rls_host: null argument");
+    CK(cudaSetDevice(s->device));
+    const size_t B = s->B;
+    cudaStream_t st = s->stream;
+    CK(cudaMemcpyAsync(s->d_meas, meas, sizeof(double) * B * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_acc, body_acc, sizeof(double) * B * 6, cudaMemcpyHostToDevice, st));
+    // p_out is in/out on the host: with compensate == 0 the reference leaves p[4..15] as they were
+    if (p_out) CK(cudaMemcpyAsync(s->d_pout, p_out, sizeof(double) * B * NP, cudaMemcpyHostToDevice, st));
+    int rc = br2_batch_rls_device(s, s->d_meas, s->d_acc, p_out ? s->d_pout : nullptr, compensate, st);
+    if (rc != BR2_OK) return rc;
+    if (p_out) CK(cudaMemcpyAsync(p_out, s->d_pout, sizeof(double) * B * NP, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_rls_get_state_host(br2_batch_solver* s, double* state)
+{
+    if (!s || !state) return fail(BR2_EINVAL, "null argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(state, s->d_rls, sizeof(double) * s->B * 4 * RLS_STRIDE, cudaMemcpyDeviceToHost));
+    return BR2_OK;
+}
+extern "C" int br2_batch_rls_set_state_host(br2_batch_solver* s, const double* state)
+{
+    if (!s || !state) return fail(BR2_EINVAL, "null argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(s->d_rls, state, sizeof(double) * s->B * 4 * RLS_STRIDE, cudaMemcpyHostToDevice));
+    return BR2_OK;
+}
+

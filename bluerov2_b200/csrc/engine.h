@@ -67,8 +67,24 @@ struct EkfArgs {
     double* wf_dist;         // [B][6] out (may be null)
     double* p_out;           // [B][16] out (may be null): OCP parameter vector per bluerov2_dob.cpp:324-355
     int compensate;          // COMPENSATE_D
+    int model;               // 0 = BLUEROV2_DOB filter, 1 = BLUEROV2_AMPC filter (no damping in f / h)
 };
 void launch_ekf(const EkfArgs& a, cudaStream_t s);
+
+// RLS with variable forgetting factor (rls.cu; BLUEROV2_AMPC::RLSFF, bluerov2_ampc.cpp:731-1004), one thread per
+// (instance, axis); state layout RLS_* below == oracle ORC_RLS_STRIDE layout
+constexpr int RLS_STRIDE = 80, RLS_THETA = 0, RLS_P = 4, RLS_LAMBDA = 20, RLS_F = 21, RLS_NN = 22, RLS_ND = 23, RLS_EN = 24,
+              RLS_ED = 29, RLS_FFN = 5, RLS_FFD = 50;
+struct RlsArgs {
+    int B;
+    double* state;           // [B][4][RLS_STRIDE] in/out
+    const double* esti_x;    // [B][18] EKF estimate (targets: components 12, 13, 14, 17)
+    const double* body_acc;  // [B][6]
+    const double* meas;      // [B][12] (body velocities in 6..11)
+    double* p_out;           // [B][16] out (may be null): parameters as BLUEROV2_AMPC::solve fills them (:340-382)
+    int compensate;
+};
+void launch_rls(const RlsArgs& a, cudaStream_t s);
 
 // nominal plant (plant.cu): x <- RK4_h(x, u, p + disturbance); optional wave disturbance, body acceleration, line counter
 struct PlantArgs {

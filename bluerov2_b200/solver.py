@@ -75,6 +75,11 @@ def load_library(path: str | None = None):
         "br2_batch_ekf_host": (C.c_int, [V, V, V, V, V, V, C.c_int]),
         "br2_batch_ekf_get_state_host": (C.c_int, [V, V, V]),
         "br2_batch_ekf_set_state_host": (C.c_int, [V, V, V]),
+        "br2_batch_rls_reset": (C.c_int, [V]),
+        "br2_batch_rls_device": (C.c_int, [V, V, V, V, C.c_int, V]),
+        "br2_batch_rls_host": (C.c_int, [V, V, V, V, C.c_int]),
+        "br2_batch_rls_get_state_host": (C.c_int, [V, V]),
+        "br2_batch_rls_set_state_host": (C.c_int, [V, V]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -300,6 +305,39 @@ class BatchSolver:
         x = None if x is None else _np(x, (self.B, NEKF))
         P = None if P is None else _np(P, (self.B, NEKF, NEKF))
         self._check(self._L.br2_batch_ekf_set_state_host(self._h, _ptr(x), _ptr(P)))
+
+    # -- RLS with variable forgetting factor (BLUEROV2_AMPC::RLSFF, bluerov2_ampc.cpp:731-1004) ---------------
+    RLS_STRIDE = 80
+
+    def rls_reset(self):
+        self._check(self._L.br2_batch_rls_reset(self._h))
+
+    def rls(self, meas, body_acc, compensate: bool = True, out=None):
+        """One RLSFF() call for all instances, fed by the EKF state in the solver (call ``ekf`` first; the AMPC node runs
+        EKF -> RLSFF -> solve, bluerov2_ampc_node.cpp:26-29).  Returns p[B,16]; ``out`` is in/out: with ``compensate`` False
+        only p[:, 0:4] = 0 is written (the reference never fills p[4..15] in that case)."""
+        if _is_torch(meas):
+            import torch
+            self._dev_check(meas, (self.B, 12)); self._dev_check(body_acc, (self.B, 6))
+            if out is None:
+                out = torch.zeros((self.B, NP), dtype=torch.float64, device=meas.device)
+            stream = C.c_void_p(torch.cuda.current_stream(meas.device).cuda_stream)
+            self._check(self._L.br2_batch_rls_device(self._h, _ptr(meas), _ptr(body_acc), _ptr(out), int(bool(compensate)), stream))
+            return out
+        meas, body_acc = _np(meas, (self.B, 12)), _np(body_acc, (self.B, 6))
+        if out is None:
+            out = np.zeros((self.B, NP))
+        self._check(self._L.br2_batch_rls_host(self._h, _ptr(meas), _ptr(body_acc), _ptr(out), int(bool(compensate))))
+        return out
+
+    def rls_state(self):
+        """[B, 4 axes (X, Y, Z, N), 80]: theta[0:4], P[4:20], lambda[20], F[21], window counts[22:24], windows[24:29], [29:79]."""
+        st = np.empty((self.B, 4, self.RLS_STRIDE))
+        self._check(self._L.br2_batch_rls_get_state_host(self._h, _ptr(st)))
+        return st
+
+    def set_rls_state(self, st):
+        self._check(self._L.br2_batch_rls_set_state_host(self._h, _ptr(_np(st, (self.B, 4, self.RLS_STRIDE)))))
 
 
 def plant_step(x, u, p, h: float = 0.05, dist=None, wave=None, tick: int = 0, body_acc=None, lines=None):

@@ -134,6 +134,25 @@ BR2_API int br2_batch_ekf_host(br2_batch_solver *s, const double *thrusts, const
                        double *wf_dist, double *p_out, int compensate);
 BR2_API int br2_batch_ekf_get_state_host(br2_batch_solver *s, double *esti_x, double *esti_P);
 BR2_API int br2_batch_ekf_set_state_host(br2_batch_solver *s, const double *esti_x, const double *esti_P);
+/* The filter of the adaptive-MPC node (BLUEROV2_AMPC::EKF, bluerov2_ampc.cpp:518-545 with f/h :658-696) is the same
+ * code with no damping in the model: select it with br2_batch_set_option_int(s, "ekf_model", 1) (0 = DOB, default). */
+
+/* == BLUEROV2_AMPC::RLSFF (bluerov2_ampc.cpp:731-1004): recursive least squares with variable forgetting factor, four
+ * estimators per instance (axes X, Y, Z, N) fed by the EKF state living in the solver (targets esti_x(12|13|14|17)),
+ * regressors [body_acc, vel, 1, vel|vel|] from body_acc[B][6] and meas[B][12] (body velocities in 6..11).
+ * State per axis, BR2_RLS_STRIDE doubles: theta[4] | P[4][4] | lambda | F-statistic | n_short | n_long |
+ * short error window[5] | long error window[50] (oldest first) | pad; br2_batch_rls_reset = constructor values
+ * (theta 0, P = I, lambda 0.9: :62-79).  p_out[B][16] (may be NULL) receives the OCP parameters as
+ * BLUEROV2_AMPC::solve fills them (:340-382): p[0..3] = theta(2) / (compensate_coef | rotor_constant) plus the nominal
+ * p[4..15] when `compensate`; otherwise p[0..3] = 0 and p[4..15] are left as they were (the reference's brace
+ * placement, :345-379) -- so p_out is in/out.  AMPC tick = ekf (ekf_model 1) -> rls -> solve on one stream. */
+#define BR2_RLS_STRIDE 80
+BR2_API int br2_batch_rls_reset(br2_batch_solver *s);
+BR2_API int br2_batch_rls_device(br2_batch_solver *s, const double *d_meas, const double *d_body_acc, double *d_p_out,
+                         int compensate, void *stream);
+BR2_API int br2_batch_rls_host(br2_batch_solver *s, const double *meas, const double *body_acc, double *p_out, int compensate);
+BR2_API int br2_batch_rls_get_state_host(br2_batch_solver *s, double *state);
+BR2_API int br2_batch_rls_set_state_host(br2_batch_solver *s, const double *state);
 
 #ifdef __cplusplus
 }

@@ -705,8 +705,20 @@ void orc_thrust_alloc(const double *u, double *t)
 static const double E_DT = 0.05, E_MASS = 11.26, E_IX = 0.3, E_IY = 0.63, E_IZ = 0.58, E_ZG = 0.02, E_G = 9.81;
 static const double E_BUOY = 0.661618;
 static const double E_AM[6] = {1.7182, 0, 5.468, 0, 1.2481, 0.4006};
-static const double E_DL[6] = {-11.7391, -20, -31.8678, -25, -44.9085, -5};
-static const double E_DNL[6] = {-18.18, -21.66, -36.99, -1.55, -1.55, -1.55};
+/* damping of the filter's process/measurement model: model 0 = BLUEROV2_DOB (bluerov2_dob.h:182-183), model 1 =
+ * BLUEROV2_AMPC, whose f/h (bluerov2_ampc.cpp:658-696) are the same expressions with Dl = 0 (:41-42) and no
+ * quadratic damping.  Selected process-wide by orc_ekf_set_model (test infrastructure: not thread-safe). */
+static const double E_DL_DOB[6] = {-11.7391, -20, -31.8678, -25, -44.9085, -5};
+static const double E_DNL_DOB[6] = {-18.18, -21.66, -36.99, -1.55, -1.55, -1.55};
+static double E_DL[6] = {-11.7391, -20, -31.8678, -25, -44.9085, -5};
+static double E_DNL[6] = {-18.18, -21.66, -36.99, -1.55, -1.55, -1.55};
+void orc_ekf_set_model(int model)
+{
+    for (int i = 0; i < 6; i++) {
+        E_DL[i] = model == 1 ? 0.0 : E_DL_DOB[i];
+        E_DNL[i] = model == 1 ? 0.0 : E_DNL_DOB[i];
+    }
+}
 static const double E_K[6][6] = {
     {0.7071067811847433, 0.7071067811847433, -0.7071067811919605, -0.7071067811919605, 0.0, 0.0},
     {0.7071067811883519, -0.7071067811883519, 0.7071067811811348, -0.7071067811811348, 0.0, 0.0},
@@ -904,4 +916,109 @@ void orc_ekf_step_batch(int nb, double *ex, double *eP, const double *thr, const
     for (int i = 0; i < nb; i++)
         orc_ekf_step(ex + (size_t)i * EN, eP + (size_t)i * EN * EN, thr + (size_t)i * 6, meas12 + (size_t)i * 12,
                      acc + (size_t)i * 6, wf ? wf + (size_t)i * 6 : 0);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Recursive least squares with variable forgetting factor -- restates BLUEROV2_AMPC::RLSFF
+ * (bluerov2_ampc.cpp:731-1004) with the initialisation of the constructor (:62-79) and the constants of
+ * bluerov2_ampc.h:231,239-240 (numParams 4, FF_n 5, FF_d 50).  Four independent estimators (axes X, Y, Z, N):
+ *   regressor x = [body_acc, vel, 1, vel*|vel|], target y = esti_x(12 | 13 | 14 | 17) (the EKF's disturbance estimate),
+ *   e = y - x.theta; e is appended to a short (5) and a long (50) window (oldest dropped); F = var_short / var_long
+ *   (population variances; 0/0 = NaN on the first tick compares false, as in the reference);
+ *   F > 0.8 ? lambda = max(lambda - 0.01, 0.5) : lambda = min(lambda + 0.01, 1);
+ *   K = P x / (lambda + x'Px); theta += K e; P = (P - (K x') P) / lambda.
+ * State of one axis, ORC_RLS_STRIDE doubles: theta[4] | P[16] row-major | lambda | F | n_short | n_long |
+ * short window [5] oldest first | long window [50] oldest first | pad.
+ * ---------------------------------------------------------------------------------------------- */
+#define RLS_NP 4
+#define RLS_FFN 5
+#define RLS_FFD 50
+enum { RLS_THETA = 0, RLS_P = 4, RLS_LAMBDA = 20, RLS_F = 21, RLS_NN = 22, RLS_ND = 23, RLS_EN = 24, RLS_ED = 29, RLS_STRIDE = 80 };
+
+void orc_rls_init(double *st)
+{
+    for (int a = 0; a < 4; a++) {
+        double *s = st + a * RLS_STRIDE;
+        memset(s, 0, sizeof(double) * RLS_STRIDE);
+        for (int i = 0; i < RLS_NP; i++) s[RLS_P + i * RLS_NP + i] = 1.0;   /* P = I (:63-68) */
+        s[RLS_LAMBDA] = 0.9;                                                 /* :70-73 */
+    }
+}
+
+static double window_push_var(double *w, double *count, int cap, double e)
+{
+    int n = (int)*count;
+    if (n < cap) w[n++] = e;
+    else { for (int i = 1; i < cap; i++) w[i - 1] = w[i]; w[cap - 1] = e; }   /* push_back + erase(begin) */
+    *count = n;
+    double sum = 0.0;
+    for (int i = 0; i < n; i++) sum += w[i];
+    const double mean = sum / n;
+    double var = 0.0;
+    for (int i = 0; i < n; i++) var += (w[i] - mean) * (w[i] - mean);         /* std::pow(v - mean, 2) */
+    return var / n;
+}
+
+static void rls_axis(double *s, double y, double acc, double vel)
+{
+    const double threshold = 0.8;
+    const double x[RLS_NP] = {acc, vel, 1.0, vel * fabs(vel)};
+    double *th = s + RLS_THETA, *P = s + RLS_P;
+    double pred = 0.0;
+    for (int i = 0; i < RLS_NP; i++) pred += x[i] * th[i];
+    const double e = y - pred;
+    const double vn = window_push_var(s + RLS_EN, s + RLS_NN, RLS_FFN, e);
+    const double vd = window_push_var(s + RLS_ED, s + RLS_ND, RLS_FFD, e);
+    const double F = vn / vd;
+    s[RLS_F] = F;
+    double lam = s[RLS_LAMBDA];
+    if (F > threshold) lam = (lam - 0.01 >= 0.5) ? lam - 0.01 : 0.5;
+    else lam = (lam + 0.01 <= 1) ? lam + 0.01 : 1;
+    s[RLS_LAMBDA] = lam;
+    double Px[RLS_NP], K[RLS_NP], xPx = 0.0;
+    for (int i = 0; i < RLS_NP; i++) {
+        double t = 0.0;
+        for (int j = 0; j < RLS_NP; j++) t += P[i * RLS_NP + j] * x[j];
+        Px[i] = t;
+    }
+    for (int i = 0; i < RLS_NP; i++) xPx += x[i] * Px[i];
+    for (int i = 0; i < RLS_NP; i++) K[i] = Px[i] / (lam + xPx);
+    for (int i = 0; i < RLS_NP; i++) th[i] += K[i] * e;
+    double Pn[RLS_NP * RLS_NP];
+    for (int i = 0; i < RLS_NP; i++)
+        for (int j = 0; j < RLS_NP; j++) {
+            double t = 0.0;
+            for (int k = 0; k < RLS_NP; k++) t += (K[i] * x[k]) * P[k * RLS_NP + j];   /* (K x') P */
+            Pn[i * RLS_NP + j] = (P[i * RLS_NP + j] - t) / lam;
+        }
+    memcpy(P, Pn, sizeof Pn);
+}
+
+/* one RLSFF() call: state[4][ORC_RLS_STRIDE]; esti_x[18] from the EKF; body_acc[6] = (x y z phi theta psi);
+ * meas12[6..11] = body velocities (v_linear_body, v_angular_body).  p_out (may be null): the OCP parameter vector
+ * BLUEROV2_AMPC::solve builds from it (:340-382): p[0..3] = theta(2) / (compensate_coef | rotor_constant) and the
+ * nominal p[4..15] when compensate, else p[0..3] = 0 and p[4..15] LEFT UNTOUCHED (brace placement :345-379). */
+void orc_rls_step(double *st, const double *esti_x, const double *body_acc, const double *meas12, int compensate,
+                  double *p_out)
+{
+    static const int yi[4] = {12, 13, 14, 17}, ai[4] = {0, 1, 2, 5}, vi[4] = {6, 7, 8, 11};
+    for (int a = 0; a < 4; a++) rls_axis(st + a * RLS_STRIDE, esti_x[yi[a]], body_acc[ai[a]], meas12[vi[a]]);
+    if (p_out) {
+        const double comp = 0.032546960744430276;
+        if (!compensate) { p_out[0] = p_out[1] = p_out[2] = p_out[3] = 0.0; return; }
+        static const double nominal[12] = {1.7182, 0, 5.468, 0.4006, -11.7391, -20, -31.8678, -5, -18.18, -21.66, -36.99, -1.55};
+        p_out[0] = st[0 * RLS_STRIDE + 2] / comp;
+        p_out[1] = st[1 * RLS_STRIDE + 2] / comp;
+        p_out[2] = st[2 * RLS_STRIDE + 2] / RC;
+        p_out[3] = st[3 * RLS_STRIDE + 2] / RC;
+        for (int i = 0; i < 12; i++) p_out[4 + i] = nominal[i];
+    }
+}
+
+void orc_rls_step_batch(int nb, double *st, const double *esti_x, const double *body_acc, const double *meas12,
+                        int compensate, double *p_out)
+{
+    for (int i = 0; i < nb; i++)
+        orc_rls_step(st + (size_t)i * 4 * RLS_STRIDE, esti_x + (size_t)i * EN, body_acc + (size_t)i * 6,
+                     meas12 + (size_t)i * 12, compensate, p_out ? p_out + (size_t)i * 16 : 0);
 }

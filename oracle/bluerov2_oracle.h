@@ -117,6 +117,19 @@ void orc_ekf_step(double *esti_x, double *esti_P, const double *thrusts6, const 
                   const double *body_acc6, double *wf_dist);
 void orc_ekf_step_batch(int nb, double *esti_x, double *esti_P, const double *thrusts6,
                         const double *meas12, const double *body_acc6, double *wf_dist, int nthreads);
+/* model 0 (default): BLUEROV2_DOB damping; model 1: BLUEROV2_AMPC's filter (bluerov2_ampc.cpp:41-42,658-696: Dl = 0,
+ * no quadratic damping).  Process-wide switch. */
+void orc_ekf_set_model(int model);
+
+/* ---- RLS with variable forgetting factor, BLUEROV2_AMPC::RLSFF (bluerov2_ampc.cpp:731-1004, init :62-79) ----
+ * state[4][ORC_RLS_STRIDE] (axes X, Y, Z, N): theta[4] | P[16] | lambda | F | n_short | n_long | short window[5] |
+ * long window[50] | pad.  p_out[16] (may be null): parameters as BLUEROV2_AMPC::solve fills them (:340-382). */
+#define ORC_RLS_STRIDE 80
+void orc_rls_init(double *state);
+void orc_rls_step(double *state, const double *esti_x18, const double *body_acc6, const double *meas12,
+                  int compensate, double *p_out);
+void orc_rls_step_batch(int nb, double *state, const double *esti_x18, const double *body_acc6,
+                        const double *meas12, int compensate, double *p_out);
 
 #ifdef __cplusplus
 }

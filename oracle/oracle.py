@@ -109,6 +109,10 @@ class Oracle:
         L.orc_ekf_h.argtypes = [D, D, D]
         L.orc_ekf_step.argtypes = [D, D, D, D, D, D]
         L.orc_ekf_step_batch.argtypes = [C.c_int, D, D, D, D, D, D, C.c_int]
+        L.orc_ekf_set_model.argtypes = [C.c_int]
+        L.orc_rls_init.argtypes = [D]
+        L.orc_rls_step.argtypes = [D, D, D, D, C.c_int, D]
+        L.orc_rls_step_batch.argtypes = [C.c_int, D, D, D, D, C.c_int, D]
         self._ref = None
 
     # -- routing of the ERK through the reference's CasADi VDE ------------------------------------------
@@ -229,3 +233,29 @@ class Oracle:
         wf = np.zeros((nb, 6))
         self.lib.orc_ekf_step_batch(nb, _p(esti_x), _p(esti_P), _p(thrusts), _p(meas12), _p(body_acc), _p(wf), int(nthreads))
         return wf
+
+    def ekf_set_model(self, model: int):
+        """0 = BLUEROV2_DOB filter (default), 1 = BLUEROV2_AMPC filter (Dl = 0, no quadratic damping). Process-wide."""
+        self.lib.orc_ekf_set_model(int(model))
+
+    # -- RLS with variable forgetting factor (BLUEROV2_AMPC::RLSFF) -----------------------------------------
+    RLS_STRIDE = 80
+    RLS_THETA, RLS_P, RLS_LAMBDA, RLS_F, RLS_NN, RLS_ND, RLS_EN, RLS_ED = 0, 4, 20, 21, 22, 23, 24, 29
+
+    def rls_init(self, nb=None):
+        """state (4, 80) -- or (nb, 4, 80) -- as the AMPC constructor leaves it (theta 0, P = I, lambda 0.9)."""
+        st = np.zeros((4, self.RLS_STRIDE))
+        self.lib.orc_rls_init(_p(st))
+        return st if nb is None else np.ascontiguousarray(np.broadcast_to(st, (nb, 4, self.RLS_STRIDE)))
+
+    def rls_step_batch(self, state, esti_x, body_acc, meas12, compensate=True, p_out=None):
+        """state (nb,4,80) updated IN PLACE; returns p_out (nb,16) (pass one in to see which entries are left untouched)."""
+        nb = state.shape[0]
+        assert state.dtype == np.float64 and state.shape == (nb, 4, self.RLS_STRIDE) and state.flags.c_contiguous
+        esti_x, body_acc, meas12 = _c(esti_x, (nb, 18)), _c(body_acc, (nb, 6)), _c(meas12, (nb, 12))
+        if p_out is None:
+            p_out = np.zeros((nb, 16))
+        assert p_out.dtype == np.float64 and p_out.shape == (nb, 16) and p_out.flags.c_contiguous
+        self.lib.orc_rls_step_batch(nb, _p(state), _p(esti_x), _p(body_acc), _p(meas12), int(bool(compensate)), _p(p_out))
+        return p_out
+

@@ -506,3 +506,88 @@ def test_hint_carried_across_ticks(solver_mod):
     assert frac_fast[0] < 0.9 and frac_fast[-1] > 0.9, frac_fast      # saturated at first, interior at the end
     for s in sols:
         s.close()
+
+
+def test_ampc_filter_and_rls_match_oracle(solver_mod, oracle):
+    """AMPC estimator chain (bluerov2_ampc_node.cpp:26-29: EKF -> RLSFF): the EKF with the AMPC model (ekf_model 1) and
+    the RLS-VFF kernel against the oracle over 70 ticks (both error windows wrap), oracle filter state carried on both
+    sides so that differences do not compound through the forward-difference Jacobians."""
+    B, T = 192, 70
+    rng = np.random.default_rng(11)
+    s = solver_mod.BatchSolver(B, 10)
+    s.set_option("ekf_model", 1)
+    s.ekf_reset(); s.rls_reset()
+    ox = np.zeros((B, 18)); oP = np.zeros((B, 18, 18))
+    for i in range(B):
+        ox[i], oP[i] = oracle.ekf_init()
+    ost = oracle.rls_init(B)
+    assert np.array_equal(s.rls_state(), ost)
+    oracle.ekf_set_model(1)
+    try:
+        for t in range(T):
+            thr = rng.uniform(-10, 10, (B, 6)); acc = rng.uniform(-1, 1, (B, 6)) * (0.02 if t > 40 else 1.0)
+            meas = np.tile(np.array([0, 0, -20, 0, 0, 0, 0, 0, 0, 0, 0, 0.0]), (B, 1)) + rng.uniform(-0.3, 0.3, (B, 12))
+            s.ekf(thr, meas, acc)
+            oracle.ekf_step_batch(ox, oP, thr, meas, acc)
+            ex, eP = s.ekf_state()
+            assert (np.abs(ex - ox) / np.maximum(1.0, np.abs(ox))).max() < 1e-6, t
+            s.set_ekf_state(ox, oP)
+            p = s.rls(meas, acc, compensate=True)
+            po = oracle.rls_step_batch(ost, ox, acc, meas, compensate=True)
+            st = s.rls_state()
+            # same arithmetic in the same order on both sides (FMA contraction aside); the lambda update is a threshold
+            # decision, so it must agree exactly
+            assert np.array_equal(st[:, :, 20], ost[:, :, 20]), t
+            assert np.array_equal(st[:, :, 22:24], ost[:, :, 22:24])
+            assert np.allclose(st[:, :, :20], ost[:, :, :20], rtol=1e-9, atol=1e-10), t
+            assert np.allclose(st[:, :, 24:79], ost[:, :, 24:79], rtol=1e-9, atol=1e-10), t
+            f_ok = np.isclose(st[:, :, 21], ost[:, :, 21], rtol=1e-8) | (np.isnan(st[:, :, 21]) & np.isnan(ost[:, :, 21]))
+            assert f_ok.all(), t
+            assert np.allclose(p, po, rtol=1e-9, atol=1e-9), t
+            s.set_rls_state(ost)
+    finally:
+        oracle.ekf_set_model(0)
+    lam = ost[:, :, 20]
+    assert lam.min() < 0.9 < lam.max()          # the forgetting factor moved both ways over the run
+    # compensate off: only p[0..3] written (reference brace placement, bluerov2_ampc.cpp:345-379)
+    p_in = np.full((B, 16), 3.0)
+    p = s.rls(meas, acc, compensate=False, out=p_in.copy())
+    assert np.array_equal(p[:, :4], np.zeros((B, 4))) and np.array_equal(p[:, 4:], p_in[:, 4:])
+    s.close()
+
+
+def test_ampc_tick_on_device_equals_host_chain(solver_mod, oracle):
+    """One AMPC tick as the node runs it (EKF -> RLSFF -> solve) with device pointers on one stream equals the same tick
+    through the host entry points, and the solve agrees with the oracle fed the oracle's parameters."""
+    import torch
+    dev = torch.device("cuda", 0)
+    B, N = 64, 20
+    w = wl.tracking_batch(B, N, seed=3, pos_spread=0.3)
+    rng = np.random.default_rng(4)
+    thr = rng.uniform(-5, 5, (B, 6)); acc = rng.uniform(-0.5, 0.5, (B, 6))
+    meas = w["x0"].copy()
+    outs = []
+    for use_dev in (False, True):
+        s = solver_mod.BatchSolver(B, N)
+        s.set_option("ekf_model", 1)
+        s.set_iterate(w["X"], w["U"])
+        if use_dev:
+            d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+            s.ekf(d(thr), d(meas), d(acc))
+            p = s.rls(d(meas), d(acc), compensate=True)
+            u0, th, st = s.solve(d(w["x0"]), d(w["yref"]), p)
+            torch.cuda.synchronize()
+            outs.append((u0.cpu().numpy(), th.cpu().numpy(), st.cpu().numpy(), p.cpu().numpy()))
+        else:
+            s.ekf(thr, meas, acc)
+            p = s.rls(meas, acc, compensate=True)
+            u0, th, st = s.solve(w["x0"], w["yref"], p)
+            outs.append((u0, th, st, p))
+        s.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    u0, th, st, p = outs[0]
+    assert (st == 0).all()
+    X, U = w["X"].copy(), w["U"].copy()
+    so, _, _ = oracle.rti_step_batch(wl.time_steps(N), w["x0"], w["yref"], p, X, U)
+    assert (so == 0).all() and np.abs(u0 - U[:, 0]).max() < TOL_U
