@@ -1,6 +1,7 @@
 """In-tree build of the CUDA library (nvcc, sm_100a only).
 
     python -m bluerov2_b200.build [--force]
+    python -m bluerov2_b200.build --stage DIR     # drop-in tree for the reference's CMake (see stage())
 
 Produces, under ``bluerov2_b200/lib/``:
 
@@ -97,6 +98,50 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def stage(dest: str) -> str:
+    """Assemble the drop-in tree the reference's CMake expects (bluerov2_dobmpc/CMakeLists.txt:39-41,71-78,94-97):
+
+        <dest>/c_generated_code/   stands in for bluerov2_dobmpc/scripts/c_generated_code (``${bluerov2_model}``):
+                                   acados_solver_bluerov2.h, bluerov2_model/, bluerov2_cost/, bluerov2_constraints/,
+                                   libacados_ocp_solver_bluerov2.so
+        <dest>/acados/include/     stands in for ~/acados/include (``${acados_include}``): acados/, acados_c/, blasfeo/
+        <dest>/acados/lib/         stands in for ~/acados/lib (``${acados_lib}``): libacados.so, libhpipm.so, libblasfeo.so
+        <dest>/cmake/              bluerov2_b200-config.cmake (find_package(bluerov2_b200 CONFIG))
+
+    With it the reference's CMakeLists needs exactly the two acados paths it already asks every user to set; the
+    generated directory is replaced wholesale.  The shims find the product library through their $ORIGIN rpath
+    (../../c_generated_code)."""
+    build_library()
+    dest = os.path.abspath(dest)
+    gen, ainc, alib = (os.path.join(dest, "c_generated_code"), os.path.join(dest, "acados", "include"),
+                       os.path.join(dest, "acados", "lib"))
+    for d in (gen, ainc, alib, os.path.join(dest, "cmake")):
+        os.makedirs(d, exist_ok=True)
+    shutil.copy2(os.path.join(INCLUDE, "acados_solver_bluerov2.h"), gen)
+    shutil.copy2(os.path.join(INCLUDE, "bluerov2_b200.h"), gen)
+    for sub in ("bluerov2_model", "bluerov2_cost", "bluerov2_constraints"):
+        shutil.copytree(os.path.join(INCLUDE, sub), os.path.join(gen, sub), dirs_exist_ok=True)
+    for sub in ("acados", "acados_c", "blasfeo"):
+        shutil.copytree(os.path.join(INCLUDE, sub), os.path.join(ainc, sub), dirs_exist_ok=True)
+    shutil.copy2(LIB, gen)
+    stub = os.path.join(alib, "_stub.c")
+    with open(stub, "w") as f:
+        f.write("/* link shim: see bluerov2_b200/build.py */\n")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    for sh in SHIMS:
+        cmd = [cc, "-shared", "-fPIC", "-o", os.path.join(alib, sh), stub, "-Wl,--no-as-needed", "-L" + gen,
+               "-lacados_ocp_solver_bluerov2", "-Wl,-rpath,$ORIGIN/../../c_generated_code", "-Wl,-soname," + sh]
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        if out.returncode != 0:
+            raise RuntimeError("shim link failed:\n" + out.stdout + out.stderr)
+    os.remove(stub)
+    shutil.copy2(os.path.join(ROOT, "cmake", "bluerov2_b200-config.cmake"), os.path.join(dest, "cmake"))
+    return dest
+
+
 if __name__ == "__main__":
-    p = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(p)
+    if "--stage" in sys.argv:
+        print(stage(sys.argv[sys.argv.index("--stage") + 1]))
+    else:
+        p = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(p)
