@@ -796,6 +796,11 @@ __device__ bool factor_sweep(Inst& I)
             // p_N = We (X_N - xref_N)
             pq0 = a.We[q] * (I.Xlin[N * NX + q] - yN[q]);
             pq1 = lo ? a.We[8 + e] * (I.Xlin[N * NX + 8 + e] - yN[8 + e]) : 0.0;
+            if (q == 4) {                       // p_N in the rows the k-tiles of lanes (4, t) hold
+                vin[0] = a.We[row0] * (I.Xlin[N * NX + row0] - yN[row0]);
+                vin[1] = a.We[row1] * (I.Xlin[N * NX + row1] - yN[row1]);
+                vin[2] = a.We[row2] * (I.Xlin[N * NX + row2] - yN[row2]);
+            }
         }
     }
     I.template begin<false, true, KIND == FS_IPM>();
@@ -829,19 +834,8 @@ __device__ bool factor_sweep(Inst& I)
         const double hx0 = shfl(h[0][1][1], src2), hx1 = shfl(h[1][1][1], src2);
         const double b02 = hi2 ? hx0 : h[0][1][0];
         const double b12 = hi2 ? hx1 : h[1][1][0];
-        if (KIND == FS_ABS) {
-            // s+ = P+ b_k + p+ : row-block dot products against b, reduced over the quad, then handed to lanes q == 4
-            const double bb0 = Gs[G_B_OFF + row0], bb1 = Gs[G_B_OFF + row1];
-            const double bb2 = hi2 ? 0.0 : Gs[G_B_OFF + 8 + 2 * t], bb3 = hi2 ? 0.0 : Gs[G_B_OFF + 9 + 2 * t];
-            double s0 = h[0][0][0] * bb0 + h[0][0][1] * bb1 + h[0][1][0] * bb2 + h[0][1][1] * bb3;
-            double s1 = h[1][0][0] * bb0 + h[1][0][1] * bb1 + h[1][1][0] * bb2 + h[1][1][1] * bb3;
-            s0 += shfl_x(s0, 1); s1 += shfl_x(s1, 1);
-            s0 += shfl_x(s0, 2); s1 += shfl_x(s1, 2);
-            s0 += pq0; s1 += pq1;                       // quad layout: s+[q], s+[8+q]
-            const double i0 = shfl(s0, 8 * t), i1 = shfl(s0, 8 * t + 4), i2 = shfl(s1, hi2 ? 4 * (2 * t - 3) : 8 * t);
-            vin[0] = (q == 4) ? i0 : 0.0; vin[1] = (q == 4) ? i1 : 0.0; vin[2] = (q == 4) ? i2 : 0.0;
-        }
-
+        // FS_ABS: vin = p+ (set at the end of the previous stage); the P+ b_k part of s+ = P+ b_k + p+ is formed AFTER the first
+        // product as (Z'P+) b_k, off the path that leads into the DMMAs
         // ---- W' = Z' [P+ | v1 | v2] ----
         double w[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
         {
@@ -869,7 +863,17 @@ __device__ bool factor_sweep(Inst& I)
             dmma(h[0][n], a02, z[2][n]);        dmma(h[1][n], a12, z[2][n]);
         }
         // ---- the vector products sit in columns 12, 13 of W': lane (q,2) holds ([A|B]'v1)[8m+q], ([A|B]'v2)[8m+q] ----
-        const double at0 = shfl(w[0][1][0], qb | 2), at1 = shfl(w[1][1][0], qb | 2);
+        double at0 = shfl(w[0][1][0], qb | 2), at1 = shfl(w[1][1][0], qb | 2);
+        if (KIND == FS_ABS) {
+            // Z's+ = Z'p+ + (Z'P+) b_k: lane (q,t) holds columns 2t, 2t+1, 8+2t, 9+2t of rows q / 8+q of Z'P+
+            const double bb0 = Gs[G_B_OFF + row0], bb1 = Gs[G_B_OFF + row1];
+            const double bb2 = hi2 ? 0.0 : Gs[G_B_OFF + 8 + 2 * t], bb3 = hi2 ? 0.0 : Gs[G_B_OFF + 9 + 2 * t];
+            double s0 = w[0][0][0] * bb0 + w[0][0][1] * bb1 + w[0][1][0] * bb2 + w[0][1][1] * bb3;
+            double s1 = w[1][0][0] * bb0 + w[1][0][1] * bb1 + w[1][1][0] * bb2 + w[1][1][1] * bb3;
+            s0 += shfl_x(s0, 1); s1 += shfl_x(s1, 1);
+            s0 += shfl_x(s0, 2); s1 += shfl_x(s1, 2);
+            at0 += s0; at1 += s1;
+        }
         double bt0 = 0.0, bt1 = 0.0;
         if (KIND == FS_IPM) { bt0 = shfl(w[0][1][1], qb | 2); bt1 = shfl(w[1][1][1], qb | 2); }
         const double gu = gu_loc + at1;          // quads 4..7: IPM: R du + r + B'pi+;  ABS: rlin + B's+ (= g)
@@ -905,24 +909,17 @@ __device__ bool factor_sweep(Inst& I)
             inv4_apply(Bi, y0, kc);              // K[:, q]
             inv4_apply(Bi, y1, kd);              // K[:, 8+q]   (garbage in quads 4..7, masked below)
             inv4_apply(Bi, gt, kf);
-            if (t == 0) {
-                *reinterpret_cast<double2*>(Fk + q * 4) = make_double2(kc[0], kc[1]);
-                *reinterpret_cast<double2*>(Fk + q * 4 + 2) = make_double2(kc[2], kc[3]);
-            }
-            if (t == 1 && lo) {
-                *reinterpret_cast<double2*>(Fk + (8 + q) * 4) = make_double2(kd[0], kd[1]);
-                *reinterpret_cast<double2*>(Fk + (8 + q) * 4 + 2) = make_double2(kd[2], kd[3]);
-            }
-            if (lane == 2) {
-                *reinterpret_cast<double2*>(Fk + F_KFF) = make_double2(kf[0], kf[1]);
-                *reinterpret_cast<double2*>(Fk + F_KFF + 2) = make_double2(kf[2], kf[3]);
-            }
             yg0 = y0[0] * kf[0] + y0[1] * kf[1] + y0[2] * kf[2] + y0[3] * kf[3];
             yg1 = y1[0] * kf[0] + y1[1] * kf[1] + y1[2] * kf[2] + y1[3] * kf[3];
             const double ys0 = (t == 0) ? y0[0] : (t == 1) ? y0[1] : (t == 2) ? y0[2] : y0[3];
             double ys1 = (t == 0) ? y1[0] : (t == 1) ? y1[1] : (t == 2) ? y1[2] : y1[3];
             const double ks0 = (t == 0) ? kc[0] : (t == 1) ? kc[1] : (t == 2) ? kc[2] : kc[3];
             double ks1 = (t == 0) ? kd[0] : (t == 1) ? kd[1] : (t == 2) ? kd[2] : kd[3];
+            // F record, branch-free: K[t][q] is element 4q + t = lane of Kt (one coalesced 256-byte store), K[t][8+q] element
+            // 32 + lane for the quads that own a second state row, kff[t] from lanes 0..3
+            Fk[lane] = ks0;
+            if (lo) Fk[32 + lane] = ks1;
+            if (lane < 4) Fk[F_KFF + lane] = (t == 0) ? kf[0] : (t == 1) ? kf[1] : (t == 2) ? kf[2] : kf[3];
             if (!lo) { ys1 = 0.0; ks1 = 0.0; }
             dmma(h[0][0], -ys0, ks0); dmma(h[0][1], -ys0, ks1);
             dmma(h[1][0], -ys1, ks0); dmma(h[1][1], -ys1, ks1);
@@ -986,6 +983,8 @@ __device__ bool factor_sweep(Inst& I)
         } else {
             pq0 = qx0 + at0 - yg0;               // p = qlin + A's+ - K'g
             pq1 = qx1 + at1 - yg1;
+            const double i0 = shfl(pq0, 8 * t), i1 = shfl(pq0, 8 * t + 4), i2 = shfl(pq1, hi2 ? 4 * (2 * t - 3) : 8 * t);
+            vin[0] = (q == 4) ? i0 : 0.0; vin[1] = (q == 4) ? i1 : 0.0; vin[2] = (q == 4) ? i2 : 0.0;
         }
     }
     __syncwarp();
