@@ -42,8 +42,9 @@ struct br2_batch_solver {
     int traj_rows;
     double *d_ex, *d_eP, *d_thr, *d_meas, *d_acc, *d_wf, *d_pout;   // EKF state + staging
     double* d_rls;                            // RLS-VFF state [B][4][RLS_STRIDE] (AMPC)
-    cudaStream_t stream;
+    cudaStream_t stream, stream_x0;   // host API: main stream; second stream carrying the x0 upload past the lineariser
     cudaEvent_t ev0, ev1, ev_mid;   // solve start / end / between linearisation and IPM
+    cudaEvent_t ev_x0;              // x0 upload complete (the IPM kernel is its first reader)
     unsigned long long* d_iter_total;   // IPM iterations executed, summed over instances and solves
     bool timed;
 };
@@ -75,7 +76,9 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev_mid) cudaEventDestroy(s->ev_mid);
+    if (s->ev_x0) cudaEventDestroy(s->ev_x0);
     if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->stream_x0) cudaStreamDestroy(s->stream_x0);
     free(s);
     return BR2_OK;
 }
@@ -129,6 +132,8 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     DA(d_lines, B);
 #undef DA
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s->stream_x0, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s->ev_x0, cudaEventDisableTiming));
     CK(cudaEventCreate(&s->ev0));
     CK(cudaEventCreate(&s->ev1));
     CK(cudaEventCreate(&s->ev_mid));
@@ -285,7 +290,42 @@ static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, con
 }
 
 static int solve_enqueue(br2_batch_solver* s, const double* d_x0, const double* d_yref, const int* d_lines, const double* d_p,
-                         int p_per_stage, double* d_u0, double* d_thrust, int* d_status, cudaStream_t st);
+                         int p_per_stage, double* d_u0, double* d_thrust, int* d_status, cudaStream_t st,
+                         cudaEvent_t before_ipm = nullptr);
+
+// Host output buffer that the device can write directly (pinned + mapped under unified addressing: cudaHostAlloc /
+// cudaHostRegister / torch pin_memory): returns its device alias, else null (-> staged copy).  Writing u0 / thrust /
+// status from the kernel epilogue straight into such a buffer removes three device-to-host copies from every host call.
+template <class T>
+static T* mapped_alias(T* host)
+{
+    if (!host) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return (T*)at.devicePointer;
+}
+
+// common tail of the two host entry points: x0 rides a second stream past the lineariser (the IPM kernel is its first
+// reader); outputs go straight to mapped host buffers when possible
+static int solve_host_common(br2_batch_solver* s, const double* x0, const double* d_yref, const int* d_lines, int p_per_stage,
+                             double* u0, double* thrust, int* status)
+{
+    const size_t B = s->B;
+    cudaStream_t st = s->stream;
+    CK(cudaMemcpyAsync(s->d_x0, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, s->stream_x0));
+    CK(cudaEventRecord(s->ev_x0, s->stream_x0));
+    double* a_u0 = mapped_alias(u0);
+    double* a_th = mapped_alias(thrust);
+    int* a_st = mapped_alias(status);
+    int rc = solve_enqueue(s, s->d_x0, d_yref, d_lines, s->d_p, p_per_stage, a_u0, a_th, a_st, st, s->ev_x0);
+    if (rc != BR2_OK) return rc;
+    if (u0 && !a_u0) CK(cudaMemcpyAsync(u0, s->d_u0, sizeof(double) * B * 4, cudaMemcpyDeviceToHost, st));
+    if (thrust && !a_th) CK(cudaMemcpyAsync(thrust, s->d_thrust, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
+    if (status && !a_st) CK(cudaMemcpyAsync(status, s->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BR2_OK;
+}
 
 extern "C" int br2_batch_solve_device(br2_batch_solver* s, const double* d_x0, const double* d_yref, const double* d_p,
                                       int p_per_stage, double* d_u0, double* d_thrust, int* d_status, void* stream)
@@ -323,20 +363,13 @@ extern "C" int br2_batch_solve_windowed_host(br2_batch_solver* s, const double* 
     CK(cudaSetDevice(s->device));
     const size_t B = s->B, N = s->N;
     cudaStream_t st = s->stream;
-    CK(cudaMemcpyAsync(s->d_x0, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->d_lines, lines, sizeof(int) * B, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->d_p, p, sizeof(double) * B * (p_per_stage ? (N + 1) * NP : NP), cudaMemcpyHostToDevice, st));
-    int rc = solve_enqueue(s, s->d_x0, nullptr, s->d_lines, s->d_p, p_per_stage, nullptr, nullptr, nullptr, st);
-    if (rc != BR2_OK) return rc;
-    if (u0) CK(cudaMemcpyAsync(u0, s->d_u0, sizeof(double) * B * 4, cudaMemcpyDeviceToHost, st));
-    if (thrust) CK(cudaMemcpyAsync(thrust, s->d_thrust, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
-    if (status) CK(cudaMemcpyAsync(status, s->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return BR2_OK;
+    CK(cudaMemcpyAsync(s->d_lines, lines, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    return solve_host_common(s, x0, nullptr, s->d_lines, p_per_stage, u0, thrust, status);
 }
 
 static int solve_enqueue(br2_batch_solver* s, const double* d_x0, const double* d_yref, const int* d_lines, const double* d_p,
-                         int p_per_stage, double* d_u0, double* d_thrust, int* d_status, cudaStream_t st)
+                         int p_per_stage, double* d_u0, double* d_thrust, int* d_status, cudaStream_t st, cudaEvent_t before_ipm)
 {
     CK(cudaSetDevice(s->device));
     SolveArgs a;
@@ -344,6 +377,7 @@ static int solve_enqueue(br2_batch_solver* s, const double* d_x0, const double* 
     CK(cudaEventRecord(s->ev0, st));
     launch_linearize(a, st);
     CK(cudaEventRecord(s->ev_mid, st));
+    if (before_ipm) CK(cudaStreamWaitEvent(st, before_ipm, 0));
     launch_ipm(a, s->sm_count, st);
     CK(cudaEventRecord(s->ev1, st));
     s->timed = true;
@@ -358,16 +392,9 @@ extern "C" int br2_batch_solve_host(br2_batch_solver* s, const double* x0, const
     CK(cudaSetDevice(s->device));
     const size_t B = s->B, N = s->N;
     cudaStream_t st = s->stream;
-    CK(cudaMemcpyAsync(s->d_x0, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->d_yref, yref, sizeof(double) * B * (N + 1) * NY, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->d_p, p, sizeof(double) * B * (p_per_stage ? (N + 1) * NP : NP), cudaMemcpyHostToDevice, st));
-    int rc = br2_batch_solve_device(s, s->d_x0, s->d_yref, s->d_p, p_per_stage, nullptr, nullptr, nullptr, st);
-    if (rc != BR2_OK) return rc;
-    if (u0) CK(cudaMemcpyAsync(u0, s->d_u0, sizeof(double) * B * 4, cudaMemcpyDeviceToHost, st));
-    if (thrust) CK(cudaMemcpyAsync(thrust, s->d_thrust, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
-    if (status) CK(cudaMemcpyAsync(status, s->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return BR2_OK;
+    CK(cudaMemcpyAsync(s->d_yref, yref, sizeof(double) * B * (N + 1) * NY, cudaMemcpyHostToDevice, st));
+    return solve_host_common(s, x0, s->d_yref, nullptr, p_per_stage, u0, thrust, status);
 }
 
 extern "C" int br2_batch_get_stats_host(br2_batch_solver* s, int* iters, double* info)
