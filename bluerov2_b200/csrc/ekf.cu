@@ -6,8 +6,11 @@
 //   COUPLED mass matrix;  RK4 with k3 = f(x + k2/3) (sic, :630);  F and H by forward differences, d = 1e-6
 //   (:722-752);  gain through an explicit 18x18 inverse (:535);  Joseph-form covariance update (:537).
 // Lane mapping: the 19 RK4 / 19 h() evaluations of the two finite-difference Jacobians run on lanes 0..18 in
-// parallel (lane 0 = unperturbed); the ten 18x18x18 products and the Gauss-Jordan inverse are row-per-lane with
-// operands in shared memory.  Output: esti_x, esti_P, world-frame disturbance (:540-545) and the OCP parameter
+// parallel (lane 0 = unperturbed); the ten 18x18x18 products use 3 x 4 register tiles on 30 lanes (operands in shared
+// memory, five 18x18 buffers per warp); the Gauss-Jordan inverse keeps one row of [S | I] per lane in registers, finds
+// the pivot with three warp reductions and exchanges row POSITIONS instead of rows.  16 warps/SM (128 registers,
+// 13.4 KB of shared memory per warp): the kernel is latency-bound and its time falls with every resident warp
+// (8 / 12 / 16 warps/SM: 0.24 / 0.18 / 0.15 ms at B = 4096, profiles/r01k_ekf_variants.txt).  Output: esti_x, esti_P, world-frame disturbance (:540-545) and the OCP parameter
 // vector handed to the solver (bluerov2_dob.cpp:324-355).
 #include "engine.h"
 
@@ -15,8 +18,14 @@ namespace br2 {
 
 #define FULL_MASK 0xffffffffu
 constexpr int EN = 18;
-constexpr int LD = 20;            // leading dimension of the shared-memory matrices (16-byte aligned rows)
-constexpr int EKF_WARPS = 2;
+constexpr int LD = 18;            // leading dimension of the shared-memory matrices (144-byte rows: 16-byte aligned)
+#ifndef BR2_EKF_WARPS
+#define BR2_EKF_WARPS 2
+#endif
+#ifndef BR2_EKF_MINB
+#define BR2_EKF_MINB 8
+#endif
+constexpr int EKF_WARPS = BR2_EKF_WARPS;
 
 namespace ekfc {
 constexpr double DT = 0.05, M = 11.26, Ix = 0.3, Iy = 0.63, Iz = 0.58, Zg = 0.02, G = 9.81, EBUOY = 0.661618;
@@ -84,46 +93,77 @@ __device__ void ekf_h(const double* x, const double* acc, double* y, const doubl
 __device__ void ekf_rk4(const double* x, const double* tau, double* xn, const double* c_Dl, const double* c_Dnl)
 {
     using namespace ekfc;
-    double k1[EN], k2[EN], k3[EN], k4[EN], xs[EN];
-    ekf_f(x, tau, k1, c_Dl, c_Dnl);
+    // x + (k1 + 2 k2 + 2 k3 + k4) / 6 with the sum accumulated left to right as the reference's expression evaluates it
+    double k[EN], xs[EN], acc[EN];
+    ekf_f(x, tau, k, c_Dl, c_Dnl);
 #pragma unroll
-    for (int i = 0; i < EN; i++) { k1[i] *= DT; xs[i] = x[i] + k1[i] / 2; }
-    ekf_f(xs, tau, k2, c_Dl, c_Dnl);
+    for (int i = 0; i < EN; i++) { k[i] *= DT; acc[i] = k[i]; xs[i] = x[i] + k[i] / 2; }
+    ekf_f(xs, tau, k, c_Dl, c_Dnl);
 #pragma unroll
-    for (int i = 0; i < EN; i++) { k2[i] *= DT; xs[i] = x[i] + k2[i] / 3; }   // sic: /3 (bluerov2_dob.cpp:630)
-    ekf_f(xs, tau, k3, c_Dl, c_Dnl);
+    for (int i = 0; i < EN; i++) { k[i] *= DT; acc[i] = acc[i] + 2 * k[i]; xs[i] = x[i] + k[i] / 3; }   // sic: /3 (bluerov2_dob.cpp:630)
+    ekf_f(xs, tau, k, c_Dl, c_Dnl);
 #pragma unroll
-    for (int i = 0; i < EN; i++) { k3[i] *= DT; xs[i] = x[i] + k3[i]; }
-    ekf_f(xs, tau, k4, c_Dl, c_Dnl);
+    for (int i = 0; i < EN; i++) { k[i] *= DT; acc[i] = acc[i] + 2 * k[i]; xs[i] = x[i] + k[i]; }
+    ekf_f(xs, tau, k, c_Dl, c_Dnl);
 #pragma unroll
-    for (int i = 0; i < EN; i++) { k4[i] *= DT; xn[i] = x[i] + (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]) / 6; }
+    for (int i = 0; i < EN; i++) { k[i] *= DT; xn[i] = x[i] + (acc[i] + k[i]) / 6; }
 }
 
-// C = A * B or A * B' (18x18, shared memory, leading dimension LD); lane i < 18 owns row i.
+// C = A * B or A * B' (18x18, shared memory, leading dimension LD).  30 lanes each own a 3 x 4 tile of C (row group
+// lane / 5, column group lane % 5; the last column group is two columns wide): 12 independent accumulators per lane,
+// each summed over k = 0..17 in order with fma -- the order of the oracle's matmul.
 __device__ __forceinline__ void mm18(const double* A, const double* B, double* C, bool transB, int lane)
 {
-    if (lane < EN) {
-        double a[EN];
+    if (lane < 30) {
+        const int r0 = 3 * (lane / 5), c0 = 4 * (lane % 5);
+        const bool edge = c0 == 16;
+        double acc[3][4];
 #pragma unroll
-        for (int k = 0; k < EN; k++) a[k] = A[lane * LD + k];
-#pragma unroll 2
-        for (int j = 0; j < EN; j++) {
-            double s = 0.0;
+        for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int k = 0; k < EN; k++) s = fma(a[k], transB ? B[j * LD + k] : B[k * LD + j], s);
-            C[lane * LD + j] = s;
+            for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+        if (!transB) {
+#pragma unroll 6
+            for (int k = 0; k < EN; k++) {
+                const double2 b01 = *reinterpret_cast<const double2*>(B + k * LD + c0);
+                const double2 b23 = edge ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(B + k * LD + c0 + 2);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const double av = A[(r0 + i) * LD + k];
+                    acc[i][0] = fma(av, b01.x, acc[i][0]); acc[i][1] = fma(av, b01.y, acc[i][1]);
+                    acc[i][2] = fma(av, b23.x, acc[i][2]); acc[i][3] = fma(av, b23.y, acc[i][3]);
+                }
+            }
+        } else {
+            const int j2 = edge ? c0 : c0 + 2, j3 = edge ? c0 : c0 + 3;     // clamped: the extra products are discarded
+#pragma unroll 6
+            for (int k = 0; k < EN; k++) {
+                const double b0 = B[c0 * LD + k], b1 = B[(c0 + 1) * LD + k], b2 = B[j2 * LD + k], b3 = B[j3 * LD + k];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const double av = A[(r0 + i) * LD + k];
+                    acc[i][0] = fma(av, b0, acc[i][0]); acc[i][1] = fma(av, b1, acc[i][1]);
+                    acc[i][2] = fma(av, b2, acc[i][2]); acc[i][3] = fma(av, b3, acc[i][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            *reinterpret_cast<double2*>(C + (r0 + i) * LD + c0) = make_double2(acc[i][0], acc[i][1]);
+            if (!edge) *reinterpret_cast<double2*>(C + (r0 + i) * LD + c0 + 2) = make_double2(acc[i][2], acc[i][3]);
         }
     }
     __syncwarp();
 }
 
 struct __align__(16) EkfSmem {
-    double Fm[EN * LD], Hm[EN * LD], Pp[EN * LD], Kal[EN * LD], T1[EN * LD], T2[EN * LD];
-    double aug[EN * 2 * LD];     // [S | I] for the Gauss-Jordan inverse
-    double vec[64];
+    double Fm[EN * LD], Hm[EN * LD], Pp[EN * LD], T1[EN * LD], T2[EN * LD];   // Fm doubles as Kal once P_pred is formed
+    double prow[2 * EN + 4];     // scaled pivot row of the Gauss-Jordan inverse: [S | I] part of one row
+    double vec[EN + 2];          // innovation
+    double xpv[2 * EN];          // x_pred | measurement vector y = [pose, body velocity, tau]
 };
 
-__global__ void __launch_bounds__(EKF_WARPS * 32) ekf_kernel(EkfArgs a)
+__global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfArgs a)
 {
     using namespace ekfc;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -165,7 +205,14 @@ __global__ void __launch_bounds__(EKF_WARPS * 32) ekf_kernel(EkfArgs a)
     for (int i = 0; i < EN; i++) {
         xp[i] = __shfl_sync(FULL_MASK, f1[i], 0);
         if (lane >= 1 && lane <= EN) sm.Fm[i * LD + lane - 1] = (f1[i] - xp[i]) / d;
+        if (lane == 0) sm.xpv[i] = f1[i];          // x_pred, read back by component for the state update
     }
+    if (lane < 6) {
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            if (i == lane) sm.xpv[EN + 12 + i] = tau[i];     // measurement vector: tau part (pose / velocities added below)
+    }
+    if (lane < 12) sm.xpv[EN + lane] = a.meas[(size_t)inst * 12 + lane];
     __syncwarp();
     // ---- P_pred = F P F' + Q (:529) ----
     mm18(sm.Fm, sm.T2, sm.T1, false, lane);
@@ -178,103 +225,105 @@ __global__ void __launch_bounds__(EKF_WARPS * 32) ekf_kernel(EkfArgs a)
         x[i] = xp[i];
         if (lane >= 1 && lane <= EN && i == lane - 1) x[i] += d;
     }
-    double y1[EN], yp[EN];
-    ekf_h(x, acc, y1, c_Dl, c_Dnl);
+    {
+        double y1[EN];
+        ekf_h(x, acc, y1, c_Dl, c_Dnl);
 #pragma unroll
-    for (int i = 0; i < EN; i++) {
-        yp[i] = __shfl_sync(FULL_MASK, y1[i], 0);
-        if (lane >= 1 && lane <= EN) sm.Hm[i * LD + lane - 1] = (y1[i] - yp[i]) / d;
+        for (int i = 0; i < EN; i++) {
+            const double yp = __shfl_sync(FULL_MASK, y1[i], 0);
+            if (lane >= 1 && lane <= EN) sm.Hm[i * LD + lane - 1] = (y1[i] - yp) / d;
+            if (lane == 0) sm.vec[i] = sm.xpv[EN + i] - y1[i];      // innovation y - y_pred
+        }
     }
     __syncwarp();
     // ---- S = H Pp H' + R ; explicit inverse by Gauss-Jordan with partial pivoting (:535) ----
     mm18(sm.Hm, sm.Pp, sm.T1, false, lane);
     mm18(sm.T1, sm.Hm, sm.T2, true, lane);
-    const int AL = 2 * LD;
-    if (lane < EN) {
-        for (int j = 0; j < EN; j++) {
-            sm.aug[lane * AL + j] = sm.T2[lane * LD + j] + (j == lane ? (DT * DT * DT * DT) / 4 : 0.0);
-            sm.aug[lane * AL + LD + j] = (j == lane) ? 1.0 : 0.0;
-        }
-    }
-    __syncwarp();
-    for (int c = 0; c < EN; c++) {
-        // pivot: largest |a[i][c]| over i >= c, first index on ties
-        double v = (lane >= c && lane < EN) ? fabs(sm.aug[lane * AL + c]) : -1.0;
-        int piv = lane;
+    {
+        // Lane i < 18 keeps one row of [S | I] in registers.  Rows are never moved: `myrow` is the row's position in the
+        // eliminated matrix, and a pivot exchange swaps positions.  Pivot = largest |entry| of column c over positions >= c,
+        // lowest position on ties (what a sequential scan finds): three warp reductions on the value's bit pattern.
+        const bool own = lane < EN;
+        const int li = own ? lane : 0;
+        double ra[EN], rb[EN];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const double vo = __shfl_xor_sync(FULL_MASK, v, o);
-            const int po = __shfl_xor_sync(FULL_MASK, piv, o);
-            if (vo > v || (vo == v && po < piv)) { v = vo; piv = po; }
+        for (int j = 0; j < EN; j++) {
+            ra[j] = sm.T2[li * LD + j] + (j == lane ? (DT * DT * DT * DT) / 4 : 0.0);
+            rb[j] = (j == lane) ? 1.0 : 0.0;
         }
-        if (piv != c) {
-            // swap rows c and piv: lanes 0..2*LD-1 each move one column (2*LD = 40 > 32: two rounds)
-            for (int j = lane; j < AL; j += 32) {
-                const double t = sm.aug[c * AL + j];
-                sm.aug[c * AL + j] = sm.aug[piv * AL + j];
-                sm.aug[piv * AL + j] = t;
+        int myrow = own ? lane : 99;
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < EN; c++) {
+            const double v = (own && myrow >= c) ? fabs(ra[c]) : -1.0;
+            const long long bits = __double_as_longlong(v);
+            const int hi = (int)(bits >> 32);
+            const int mhi = __reduce_max_sync(FULL_MASK, hi);
+            const unsigned lo = (hi == mhi) ? (unsigned)bits : 0u;
+            const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
+            const bool cand = (hi == mhi) && ((unsigned)bits == mlo);
+            const int pr = __reduce_min_sync(FULL_MASK, cand ? myrow : 99);      // position of the pivot row
+            const bool is_piv = own && (myrow == pr);
+            // exchange positions c <-> pr
+            if (is_piv) myrow = c;
+            else if (myrow == c) myrow = pr;
+            // pivot lane: scale its row and publish it
+            const double dinv = 1.0 / ra[c];
+            if (is_piv) {
+#pragma unroll
+                for (int j = 0; j < EN; j++) { ra[j] *= dinv; rb[j] *= dinv; }
+#pragma unroll
+                for (int j = 0; j < EN; j += 2) {
+                    *reinterpret_cast<double2*>(sm.prow + j) = make_double2(ra[j], ra[j + 1]);
+                    *reinterpret_cast<double2*>(sm.prow + EN + j) = make_double2(rb[j], rb[j + 1]);
+                }
             }
-        }
-        __syncwarp();
-        const double dinv = 1.0 / sm.aug[c * AL + c];
-        __syncwarp();
-        for (int j = lane; j < AL; j += 32) sm.aug[c * AL + j] *= dinv;
-        __syncwarp();
-        if (lane < EN && lane != c) {
-            const double f = sm.aug[lane * AL + c];
-            if (f != 0.0) {
-                for (int j = 0; j < EN; j++) sm.aug[lane * AL + j] -= f * sm.aug[c * AL + j];
-                for (int j = 0; j < EN; j++) sm.aug[lane * AL + LD + j] -= f * sm.aug[c * AL + LD + j];
+            __syncwarp();
+            if (!is_piv) {
+                const double f = ra[c];
+                if (f != 0.0) {
+#pragma unroll
+                    for (int j = 0; j < EN; j += 2) {
+                        const double2 pa = *reinterpret_cast<const double2*>(sm.prow + j);
+                        const double2 pb = *reinterpret_cast<const double2*>(sm.prow + EN + j);
+                        ra[j] -= f * pa.x; ra[j + 1] -= f * pa.y;
+                        rb[j] -= f * pb.x; rb[j + 1] -= f * pb.y;
+                    }
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
+        // Si -> T2: the lane at position r holds row r of the inverse
+        if (own) {
+#pragma unroll
+            for (int j = 0; j < EN; j += 2)
+                *reinterpret_cast<double2*>(sm.T2 + myrow * LD + j) = make_double2(rb[j], rb[j + 1]);
+        }
     }
-    // Si -> T2
-    if (lane < EN)
-        for (int j = 0; j < EN; j++) sm.T2[lane * LD + j] = sm.aug[lane * AL + LD + j];
     __syncwarp();
     // ---- Kal = Pp H' Si ----
     mm18(sm.Pp, sm.Hm, sm.T1, true, lane);
-    mm18(sm.T1, sm.T2, sm.Kal, false, lane);
+    double* const Kal = sm.Fm;                     // F is dead: its buffer takes the gain
+    mm18(sm.T1, sm.T2, Kal, false, lane);
     // ---- esti_x = x_pred + Kal (y - y_pred) (:536) ----
-    if (lane < EN) {
-        double ym;
-        if (lane < 12) ym = a.meas[(size_t)inst * 12 + lane];
-        else {
-            ym = 0.0;
-#pragma unroll
-            for (int i = 0; i < 6; i++)
-                if (i == lane - 12) ym = tau[i];
-        }
-        double ypl = 0.0;
-#pragma unroll
-        for (int i = 0; i < EN; i++)
-            if (i == lane) ypl = yp[i];
-        sm.vec[lane] = ym - ypl;
-        sm.vec[32 + lane] = ym;
-    }
-    __syncwarp();
     double exn = 0.0;
     if (lane < EN) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < EN; i++)
-            if (i == lane) s = xp[i];
-        for (int j = 0; j < EN; j++) s += sm.Kal[lane * LD + j] * sm.vec[j];
+        double s = sm.xpv[lane];
+        for (int j = 0; j < EN; j++) s += Kal[lane * LD + j] * sm.vec[j];
         exn = s;
         ex[lane] = s;
     }
     // ---- Joseph form (:537): P = (I - K H) Pp (I - K H)' + K R K' ----
-    mm18(sm.Kal, sm.Hm, sm.T1, false, lane);
+    mm18(Kal, sm.Hm, sm.T1, false, lane);
     if (lane < EN)
         for (int j = 0; j < EN; j++) sm.T1[lane * LD + j] = (j == lane ? 1.0 : 0.0) - sm.T1[lane * LD + j];
     __syncwarp();
     mm18(sm.T1, sm.Pp, sm.T2, false, lane);
-    mm18(sm.T2, sm.T1, sm.Fm, true, lane);          // Fm reused: (I-KH) Pp (I-KH)'
-    mm18(sm.Kal, sm.Kal, sm.T2, true, lane);        // K K'
+    mm18(sm.T2, sm.T1, sm.Hm, true, lane);          // Hm reused (H is dead): (I-KH) Pp (I-KH)'
+    mm18(Kal, Kal, sm.T2, true, lane);              // K K'
     for (int idx = lane; idx < EN * EN; idx += 32) {
         const int i = idx / EN, j = idx % EN;
-        eP[idx] = sm.Fm[i * LD + j] + sm.T2[i * LD + j] * ((DT * DT * DT * DT) / 4);
+        eP[idx] = sm.Hm[i * LD + j] + sm.T2[i * LD + j] * ((DT * DT * DT * DT) / 4);
     }
     // ---- world-frame disturbance (:540-545) and OCP parameters (:324-355) ----
     const double e12 = __shfl_sync(FULL_MASK, exn, 12), e13 = __shfl_sync(FULL_MASK, exn, 13), e14 = __shfl_sync(FULL_MASK, exn, 14);
@@ -282,7 +331,7 @@ __global__ void __launch_bounds__(EKF_WARPS * 32) ekf_kernel(EkfArgs a)
     if (lane == 0) {
         if (a.wf_dist) {
             double s3, c3, s4, c4, s5, c5;
-            sincos(sm.vec[32 + 3], &s3, &c3); sincos(sm.vec[32 + 4], &s4, &c4); sincos(sm.vec[32 + 5], &s5, &c5);
+            sincos(sm.xpv[EN + 3], &s3, &c3); sincos(sm.xpv[EN + 4], &s4, &c4); sincos(sm.xpv[EN + 5], &s5, &c5);
             double* wf = a.wf_dist + (size_t)inst * 6;
             wf[0] = (c5 * c4) * e12 + (-s5 * c3 + c5 * s4 * s3) * e13 + (s5 * s3 + c5 * c3 * s4) * e14;
             wf[1] = (s5 * c4) * e12 + (c5 * c3 + s3 * s4 * s5) * e13 + (-c5 * s3 + s4 * s5 * c3) * e14;
