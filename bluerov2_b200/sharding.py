@@ -50,3 +50,55 @@ class ThrustGather:
                 if r != self.rank:
                     self.buf[lo:hi] = recv[r, : hi - lo]
         return self.buf
+
+
+class PipelinedThrustGather:
+    """Double-buffered ThrustGather: the all-gather of tick t runs on the collective's own stream while tick t + 1 is
+    already linearising (the thrust vectors are an OUTPUT of the tick -- nothing in the next solve reads them), so the
+    collective's launch + NVLink latency leaves the critical path.  Still exactly one all-gather per tick.
+
+        thr = g.slot(t)          # this rank's block of buffer t % depth; waits (stream-side) for the gather that last read it
+        solver.solve_*(..., out=(u0, thr, status))
+        g.all_gather_async(t)    # enqueued behind the solve, returns at once
+        ...
+        full = g.result(t)       # [total, 6] of tick t, valid on the current stream from here on
+    """
+
+    def __init__(self, total: int, device, depth: int = 2, group=None):
+        if depth < 1:
+            raise ValueError(depth)
+        self.gathers = [ThrustGather(total, device, group) for _ in range(depth)]
+        self.works = [None] * depth
+        self.depth = depth
+        self.world = self.gathers[0].world
+        self.bounds = self.gathers[0].bounds
+
+    def _wait(self, i):
+        if self.works[i] is not None:
+            self.works[i].wait()          # NCCL: the current stream waits for the collective; gloo: the host does
+            self.works[i] = None
+
+    def slot(self, t: int):
+        i = t % self.depth
+        self._wait(i)
+        return self.gathers[i].slot
+
+    def all_gather_async(self, t: int):
+        i = t % self.depth
+        g = self.gathers[i]
+        if g.world == 1:
+            return
+        if not g.equal:
+            g.all_gather()                # ragged shards: the padded blocking path
+            return
+        self.works[i] = dist.all_gather_into_tensor(g.buf, g.slot, group=g.group, async_op=True)
+
+    def result(self, t: int):
+        i = t % self.depth
+        self._wait(i)
+        return self.gathers[i].buf
+
+    def wait_all(self):
+        for i in range(self.depth):
+            self._wait(i)
+

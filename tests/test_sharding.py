@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from bluerov2_b200.sharding import ThrustGather, shard_bounds
+from bluerov2_b200.sharding import PipelinedThrustGather, ThrustGather, shard_bounds
 
 RC = 0.026546960744430276
 
@@ -58,3 +58,39 @@ def test_two_rank_all_gather_gloo(total):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert sorted(b for _, _, b in res) == [shard_bounds(total, 2, 0), shard_bounds(total, 2, 1)]
+
+
+def _worker_pipelined(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = PipelinedThrustGather(total, "cpu", depth=2)
+        lo, hi = g.bounds[rank]
+        T, ok = 5, True
+        us = [np.random.default_rng(t).uniform(-50, 50, (total, 4)) for t in range(T)]
+        for t in range(T):
+            g.slot(t).copy_(torch.from_numpy(_alloc(us[t][lo:hi])))    # tick t's epilogue writes its block of buffer t % 2
+            g.all_gather_async(t)
+            if t >= 1:                                                  # tick t-1 is read while tick t is in flight
+                ok &= bool(np.array_equal(g.result(t - 1).numpy(), _alloc(us[t - 1])))
+        ok &= bool(np.array_equal(g.result(T - 1).numpy(), _alloc(us[T - 1])))
+        g.wait_all()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [10, 11])
+def test_two_rank_pipelined_all_gather_gloo(total):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_pipelined, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
+
