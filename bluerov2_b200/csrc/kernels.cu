@@ -459,7 +459,8 @@ __device__ __forceinline__ double warp_sum(double v)
 // ---- per-warp TMA bulk-copy pipeline: stage records are prefetched HBM -> shared memory one stage ahead ----
 struct __align__(128) StageBuf { double G[GREC]; double F[FREC]; double V[VREC]; };
 constexpr int NSLOT = BR2_NSLOT;     // ring depth: records of NSLOT-1 stages are in flight ahead of the one being computed
-struct __align__(128) WarpSmem { StageBuf st[NSLOT]; unsigned long long bar[NSLOT]; };
+// xch: per-warp exchange buffer of the factor sweep: H[:, 12..15] (16 rows x 4) + g (4)
+struct __align__(128) WarpSmem { StageBuf st[NSLOT]; double xch[72]; unsigned long long bar[NSLOT]; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
@@ -882,22 +883,36 @@ __device__ bool factor_sweep(Inst& I)
         if (!lo && t == 2 + (e >> 1)) {
             if (e & 1) h[1][1][1] += rt; else h[1][1][0] += rt;
         }
+        // ---- H[:, 12..15] (= H_xu rows and Lam) and g go through the warp's exchange buffer: the lanes t = 2, 3 of every quad
+        //      hold columns 12..15 of rows q and 8+q; one 128-bit store each, then every lane reads what it needs (the 4x4 system
+        //      is solved redundantly per lane) -- 12 shared-memory loads instead of 22 64-bit shuffles ----
+        double* xch = I.sm.xch;
+        if (t >= 2) {
+            *reinterpret_cast<double2*>(xch + q * 4 + 2 * (t - 2)) = make_double2(h[0][1][0], h[0][1][1]);
+            *reinterpret_cast<double2*>(xch + (8 + q) * 4 + 2 * (t - 2)) = make_double2(h[1][1][0], h[1][1][1]);
+            if (!lo && t == 2) xch[64 + e] = gval;
+        }
+        __syncwarp();
         double m10[10];
-        m10[0] = shfl(h[1][1][0], 4 * 4 + 2);
-        m10[1] = shfl(h[1][1][0], 4 * 5 + 2); m10[2] = shfl(h[1][1][1], 4 * 5 + 2);
-        m10[3] = shfl(h[1][1][0], 4 * 6 + 2); m10[4] = shfl(h[1][1][1], 4 * 6 + 2); m10[5] = shfl(h[1][1][0], 4 * 6 + 3);
-        m10[6] = shfl(h[1][1][0], 4 * 7 + 2); m10[7] = shfl(h[1][1][1], 4 * 7 + 2); m10[8] = shfl(h[1][1][0], 4 * 7 + 3);
-        m10[9] = shfl(h[1][1][1], 4 * 7 + 3);
-        // ---- rows q and 8+q of H_xu (columns 12..15 live in lanes t = 2, 3 of the quad) ----
-        double y0[4], y1[4];
-        y0[0] = shfl(h[0][1][0], qb | 2); y0[1] = shfl(h[0][1][1], qb | 2);
-        y0[2] = shfl(h[0][1][0], qb | 3); y0[3] = shfl(h[0][1][1], qb | 3);
-        y1[0] = shfl(h[1][1][0], qb | 2); y1[1] = shfl(h[1][1][1], qb | 2);
-        y1[2] = shfl(h[1][1][0], qb | 3); y1[3] = shfl(h[1][1][1], qb | 3);
-        // ---- g to every lane ----
-        double gt[4];
-#pragma unroll
-        for (int c = 0; c < 4; c++) gt[c] = shfl(gval, 4 * (4 + c) + 2);
+        {
+            const double2 r1 = *reinterpret_cast<const double2*>(xch + 13 * 4);
+            const double2 r2a = *reinterpret_cast<const double2*>(xch + 14 * 4), r3a = *reinterpret_cast<const double2*>(xch + 15 * 4);
+            const double2 r3b = *reinterpret_cast<const double2*>(xch + 15 * 4 + 2);
+            m10[0] = xch[12 * 4];
+            m10[1] = r1.x; m10[2] = r1.y;
+            m10[3] = r2a.x; m10[4] = r2a.y; m10[5] = xch[14 * 4 + 2];
+            m10[6] = r3a.x; m10[7] = r3a.y; m10[8] = r3b.x; m10[9] = r3b.y;
+        }
+        // ---- rows q and 8+q of H_xu ----
+        double y0[4], y1[4], gt[4];
+        {
+            const double2 a0 = *reinterpret_cast<const double2*>(xch + q * 4), a1 = *reinterpret_cast<const double2*>(xch + q * 4 + 2);
+            const double2 b0 = *reinterpret_cast<const double2*>(xch + (8 + q) * 4), b1 = *reinterpret_cast<const double2*>(xch + (8 + q) * 4 + 2);
+            const double2 g0 = *reinterpret_cast<const double2*>(xch + 64), g1 = *reinterpret_cast<const double2*>(xch + 66);
+            y0[0] = a0.x; y0[1] = a0.y; y0[2] = a1.x; y0[3] = a1.y;
+            y1[0] = b0.x; y1[1] = b0.y; y1[2] = b1.x; y1[3] = b1.y;
+            gt[0] = g0.x; gt[1] = g0.y; gt[2] = g1.x; gt[3] = g1.y;       // g on every lane
+        }
         if (KIND == FS_IPM && !lo && t == 2) Vk[V_GU + e] = gu;
         double yg0, yg1;                         // (K'g)[q], (K'g)[8+q]
         if (KIND == FS_ABS) {
