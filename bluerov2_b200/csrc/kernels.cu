@@ -641,6 +641,16 @@ struct Inst {
     }
 };
 
+// pull the instance's iterate (X, U rows) into L2 ahead of the epilogue that updates it
+__device__ __forceinline__ void prefetch_iterate(const Inst& I)
+{
+    const char* xb = reinterpret_cast<const char*>(I.Xlin);
+    const char* ub = reinterpret_cast<const char*>(I.Ulin);
+    const int xbytes = (I.N + 1) * NX * 8, ubytes = I.N * NU * 8;
+    for (int o = I.lane * 128; o < xbytes + 128; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + (o < xbytes ? o : xbytes - 8)));
+    for (int o = I.lane * 128; o < ubytes + 128; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ub + (o < ubytes ? o : ubytes - 8)));
+}
+
 // E0: cold start of the IPM iterate (qp_solver_warm_start 0): du = 0 pushed strictly inside the box, slacks
 // exactly consistent, lam = mu0 / t.
 __device__ void ipm_init(Inst& I)
@@ -1094,6 +1104,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         bool active = false;                    // a bound is (nearly) active at the solution -> hint for the next solve
         if (a.fast_path && a.hint[inst] == 0) {
             if (factor_sweep<FS_ABS>(I)) {
+                prefetch_iterate(I);
                 bmax = forward_sweep<2>(I);     // leaves (dx, du) in V_X, V_V
                 bool inside = true;
 #pragma unroll 5
@@ -1163,6 +1174,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             }
             __syncwarp();
             // ---------- B2 / F2: corrector ----------
+            prefetch_iterate(I);            // this may be the last iteration: have X, U in L2 for the epilogue
             backward_vec_sweep(I);
             forward_sweep<1>(I);
             // ---------- E2: step lengths and update ----------
@@ -1229,14 +1241,40 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         active = __any_sync(FULL_MASK, active);
         if (lane == 0) a.hint[inst] = (active || status != 0) ? 1 : 0;
         if (finite) {
-            // restrict: X/U never alias the V workspace, so the loads of an unrolled batch may be issued ahead of its stores
-            const double* __restrict__ Vr = I.V;
-            double* __restrict__ Ur = Uo;
-            double* __restrict__ Xr = Xo;
-#pragma unroll 5
-            for (int idx = lane; idx < nb; idx += 32) Ur[idx] += Vr[(size_t)(idx >> 2) * VREC + V_V + (idx & 3)];
-#pragma unroll 4
-            for (int idx = lane; idx < 12 * (N + 1); idx += 32) Xr[idx] += Vr[(size_t)(idx / 12) * VREC + V_X + idx % 12];
+            // X / U were last touched by the lineariser, before ~300 MB of stage records went through L2: without care this is
+            // a chain of DRAM round trips (it was 11 % of the kernel).  The lines are prefetched into L2 ahead of the forward
+            // sweep (prefetch_iterate) and each batch issues all of its loads before its first store.
+            for (int base = lane; base < nb; base += 32 * 5) {
+                double d[5], u[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const int idx = base + 32 * j;
+                    const bool p = idx < nb;
+                    d[j] = p ? I.V[(size_t)(idx >> 2) * VREC + V_V + (idx & 3)] : 0.0;
+                    u[j] = p ? Uo[idx] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const int idx = base + 32 * j;
+                    if (idx < nb) Uo[idx] = u[j] + d[j];
+                }
+            }
+            const int nxs = 12 * (N + 1);
+            for (int base = lane; base < nxs; base += 32 * 4) {
+                double d[4], x[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int idx = base + 32 * j;
+                    const bool p = idx < nxs;
+                    d[j] = p ? I.V[(size_t)(idx / 12) * VREC + V_X + idx % 12] : 0.0;
+                    x[j] = p ? Xo[idx] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int idx = base + 32 * j;
+                    if (idx < nxs) Xo[idx] = x[j] + d[j];
+                }
+            }
         } else {
             status = 1;
         }
