@@ -537,7 +537,7 @@ __device__ __forceinline__ void load_chol(const double* Fk, Chol4& L)
 // Explicit inverse of the symmetric positive definite 4x4 matrix with lower entries m (same packing as chol4) by
 // 2x2 sub-determinants: no dependent rsqrt/divide chain (one reciprocal), used where Lam is well conditioned (the
 // unconstrained LQR of the fast path: Lam = R + B'PB).  Returns false unless all leading minors are positive.
-struct Inv4 { double b00, b10, b11, b20, b21, b22, b30, b31, b32, b33; };
+struct Inv4 { double b00, b10, b11, b20, b21, b22, b30, b31, b32, b33, id; };   // adjugate (unscaled) and 1 / det
 __device__ __forceinline__ bool inv4(const double* m, Inv4& B)
 {
     const double m00 = m[0], m10 = m[1], m11 = m[2], m20 = m[3], m21 = m[4], m22 = m[5], m30 = m[6], m31 = m[7],
@@ -549,26 +549,26 @@ __device__ __forceinline__ bool inv4(const double* m, Inv4& B)
     const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
     const double minor3 = m20 * s3 - m21 * s1 + m22 * s0;
     const bool ok = (m00 > 0.0) && (s0 > 0.0) && (minor3 > 0.0) && (det > 0.0);
-    const double id = 1.0 / det;
-    B.b00 = (m11 * c5 - m21 * c4 + m31 * c3) * id;
-    B.b10 = (-m10 * c5 + m20 * c4 - m30 * c3) * id;
-    B.b11 = (m00 * c5 - m20 * c2 + m30 * c1) * id;
-    B.b20 = (m31 * s5 - m32 * s4 + m33 * s3) * id;
-    B.b21 = (-m30 * s5 + m32 * s2 - m33 * s1) * id;
-    B.b22 = (m30 * s4 - m31 * s2 + m33 * s0) * id;
-    B.b30 = (-m21 * s5 + m22 * s4 - m32 * s3) * id;
-    B.b31 = (m20 * s5 - m22 * s2 + m32 * s1) * id;
-    B.b32 = (-m20 * s4 + m21 * s2 - m32 * s0) * id;
-    B.b33 = minor3 * id;
+    B.id = 1.0 / det;
+    B.b00 = m11 * c5 - m21 * c4 + m31 * c3;
+    B.b10 = -m10 * c5 + m20 * c4 - m30 * c3;
+    B.b11 = m00 * c5 - m20 * c2 + m30 * c1;
+    B.b20 = m31 * s5 - m32 * s4 + m33 * s3;
+    B.b21 = -m30 * s5 + m32 * s2 - m33 * s1;
+    B.b22 = m30 * s4 - m31 * s2 + m33 * s0;
+    B.b30 = -m21 * s5 + m22 * s4 - m32 * s3;
+    B.b31 = m20 * s5 - m22 * s2 + m32 * s1;
+    B.b32 = -m20 * s4 + m21 * s2 - m32 * s0;
+    B.b33 = minor3;
     return ok;
 }
-// v <- B v
+// o <- (adj v) / det: the adjugate products run while the reciprocal of the determinant is still in flight
 __device__ __forceinline__ void inv4_apply(const Inv4& B, const double* v, double* o)
 {
-    o[0] = B.b00 * v[0] + B.b10 * v[1] + B.b20 * v[2] + B.b30 * v[3];
-    o[1] = B.b10 * v[0] + B.b11 * v[1] + B.b21 * v[2] + B.b31 * v[3];
-    o[2] = B.b20 * v[0] + B.b21 * v[1] + B.b22 * v[2] + B.b32 * v[3];
-    o[3] = B.b30 * v[0] + B.b31 * v[1] + B.b32 * v[2] + B.b33 * v[3];
+    o[0] = (B.b00 * v[0] + B.b10 * v[1] + B.b20 * v[2] + B.b30 * v[3]) * B.id;
+    o[1] = (B.b10 * v[0] + B.b11 * v[1] + B.b21 * v[2] + B.b31 * v[3]) * B.id;
+    o[2] = (B.b20 * v[0] + B.b21 * v[1] + B.b22 * v[2] + B.b32 * v[3]) * B.id;
+    o[3] = (B.b30 * v[0] + B.b31 * v[1] + B.b32 * v[2] + B.b33 * v[3]) * B.id;
 }
 
 // Per-instance pointers
@@ -683,6 +683,7 @@ __device__ double forward_sweep(Inst& I)
     const int q = I.q, t = I.t, N = I.N;
     const bool lo = q < 4;                      // quad owns a second state row 8 + q (else: no row 12..15)
     constexpr bool FEEDBACK = MODE != 0, AFFINE = MODE != 1;
+    I.template begin<FEEDBACK, false, !FEEDBACK>();     // records in flight while the start values below are fetched
     double zr[3];                               // propagated vector, row layout: x[4ki + t]
     double bmax = 0.0;
 #pragma unroll
@@ -693,7 +694,6 @@ __device__ double forward_sweep(Inst& I)
     int o0[4], o1[4];                           // shared-memory offsets of my rows of Z (constant over the sweep)
 #pragma unroll
     for (int ki = 0; ki < 4; ki++) { o0[ki] = g_off(q, 4 * ki + t); o1[ki] = g_off(8 + (q & 3), 4 * ki + t); }
-    I.template begin<FEEDBACK, false, !FEEDBACK>();
     for (int k = 0; k < N; k++) {
         const int s = I.template advance<FEEDBACK, false, !FEEDBACK>(k);
         const double* Gs = I.sm.st[s].G;
@@ -781,6 +781,7 @@ __device__ bool factor_sweep(Inst& I)
     const int row0 = 2 * t, row1 = 2 * t + 1, row2 = hi2 ? 2 * t + 5 : 8 + 2 * t;
     const int zo0 = g_off(row0, q), zo1 = g_off(row1, q), zo2 = g_off(row2, q);
     // P+ in C layout: h[m][n][j] = P[8m+q][8n+2t+j]; vin[kt] = (q == 4 ? v1 : q == 5 ? v2 : 0)[row(kt)]
+    I.template begin<false, true, KIND == FS_IPM>();    // records in flight while the terminal values are fetched
     double h[2][2][2];
     double vin[3] = {0.0, 0.0, 0.0};
     double pq0 = 0.0, pq1 = 0.0;                // FS_ABS: p+ in quad layout (rows q, 8+q)
@@ -814,7 +815,6 @@ __device__ bool factor_sweep(Inst& I)
             }
         }
     }
-    I.template begin<false, true, KIND == FS_IPM>();
     for (int k = N - 1, it = 0; k >= 0; k--, it++) {
         const int s = I.template advance<false, true, KIND == FS_IPM>(it);
         const double* Gs = I.sm.st[s].G;
@@ -1086,9 +1086,17 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
     }
     __syncwarp();
 
+    // Work distribution: the first instance of a warp is its global warp index; further ones come from an atomic queue
+    // that starts behind the statically assigned block.  On the fast path the next index is reserved when the final sweep
+    // of the current instance starts, so the atomic's round trip is off the path between two instances (it was ~4 % of
+    // the kernel).  Only lane 0 holds the reservation.
+    const int nwarps = gridDim.x * IPM_WARPS;
+    int reserved = blockIdx.x * IPM_WARPS + (threadIdx.x >> 5);
+    bool have = true;
     for (;;) {
-        int inst = 0;
-        if (lane == 0) inst = atomicAdd(a.work_counter, 1);
+        int inst = reserved;
+        if (!have && lane == 0) inst = nwarps + atomicAdd(a.work_counter, 1);
+        have = false;
         inst = __shfl_sync(FULL_MASK, inst, 0);
         if (inst >= a.B) break;
         Inst I(a, sm, phase, inst, lane);
@@ -1105,6 +1113,8 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         if (a.fast_path && a.hint[inst] == 0) {
             if (factor_sweep<FS_ABS>(I)) {
                 prefetch_iterate(I);
+                if (lane == 0) reserved = nwarps + atomicAdd(a.work_counter, 1);
+                have = true;
                 bmax = forward_sweep<2>(I);     // leaves (dx, du) in V_X, V_V
                 bool inside = true;
 #pragma unroll 5
@@ -1260,17 +1270,17 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
                 }
             }
             const int nxs = 12 * (N + 1);
-            for (int base = lane; base < nxs; base += 32 * 4) {
-                double d[4], x[4];
+            for (int base = lane; base < nxs; base += 32 * 8) {
+                double d[8], x[8];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < 8; j++) {
                     const int idx = base + 32 * j;
                     const bool p = idx < nxs;
                     d[j] = p ? I.V[(size_t)(idx / 12) * VREC + V_X + idx % 12] : 0.0;
                     x[j] = p ? Xo[idx] : 0.0;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < 8; j++) {
                     const int idx = base + 32 * j;
                     if (idx < nxs) Xo[idx] = x[j] + d[j];
                 }
