@@ -23,6 +23,16 @@ def test_bit_identical_to_reference_files():
     assert np.array_equal(traj.lemniscate(), np.loadtxt(os.path.join(REF, "lemniscate.txt")))
 
 
+def test_checksums_of_the_reference_files():
+    """sha256 of the parsed reference files (bluerov2_path/config/traj/{circle,lemniscate}.txt), recorded with the reference
+    present: pins the generators on machines that do not have /root/reference (the GPU box)."""
+    import hashlib
+    want = {"circle": "add3016bd03d34de26a424635db2aca70c5932b6ef0dcbbd52f57bcaed153212",
+            "lemniscate": "a869953bcfffe244282e882262234088cccdd098654f6da5744fb05ce2133699"}
+    for name, fn in (("circle", traj.circle), ("lemniscate", traj.lemniscate)):
+        assert hashlib.sha256(np.ascontiguousarray(fn()).tobytes()).hexdigest() == want[name], name
+
+
 def test_window_clamps_to_last_row():
     """ref_cb (bluerov2_dob.cpp:218-265): all three branches."""
     t = np.arange(10 * 16, dtype=float).reshape(10, 16)
