@@ -1,8 +1,9 @@
 // kernels.cu -- hand-written sm_100a kernels of the batched SQP-RTI step.
 //
-//   linearize_kernel : ERK4 + forward sensitivities of the 6-DOF model, one 16-lane team per (instance, stage)
-//                      (replaces acados' ERK integrator driving bluerov2_expl_vde_forw, acados_solver_bluerov2.c:
-//                      310-318,633-639) -> stage records G_k = [A_k | B_k], b_k in HBM.
+//   linearize_kernel : ERK4 + forward sensitivities of the 6-DOF model, one warp per round of 16 (instance, stage) pairs
+//                      in three phases (state trajectory / Jacobians / sensitivities); replaces acados' ERK integrator
+//                      driving bluerov2_expl_vde_forw (acados_solver_bluerov2.c:310-318,633-639) -> stage records
+//                      G_k = [A_k | B_k], b_k, cost gradients in HBM.
 //   ipm_kernel       : one warp per OCP instance, persistent over the batch.  Mehrotra predictor-corrector
 //                      primal-dual IPM on the box-constrained OCP-QP of the RTI step; every Newton system is an
 //                      LQR solved by a Riccati recursion over the horizon (replaces acados full condensing + HPIPM
@@ -29,11 +30,7 @@
 #define BR2_IPM_MINB (16 / BR2_IPM_WARPS)
 #endif
 #ifndef BR2_LIN_MINB
-#ifdef BR2_LIN_V1
-#define BR2_LIN_MINB 2
-#else
 #define BR2_LIN_MINB 12
-#endif
 #endif
 
 namespace br2 {
@@ -43,7 +40,6 @@ namespace br2 {
 // ------------------------------------------------------------------------------------------------------
 // linearisation
 // ------------------------------------------------------------------------------------------------------
-#ifndef BR2_LIN_V1
 // v2: one warp per round of LRND (instance, stage) pairs, three phases with three lane mappings so that nothing is
 // computed redundantly:
 //   A   lane per stage: the RK4 STATE trajectory only (x_1..x_4, 3 sincos + f per RK stage; the sensitivities do not
@@ -289,133 +285,6 @@ void launch_linearize(const SolveArgs& a, cudaStream_t s)
     linearize_kernel<<<grid, 32, 0, s>>>(a);
 }
 
-#else   // BR2_LIN_V1
-// One 8-lane team per (instance, stage); a lane carries TWO of the 16 column slots of the augmented state through
-// the RK4 stages, so the stage Jacobian (the 48 non-zeros of df/dx) is formed once per two columns:
-//   slot 0 = state x (evolves by f), slots 1..9 = Sx columns 3..11, slots 10..13 = Su columns 0..3,
-//   slots 14, 15 (lane 7) carry nothing: that lane writes the constant [I;0] columns 0..2 of A (positions do not
-//   enter f) and the cost-gradient tail of the stage record.
-// lane l of the team holds slots 2l and 2l+1.
-constexpr int LIN_TEAM = 8;
-
-__global__ void __launch_bounds__(128, BR2_LIN_MINB) linearize_kernel(SolveArgs a)
-{
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int l = lane & (LIN_TEAM - 1);
-    const unsigned tmask = 0xffu << (lane & ~(LIN_TEAM - 1));
-    const int total = a.B * a.N;
-    int team = gtid / LIN_TEAM;
-    const bool live = team < total;
-    if (!live) team = total - 1;            // keep the lanes alive for the team shuffles; stores are predicated
-    const int inst = team / a.N, k = team - inst * a.N;
-
-    const double* p = a.p + (size_t)inst * a.p_inst_stride + (size_t)k * a.p_stage_stride;
-    ModelConst mc;
-    {
-        double pl[NP];
-#pragma unroll
-        for (int i = 0; i < NP; i++) pl[i] = __ldg(p + i);
-        mc.set(pl);
-    }
-    const double h = __ldg(a.Ts + k);
-    const double* Xk = a.X + ((size_t)inst * (a.N + 1) + k) * NX;
-    double u[NU];
-#pragma unroll
-    for (int i = 0; i < NU; i++) u[i] = __ldg(a.U + ((size_t)inst * a.N + k) * NU + i);
-
-    // slot sa = 2l, sb = 2l+1; the unit / zero seed of a sensitivity slot is implicit (seed_a, seed_b = its row or -1)
-    const int sa = 2 * l, sb = 2 * l + 1;
-    const int seed_a = (sa >= 1 && sa <= 9) ? sa + 2 : -1;
-    const int seed_b = (sb >= 1 && sb <= 9) ? sb + 2 : -1;
-    const int su_a = sa - 10, su_b = sb - 10;            // Su column when in 0..3
-    double x0v[NX];                                      // linearisation state (every lane: stage 1 needs it anyway)
-#pragma unroll
-    for (int i = 0; i < NX; i++) x0v[i] = __ldg(Xk + i);
-    double ca[NX], cb[NX], aa[NX], ab[NX];               // current stage value and weighted sum of the two slots
-#pragma unroll
-    for (int i = 0; i < NX; i++) {
-        ca[i] = (sa == 0) ? x0v[i] : (i == seed_a ? 1.0 : 0.0);
-        cb[i] = (i == seed_b) ? 1.0 : 0.0;
-        aa[i] = 0.0; ab[i] = 0.0;
-    }
-
-#pragma unroll 1
-    for (int s = 0; s < 4; s++) {
-        // stage state (only components 3..11 enter f and J): slot 0 lives in lane 0 of the team
-        double xs[NX];
-        xs[0] = xs[1] = xs[2] = 0.0;
-#pragma unroll
-        for (int i = 3; i < NX; i++) xs[i] = __shfl_sync(tmask, ca[i], 0, LIN_TEAM);
-        // one sincos per lane: lanes 0,1,2 of the team own phi, theta, psi
-        double sn, cs;
-        const int which = l % 3;
-        sincos(which == 0 ? xs[3] : (which == 1 ? xs[4] : xs[5]), &sn, &cs);
-        Trig t;
-        t.sphi = __shfl_sync(tmask, sn, 0, LIN_TEAM); t.cphi = __shfl_sync(tmask, cs, 0, LIN_TEAM);
-        t.sth = __shfl_sync(tmask, sn, 1, LIN_TEAM);  t.cth = __shfl_sync(tmask, cs, 1, LIN_TEAM);
-        t.spsi = __shfl_sync(tmask, sn, 2, LIN_TEAM); t.cpsi = __shfl_sync(tmask, cs, 2, LIN_TEAM);
-        Jac J;
-        jac_of(xs, mc, t, J);
-        double ka[NX], kb[NX];
-        jac_mul(J, ca, ka);
-        jac_mul(J, cb, kb);
-        if (sa == 0) ode_from_jac(xs, u, mc, t, J, ka);
-        if (su_a >= 0 && su_a < NU) ju_add(mc, su_a, ka);
-        if (su_b >= 0 && su_b < NU) ju_add(mc, su_b, kb);
-        const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
-        const double cn = (s == 2) ? 1.0 : 0.5;     // c_{s+1} of the classical tableau
-#pragma unroll
-        for (int i = 0; i < NX; i++) {
-            aa[i] += bw * ka[i];
-            ab[i] += bw * kb[i];
-            ca[i] = ((sa == 0) ? x0v[i] : (i == seed_a ? 1.0 : 0.0)) + cn * h * ka[i];
-            cb[i] = ((i == seed_b) ? 1.0 : 0.0) + cn * h * kb[i];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NX; i++) {
-        ca[i] = ((sa == 0) ? x0v[i] : (i == seed_a ? 1.0 : 0.0)) + h * aa[i];
-        cb[i] = ((i == seed_b) ? 1.0 : 0.0) + h * ab[i];
-    }
-
-    if (!live) return;
-    double* Gk = a.G + ((size_t)inst * a.N + k) * GREC;
-    const double* yr = yref_row(a, inst, k);
-    // slot c >= 1 is column c + 2 of Z = [A|B]; in fragment order rows 4ki..4ki+3 of a column are contiguous (32 B)
-    if (l == 0) {
-        const double* Xn = Xk + NX;
-#pragma unroll
-        for (int i = 0; i < NX; i++) Gk[G_B_OFF + i] = ca[i] - __ldg(Xn + i);
-#pragma unroll
-        for (int i = 0; i < NX; i++) Gk[G_QLIN + i] = h * a.W[i] * (x0v[i] - __ldg(yr + i));
-#pragma unroll
-        for (int r = 0; r < NX; r++) Gk[g_off(r, 3)] = cb[r];
-    } else if (l < LIN_TEAM - 1) {
-#pragma unroll
-        for (int r = 0; r < NX; r++) { Gk[g_off(r, sa + 2)] = ca[r]; Gk[g_off(r, sb + 2)] = cb[r]; }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int r = 0; r < NX; r++) Gk[g_off(r, j)] = (r == j) ? 1.0 : 0.0;
-#pragma unroll
-        for (int i = 0; i < NU; i++) Gk[G_RLIN + i] = h * a.W[NX + i] * (u[i] - __ldg(yr + NX + i));
-        Gk[G_TS] = h;
-#pragma unroll
-        for (int i = G_TS + 1; i < GREC; i++) Gk[i] = 0.0;
-    }
-}
-
-void launch_linearize(const SolveArgs& a, cudaStream_t s)
-{
-    const long long threads = (long long)a.B * a.N * LIN_TEAM;
-    const int block = 128;
-    const int grid = (int)((threads + block - 1) / block);
-    linearize_kernel<<<grid, block, 0, s>>>(a);
-}
-
-#endif  // BR2_LIN_V1
 
 // ------------------------------------------------------------------------------------------------------
 // Riccati interior-point kernel

@@ -156,12 +156,13 @@ def test_weights_bounds_and_ragged_batch(solver_mod, oracle):
     s.close()
 
 
-@pytest.mark.parametrize("spread", [0.5, 3.0])
-def test_full_size_batch_properties(solver_mod, oracle, spread):
-    """BASELINE config 2 at full size (B = 4096, N = 40): a sample of instances against the oracle, the rest through
-    size-independent properties: bounds respected, states = exact roll-out of the inputs (dynamics residual of the QP),
-    instance independence (a permuted batch gives the permuted answer bit for bit)."""
-    N, B = 40, 4096
+@pytest.mark.parametrize("B,N,spread", [(4096, 40, 0.5), (4096, 40, 3.0),          # BASELINE config 2 (both input sets)
+                                         (8192, 40, 0.5),                            # config 4: the per-GPU shard of 65536 / 8
+                                         (8192, 10, 0.5), (8192, 20, 3.0), (8192, 80, 0.5)])   # config 5: horizon sweep
+def test_full_size_batch_properties(solver_mod, oracle, B, N, spread):
+    """BASELINE configurations at full size: a sample of instances against the oracle, the rest through size-independent
+    properties: bounds respected, states = exact roll-out of the inputs (dynamics residual of the QP), instance
+    independence (a permuted batch gives the permuted answer bit for bit)."""
     w = wl.tracking_batch(B, N, seed=0, pos_spread=spread)
     s = solver_mod.BatchSolver(B, N)
     s.set_iterate(w["X"], w["U"])
@@ -177,7 +178,7 @@ def test_full_size_batch_properties(solver_mod, oracle, spread):
     roll = np.einsum("bkij,bkj->bki", A, dX[:, :-1]) + np.einsum("bkij,bkj->bki", Bm, dU) + b
     assert np.abs(roll - dX[:, 1:]).max() < 1e-9
     Ts = wl.time_steps(N)
-    idx = np.arange(0, B, 64)
+    idx = np.arange(0, B, B // 64)
     Xo, Uo = w["X"][idx].copy(), w["U"][idx].copy()
     sto, _, _ = oracle.rti_step_batch(Ts, w["x0"][idx], w["yref"][idx], w["p"][idx], Xo, Uo)
     assert (sto == 0).all()
