@@ -108,12 +108,41 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
+class _HostArgs:
+    """Host-array marshalling for the hot calls.  Callers pass the same numpy buffers tick after tick; checking layout and
+    building a ctypes pointer costs ~2.5 us per array per call, 15 us per solve -- 4 % of a 0.4 ms tick.  An array object
+    that already has the right dtype / shape / contiguity is validated once and remembered (by identity; the entry keeps
+    the array alive, so its id and data pointer cannot be recycled)."""
+
+    def __init__(self, cap: int = 64):
+        self._d, self._cap = {}, cap
+
+    def get(self, a, shape, dtype=np.float64, out: bool = False):
+        """-> (array kept alive by the caller for the duration of the C call, c_void_p)"""
+        e = self._d.get(id(a))
+        if e is not None and e[0] is a and e[2] == shape and e[3] is dtype:
+            return a, e[1]
+        ok = (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous and a.shape == tuple(shape)
+              and (a.flags.writeable or not out))
+        if not ok:
+            if out:
+                raise ValueError(f"output buffer must be a writable C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
+            b = _np(a, shape, dtype)              # converted copy: valid for this call only
+            return b, C.c_void_p(b.ctypes.data)
+        if len(self._d) >= self._cap:
+            self._d.clear()
+        ptr = C.c_void_p(a.ctypes.data)
+        self._d[id(a)] = (a, ptr, shape, dtype)
+        return a, ptr
+
+
 class BatchSolver:
     """B independent BlueROV2 OCP instances advanced by one SQP-RTI step per ``solve`` call."""
 
     def __init__(self, batch: int, N: int = 40, time_steps=None, device: int = 0, lib_path: str | None = None):
         self._L = load_library(lib_path)
         self._h = C.c_void_p()
+        self._hostargs = _HostArgs()
         ts = None if time_steps is None else _np(time_steps, (N,))
         self._check(self._L.br2_batch_create(C.byref(self._h), int(batch), int(N), _ptr(ts), int(device)))
         self.B, self.N, self.device = int(batch), int(N), int(device)
@@ -201,12 +230,14 @@ class BatchSolver:
             self._check(self._L.br2_batch_solve_device(self._h, _ptr(x0), _ptr(yref), _ptr(p), per_stage,
                                                        _ptr(u0), _ptr(th), _ptr(st), stream))
             return u0, th, st
-        x0, yref, p = _np(x0, (self.B, NX)), _np(yref, (self.B, self.N + 1, NY)), _np(p, pshape)
+        H = self._hostargs.get
+        (k0, a0), (k1, a1), (k2, a2) = H(x0, (self.B, NX)), H(yref, (self.B, self.N + 1, NY)), H(p, pshape)
         if out is None:
             out = (np.empty((self.B, NU)), np.empty((self.B, NTHRUST)), np.empty((self.B,), dtype=np.int32))
         u0, th, st = out
-        self._check(self._L.br2_batch_solve_host(self._h, _ptr(x0), _ptr(yref), _ptr(p), per_stage,
-                                                 _ptr(u0), _ptr(th), _ptr(st)))
+        (_, o0), (_, o1), (_, o2) = (H(u0, (self.B, NU), out=True), H(th, (self.B, NTHRUST), out=True),
+                                     H(st, (self.B,), np.int32, out=True))
+        self._check(self._L.br2_batch_solve_host(self._h, a0, a1, a2, per_stage, o0, o1, o2))
         return u0, th, st
 
     def set_trajectory(self, traj):
@@ -236,13 +267,14 @@ class BatchSolver:
             self._check(self._L.br2_batch_solve_windowed_device(self._h, _ptr(x0), _ptr(lines), _ptr(p), per_stage,
                                                                 _ptr(u0), _ptr(th), _ptr(st), stream))
             return u0, th, st
-        x0, p = _np(x0, (self.B, NX)), _np(p, pshape)
-        lines = _np(lines, (self.B,), dtype=np.int32)
+        H = self._hostargs.get
+        (k0, a0), (k1, a1), (k2, a2) = H(x0, (self.B, NX)), H(lines, (self.B,), np.int32), H(p, pshape)
         if out is None:
             out = (np.empty((self.B, NU)), np.empty((self.B, NTHRUST)), np.empty((self.B,), dtype=np.int32))
         u0, th, st = out
-        self._check(self._L.br2_batch_solve_windowed_host(self._h, _ptr(x0), _ptr(lines), _ptr(p), per_stage,
-                                                          _ptr(u0), _ptr(th), _ptr(st)))
+        (_, o0), (_, o1), (_, o2) = (H(u0, (self.B, NU), out=True), H(th, (self.B, NTHRUST), out=True),
+                                     H(st, (self.B,), np.int32, out=True))
+        self._check(self._L.br2_batch_solve_windowed_host(self._h, a0, a1, a2, per_stage, o0, o1, o2))
         return u0, th, st
 
     def stats(self):
@@ -288,12 +320,13 @@ class BatchSolver:
             self._check(self._L.br2_batch_ekf_device(self._h, _ptr(thrusts), _ptr(meas), _ptr(body_acc), _ptr(wf), _ptr(pp),
                                                      int(bool(compensate)), stream))
             return wf, pp
-        thrusts, meas, body_acc = _np(thrusts, (self.B, 6)), _np(meas, (self.B, 12)), _np(body_acc, (self.B, 6))
+        H = self._hostargs.get
+        (k0, a0), (k1, a1), (k2, a2) = H(thrusts, (self.B, 6)), H(meas, (self.B, 12)), H(body_acc, (self.B, 6))
         if out is None:
             out = (np.empty((self.B, 6)), np.empty((self.B, NP)))
         wf, pp = out
-        self._check(self._L.br2_batch_ekf_host(self._h, _ptr(thrusts), _ptr(meas), _ptr(body_acc), _ptr(wf), _ptr(pp),
-                                               int(bool(compensate))))
+        (_, o0), (_, o1) = H(wf, (self.B, 6), out=True), H(pp, (self.B, NP), out=True)
+        self._check(self._L.br2_batch_ekf_host(self._h, a0, a1, a2, o0, o1, int(bool(compensate))))
         return wf, pp
 
     def ekf_state(self):
@@ -324,10 +357,12 @@ class BatchSolver:
             stream = C.c_void_p(torch.cuda.current_stream(meas.device).cuda_stream)
             self._check(self._L.br2_batch_rls_device(self._h, _ptr(meas), _ptr(body_acc), _ptr(out), int(bool(compensate)), stream))
             return out
-        meas, body_acc = _np(meas, (self.B, 12)), _np(body_acc, (self.B, 6))
+        H = self._hostargs.get
+        (k0, a0), (k1, a1) = H(meas, (self.B, 12)), H(body_acc, (self.B, 6))
         if out is None:
             out = np.zeros((self.B, NP))
-        self._check(self._L.br2_batch_rls_host(self._h, _ptr(meas), _ptr(body_acc), _ptr(out), int(bool(compensate))))
+        _, o0 = H(out, (self.B, NP), out=True)
+        self._check(self._L.br2_batch_rls_host(self._h, a0, a1, o0, int(bool(compensate))))
         return out
 
     def rls_state(self):
