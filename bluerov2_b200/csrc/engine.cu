@@ -313,13 +313,27 @@ static int solve_host_common(br2_batch_solver* s, const double* x0, const double
 {
     const size_t B = s->B;
     cudaStream_t st = s->stream;
+    // the lineariser goes out first (its inputs -- p, reference -- are already enqueued): everything below is host work and
+    // an upload that the GPU does not have to wait for before it starts
+    CK(cudaSetDevice(s->device));
+    SolveArgs a;
+    fill_args(s, a, s->d_x0, d_yref, d_lines, s->d_p, p_per_stage, nullptr, nullptr, nullptr);
+    CK(cudaEventRecord(s->ev0, st));
+    launch_linearize(a, st);
+    CK(cudaEventRecord(s->ev_mid, st));
     CK(cudaMemcpyAsync(s->d_x0, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, s->stream_x0));
     CK(cudaEventRecord(s->ev_x0, s->stream_x0));
     double* a_u0 = mapped_alias(u0);
     double* a_th = mapped_alias(thrust);
     int* a_st = mapped_alias(status);
-    int rc = solve_enqueue(s, s->d_x0, d_yref, d_lines, s->d_p, p_per_stage, a_u0, a_th, a_st, st, s->ev_x0);
-    if (rc != BR2_OK) return rc;
+    if (a_u0) a.u0 = a_u0;
+    if (a_th) a.thrust = a_th;
+    if (a_st) a.status = a_st;
+    CK(cudaStreamWaitEvent(st, s->ev_x0, 0));
+    launch_ipm(a, s->sm_count, st);
+    CK(cudaEventRecord(s->ev1, st));
+    s->timed = true;
+    CK(cudaGetLastError());
     if (u0 && !a_u0) CK(cudaMemcpyAsync(u0, s->d_u0, sizeof(double) * B * 4, cudaMemcpyDeviceToHost, st));
     if (thrust && !a_th) CK(cudaMemcpyAsync(thrust, s->d_thrust, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
     if (status && !a_st) CK(cudaMemcpyAsync(status, s->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
