@@ -7,11 +7,12 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* (x[12], u[4], z[0], p[16]) -> y[16]                     reference: bluerov2_cost_y_fun.c:60 */
-int bluerov2_cost_y_0_fun(const real_t** arg, real_t** res, int* iw, real_t* w, void *mem);
-int bluerov2_cost_y_fun(const real_t** arg, real_t** res, int* iw, real_t* w, void *mem);
-/* (x[12], u[0], z[0], p[16]) -> y[12]                     reference: bluerov2_cost_y_e_fun.c:58 */
-int bluerov2_cost_y_e_fun(const real_t** arg, real_t** res, int* iw, real_t* w, void *mem);
+/* CasADi evaluation signature: inputs in[], outputs out[], unused work vectors */
+#define BR2_COST_EVAL(f) int f(const real_t **in, real_t **out, int *iwork, real_t *rwork, void *mem);
+BR2_COST_EVAL(bluerov2_cost_y_0_fun)   /* (x[12], u[4], z[0], p[16]) -> y[16]   ref bluerov2_cost_y_0_fun.c */
+BR2_COST_EVAL(bluerov2_cost_y_fun)     /* same residual on the path stages      ref bluerov2_cost_y_fun.c:60 */
+BR2_COST_EVAL(bluerov2_cost_y_e_fun)   /* (x[12], u[0], z[0], p[16]) -> y[12]   ref bluerov2_cost_y_e_fun.c:58 */
+#undef BR2_COST_EVAL
 #ifdef __cplusplus
 }
 #endif

@@ -8,31 +8,23 @@
 extern "C" {
 #endif
 
-/* (x[12], u[4], p[16]) -> f[12]                          reference: bluerov2_expl_ode_fun.c:66 */
-int bluerov2_expl_ode_fun(const real_t** arg, real_t** res, int* iw, real_t* w, void *mem);
-int bluerov2_expl_ode_fun_work(int *, int *, int *, int *);
-const int *bluerov2_expl_ode_fun_sparsity_in(int);
-const int *bluerov2_expl_ode_fun_sparsity_out(int);
-int bluerov2_expl_ode_fun_n_in(void);
-int bluerov2_expl_ode_fun_n_out(void);
+/* The six entry points CasADi's C code generator emits per function f: evaluation (arg / res pointer arrays, integer and
+ * real work vectors, memory slot), work sizes, CCS sparsity of input / output i, number of inputs / outputs. */
+#ifndef BR2_CASADI_FUNCTION
+#define BR2_CASADI_FUNCTION(f)                                                                         \
+    int f(const real_t **arg, real_t **res, int *iw, real_t *w, void *mem);                            \
+    int f##_work(int *sz_arg, int *sz_res, int *sz_iw, int *sz_w);                                     \
+    const int *f##_sparsity_in(int i);                                                                 \
+    const int *f##_sparsity_out(int i);                                                                \
+    int f##_n_in(void);                                                                                \
+    int f##_n_out(void);
+#endif
 
-/* (x, Sx[12x12], Su[12x4], u, p) -> (f, Jx Sx, Jx Su + Ju)   reference: bluerov2_expl_vde_forw.c:73 */
-int bluerov2_expl_vde_forw(const real_t** arg, real_t** res, int* iw, real_t* w, void *mem);
-int bluerov2_expl_vde_forw_work(int *, int *, int *, int *);
-const int *bluerov2_expl_vde_forw_sparsity_in(int);
-const int *bluerov2_expl_vde_forw_sparsity_out(int);
-int bluerov2_expl_vde_forw_n_in(void);
-int bluerov2_expl_vde_forw_n_out(void);
-
-/* (x, lam[12], u, p) -> [Jx' lam; Ju' lam] (16)            reference: bluerov2_expl_vde_adj.c:69 */
-int bluerov2_expl_vde_adj(const real_t** arg, real_t** res, int* iw, real_t* w, void *mem);
-int bluerov2_expl_vde_adj_work(int *, int *, int *, int *);
-const int *bluerov2_expl_vde_adj_sparsity_in(int);
-const int *bluerov2_expl_vde_adj_sparsity_out(int);
-int bluerov2_expl_vde_adj_n_in(void);
-int bluerov2_expl_vde_adj_n_out(void);
+BR2_CASADI_FUNCTION(bluerov2_expl_ode_fun)   /* (x[12], u[4], p[16]) -> f[12]                               ref bluerov2_expl_ode_fun.c:66  */
+BR2_CASADI_FUNCTION(bluerov2_expl_vde_forw)  /* (x, Sx[12x12], Su[12x4], u, p) -> (f, Jx Sx, Jx Su + Ju)    ref bluerov2_expl_vde_forw.c:73 */
+BR2_CASADI_FUNCTION(bluerov2_expl_vde_adj)   /* (x, lam[12], u, p) -> [Jx' lam; Ju' lam] (16)               ref bluerov2_expl_vde_adj.c:69  */
 
 #ifdef __cplusplus
-} /* extern "C" */
+}
 #endif
-#endif  // bluerov2_MODEL
+#endif

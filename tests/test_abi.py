@@ -22,18 +22,30 @@ def lib_path():
 
 
 def _declared_functions():
-    """every function prototype in include/**/*.h (name followed by '(' at prototype level, not a macro/typedef)"""
+    """every function prototype in include/**/*.h after preprocessing (some headers stamp their prototypes out of a macro);
+    only text that originates from files under include/ is scanned (line markers), so libc prototypes do not count"""
     names = set()
-    proto = re.compile(r"^\s*(?:ACADOS_SYMBOL_EXPORT|BR2_API|__attribute__\(\(visibility\(\"default\"\)\)\))?\s*"
-                       r"(?:const\s+)?(?:unsigned\s+)?[A-Za-z_][A-Za-z0-9_]*\s*\**\s*\**\s*([A-Za-z_][A-Za-z0-9_]*)\s*\(", re.M)
+    proto = re.compile(r"^\s*(?:[A-Za-z_]\w*[\s\*]+)+([A-Za-z_]\w*)\s*\(", re.M)     # type words / stars, then name(
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     for r, _, fs in os.walk(INCLUDE):
         for f in fs:
             if not f.endswith(".h"):
                 continue
-            src = open(os.path.join(r, f)).read()
-            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-            src = re.sub(r"//.*", "", src)
+            out = subprocess.run([cc, "-E", "-I", INCLUDE, "-I", os.path.join(INCLUDE, "blasfeo", "include"), os.path.join(r, f)],
+                                 capture_output=True, text=True)
+            assert out.returncode == 0, (f, out.stderr[-2000:])
+            keep, ours = [], False
+            for line in out.stdout.splitlines():
+                if line.startswith("# "):
+                    m = re.match(r'# \d+ "([^"]*)"', line)
+                    ours = bool(m) and os.path.abspath(m.group(1)).startswith(INCLUDE)
+                    continue
+                if ours:
+                    keep.append(line)
+            src = "\n".join(keep)
             src = re.sub(r"typedef\s+struct[^{;]*\{.*?\}\s*[A-Za-z_0-9]*\s*;", "", src, flags=re.S)   # drop struct bodies
+            src = re.sub(r"__attribute__\s*\(\(.*?\)\)\)?", "", src)                                    # export attributes
+            src = src.replace(";", ";\n")                                                            # one declaration per line
             for m in proto.finditer(src):
                 n = m.group(1)
                 if n not in ("defined", "sizeof", "if", "visibility", "__attribute__", "__declspec"):
