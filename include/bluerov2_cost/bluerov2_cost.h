@@ -1,8 +1,8 @@
 /* bluerov2_cost/bluerov2_cost.h -- drop-in for c_generated_code/bluerov2_cost/bluerov2_cost.h.
  * The NLS residual is y = [x; u] (terminal y = x), bluerov2.py:144,153-154; its Jacobian is a permuted identity
  * and its Hessian structurally empty, so the engine never calls these: they exist for link compatibility. */
-#ifndef bluerov2_COST
-#define bluerov2_COST
+#ifndef BR2_DROPIN_BLUEROV2_COST_H
+#define BR2_DROPIN_BLUEROV2_COST_H
 #include "acados/utils/types.h"
 #ifdef __cplusplus
 extern "C" {

@@ -1,8 +1,8 @@
 /* bluerov2_model/bluerov2_model.h -- drop-in for c_generated_code/bluerov2_model/bluerov2_model.h:46-67.
  * Same CasADi calling convention; the bodies are hand-written (bluerov2_b200/csrc/model.cuh evaluated on the
  * host) instead of CasADi-generated.  Sparsities are dense column-major like the generated code. */
-#ifndef bluerov2_MODEL
-#define bluerov2_MODEL
+#ifndef BR2_DROPIN_BLUEROV2_MODEL_H
+#define BR2_DROPIN_BLUEROV2_MODEL_H
 #include "acados/utils/types.h"
 #ifdef __cplusplus
 extern "C" {
