@@ -42,6 +42,7 @@ struct br2_batch_solver {
     int traj_rows;
     double *d_ex, *d_eP, *d_thr, *d_meas, *d_acc, *d_wf, *d_pout;   // EKF state + staging
     double* d_rls;                            // RLS-VFF state [B][4][RLS_STRIDE] (AMPC)
+    float* d_yaw;                             // continuous-yaw accumulators [B][2] = (pre_yaw, yaw_sum), floats as in the node
     cudaStream_t stream, stream_x0;   // host API: main stream; second stream carrying the x0 upload past the lineariser
     cudaEvent_t ev0, ev1, ev_mid;   // solve start / end / between linearisation and IPM
     cudaEvent_t ev_x0;              // x0 upload complete (the IPM kernel is its first reader)
@@ -70,7 +71,7 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
     cudaSetDevice(s->device);
     void* ptrs[] = {s->d_Ts, s->d_X, s->d_U, s->d_G, s->d_F, s->d_V, s->d_u0, s->d_thrust, s->d_info, s->d_status,
                     s->d_iters, s->d_counter, s->d_x0, s->d_yref, s->d_p, s->d_ex, s->d_eP, s->d_thr, s->d_meas,
-                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls};
+                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls, s->d_yaw};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -127,6 +128,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     DA(d_ex, B * 18); DA(d_eP, B * 324); DA(d_thr, B * 6); DA(d_meas, B * 12); DA(d_acc, B * 6); DA(d_wf, B * 6);
     DA(d_pout, B * NP);
     DA(d_rls, B * 4 * RLS_STRIDE);
+    DA(d_yaw, B * 2);
     DA(d_iter_total, 1);
     DA(d_hint, B);
     DA(d_lines, B);
@@ -148,6 +150,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     int rc = br2_batch_reset(s, 0);
     if (rc == BR2_OK) rc = br2_batch_ekf_reset(s);
     if (rc == BR2_OK) rc = br2_batch_rls_reset(s);
+    if (rc == BR2_OK) rc = br2_batch_yaw_reset(s);
     if (rc == BR2_OK) { cudaError_t e2 = cudaMemset(s->d_pout, 0, sizeof(double) * B * NP); if (e2 != cudaSuccess) rc = fail(BR2_ECUDA, "cudaMemset failed"); }
     if (rc != BR2_OK) { br2_batch_free(s); *out = nullptr; }
     return rc;
@@ -625,6 +628,50 @@ extern "C" int br2_batch_rls_set_state_host(br2_batch_solver* s, const double* s
     CK(cudaSetDevice(s->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(s->d_rls, state, sizeof(double) * s->B * 4 * RLS_STRIDE, cudaMemcpyHostToDevice));
+    return BR2_OK;
+}
+
+// ---- continuous yaw (node glue, bluerov2_dob.cpp:272-304) ------------------------------------------------------
+extern "C" int br2_batch_yaw_reset(br2_batch_solver* s)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemset(s->d_yaw, 0, sizeof(float) * 2 * s->B));      // yaw_sum = pre_yaw = 0 (bluerov2_dob.h:234-235)
+    return BR2_OK;
+}
+extern "C" int br2_batch_yaw_unwrap_device(br2_batch_solver* s, double* d_x0, void* stream)
+{
+    if (!s || !d_x0) return fail(BR2_EINVAL, "br2_batch_yaw_unwrap_device: null argument");
+    CK(cudaSetDevice(s->device));
+    launch_yaw_unwrap(s->B, s->d_yaw, d_x0, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+extern "C" int br2_batch_yaw_unwrap_host(br2_batch_solver* s, double* x0)
+{
+    if (!s || !x0) return fail(BR2_EINVAL, "br2_batch_yaw_unwrap_host: null argument");
+    CK(cudaSetDevice(s->device));
+    const size_t n = sizeof(double) * s->B * NX;
+    CK(cudaMemcpyAsync(s->d_x0, x0, n, cudaMemcpyHostToDevice, s->stream));
+    launch_yaw_unwrap(s->B, s->d_yaw, s->d_x0, s->stream);
+    CK(cudaMemcpyAsync(x0, s->d_x0, n, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return BR2_OK;
+}
+extern "C" int br2_batch_yaw_get_state_host(br2_batch_solver* s, float* state)
+{
+    if (!s || !state) return fail(BR2_EINVAL, "null argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(state, s->d_yaw, sizeof(float) * 2 * s->B, cudaMemcpyDeviceToHost));
+    return BR2_OK;
+}
+extern "C" int br2_batch_yaw_set_state_host(br2_batch_solver* s, const float* state)
+{
+    if (!s || !state) return fail(BR2_EINVAL, "null argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(s->d_yaw, state, sizeof(float) * 2 * s->B, cudaMemcpyHostToDevice));
     return BR2_OK;
 }
 

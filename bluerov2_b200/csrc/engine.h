@@ -86,6 +86,10 @@ struct RlsArgs {
 };
 void launch_rls(const RlsArgs& a, cudaStream_t s);
 
+// continuous-yaw accumulator of the node glue (glue.cu; bluerov2_dob.cpp:272-304): state[B][2] = (pre_yaw, yaw_sum) floats,
+// x0[B][12] in place on column 5
+void launch_yaw_unwrap(int B, float* state, double* x0, cudaStream_t s);
+
 // nominal plant (plant.cu): x <- RK4_h(x, u, p + disturbance); optional wave disturbance, body acceleration, line counter
 struct PlantArgs {
     int B;

@@ -75,6 +75,11 @@ def load_library(path: str | None = None):
         "br2_batch_ekf_host": (C.c_int, [V, V, V, V, V, V, C.c_int]),
         "br2_batch_ekf_get_state_host": (C.c_int, [V, V, V]),
         "br2_batch_ekf_set_state_host": (C.c_int, [V, V, V]),
+        "br2_batch_yaw_reset": (C.c_int, [V]),
+        "br2_batch_yaw_unwrap_device": (C.c_int, [V, V, V]),
+        "br2_batch_yaw_unwrap_host": (C.c_int, [V, V]),
+        "br2_batch_yaw_get_state_host": (C.c_int, [V, V]),
+        "br2_batch_yaw_set_state_host": (C.c_int, [V, V]),
         "br2_batch_rls_reset": (C.c_int, [V]),
         "br2_batch_rls_device": (C.c_int, [V, V, V, V, C.c_int, V]),
         "br2_batch_rls_host": (C.c_int, [V, V, V, V, C.c_int]),
@@ -338,6 +343,31 @@ class BatchSolver:
         x = None if x is None else _np(x, (self.B, NEKF))
         P = None if P is None else _np(P, (self.B, NEKF, NEKF))
         self._check(self._L.br2_batch_ekf_set_state_host(self._h, _ptr(x), _ptr(P)))
+
+    # -- continuous yaw (top of BLUEROV2_DOB::solve, bluerov2_dob.cpp:272-304) ---------------------------------
+    def yaw_reset(self):
+        self._check(self._L.br2_batch_yaw_reset(self._h))
+
+    def unwrap_yaw(self, x0):
+        """In place on ``x0[:, 5]``: measured yaw in (-pi, pi] -> the node's continuous ``yaw_sum`` (float accumulators, as in
+        the reference).  numpy [B,12] (round trip through the device) or a CUDA tensor (enqueued on torch's current stream)."""
+        if _is_torch(x0):
+            import torch
+            self._dev_check(x0, (self.B, NX))
+            stream = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)
+            self._check(self._L.br2_batch_yaw_unwrap_device(self._h, _ptr(x0), stream))
+            return x0
+        _, a0 = self._hostargs.get(x0, (self.B, NX), out=True)
+        self._check(self._L.br2_batch_yaw_unwrap_host(self._h, a0))
+        return x0
+
+    def yaw_state(self):
+        st = np.empty((self.B, 2), dtype=np.float32)
+        self._check(self._L.br2_batch_yaw_get_state_host(self._h, _ptr(st)))
+        return st
+
+    def set_yaw_state(self, st):
+        self._check(self._L.br2_batch_yaw_set_state_host(self._h, _ptr(_np(st, (self.B, 2), dtype=np.float32))))
 
     # -- RLS with variable forgetting factor (BLUEROV2_AMPC::RLSFF, bluerov2_ampc.cpp:731-1004) ---------------
     RLS_STRIDE = 80

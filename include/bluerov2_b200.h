@@ -154,6 +154,17 @@ BR2_API int br2_batch_rls_host(br2_batch_solver *s, const double *meas, const do
 BR2_API int br2_batch_rls_get_state_host(br2_batch_solver *s, double *state);
 BR2_API int br2_batch_rls_set_state_host(br2_batch_solver *s, const double *state);
 
+/* == the continuous-yaw accumulator at the top of BLUEROV2_DOB::solve (bluerov2_dob.cpp:272-304; same in
+ * bluerov2_ampc.cpp:285-317): x0[B][12] arrives with the measured yaw in (-pi, pi] in column 5 (tf getRPY, pose_cb) and
+ * leaves with yaw_sum, the accumulated shortest signed differences.  pre_yaw / yaw_sum are FLOATS in the reference
+ * (bluerov2_dob.h:234-236) and so are they here: x0[psi] carries that float32 rounding.  State per instance:
+ * (pre_yaw, yaw_sum), both 0 after br2_batch_yaw_reset / creation.  In place; the host variant round-trips x0. */
+BR2_API int br2_batch_yaw_reset(br2_batch_solver *s);
+BR2_API int br2_batch_yaw_unwrap_device(br2_batch_solver *s, double *d_x0, void *stream);
+BR2_API int br2_batch_yaw_unwrap_host(br2_batch_solver *s, double *x0);
+BR2_API int br2_batch_yaw_get_state_host(br2_batch_solver *s, float *state /* [B][2] */);
+BR2_API int br2_batch_yaw_set_state_host(br2_batch_solver *s, const float *state);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1022,3 +1022,30 @@ void orc_rls_step_batch(int nb, double *st, const double *esti_x, const double *
         orc_rls_step(st + (size_t)i * 4 * RLS_STRIDE, esti_x + (size_t)i * EN, body_acc + (size_t)i * 6,
                      meas12 + (size_t)i * 12, compensate, p_out ? p_out + (size_t)i * 16 : 0);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Continuous-yaw accumulator at the top of BLUEROV2_DOB::solve (bluerov2_dob.cpp:272-304).  pre_yaw, yaw_sum and
+ * yaw_diff are floats in the reference (bluerov2_dob.h:234-236); psi is a double (struct Euler, :79-83).  Every
+ * conversion below is the one the C++ expression performs.  state[2] = (pre_yaw, yaw_sum); returns x0[psi].
+ * ---------------------------------------------------------------------------------------------- */
+double orc_yaw_unwrap(float *state, double psi)
+{
+    const double TWO_PI = 2 * 3.14159265358979323846;
+    const float pre_yaw = state[0];
+    float yaw_diff;
+    if (pre_yaw >= 0 && psi >= 0) {
+        yaw_diff = (float)(psi - pre_yaw);
+    } else if (pre_yaw >= 0 && psi < 0) {
+        if (TWO_PI + psi - pre_yaw >= pre_yaw + fabs(psi)) yaw_diff = (float)(-(pre_yaw + fabs(psi)));
+        else yaw_diff = (float)(TWO_PI + psi - pre_yaw);
+    } else if (pre_yaw < 0 && psi >= 0) {
+        if (TWO_PI - psi + pre_yaw >= fabsf(pre_yaw) + psi) yaw_diff = (float)(fabsf(pre_yaw) + psi);
+        else yaw_diff = (float)(-(TWO_PI - psi + pre_yaw));
+    } else {
+        yaw_diff = (float)(psi - pre_yaw);
+    }
+    state[1] = state[1] + yaw_diff;
+    state[0] = (float)psi;
+    return (double)state[1];
+}
+

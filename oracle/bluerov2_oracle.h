@@ -131,6 +131,10 @@ void orc_rls_step(double *state, const double *esti_x18, const double *body_acc6
 void orc_rls_step_batch(int nb, double *state, const double *esti_x18, const double *body_acc6,
                         const double *meas12, int compensate, double *p_out);
 
+/* ---- continuous yaw of BLUEROV2_DOB::solve (bluerov2_dob.cpp:272-304): state[2] = (pre_yaw, yaw_sum) as FLOATS
+ * (bluerov2_dob.h:234-236); returns the value the node writes into x0[psi] ---- */
+double orc_yaw_unwrap(float *state, double psi);
+
 #ifdef __cplusplus
 }
 #endif

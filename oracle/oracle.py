@@ -110,6 +110,8 @@ class Oracle:
         L.orc_ekf_step.argtypes = [D, D, D, D, D, D]
         L.orc_ekf_step_batch.argtypes = [C.c_int, D, D, D, D, D, D, C.c_int]
         L.orc_ekf_set_model.argtypes = [C.c_int]
+        L.orc_yaw_unwrap.argtypes = [C.POINTER(C.c_float), C.c_double]
+        L.orc_yaw_unwrap.restype = C.c_double
         L.orc_rls_init.argtypes = [D]
         L.orc_rls_step.argtypes = [D, D, D, D, C.c_int, D]
         L.orc_rls_step_batch.argtypes = [C.c_int, D, D, D, D, C.c_int, D]
@@ -258,4 +260,15 @@ class Oracle:
         assert p_out.dtype == np.float64 and p_out.shape == (nb, 16) and p_out.flags.c_contiguous
         self.lib.orc_rls_step_batch(nb, _p(state), _p(esti_x), _p(body_acc), _p(meas12), int(bool(compensate)), _p(p_out))
         return p_out
+
+    # -- continuous yaw (BLUEROV2_DOB::solve, bluerov2_dob.cpp:272-304) ------------------------------------
+    def yaw_unwrap_batch(self, state, psi):
+        """state (nb,2) float32 = (pre_yaw, yaw_sum) updated IN PLACE; psi (nb,) measured yaw in (-pi, pi]; returns x0[psi] (nb,)"""
+        nb = state.shape[0]
+        assert state.dtype == np.float32 and state.shape == (nb, 2) and state.flags.c_contiguous
+        psi = _c(psi, (nb,))
+        out = np.empty(nb)
+        for i in range(nb):
+            out[i] = self.lib.orc_yaw_unwrap(state[i].ctypes.data_as(C.POINTER(C.c_float)), float(psi[i]))
+        return out
 

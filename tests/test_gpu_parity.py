@@ -592,3 +592,34 @@ def test_ampc_tick_on_device_equals_host_chain(solver_mod, oracle):
     X, U = w["X"].copy(), w["U"].copy()
     so, _, _ = oracle.rti_step_batch(wl.time_steps(N), w["x0"], w["yref"], p, X, U)
     assert (so == 0).all() and np.abs(u0 - U[:, 0]).max() < TOL_U
+
+
+def test_yaw_unwrap_matches_oracle_bit_for_bit(solver_mod, oracle):
+    """node glue ahead of the solve (bluerov2_dob.cpp:272-304): float accumulators, only adds / compares / conversions ->
+    the kernel must agree with the C restatement exactly, through the host and the device entry point"""
+    import torch
+    B, T = 300, 120
+    rng = np.random.default_rng(9)
+    true = rng.uniform(-0.5, 0.5, B); rate = rng.uniform(-0.7, 0.7, B)
+    s = solver_mod.BatchSolver(B, 10)
+    st = np.zeros((B, 2), dtype=np.float32)
+    assert np.array_equal(s.yaw_state(), st)
+    dev = torch.device("cuda", 0)
+    for t in range(T):
+        true = true + rate + rng.normal(0, 0.05, B)
+        psi = (true + np.pi) % (2 * np.pi) - np.pi
+        x0 = rng.uniform(-1, 1, (B, 12)); x0[:, 5] = psi
+        want = oracle.yaw_unwrap_batch(st, psi)
+        if t % 2 == 0:
+            got = s.unwrap_yaw(x0.copy())
+        else:
+            d = torch.from_numpy(x0).to(dev)
+            s.unwrap_yaw(d); torch.cuda.synchronize()
+            got = d.cpu().numpy()
+        assert np.array_equal(got[:, 5], want), t
+        assert np.array_equal(np.delete(got, 5, axis=1), np.delete(x0, 5, axis=1))      # other columns untouched
+        assert np.array_equal(s.yaw_state(), st), t
+    assert np.abs(true).max() > 4 * np.pi
+    s.yaw_reset()
+    assert np.array_equal(s.yaw_state(), np.zeros((B, 2), dtype=np.float32))
+    s.close()
