@@ -85,6 +85,32 @@ def dob_params(esti_x: np.ndarray, compensate: bool = True) -> np.ndarray:
     return p
 
 
+def ctrl_params(disturb: np.ndarray | None = None, dompc: bool = False) -> np.ndarray:
+    """OCP parameter fill of the consolidated node, BLUEROV2_CTRL::set_mpc_constraints (src/ctrller/mpc.cpp:139-187):
+    ctrller_type MPC -> p[0..3] = 0; DOMPC -> the ``/disturbance`` estimate (x, y, z) [B,3] divided by the hard-coded
+    0.032546960744430276 (x, y) / rotor_constant (z) and p[3] = 0 (the yaw moment is never compensated there, :165);
+    p[4..15] nominal in both modes."""
+    if not dompc:
+        return NOMINAL_P[None, :].copy() if disturb is None else np.tile(NOMINAL_P, (np.asarray(disturb).shape[0], 1))
+    d = np.ascontiguousarray(disturb, dtype=np.float64)
+    p = np.tile(NOMINAL_P, (d.shape[0], 1))
+    p[:, 0] = d[:, 0] / COMPENSATE_COEF
+    p[:, 1] = d[:, 1] / COMPENSATE_COEF
+    p[:, 2] = d[:, 2] / ROTOR_CONSTANT
+    p[:, 3] = 0.0
+    return p
+
+
+def ctrl_yref(ref12: np.ndarray) -> np.ndarray:
+    """Horizon reference of the consolidated node, BLUEROV2_CTRL::set_ref (src/ctrller/mpc.cpp:199-262): only the 12 state
+    columns of each yref row are written from the ``/ref_traj`` preview, the input reference stays 0.
+    ref12 [..., N+1, 12] -> yref [..., N+1, 16]."""
+    r = np.asarray(ref12, dtype=np.float64)
+    y = np.zeros(r.shape[:-1] + (NY,))
+    y[..., :12] = r
+    return y
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Nominal plant for closed-loop input generation (numpy, vectorised over the batch).  Same equations as the
 # OCP model (bluerov2.py:103-137) -- this is workload synthesis on the host, not a solver path.

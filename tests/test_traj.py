@@ -44,3 +44,16 @@ def test_window_clamps_to_last_row():
     assert np.all(w == t[9])
     wb = traj.window_batch(t, np.array([2, 7, 40]), 4)
     assert np.array_equal(wb[0], traj.window(t, 2, 4)) and np.array_equal(wb[1], traj.window(t, 7, 4))
+
+
+def test_ctrl_node_glue():
+    """parameter / reference fill of the consolidated node (src/ctrller/mpc.cpp:139-187, 199-262)"""
+    from bluerov2_b200 import workloads as wl
+    d = np.array([[4.0, -2.0, 1.0], [0.0, 0.5, -3.0]])
+    p = wl.ctrl_params(d, dompc=True)
+    assert np.allclose(p[:, 0], d[:, 0] / 0.032546960744430276) and np.allclose(p[:, 1], d[:, 1] / 0.032546960744430276)
+    assert np.allclose(p[:, 2], d[:, 2] / 0.026546960744430276) and np.all(p[:, 3] == 0.0)
+    assert np.array_equal(p[:, 4:], np.tile(wl.NOMINAL_P[4:], (2, 1)))
+    assert np.array_equal(wl.ctrl_params(d, dompc=False), np.tile(wl.NOMINAL_P, (2, 1)))
+    y = wl.ctrl_yref(np.ones((3, 5, 12)))
+    assert y.shape == (3, 5, 16) and np.all(y[..., :12] == 1.0) and np.all(y[..., 12:] == 0.0)
