@@ -239,10 +239,8 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
                 Jac J;
                 jac_load(J, sm.jb + (si * 4 + s) * JREC);
                 double ka[NX], kb[NX];
-                jac_mul(J, ca, ka);
-                jac_mul(J, cb, kb);
-                ka[6] += ja6; ka[7] += ja7; ka[8] += ja8; ka[11] += jab_;
-                kb[6] += jb6; kb[7] += jb7; kb[8] += jb8; kb[11] += jbb_;
+                jac_mul_add(J, ca, ja6, ja7, ja8, jab_, ka);
+                jac_mul_add(J, cb, jb6, jb7, jb8, jbb_, kb);
                 const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
                 const double ch = ((s == 2) ? 1.0 : 0.5) * h;
 #pragma unroll
@@ -250,10 +248,12 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
                     aa[i] = fma(bw, ka[i], aa[i]);
                     ab[i] = fma(bw, kb[i], ab[i]);
                 }
+                if (s < 3) {                        // the last stage's slope only enters the weighted sum
 #pragma unroll
-                for (int i = 3; i < NX; i++) {      // rows 0..2 never feed back (columns 0..2 of J are zero)
-                    ca[i] = fma(ch, ka[i], (i == seed_a) ? 1.0 : 0.0);
-                    cb[i] = fma(ch, kb[i], (i == seed_b) ? 1.0 : 0.0);
+                    for (int i = 3; i < NX; i++) {  // rows 0..2 never feed back (columns 0..2 of J are zero)
+                        ca[i] = fma(ch, ka[i], (i == seed_a) ? 1.0 : 0.0);
+                        cb[i] = fma(ch, kb[i], (i == seed_b) ? 1.0 : 0.0);
+                    }
                 }
             }
             if (gs < total) {

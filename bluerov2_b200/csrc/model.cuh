@@ -194,6 +194,24 @@ BR2_HD void jac_mul(const Jac& J, const double* s, double* o)
     o[11] = J.jb9 * s[9] + J.jba * s[10] + J.jbb * s[11];
 }
 
+// out = Jx * s + c for a column of Su, where c = (df/du)[:, a] has non-zeros in rows 6, 7, 8, 11 only: the constant rides
+// in the accumulator of those rows' first multiply-add.
+BR2_HD void jac_mul_add(const Jac& J, const double* s, double c6, double c7, double c8, double c11, double* o)
+{
+    o[0] = J.j03 * s[3] + J.j04 * s[4] + J.j05 * s[5] + J.j06 * s[6] + J.j07 * s[7] + J.j08 * s[8];
+    o[1] = J.j13 * s[3] + J.j14 * s[4] + J.j15 * s[5] + J.j16 * s[6] + J.j17 * s[7] + J.j18 * s[8];
+    o[2] = J.j23 * s[3] + J.j24 * s[4] + J.j26 * s[6] + J.j27 * s[7] + J.j28 * s[8];
+    o[3] = J.j33 * s[3] + J.j34 * s[4] + J.j35 * s[5] + s[9] + J.j3a * s[10] + J.j3b * s[11];
+    o[4] = J.j43 * s[3] + J.j4a * s[10] + J.j4b * s[11];
+    o[5] = J.j53 * s[3] + J.j54 * s[4] + J.j5a * s[10] + J.j5b * s[11];
+    o[6] = fma(J.j64, s[4], c6) + J.j66 * s[6];
+    o[7] = fma(J.j73, s[3], c7) + J.j74 * s[4] + J.j77 * s[7];
+    o[8] = fma(J.j83, s[3], c8) + J.j84 * s[4] + J.j88 * s[8];
+    o[9] = J.j93 * s[3] + J.j94 * s[4] + J.j9a * s[10] + J.j9b * s[11];
+    o[10] = J.ja4 * s[4] + J.ja9 * s[9] + J.jab * s[11];
+    o[11] = fma(J.jb9, s[9], c11) + J.jba * s[10] + J.jbb * s[11];
+}
+
 // o += (df/du)[:, a]  (constant in x and u)
 BR2_HD void ju_add(const ModelConst& c, int a, double* o)
 {
