@@ -158,7 +158,7 @@ __device__ __forceinline__ void mm18(const double* A, const double* B, double* C
 
 struct __align__(16) EkfSmem {
     double Fm[EN * LD], Hm[EN * LD], Pp[EN * LD], T1[EN * LD], T2[EN * LD];   // Fm doubles as Kal once P_pred is formed
-    double prow[2 * EN + 4];     // scaled pivot row of the Gauss-Jordan inverse: [S | I] part of one row
+    double prow[EN + 2];         // scaled pivot row of the Gauss-Jordan inverse
     double vec[EN + 2];          // innovation
     double xpv[2 * EN];          // x_pred | measurement vector y = [pose, body velocity, tau]
 };
@@ -240,17 +240,18 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
     mm18(sm.Hm, sm.Pp, sm.T1, false, lane);
     mm18(sm.T1, sm.Hm, sm.T2, true, lane);
     {
-        // Lane i < 18 keeps one row of [S | I] in registers.  Rows are never moved: `myrow` is the row's position in the
-        // eliminated matrix, and a pivot exchange swaps positions.  Pivot = largest |entry| of column c over positions >= c,
-        // lowest position on ties (what a sequential scan finds): three warp reductions on the value's bit pattern.
+        // In-place Gauss-Jordan with partial pivoting.  Lane i < 18 keeps one row of the working matrix in registers.  Rows are
+        // never moved: `myrow` is the row's position in the eliminated matrix, and a pivot exchange swaps positions.  Pivot =
+        // largest |entry| of column c over positions >= c, lowest position on ties (what a sequential scan finds): three warp
+        // reductions on the value's bit pattern.  Column c of the working matrix is dead once it has been eliminated, so it
+        // takes the one column of the inverse that step c creates -- the column of the identity that belongs to the pivot
+        // row, i.e. inverse column (lane id of the pivot lane): the same multiplications as on the augmented [S | I], half
+        // the registers, shared-memory traffic and FMAs.
         const bool own = lane < EN;
         const int li = own ? lane : 0;
-        double ra[EN], rb[EN];
+        double ra[EN];
 #pragma unroll
-        for (int j = 0; j < EN; j++) {
-            ra[j] = sm.T2[li * LD + j] + (j == lane ? (DT * DT * DT * DT) / 4 : 0.0);
-            rb[j] = (j == lane) ? 1.0 : 0.0;
-        }
+        for (int j = 0; j < EN; j++) ra[j] = sm.T2[li * LD + j] + (j == lane ? (DT * DT * DT * DT) / 4 : 0.0);
         int myrow = own ? lane : 99;
         __syncwarp();
 #pragma unroll
@@ -267,16 +268,13 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
             // exchange positions c <-> pr
             if (is_piv) myrow = c;
             else if (myrow == c) myrow = pr;
-            // pivot lane: scale its row and publish it
+            // pivot lane: scale its row (its own identity entry 1 becomes 1/pivot) and publish it
             const double dinv = 1.0 / ra[c];
             if (is_piv) {
 #pragma unroll
-                for (int j = 0; j < EN; j++) { ra[j] *= dinv; rb[j] *= dinv; }
+                for (int j = 0; j < EN; j++) ra[j] = (j == c) ? dinv : ra[j] * dinv;
 #pragma unroll
-                for (int j = 0; j < EN; j += 2) {
-                    *reinterpret_cast<double2*>(sm.prow + j) = make_double2(ra[j], ra[j + 1]);
-                    *reinterpret_cast<double2*>(sm.prow + EN + j) = make_double2(rb[j], rb[j + 1]);
-                }
+                for (int j = 0; j < EN; j += 2) *reinterpret_cast<double2*>(sm.prow + j) = make_double2(ra[j], ra[j + 1]);
             }
             __syncwarp();
             if (!is_piv) {
@@ -285,19 +283,18 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
 #pragma unroll
                     for (int j = 0; j < EN; j += 2) {
                         const double2 pa = *reinterpret_cast<const double2*>(sm.prow + j);
-                        const double2 pb = *reinterpret_cast<const double2*>(sm.prow + EN + j);
-                        ra[j] -= f * pa.x; ra[j + 1] -= f * pa.y;
-                        rb[j] -= f * pb.x; rb[j + 1] -= f * pb.y;
+                        ra[j] = (j == c) ? -(f * pa.x) : ra[j] - f * pa.x;
+                        ra[j + 1] = (j + 1 == c) ? -(f * pa.y) : ra[j + 1] - f * pa.y;
                     }
                 }
             }
             __syncwarp();
         }
-        // Si -> T2: the lane at position r holds row r of the inverse
-        if (own) {
+        // Si -> T2: the lane at position r holds row r of the inverse; working column c is inverse column (lane at position c)
 #pragma unroll
-            for (int j = 0; j < EN; j += 2)
-                *reinterpret_cast<double2*>(sm.T2 + myrow * LD + j) = make_double2(rb[j], rb[j + 1]);
+        for (int c = 0; c < EN; c++) {
+            const int col = __ffs(__ballot_sync(FULL_MASK, myrow == c)) - 1;
+            if (own) sm.T2[myrow * LD + col] = ra[c];
         }
     }
     __syncwarp();
