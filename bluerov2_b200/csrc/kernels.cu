@@ -325,7 +325,7 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 
-// ---- per-warp TMA bulk-copy pipeline: stage records are prefetched HBM -> shared memory one stage ahead ----
+// ---- per-warp TMA bulk-copy pipeline: stage records are prefetched HBM -> shared memory NSLOT-1 stages ahead ----
 struct __align__(128) StageBuf { double G[GREC]; double F[FREC]; double V[VREC]; };
 constexpr int NSLOT = BR2_NSLOT;     // ring depth: records of NSLOT-1 stages are in flight ahead of the one being computed
 // xch: per-warp exchange buffer of the factor sweep: H[:, 12..15] (16 rows x 4) + g (4)
@@ -444,7 +444,7 @@ __device__ __forceinline__ void inv4_apply(const Inv4& B, const double* v, doubl
 struct Inst {
     const SolveArgs& a;
     WarpSmem& sm;
-    uint32_t& phase;            // parity of the two slot barriers (bit s = next parity to wait for on slot s)
+    uint32_t& phase;            // parities of the slot barriers (bit s = next parity to wait for on slot s)
     int inst, lane, q, t, N;
     const double* G;
     double* F;
