@@ -228,3 +228,21 @@ def test_node_call_sequence_matches_oracle(lib_path, oracle, N, tmp_path):
     tail = np.frombuffer(raw, dtype=np.float64, offset=T * rec)
     Xg, Ug = tail[:(N + 1) * 12].reshape(N + 1, 12), tail[(N + 1) * 12:].reshape(N, 4)
     assert np.abs(Ug - U).max() < 1e-5 and np.abs(Xg - X).max() < 1e-5
+
+
+@pytest.mark.parametrize("lang", ["c", "c++"])
+def test_public_headers_compile_standalone(tmp_path, lang):
+    """every header a consumer includes (the list of bluerov2_dob.h:25-35 plus the batched API) compiles on its own as C99
+    and as C++, warnings as errors -- no CUDA, no torch types in the signatures"""
+    hdrs = ["acados/utils/print.h", "acados/utils/types.h", "acados/utils/math.h", "acados_c/ocp_nlp_interface.h",
+            "acados_c/external_function_interface.h", "acados/ocp_nlp/ocp_nlp_constraints_bgh.h", "acados/ocp_nlp/ocp_nlp_cost_ls.h",
+            "blasfeo/include/blasfeo_d_aux.h", "blasfeo/include/blasfeo_d_aux_ext_dep.h", "bluerov2_model/bluerov2_model.h",
+            "bluerov2_cost/bluerov2_cost.h", "bluerov2_constraints/bluerov2_constraints.h", "acados_solver_bluerov2.h",
+            "bluerov2_b200.h"]
+    ext = "c" if lang == "c" else "cpp"
+    src = tmp_path / f"hdr.{ext}"
+    src.write_text("".join(f'#include "{h}"\n' for h in hdrs) + "int main(void) { return (int)sizeof(bluerov2_solver_capsule) == 0; }\n")
+    cc = ("/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc") if lang == "c" else ("/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++")
+    std = "-std=c99" if lang == "c" else "-std=c++14"
+    out = subprocess.run([cc, std, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", INCLUDE, str(src)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
