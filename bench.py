@@ -257,6 +257,8 @@ def run_ours(args):
     sol = S.BatchSolver(B, N, device=local)
     if args.no_fast_path:
         sol.set_option("fast_path", 0)
+    if args.active_set_path is not None:
+        sol.set_option("active_set_path", args.active_set_path)
     if dob:
         rec, dob0 = record_closed_loop_dob(sol, w, W + K, N, seed=1000 * rank)
         x0s, lns = rec["meas"], rec["lines"]
@@ -435,6 +437,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline / reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fast-path", action="store_true", help="always run the interior-point iteration (diagnostic)")
+    ap.add_argument("--active-set-path", type=int, default=None, choices=[0, 1],
+                    help="override the library default of the active-set fast path (diagnostic)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -31,11 +31,11 @@ struct br2_batch_solver {
     int B, N, device, sm_count;
     double Ts[NMAX];
     double W[16], We[12], lbu[4], ubu[4];
-    int max_iter, fast_path, ekf_model;
+    int max_iter, fast_path, ekf_model, active_set;
     double tol;
     // device state
     double *d_Ts, *d_X, *d_U, *d_G, *d_F, *d_V, *d_u0, *d_thrust, *d_info;
-    int *d_status, *d_iters, *d_counter, *d_hint;
+    int *d_status, *d_iters, *d_counter, *d_hint, *d_aset;
     double *d_x0, *d_yref, *d_p;              // staging for the host API
     double* d_traj;                           // reference trajectory for device-side windowing [traj_rows][16]
     int* d_lines;                             // staging: first trajectory row per instance
@@ -71,7 +71,7 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
     cudaSetDevice(s->device);
     void* ptrs[] = {s->d_Ts, s->d_X, s->d_U, s->d_G, s->d_F, s->d_V, s->d_u0, s->d_thrust, s->d_info, s->d_status,
                     s->d_iters, s->d_counter, s->d_x0, s->d_yref, s->d_p, s->d_ex, s->d_eP, s->d_thr, s->d_meas,
-                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls, s->d_yaw};
+                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls, s->d_yaw, s->d_aset};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -111,6 +111,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     for (int i = 0; i < 4; i++) { s->lbu[i] = -50.0; s->ubu[i] = 50.0; }
     s->max_iter = 50;
     s->fast_path = 1;
+    s->active_set = 0;      // opt-in this round (option "active_set_path"): see DESIGN.md section 10
     s->tol = 1e-12;
     const size_t B = batch;
 #define DA(p, n)                                                                                          \
@@ -131,6 +132,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     DA(d_yaw, B * 2);
     DA(d_iter_total, 1);
     DA(d_hint, B);
+    DA(d_aset, B * N);
     DA(d_lines, B);
 #undef DA
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -144,6 +146,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     CK(cudaMemset(s->d_status, 0, sizeof(int) * B));
     CK(cudaMemset(s->d_iters, 0, sizeof(int) * B));
     CK(cudaMemset(s->d_hint, 0, sizeof(int) * B));
+    CK(cudaMemset(s->d_aset, 0, sizeof(int) * B * N));
     CK(cudaMemset(s->d_info, 0, sizeof(double) * B * 4));
     CK(cudaMemset(s->d_V, 0, sizeof(double) * B * (N + 1) * VREC));
     *out = s;
@@ -206,6 +209,10 @@ extern "C" int br2_batch_set_option_int(br2_batch_solver* s, const char* name, i
     }
     if (!strcmp(name, "fast_path")) {
         s->fast_path = v != 0;
+        return BR2_OK;
+    }
+    if (!strcmp(name, "active_set_path")) {   // active-set fast path for instances whose previous solution had active bounds
+        s->active_set = v != 0;
         return BR2_OK;
     }
     if (!strcmp(name, "ekf_model")) {      // 0 = BLUEROV2_DOB filter, 1 = BLUEROV2_AMPC filter (bluerov2_ampc.cpp:658-696)
@@ -288,7 +295,7 @@ static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, con
     a.u0 = d_u0 ? d_u0 : s->d_u0;
     a.thrust = d_thrust ? d_thrust : s->d_thrust;
     a.status = d_status ? d_status : s->d_status;
-    a.iters = s->d_iters; a.info = s->d_info; a.work_counter = s->d_counter; a.iter_total = s->d_iter_total; a.hint = s->d_hint; a.fast_path = s->fast_path;
+    a.iters = s->d_iters; a.info = s->d_info; a.work_counter = s->d_counter; a.iter_total = s->d_iter_total; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
     a.max_iter = s->max_iter; a.tol = s->tol;
 }
 

@@ -38,6 +38,8 @@ struct SolveArgs {
     int* work_counter;     // [1] persistent-kernel instance queue
     int* hint;             // [B] 1 = a bound was active at the previous solution (skip the interior fast path)
     int fast_path;         // try the interior-solution fast path (option "fast_path", default 1)
+    int* aset;             // [B][N] guessed active set per stage, 2 bits per input (0 free, 1 at lbu, 2 at ubu)
+    int active_set;        // try the active-set fast path when bounds were active (option "active_set_path")
     unsigned long long* iter_total;   // [1] IPM iterations executed, accumulated over instances and solves
     // options
     int max_iter;          // qp_solver_iter_max (50)

@@ -633,13 +633,15 @@ __device__ double forward_sweep(Inst& I)
 //   - and ONE gather of Z, z[kt][m] = Z[row(kt,t)][8m+q], is the A fragment of Z' (first product) and the B fragment
 //     of Z (second product).
 // Returns false if a Cholesky pivot failed.
-enum { FS_IPM = 0, FS_ABS = 1 };
+enum { FS_IPM = 0, FS_ABS = 1, FS_AS = 2 };    // FS_AS: FS_ABS with the inputs of the guessed active set pinned at their bounds
 
 template <int KIND>
 __device__ bool factor_sweep(Inst& I)
 {
     const int q = I.q, t = I.t, N = I.N, lane = I.lane;
     const SolveArgs& a = I.a;
+    constexpr bool ABSF = KIND != FS_IPM;       // absolute-form LQR sweep (fast paths)
+    constexpr bool PIN = KIND == FS_AS;         // ... with pinned inputs
     const bool lo = q < 4;
     const int e = q & 3;                        // input index owned by quads 4..7
     const int qb = lane & ~3;                   // first lane of my quad
@@ -690,6 +692,18 @@ __device__ bool factor_sweep(Inst& I)
         const double* Vs = I.sm.st[s].V;
         double* Fk = I.F + (size_t)k * FREC;
         double* Vk = I.V + (size_t)k * VREC;
+        // FS_AS: the stage's guessed active set (2 bits per input: 1 = at the lower, 2 = at the upper bound) and the pinned values
+        // du_e = bound_e - U_k[e] (uniform over the warp)
+        int code = 0;
+        double ubar[4] = {0.0, 0.0, 0.0, 0.0};
+        if (PIN) {
+            code = a.aset[(size_t)I.inst * N + k];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int cc = (code >> (2 * c)) & 3;
+                ubar[c] = (cc == 2 ? a.ubu[c] : a.lbu[c]) - I.Ulin[k * NU + c];
+            }
+        }
         double z[3][2];
         z[0][0] = Gs[zo0]; z[0][1] = Gs[zo0 + 32];
         z[1][0] = Gs[zo1]; z[1][1] = Gs[zo1 + 32];
@@ -744,7 +758,7 @@ __device__ bool factor_sweep(Inst& I)
         }
         // ---- the vector products sit in columns 12, 13 of W': lane (q,2) holds ([A|B]'v1)[8m+q], ([A|B]'v2)[8m+q] ----
         double at0 = shfl(w[0][1][0], qb | 2), at1 = shfl(w[1][1][0], qb | 2);
-        if (KIND == FS_ABS) {
+        if (ABSF) {
             // Z's+ = Z'p+ + (Z'P+) b_k: lane (q,t) holds columns 2t, 2t+1, 8+2t, 9+2t of rows q / 8+q of Z'P+
             const double bb0 = Gs[G_B_OFF + row0], bb1 = Gs[G_B_OFF + row1];
             const double bb2 = hi2 ? 0.0 : Gs[G_B_OFF + 8 + 2 * t], bb3 = hi2 ? 0.0 : Gs[G_B_OFF + 9 + 2 * t];
@@ -793,8 +807,41 @@ __device__ bool factor_sweep(Inst& I)
             gt[0] = g0.x; gt[1] = g0.y; gt[2] = g1.x; gt[3] = g1.y;       // g on every lane
         }
         if (KIND == FS_IPM && !lo && t == 2) Vk[V_GU + e] = gu;
+        if (PIN && code != 0) {
+            // pinned inputs F: b_k <- b_k + B_F ubar_F reaches the vector recursion through H[:, 12+F] (state rows: at, input rows:
+            // g), then their rows / columns leave the 4x4 system (identity row, g_F = -ubar_F so that u_F = -kff_F = ubar_F)
+            double Lm[4][4];
+            Lm[0][0] = m10[0]; Lm[1][0] = Lm[0][1] = m10[1]; Lm[1][1] = m10[2]; Lm[2][0] = Lm[0][2] = m10[3];
+            Lm[2][1] = Lm[1][2] = m10[4]; Lm[2][2] = m10[5]; Lm[3][0] = Lm[0][3] = m10[6]; Lm[3][1] = Lm[1][3] = m10[7];
+            Lm[3][2] = Lm[2][3] = m10[8]; Lm[3][3] = m10[9];
+            double gn[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                double gsum = gt[r];
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if ((code >> (2 * c)) & 3) gsum = fma(Lm[r][c], ubar[c], gsum);
+                gn[r] = gsum;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if ((code >> (2 * c)) & 3) {
+                    at0 = fma(y0[c], ubar[c], at0);
+                    at1 = fma(y1[c], ubar[c], at1);
+                    y0[c] = 0.0; y1[c] = 0.0;
+                    gn[c] = -ubar[c];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) { Lm[r][c] = 0.0; Lm[c][r] = 0.0; }
+                    Lm[c][c] = 1.0;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) gt[r] = gn[r];
+            m10[0] = Lm[0][0]; m10[1] = Lm[1][0]; m10[2] = Lm[1][1]; m10[3] = Lm[2][0]; m10[4] = Lm[2][1]; m10[5] = Lm[2][2];
+            m10[6] = Lm[3][0]; m10[7] = Lm[3][1]; m10[8] = Lm[3][2]; m10[9] = Lm[3][3];
+        }
         double yg0, yg1;                         // (K'g)[q], (K'g)[8+q]
-        if (KIND == FS_ABS) {
+        if (ABSF) {
             // Lam = R + B'P+B is well conditioned here: explicit inverse, no dependent rsqrt / substitution chains.
             //   K = Lam^-1 H_ux,  kff = Lam^-1 g,  P = Q + H_xx - H_xu K
             Inv4 Bi;
@@ -936,6 +983,78 @@ __device__ void backward_vec_sweep(Inst& I)
     __syncwarp();
 }
 
+// Costate sweep over a candidate solution (dx, du in V_X / V_V) of the active-set fast path:
+//   lam_N = We (dx_N + X_N - xref_N),  lam_k = qlin_k + Ts W_x dx_k + A_k' lam_{k+1},
+//   mu_k  = Ts W_u du_k + rlin_k + B_k' lam_{k+1}          (gradient of the Lagrangian with respect to the inputs)
+// The candidate solves the LQR with the guessed active set pinned, so mu = 0 on the free inputs; it is the minimiser of the
+// box-constrained QP iff every free input lies inside its box and mu >= 0 (<= 0) on the inputs pinned at the lower (upper)
+// bound -- the KKT conditions of a strictly convex QP.  Where the test fails the guess is repaired in place (a free input
+// outside its box is pinned at the violated bound, a pinned input with the wrong multiplier sign is released): one step
+// of a primal-dual active-set method.  Returns true iff the candidate passed.
+__device__ bool costate_check(Inst& I)
+{
+    const int q = I.q, t = I.t, N = I.N, lane = I.lane;
+    const SolveArgs& a = I.a;
+    const bool lo = q < 4;
+    const int e = q & 3;
+    I.template begin<false, true, true>();
+    double pr[3];                               // lam+ in row layout
+    {
+        const double* VN = I.V + (size_t)N * VREC;
+        const double* yN = yref_row(a, I.inst, N);
+#pragma unroll
+        for (int ki = 0; ki < 3; ki++) {
+            const int r = 4 * ki + t;
+            pr[ki] = a.We[r] * (VN[V_X + r] + I.Xlin[N * NX + r] - yN[r]);
+        }
+    }
+    bool good = true;
+    for (int k = N - 1, it = 0; k >= 0; k--, it++) {
+        const int s = I.template advance<false, true, true>(it);
+        const double* Gk = I.sm.st[s].G;
+        const double* Vs = I.sm.st[s].V;
+        double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+        for (int ki = 0; ki < 3; ki++) {
+            o0 = fma(Gk[((ki * 2 + 0) << 5) + lane], pr[ki], o0);
+            o1 = fma(Gk[((ki * 2 + 1) << 5) + lane], pr[ki], o1);
+        }
+        const double tsk = Gk[G_TS];
+        const int code = a.aset[(size_t)I.inst * N + k];
+        const double uk = I.Ulin[k * NU + e];
+        o0 += shfl_x(o0, 1); o1 += shfl_x(o1, 1);
+        o0 += shfl_x(o0, 2); o1 += shfl_x(o1, 2);          // (Z'lam+)[q], (Z'lam+)[8+q]
+        // input e of this stage lives in quad 4 + e
+        const double du = Vs[V_V + e];
+        const double mu = fma(tsk * a.W[12 + e], du, Gk[G_RLIN + e]) + o1;
+        const double lb = a.lbu[e] - uk, ub = a.ubu[e] - uk;
+        const double tolu = 1e-9 * fmax(1.0, ub - lb), tolm = 1e-9 * fmax(1.0, fabs(Gk[G_RLIN + e]) + fabs(o1));
+        const int cc = (code >> (2 * e)) & 3;
+        int nc = cc;
+        if (cc == 0) {
+            if (!(du >= lb - tolu)) nc = 1;                 // written so that a NaN fails
+            else if (!(du <= ub + tolu)) nc = 2;
+        } else if (cc == 1) {
+            if (!(mu >= -tolm)) nc = 0;
+        } else {
+            if (!(mu <= tolm)) nc = 0;
+        }
+        if (!lo && (nc != cc || !isfinite(du) || !isfinite(mu))) good = false;
+        const int c0 = __shfl_sync(FULL_MASK, nc, 16), c1 = __shfl_sync(FULL_MASK, nc, 20), c2 = __shfl_sync(FULL_MASK, nc, 24),
+                  c3 = __shfl_sync(FULL_MASK, nc, 28);
+        const int ncode = c0 | (c1 << 2) | (c2 << 4) | (c3 << 6);
+        if (lane == 0 && ncode != code) a.aset[(size_t)I.inst * N + k] = ncode;
+        // lam_k, then quad layout -> row layout
+        const double pv0 = fma(tsk * a.W[q], Vs[V_X + q], Gk[G_QLIN + q]) + o0;
+        const double pv1 = lo ? fma(tsk * a.W[8 + e], Vs[V_X + 8 + e], Gk[G_QLIN + 8 + e]) + o1 : 0.0;
+        pr[0] = shfl(pv0, 4 * t);
+        pr[1] = shfl(pv0, 4 * (4 + t));
+        pr[2] = shfl(pv1, 4 * t);
+    }
+    __syncwarp();
+    return __all_sync(FULL_MASK, good);
+}
+
 __device__ __forceinline__ double step_to_boundary(double v, double dv)
 {
     return dv < 0.0 ? -v / dv : 2.0;   // 2 = "not blocking" (callers clamp at 1)
@@ -995,6 +1114,27 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
                     active |= fmin(tl, tu) < 1e-3;
                 }
                 if (__all_sync(FULL_MASK, inside)) { solved = true; status = 0; it = 1; }
+            }
+        }
+        // ---------- active-set fast path ----------
+        // Bounds were active at the previous solution: solve the LQR with the previous active set pinned (one factorisation +
+        // one roll-out), verify the KKT conditions with a costate sweep, repair the guess and retry up to twice; exact whenever
+        // it accepts, interior-point iteration otherwise.
+        bool by_as = false;
+        if (!solved && a.active_set && a.hint[inst] == 1) {
+            for (int att = 0; att < 3 && !solved; att++) {
+                if (!factor_sweep<FS_AS>(I)) break;
+                if (att == 0) prefetch_iterate(I);
+                bmax = forward_sweep<2>(I);
+                if (costate_check(I)) { solved = true; by_as = true; status = 0; it = att + 1; }
+            }
+            if (by_as) {
+#pragma unroll 5
+                for (int idx = lane; idx < nb; idx += 32) {
+                    const int e = idx & 3;
+                    const double un = I.Ulin[idx] + I.V[(size_t)(idx >> 2) * VREC + V_V + e];
+                    active |= fmin(un - a.lbu[e], a.ubu[e] - un) < 1e-3;
+                }
             }
         }
         if (!solved) {
@@ -1118,6 +1258,20 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         finite = __all_sync(FULL_MASK, finite);
         if (!solved) active = act2;
         active = __any_sync(FULL_MASK, active);
+        if (!solved && a.active_set && status == 0) {
+            // the interior-point solution's active set (slack ~ mu / lam at an active bound) is the next solve's guess
+            for (int base = 0; base < nb; base += 32) {
+                const int idx = base + lane;
+                const bool valid = idx < nb;
+                const double* Vk = I.V + (size_t)((valid ? idx : 0) >> 2) * VREC;
+                int cc = 0;
+                if (valid) cc = Vk[V_TL + (idx & 3)] < 1e-7 ? 1 : (Vk[V_TU + (idx & 3)] < 1e-7 ? 2 : 0);
+                int code = cc << (2 * (lane & 3));
+                code |= __shfl_xor_sync(FULL_MASK, code, 1);
+                code |= __shfl_xor_sync(FULL_MASK, code, 2);
+                if (valid && (lane & 3) == 0) a.aset[(size_t)inst * N + (idx >> 2)] = code;
+            }
+        }
         if (lane == 0) a.hint[inst] = (active || status != 0) ? 1 : 0;
         if (finite) {
             // X / U were last touched by the lineariser, before ~300 MB of stage records went through L2: without care this is

@@ -65,7 +65,11 @@ BR2_API int br2_batch_set_bounds(br2_batch_solver *s, const double *lbu4, const 
 BR2_API int br2_batch_set_time_steps(br2_batch_solver *s, const double *time_steps);
 /* options: "qp_iter_max" (int, default 50), "qp_tol" (double, default 1e-12), "fast_path" (int, default 1: try the
  * unconstrained Riccati solution first and accept it when it lies inside the input box -- it is then the exact QP
- * minimiser; 0 = always run the interior-point iteration) */
+ * minimiser; 0 = always run the interior-point iteration), "active_set_path" (int, default 0 = off, opt-in: an instance whose previous
+ * solution had active input bounds is first solved as the LQR with that active set pinned; a costate sweep checks the KKT
+ * conditions -- free inputs inside the box, multipliers of the pinned inputs of the right sign --, repairs the guess and
+ * retries up to twice; accepted solutions are exact, everything else falls through to the interior-point iteration),
+ * "ekf_model" (int, 0 = DOB filter, 1 = AMPC filter) */
 BR2_API int br2_batch_set_option_int(br2_batch_solver *s, const char *name, int v);
 BR2_API int br2_batch_set_option_double(br2_batch_solver *s, const char *name, double v);
 

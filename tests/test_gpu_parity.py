@@ -623,3 +623,40 @@ def test_yaw_unwrap_matches_oracle_bit_for_bit(solver_mod, oracle):
     s.yaw_reset()
     assert np.array_equal(s.yaw_state(), np.zeros((B, 2), dtype=np.float32))
     s.close()
+
+
+def test_active_set_fast_path_equals_ipm(solver_mod, oracle):
+    """Option active_set_path: instances whose previous solution had active bounds are solved by the pinned LQR + KKT check
+    (exact whenever it accepts) instead of interior-point iterations.  Closed loop from a 3 m start (saturated thrusters for
+    the first ticks): every tick against the interior-point-only solver on the same inputs, and against the oracle."""
+    N, B, T = 40, 512, 10
+    w = wl.tracking_batch(B, N, seed=21, pos_spread=3.0)
+    Ts = wl.time_steps(N)
+    s_as = solver_mod.BatchSolver(B, N); s_as.set_option("active_set_path", 1)
+    s_ip = solver_mod.BatchSolver(B, N); s_ip.set_option("fast_path", 0); s_ip.set_option("active_set_path", 0)
+    X, U = w["X"].copy(), w["U"].copy()
+    x0, lines = w["x0"].copy(), w["lines"].copy()
+    s_as.set_iterate(X, U); s_ip.set_iterate(X, U)
+    took_as = took_sat = 0
+    for t in range(T):
+        yref = traj.window_batch(w["traj"], lines, N)
+        u_a, _, st_a = s_as.solve(x0, yref, w["p"])
+        u_i, _, st_i = s_ip.solve(x0, yref, w["p"])
+        assert (st_a == 0).all() and (st_i == 0).all(), (t, np.unique(st_a), np.unique(st_i))
+        Xa, Ua = s_as.get_iterate(); Xi, Ui = s_ip.get_iterate()
+        assert np.abs(Ua - Ui).max() < 1e-5 and np.abs(Xa - Xi).max() < 1e-5, (t, np.abs(Ua - Ui).max())   # iterates carried separately
+        assert (np.abs(Ua) <= 50 + 1e-9).all()
+        it_a, _ = s_as.stats(); it_i, _ = s_ip.stats()
+        sat = (np.abs(np.abs(Ui) - 50.0) < 1e-6).any(axis=(1, 2))
+        if t >= 1:      # from the second tick on the previous solution's active set is the guess
+            took_sat += int(sat.sum()); took_as += int((sat & (it_a <= 3) & (it_i > 3)).sum())
+        if t == 2:
+            Xo, Uo = X[:64].copy(), U[:64].copy()       # the interior-point solver's iterate before this tick
+            so, _, _ = oracle.rti_step_batch(Ts, x0[:64], yref[:64], w["p"][:64], Xo, Uo)
+            assert (so == 0).all() and np.abs(Uo - Ui[:64]).max() < TOL_U and np.abs(Uo - Ua[:64]).max() < 1e-5
+        for i in range(B):
+            x0[i] = oracle.erk4(x0[i], Ui[i, 0], w["p"][i], 0.05)
+        lines = lines + 1
+        X, U = Xi, Ui                # (each solver carries its own iterate: set_iterate would clear the active-set history)
+    s_as.close(); s_ip.close()
+    assert took_sat > 0 and took_as > 0.5 * took_sat, (took_as, took_sat)     # the guess was accepted on most saturated instances
