@@ -1060,6 +1060,9 @@ __device__ __forceinline__ double step_to_boundary(double v, double dv)
     return dv < 0.0 ? -v / dv : 2.0;   // 2 = "not blocking" (callers clamp at 1)
 }
 
+// WITH_AS = false is the default build of the kernel (the active-set sweep variants are not even compiled into it, so the
+// option costs nothing when it is off); WITH_AS = true serves option "active_set_path".
+template <bool WITH_AS>
 __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(SolveArgs a)
 {
     __shared__ WarpSmem smem[IPM_WARPS];
@@ -1121,7 +1124,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         // one roll-out), verify the KKT conditions with a costate sweep, repair the guess and retry up to twice; exact whenever
         // it accepts, interior-point iteration otherwise.
         bool by_as = false;
-        if (!solved && a.active_set && a.hint[inst] == 1) {
+        if (WITH_AS && !solved && a.hint[inst] == 1) {
             for (int att = 0; att < 3 && !solved; att++) {
                 if (!factor_sweep<FS_AS>(I)) break;
                 if (att == 0) prefetch_iterate(I);
@@ -1258,7 +1261,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         finite = __all_sync(FULL_MASK, finite);
         if (!solved) active = act2;
         active = __any_sync(FULL_MASK, active);
-        if (!solved && a.active_set && status == 0) {
+        if (WITH_AS && !solved && status == 0) {
             // the interior-point solution's active set (slack ~ mu / lam at an active bound) is the next solve's guess
             for (int base = 0; base < nb; base += 32) {
                 const int idx = base + lane;
@@ -1335,8 +1338,9 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
 {
     static bool configured = false;
-    if (!configured) {   // the resident blocks need MINB x WARPS x 11.4 KB of staging buffers: ask for the largest carve-out
-        cudaFuncSetAttribute(ipm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (!configured) {   // the resident blocks need MINB x WARPS x 11.6 KB of staging buffers: ask for the largest carve-out
+        cudaFuncSetAttribute(ipm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(ipm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
     cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
@@ -1345,7 +1349,8 @@ void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
     // number of resident warps and the queue already evens out the tail; profiles/r01h_ipm_variants.txt.)
     int blocks = (a.B + IPM_WARPS - 1) / IPM_WARPS;
     if (blocks > sm_count * BR2_IPM_MINB) blocks = sm_count * BR2_IPM_MINB;
-    ipm_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
+    if (a.active_set) ipm_kernel<true><<<blocks, IPM_WARPS * 32, 0, s>>>(a);
+    else ipm_kernel<false><<<blocks, IPM_WARPS * 32, 0, s>>>(a);
 }
 
 }  // namespace br2
