@@ -426,13 +426,14 @@ int bluerov2_acados_create_with_discretization(bluerov2_solver_capsule* capsule,
     c->p = (double*)calloc((size_t)(N + 1) * NP, sizeof(double));         // parameters default to zero (gen.c:355-364)
     c->X = (double*)calloc((size_t)(N + 1) * NX, sizeof(double));
     c->U = (double*)calloc((size_t)N * NU, sizeof(double));
-    for (int k = 0; k < N; k++) c->Ts[k] = new_time_steps ? new_time_steps[k] : 0.0125;   // gen.c:389
-    static const double kW[16] = {300, 480, 200, 10, 10, 200, 40, 40, 10, 10, 10, 10, 1, 1, 0.1, 0.05};  // gen.c:424-459
-    memcpy(c->W, kW, sizeof kW);
-    memcpy(c->We, kW, sizeof(double) * 12);                                                // gen.c:468-479
-    for (int i = 0; i < NU; i++) { c->lbu[i] = -50.0; c->ubu[i] = 50.0; }                  // gen.c:547-571
-    c->lbx0[2] = c->ubx0[2] = -20.0;                                                       // gen.c:522-541
-    for (int k = 0; k <= N; k++) c->X[k * NX + 2] = -20.0;                                 // gen.c:681-708
+    br2_ocp_defaults dflt;                                  // the one table of baked problem data (include/bluerov2_b200.h)
+    br2_get_ocp_defaults(&dflt);
+    for (int k = 0; k < N; k++) c->Ts[k] = new_time_steps ? new_time_steps[k] : dflt.Tf / dflt.N;   // gen.c:389 (0.0125)
+    memcpy(c->W, dflt.W, sizeof c->W);                                                     // gen.c:424-459
+    memcpy(c->We, dflt.We, sizeof c->We);                                                  // gen.c:468-479
+    memcpy(c->lbu, dflt.lbu, sizeof c->lbu); memcpy(c->ubu, dflt.ubu, sizeof c->ubu);      // gen.c:547-571
+    memcpy(c->lbx0, dflt.x_init, sizeof c->lbx0); memcpy(c->ubx0, dflt.x_init, sizeof c->ubx0);   // gen.c:522-541
+    for (int k = 0; k <= N; k++) memcpy(c->X + k * NX, dflt.x_init, sizeof dflt.x_init);  // gen.c:681-708
     c->iterate_dirty = true;
 
     // the engine needs a CUDA device; like a failed ocp_nlp_precompute (gen.c:725-728) a failure here is fatal

@@ -350,14 +350,15 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
     }
 }
 
+void configure_ekf()
+{
+    // function attributes are per device: called from br2_batch_create with the solver's device current
+    cudaFuncSetAttribute(ekf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(EkfSmem) * EKF_WARPS));
+}
+
 void launch_ekf(const EkfArgs& a, cudaStream_t s)
 {
-    static bool configured = false;
     const size_t smem = sizeof(EkfSmem) * EKF_WARPS;
-    if (!configured) {
-        cudaFuncSetAttribute(ekf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
     const int grid = (a.B + EKF_WARPS - 1) / EKF_WARPS;
     ekf_kernel<<<grid, EKF_WARPS * 32, smem, s>>>(a);
 }

@@ -35,7 +35,7 @@ struct br2_batch_solver {
     double tol;
     // device state
     double *d_Ts, *d_X, *d_U, *d_G, *d_F, *d_V, *d_u0, *d_thrust, *d_info;
-    int *d_status, *d_iters, *d_counter, *d_hint, *d_aset;
+    int *d_status, *d_iters, *d_counter, *d_hint, *d_aset, *d_order;
     double *d_x0, *d_yref, *d_p;              // staging for the host API
     double* d_traj;                           // reference trajectory for device-side windowing [traj_rows][16]
     int* d_lines;                             // staging: first trajectory row per instance
@@ -50,8 +50,23 @@ struct br2_batch_solver {
     bool timed;
 };
 
-// generated-C defaults: acados_solver_bluerov2.c:424-459 (W), :468-479 (W_e), :547-571 (bounds)
+// generated-C defaults: acados_solver_bluerov2.c:424-459 (W), :468-479 (W_e), :547-571 (bounds), :522-541 / :681-708 (x init);
+// pinned on the reference's scripts/acados_ocp.json by tests/test_ocp_json_pins.py
 static const double kW[16] = {300, 480, 200, 10, 10, 200, 40, 40, 10, 10, 10, 10, 1, 1, 0.1, 0.05};
+
+extern "C" void br2_get_ocp_defaults(br2_ocp_defaults* d)
+{
+    if (!d) return;
+    memset(d, 0, sizeof *d);
+    d->N = 80; d->nx = NX; d->nu = NU; d->np = NP; d->ny = NY; d->ny_e = NX;
+    d->nbu = NU; d->nbx0 = NX; d->nbxe0 = NX;
+    d->qp_iter_max = 50; d->qp_warm_start = 0; d->erk_stages = 4; d->erk_steps = 1;
+    d->Tf = 1.0;
+    memcpy(d->W, kW, sizeof kW);
+    memcpy(d->We, kW, sizeof(double) * 12);
+    for (int i = 0; i < 4; i++) { d->lbu[i] = -50.0; d->ubu[i] = 50.0; }
+    d->x_init[2] = -20.0;
+}
 
 extern "C" const char* br2_last_error(void) { return g_err; }
 extern "C" const char* br2_version(void) { return "bluerov2_b200 0.1 (sm_100a)"; }
@@ -65,13 +80,26 @@ extern "C" int br2_device_count(void)
 template <class T>
 static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
 
+// Every entry point works on the solver's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        err = (prev == dev) ? cudaSuccess : cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(s) DeviceGuard guard_((s)->device); CK(guard_.err)
+
 extern "C" int br2_batch_free(br2_batch_solver* s)
 {
     if (!s) return BR2_OK;
-    cudaSetDevice(s->device);
+    DeviceGuard guard_(s->device);
     void* ptrs[] = {s->d_Ts, s->d_X, s->d_U, s->d_G, s->d_F, s->d_V, s->d_u0, s->d_thrust, s->d_info, s->d_status,
                     s->d_iters, s->d_counter, s->d_x0, s->d_yref, s->d_p, s->d_ex, s->d_eP, s->d_thr, s->d_meas,
-                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls, s->d_yaw, s->d_aset};
+                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls, s->d_yaw, s->d_aset, s->d_order};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -98,20 +126,32 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
     }
     if (device < 0 || device >= ndev) return fail(BR2_EINVAL, "br2_batch_create: device %d of %d", device, ndev);
-    CK(cudaSetDevice(device));
+    DeviceGuard guard_(device);
+    CK(guard_.err);
     br2_batch_solver* s = (br2_batch_solver*)calloc(1, sizeof(br2_batch_solver));
     if (!s) return fail(BR2_ENOMEM, "br2_batch_create: out of host memory");
     s->B = batch; s->N = N; s->device = device;
+#define CKF(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            br2_batch_free(s);                                                                           \
+            return fail(BR2_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    CKF(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;
-    for (int k = 0; k < N; k++) s->Ts[k] = time_steps ? time_steps[k] : 1.0 / N;
-    memcpy(s->W, kW, sizeof kW);
-    memcpy(s->We, kW, sizeof(double) * 12);
-    for (int i = 0; i < 4; i++) { s->lbu[i] = -50.0; s->ubu[i] = 50.0; }
-    s->max_iter = 50;
+    br2_ocp_defaults dflt;
+    br2_get_ocp_defaults(&dflt);
+    for (int k = 0; k < N; k++) s->Ts[k] = time_steps ? time_steps[k] : dflt.Tf / N;
+    memcpy(s->W, dflt.W, sizeof s->W);
+    memcpy(s->We, dflt.We, sizeof s->We);
+    memcpy(s->lbu, dflt.lbu, sizeof s->lbu);
+    memcpy(s->ubu, dflt.ubu, sizeof s->ubu);
+    s->max_iter = dflt.qp_iter_max;
     s->fast_path = 1;
-    s->active_set = 0;      // opt-in this round (option "active_set_path"): see DESIGN.md section 10
+    s->active_set = 1;      // primal-dual active-set iteration on by default (option "active_set_path")
     s->tol = 1e-12;
     const size_t B = batch;
 #define DA(p, n)                                                                                          \
@@ -124,7 +164,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     } while (0)
     DA(d_Ts, N); DA(d_X, B * (N + 1) * NX); DA(d_U, B * N * NU);
     DA(d_G, B * N * GREC); DA(d_F, B * N * FREC); DA(d_V, B * (N + 1) * VREC);
-    DA(d_u0, B * 4); DA(d_thrust, B * 6); DA(d_info, B * 4); DA(d_status, B); DA(d_iters, B); DA(d_counter, 1);
+    DA(d_u0, B * 4); DA(d_thrust, B * 6); DA(d_info, B * 4); DA(d_status, B); DA(d_iters, B); DA(d_counter, 4); DA(d_order, 2 * B);
     DA(d_x0, B * NX); DA(d_yref, B * (N + 1) * NY); DA(d_p, B * (N + 1) * NP);
     DA(d_ex, B * 18); DA(d_eP, B * 324); DA(d_thr, B * 6); DA(d_meas, B * 12); DA(d_acc, B * 6); DA(d_wf, B * 6);
     DA(d_pout, B * NP);
@@ -135,20 +175,31 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     DA(d_aset, B * N);
     DA(d_lines, B);
 #undef DA
-    CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&s->stream_x0, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&s->ev_x0, cudaEventDisableTiming));
-    CK(cudaEventCreate(&s->ev0));
-    CK(cudaEventCreate(&s->ev1));
-    CK(cudaEventCreate(&s->ev_mid));
-    CK(cudaMemset(s->d_iter_total, 0, sizeof(unsigned long long)));
-    CK(cudaMemcpy(s->d_Ts, s->Ts, sizeof(double) * N, cudaMemcpyHostToDevice));
-    CK(cudaMemset(s->d_status, 0, sizeof(int) * B));
-    CK(cudaMemset(s->d_iters, 0, sizeof(int) * B));
-    CK(cudaMemset(s->d_hint, 0, sizeof(int) * B));
-    CK(cudaMemset(s->d_aset, 0, sizeof(int) * B * N));
-    CK(cudaMemset(s->d_info, 0, sizeof(double) * B * 4));
-    CK(cudaMemset(s->d_V, 0, sizeof(double) * B * (N + 1) * VREC));
+    CKF(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CKF(cudaStreamCreateWithFlags(&s->stream_x0, cudaStreamNonBlocking));
+    CKF(cudaEventCreateWithFlags(&s->ev_x0, cudaEventDisableTiming));
+    CKF(cudaEventCreate(&s->ev0));
+    CKF(cudaEventCreate(&s->ev1));
+    CKF(cudaEventCreate(&s->ev_mid));
+    CKF(cudaMemset(s->d_iter_total, 0, sizeof(unsigned long long)));
+    CKF(cudaMemcpy(s->d_Ts, s->Ts, sizeof(double) * N, cudaMemcpyHostToDevice));
+    CKF(cudaMemset(s->d_status, 0, sizeof(int) * B));
+    CKF(cudaMemset(s->d_iters, 0, sizeof(int) * B));
+    CKF(cudaMemset(s->d_hint, 0, sizeof(int) * B));
+    CKF(cudaMemset(s->d_aset, 0, sizeof(int) * B * N));
+    CKF(cudaMemset(s->d_counter, 0, sizeof(int) * 4));
+    {   // visiting order of the IPM kernel: identity in both halves until a solve has ranked the instances
+        int* h = (int*)malloc(sizeof(int) * 2 * B);
+        if (!h) { br2_batch_free(s); return fail(BR2_ENOMEM, "br2_batch_create: out of host memory"); }
+        for (size_t i = 0; i < 2 * B; i++) h[i] = (int)(i % B);
+        cudaError_t e3 = cudaMemcpy(s->d_order, h, sizeof(int) * 2 * B, cudaMemcpyHostToDevice);
+        free(h);
+        if (e3 != cudaSuccess) { br2_batch_free(s); return fail(BR2_ECUDA, "cudaMemcpy(order) failed: %s", cudaGetErrorString(e3)); }
+    }
+    configure_kernels();
+    configure_ekf();
+    CKF(cudaMemset(s->d_info, 0, sizeof(double) * B * 4));
+    CKF(cudaMemset(s->d_V, 0, sizeof(double) * B * (N + 1) * VREC));
     *out = s;
     int rc = br2_batch_reset(s, 0);
     if (rc == BR2_OK) rc = br2_batch_ekf_reset(s);
@@ -157,6 +208,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     if (rc == BR2_OK) { cudaError_t e2 = cudaMemset(s->d_pout, 0, sizeof(double) * B * NP); if (e2 != cudaSuccess) rc = fail(BR2_ECUDA, "cudaMemset failed"); }
     if (rc != BR2_OK) { br2_batch_free(s); *out = nullptr; }
     return rc;
+#undef CKF
 }
 
 extern "C" int br2_batch_size(const br2_batch_solver* s) { return s ? s->B : 0; }
@@ -194,7 +246,7 @@ extern "C" int br2_batch_set_time_steps(br2_batch_solver* s, const double* ts)
     for (int k = 0; k < s->N; k++)
         if (!(ts[k] > 0)) return fail(BR2_EINVAL, "time_steps[%d] = %g", k, ts[k]);
     memcpy(s->Ts, ts, sizeof(double) * s->N);
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaMemcpy(s->d_Ts, s->Ts, sizeof(double) * s->N, cudaMemcpyHostToDevice));
     return BR2_OK;
 }
@@ -236,7 +288,7 @@ extern "C" int br2_batch_set_option_double(br2_batch_solver* s, const char* name
 extern "C" int br2_batch_reset(br2_batch_solver* s, int mode)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     const size_t nX = (size_t)s->B * (s->N + 1) * NX, nU = (size_t)s->B * s->N * NU;
     CK(cudaMemset(s->d_U, 0, sizeof(double) * nU));
     CK(cudaMemset(s->d_X, 0, sizeof(double) * nX));
@@ -245,7 +297,9 @@ extern "C" int br2_batch_reset(br2_batch_solver* s, int mode)
         // x_k = (0, 0, -20, 0, ...) for every stage: acados_solver_bluerov2.c:681-708
         double* h = (double*)calloc(nX, sizeof(double));
         if (!h) return fail(BR2_ENOMEM, "out of host memory");
-        for (size_t i = 0; i < nX / NX; i++) h[i * NX + 2] = -20.0;
+        br2_ocp_defaults dflt;
+        br2_get_ocp_defaults(&dflt);
+        for (size_t i = 0; i < nX / NX; i++) memcpy(h + i * NX, dflt.x_init, sizeof dflt.x_init);
         cudaError_t e = cudaMemcpy(s->d_X, h, sizeof(double) * nX, cudaMemcpyHostToDevice);
         free(h);
         CK(e);
@@ -256,7 +310,7 @@ extern "C" int br2_batch_reset(br2_batch_solver* s, int mode)
 extern "C" int br2_batch_set_iterate_host(br2_batch_solver* s, const double* X, const double* U)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     if (X) CK(cudaMemcpy(s->d_X, X, sizeof(double) * s->B * (s->N + 1) * NX, cudaMemcpyHostToDevice));
     if (U) CK(cudaMemcpy(s->d_U, U, sizeof(double) * s->B * s->N * NU, cudaMemcpyHostToDevice));
@@ -266,7 +320,7 @@ extern "C" int br2_batch_set_iterate_host(br2_batch_solver* s, const double* X, 
 extern "C" int br2_batch_get_iterate_host(br2_batch_solver* s, double* X, double* U)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     if (X) CK(cudaMemcpy(X, s->d_X, sizeof(double) * s->B * (s->N + 1) * NX, cudaMemcpyDeviceToHost));
     if (U) CK(cudaMemcpy(U, s->d_U, sizeof(double) * s->B * s->N * NU, cudaMemcpyDeviceToHost));
@@ -295,7 +349,7 @@ static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, con
     a.u0 = d_u0 ? d_u0 : s->d_u0;
     a.thrust = d_thrust ? d_thrust : s->d_thrust;
     a.status = d_status ? d_status : s->d_status;
-    a.iters = s->d_iters; a.info = s->d_info; a.work_counter = s->d_counter; a.iter_total = s->d_iter_total; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
+    a.iters = s->d_iters; a.info = s->d_info; a.ctr = s->d_counter; a.order = s->d_order; a.iter_total = s->d_iter_total; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
     a.max_iter = s->max_iter; a.tol = s->tol;
 }
 
@@ -325,7 +379,7 @@ static int solve_host_common(br2_batch_solver* s, const double* x0, const double
     cudaStream_t st = s->stream;
     // the lineariser goes out first (its inputs -- p, reference -- are already enqueued): everything below is host work and
     // an upload that the GPU does not have to wait for before it starts
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     SolveArgs a;
     fill_args(s, a, s->d_x0, d_yref, d_lines, s->d_p, p_per_stage, nullptr, nullptr, nullptr);
     CK(cudaEventRecord(s->ev0, st));
@@ -361,7 +415,7 @@ extern "C" int br2_batch_solve_device(br2_batch_solver* s, const double* d_x0, c
 extern "C" int br2_batch_set_trajectory(br2_batch_solver* s, const double* traj, int rows)
 {
     if (!s || !traj || rows < 1) return fail(BR2_EINVAL, "br2_batch_set_trajectory: bad argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     if (s->d_traj) { cudaFree(s->d_traj); s->d_traj = nullptr; }
     cudaError_t e = dalloc(&s->d_traj, (size_t)rows * NY);
@@ -384,7 +438,7 @@ extern "C" int br2_batch_solve_windowed_host(br2_batch_solver* s, const double* 
 {
     if (!s || !x0 || !lines || !p) return fail(BR2_EINVAL, "br2_batch_solve_windowed_host: null argument");
     if (!s->d_traj) return fail(BR2_EINVAL, "br2_batch_solve_windowed_host: no trajectory set (br2_batch_set_trajectory)");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     const size_t B = s->B, N = s->N;
     cudaStream_t st = s->stream;
     CK(cudaMemcpyAsync(s->d_p, p, sizeof(double) * B * (p_per_stage ? (N + 1) * NP : NP), cudaMemcpyHostToDevice, st));
@@ -395,7 +449,7 @@ extern "C" int br2_batch_solve_windowed_host(br2_batch_solver* s, const double* 
 static int solve_enqueue(br2_batch_solver* s, const double* d_x0, const double* d_yref, const int* d_lines, const double* d_p,
                          int p_per_stage, double* d_u0, double* d_thrust, int* d_status, cudaStream_t st, cudaEvent_t before_ipm)
 {
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     SolveArgs a;
     fill_args(s, a, d_x0, d_yref, d_lines, d_p, p_per_stage, d_u0, d_thrust, d_status);
     CK(cudaEventRecord(s->ev0, st));
@@ -413,7 +467,7 @@ extern "C" int br2_batch_solve_host(br2_batch_solver* s, const double* x0, const
                                     int p_per_stage, double* u0, double* thrust, int* status)
 {
     if (!s || !x0 || !yref || !p) return fail(BR2_EINVAL, "br2_batch_solve_host: null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     const size_t B = s->B, N = s->N;
     cudaStream_t st = s->stream;
     CK(cudaMemcpyAsync(s->d_p, p, sizeof(double) * B * (p_per_stage ? (N + 1) * NP : NP), cudaMemcpyHostToDevice, st));
@@ -424,7 +478,7 @@ extern "C" int br2_batch_solve_host(br2_batch_solver* s, const double* x0, const
 extern "C" int br2_batch_get_stats_host(br2_batch_solver* s, int* iters, double* info)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     if (iters) CK(cudaMemcpy(iters, s->d_iters, sizeof(int) * s->B, cudaMemcpyDeviceToHost));
     if (info) CK(cudaMemcpy(info, s->d_info, sizeof(double) * s->B * 4, cudaMemcpyDeviceToHost));
@@ -434,7 +488,7 @@ extern "C" int br2_batch_get_stats_host(br2_batch_solver* s, int* iters, double*
 extern "C" int br2_batch_get_linearization_host(br2_batch_solver* s, double* AB, double* b)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     const size_t n = (size_t)s->B * s->N;
     double* h = (double*)malloc(sizeof(double) * n * GREC);
@@ -455,7 +509,7 @@ extern "C" int br2_batch_get_linearization_host(br2_batch_solver* s, double* AB,
 extern "C" double br2_batch_last_solve_time(br2_batch_solver* s)
 {
     if (!s || !s->timed) return 0.0;
-    cudaSetDevice(s->device);
+    DeviceGuard guard_(s->device);
     if (cudaEventSynchronize(s->ev1) != cudaSuccess) return 0.0;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) != cudaSuccess) return 0.0;
@@ -465,7 +519,7 @@ extern "C" double br2_batch_last_solve_time(br2_batch_solver* s)
 extern "C" int br2_batch_last_kernel_times(br2_batch_solver* s, double* t_linearize, double* t_ipm)
 {
     if (!s || !s->timed) return fail(BR2_EINVAL, "no solve recorded");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaEventSynchronize(s->ev1));
     float a = 0.f, b = 0.f;
     CK(cudaEventElapsedTime(&a, s->ev0, s->ev_mid));
@@ -478,7 +532,7 @@ extern "C" int br2_batch_last_kernel_times(br2_batch_solver* s, double* t_linear
 extern "C" long long br2_batch_ipm_iterations_total(br2_batch_solver* s, int reset)
 {
     if (!s) return -1;
-    cudaSetDevice(s->device);
+    DeviceGuard guard_(s->device);
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     unsigned long long v = 0;
     if (cudaMemcpy(&v, s->d_iter_total, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
@@ -493,6 +547,14 @@ extern "C" int br2_plant_step_device(int batch, double* d_x, const double* d_u, 
 {
     if (batch < 1 || !d_x || !d_u || !d_p || !(h > 0)) return fail(BR2_EINVAL, "br2_plant_step_device: bad argument");
     if ((d_wave_amp == nullptr) != (d_wave_tau0 == nullptr)) return fail(BR2_EINVAL, "br2_plant_step_device: wave_amp and wave_tau0 go together");
+    // the launch goes to the device that owns the state vector, whatever the caller's current device is
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, d_x) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return fail(BR2_EINVAL, "br2_plant_step_device: d_x is not a device pointer");
+    }
+    DeviceGuard guard_(at.device);
+    CK(guard_.err);
     PlantArgs a;
     a.B = batch; a.x = d_x; a.u = d_u; a.p = d_p; a.dist = d_dist; a.wave_amp = d_wave_amp; a.wave_tau0 = d_wave_tau0;
     a.body_acc = d_body_acc; a.lines = d_lines; a.h = h; a.tick = tick;
@@ -505,7 +567,7 @@ extern "C" int br2_plant_step_device(int batch, double* d_x, const double* d_u, 
 extern "C" int br2_batch_ekf_reset(br2_batch_solver* s)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     const size_t B = s->B;
     double* hx = (double*)calloc(B * 18, sizeof(double));
     double* hP = (double*)calloc(B * 324, sizeof(double));
@@ -526,7 +588,7 @@ extern "C" int br2_batch_ekf_device(br2_batch_solver* s, const double* d_thrusts
                                     const double* d_body_acc, double* d_wf_dist, double* d_p_out, int compensate, void* stream)
 {
     if (!s || !d_thrusts || !d_meas || !d_body_acc) return fail(BR2_EINVAL, "br2_batch_ekf_device: null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     EkfArgs a;
     a.B = s->B; a.esti_x = s->d_ex; a.esti_P = s->d_eP;
     a.thrusts = d_thrusts; a.meas = d_meas; a.body_acc = d_body_acc;
@@ -540,7 +602,7 @@ extern "C" int br2_batch_ekf_host(br2_batch_solver* s, const double* thrusts, co
                                   double* wf_dist, double* p_out, int compensate)
 {
     if (!s || !thrusts || !meas || !body_acc) return fail(BR2_EINVAL, "br2_batch_ekf_host: null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     const size_t B = s->B;
     cudaStream_t st = s->stream;
     CK(cudaMemcpyAsync(s->d_thr, thrusts, sizeof(double) * B * 6, cudaMemcpyHostToDevice, st));
@@ -557,7 +619,7 @@ extern "C" int br2_batch_ekf_host(br2_batch_solver* s, const double* thrusts, co
 extern "C" int br2_batch_ekf_get_state_host(br2_batch_solver* s, double* esti_x, double* esti_P)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     if (esti_x) CK(cudaMemcpy(esti_x, s->d_ex, sizeof(double) * s->B * 18, cudaMemcpyDeviceToHost));
     if (esti_P) CK(cudaMemcpy(esti_P, s->d_eP, sizeof(double) * s->B * 324, cudaMemcpyDeviceToHost));
@@ -566,7 +628,7 @@ extern "C" int br2_batch_ekf_get_state_host(br2_batch_solver* s, double* esti_x,
 extern "C" int br2_batch_ekf_set_state_host(br2_batch_solver* s, const double* esti_x, const double* esti_P)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     if (esti_x) CK(cudaMemcpy(s->d_ex, esti_x, sizeof(double) * s->B * 18, cudaMemcpyHostToDevice));
     if (esti_P) CK(cudaMemcpy(s->d_eP, esti_P, sizeof(double) * s->B * 324, cudaMemcpyHostToDevice));
@@ -577,7 +639,7 @@ extern "C" int br2_batch_ekf_set_state_host(br2_batch_solver* s, const double* e
 extern "C" int br2_batch_rls_reset(br2_batch_solver* s)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     const size_t n = (size_t)s->B * 4;
     double* h = (double*)calloc(n * RLS_STRIDE, sizeof(double));
     if (!h) return fail(BR2_ENOMEM, "out of host memory");
@@ -595,7 +657,7 @@ extern "C" int br2_batch_rls_device(br2_batch_solver* s, const double* d_meas, c
                                     int compensate, void* stream)
 {
     if (!s || !d_meas || !d_body_acc) return fail(BR2_EINVAL, "br2_batch_rls_device: null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     RlsArgs a;
     a.B = s->B; a.state = s->d_rls; a.esti_x = s->d_ex; a.body_acc = d_body_acc; a.meas = d_meas; a.p_out = d_p_out;
     a.compensate = compensate;
@@ -607,7 +669,7 @@ extern "C" int br2_batch_rls_device(br2_batch_solver* s, const double* d_meas, c
 extern "C" int br2_batch_rls_host(br2_batch_solver* s, const double* meas, const double* body_acc, double* p_out, int compensate)
 {
     if (!s || !meas || !body_acc) return fail(BR2_EINVAL, "br2_batch_rls_host: null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     const size_t B = s->B;
     cudaStream_t st = s->stream;
     CK(cudaMemcpyAsync(s->d_meas, meas, sizeof(double) * B * 12, cudaMemcpyHostToDevice, st));
@@ -624,7 +686,7 @@ extern "C" int br2_batch_rls_host(br2_batch_solver* s, const double* meas, const
 extern "C" int br2_batch_rls_get_state_host(br2_batch_solver* s, double* state)
 {
     if (!s || !state) return fail(BR2_EINVAL, "null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(state, s->d_rls, sizeof(double) * s->B * 4 * RLS_STRIDE, cudaMemcpyDeviceToHost));
     return BR2_OK;
@@ -632,7 +694,7 @@ extern "C" int br2_batch_rls_get_state_host(br2_batch_solver* s, double* state)
 extern "C" int br2_batch_rls_set_state_host(br2_batch_solver* s, const double* state)
 {
     if (!s || !state) return fail(BR2_EINVAL, "null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(s->d_rls, state, sizeof(double) * s->B * 4 * RLS_STRIDE, cudaMemcpyHostToDevice));
     return BR2_OK;
@@ -642,14 +704,14 @@ extern "C" int br2_batch_rls_set_state_host(br2_batch_solver* s, const double* s
 extern "C" int br2_batch_yaw_reset(br2_batch_solver* s)
 {
     if (!s) return fail(BR2_EINVAL, "null solver");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaMemset(s->d_yaw, 0, sizeof(float) * 2 * s->B));      // yaw_sum = pre_yaw = 0 (bluerov2_dob.h:234-235)
     return BR2_OK;
 }
 extern "C" int br2_batch_yaw_unwrap_device(br2_batch_solver* s, double* d_x0, void* stream)
 {
     if (!s || !d_x0) return fail(BR2_EINVAL, "br2_batch_yaw_unwrap_device: null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     launch_yaw_unwrap(s->B, s->d_yaw, d_x0, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return BR2_OK;
@@ -657,7 +719,7 @@ extern "C" int br2_batch_yaw_unwrap_device(br2_batch_solver* s, double* d_x0, vo
 extern "C" int br2_batch_yaw_unwrap_host(br2_batch_solver* s, double* x0)
 {
     if (!s || !x0) return fail(BR2_EINVAL, "br2_batch_yaw_unwrap_host: null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     const size_t n = sizeof(double) * s->B * NX;
     CK(cudaMemcpyAsync(s->d_x0, x0, n, cudaMemcpyHostToDevice, s->stream));
     launch_yaw_unwrap(s->B, s->d_yaw, s->d_x0, s->stream);
@@ -668,7 +730,7 @@ extern "C" int br2_batch_yaw_unwrap_host(br2_batch_solver* s, double* x0)
 extern "C" int br2_batch_yaw_get_state_host(br2_batch_solver* s, float* state)
 {
     if (!s || !state) return fail(BR2_EINVAL, "null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(state, s->d_yaw, sizeof(float) * 2 * s->B, cudaMemcpyDeviceToHost));
     return BR2_OK;
@@ -676,7 +738,7 @@ extern "C" int br2_batch_yaw_get_state_host(br2_batch_solver* s, float* state)
 extern "C" int br2_batch_yaw_set_state_host(br2_batch_solver* s, const float* state)
 {
     if (!s || !state) return fail(BR2_EINVAL, "null argument");
-    CK(cudaSetDevice(s->device));
+    ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(s->d_yaw, state, sizeof(float) * 2 * s->B, cudaMemcpyHostToDevice));
     return BR2_OK;

@@ -35,11 +35,13 @@ struct SolveArgs {
     int* status;           // [B]
     int* iters;            // [B]
     double* info;          // [B][4]: mu, res_stat, max|b| (dynamics gap at the linearisation point), max step
-    int* work_counter;     // [1] persistent-kernel instance queue
+    int* ctr;              // [4] CTR_QUEUE: persistent-kernel work queue; CTR_HARD / CTR_EASY: fill counts of the next solve's
+                           //     visiting order; CTR_PARITY: which half of `order` is current (reset / flipped by the lineariser)
+    int* order;            // [2][B] visiting order of the instances (a permutation), double-buffered: hint = 1 instances first
     int* hint;             // [B] 1 = a bound was active at the previous solution (skip the interior fast path)
     int fast_path;         // try the interior-solution fast path (option "fast_path", default 1)
     int* aset;             // [B][N] guessed active set per stage, 2 bits per input (0 free, 1 at lbu, 2 at ubu)
-    int active_set;        // try the active-set fast path when bounds were active (option "active_set_path")
+    int active_set;        // primal-dual active-set iteration when the interior solution leaves the box (option "active_set_path")
     unsigned long long* iter_total;   // [1] IPM iterations executed, accumulated over instances and solves
     // options
     int max_iter;          // qp_solver_iter_max (50)
@@ -57,6 +59,8 @@ __device__ __forceinline__ const double* yref_row(const SolveArgs& a, int inst, 
 
 void launch_linearize(const SolveArgs& a, cudaStream_t s);
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s);
+void configure_kernels();      // per-device function attributes (call with the solver's device current)
+enum { CTR_QUEUE = 0, CTR_HARD = 1, CTR_EASY = 2, CTR_PARITY = 3 };
 
 // EKF (bluerov2_dob.cpp:495-545), one warp per instance
 struct EkfArgs {
@@ -72,6 +76,7 @@ struct EkfArgs {
     int model;               // 0 = BLUEROV2_DOB filter, 1 = BLUEROV2_AMPC filter (no damping in f / h)
 };
 void launch_ekf(const EkfArgs& a, cudaStream_t s);
+void configure_ekf();          // per-device function attributes
 
 // RLS with variable forgetting factor (rls.cu; BLUEROV2_AMPC::RLSFF, bluerov2_ampc.cpp:731-1004), one thread per
 // (instance, axis); state layout RLS_* below == oracle ORC_RLS_STRIDE layout

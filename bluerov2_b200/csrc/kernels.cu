@@ -177,6 +177,10 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
     const int lane = threadIdx.x;
     const int total = a.B * a.N;
     const int base = blockIdx.x * LRND;
+    if (blockIdx.x == 0 && lane == 0) {
+        // housekeeping for the IPM kernel that follows in the stream: reset its work-queue counters, flip the order buffers
+        a.ctr[CTR_QUEUE] = 0; a.ctr[CTR_HARD] = 0; a.ctr[CTR_EASY] = 0; a.ctr[CTR_PARITY] ^= 1;
+    }
     if (lane < LRND) {
         const int gs = base + lane;
         lin_phase_a(a, sm, lane, gs < total ? gs : total - 1, gs < total);
@@ -1028,7 +1032,9 @@ __device__ bool costate_check(Inst& I)
         const double du = Vs[V_V + e];
         const double mu = fma(tsk * a.W[12 + e], du, Gk[G_RLIN + e]) + o1;
         const double lb = a.lbu[e] - uk, ub = a.ubu[e] - uk;
-        const double tolu = 1e-9 * fmax(1.0, ub - lb), tolm = 1e-9 * fmax(1.0, fabs(Gk[G_RLIN + e]) + fabs(o1));
+        // tolerances in units of the answer: a free input may leave its box by 1e-12 of the box width (the epilogue clamps), and a
+        // pinned input is released when doing so would move it by more than 1e-9 of the width (|mu| / Lam_ee, Lam_ee >= Ts R_ee)
+        const double tolu = 1e-12 * (ub - lb), tolm = 1e-9 * (ub - lb) * tsk * a.W[12 + e];
         const int cc = (code >> (2 * e)) & 3;
         int nc = cc;
         if (cc == 0) {
@@ -1055,14 +1061,60 @@ __device__ bool costate_check(Inst& I)
     return __all_sync(FULL_MASK, good);
 }
 
+// Primal half of the active-set test on the candidate (dx, du) that forward_sweep<2> left in V_X / V_V: a free input outside its
+// box is pinned at the violated bound (the other half, the multiplier signs of the pinned inputs, is costate_check).  `fresh`:
+// the stage codes in a.aset are stale (first attempt of an instance without a guess): they count as 0 and are rewritten.
+// Returns bit 0: a code changed, bit 1: some input is pinned, bit 2: some input ends within 1e-3 of a bound (hint for the
+// next solve), bit 3: NaN / Inf in the candidate.
+enum { PC_CHANGED = 1, PC_PINNED = 2, PC_ACTIVE = 4, PC_NAN = 8 };
+__device__ int primal_check(Inst& I, bool fresh)
+{
+    const SolveArgs& a = I.a;
+    const int nb = 4 * I.N, lane = I.lane, e = lane & 3;
+    int* as = a.aset + (size_t)I.inst * I.N;
+    int flags = 0;
+#pragma unroll 2
+    for (int base = 0; base < nb; base += 32) {
+        const int idx = base + lane;
+        const bool valid = idx < nb;
+        const int k = (valid ? idx : 0) >> 2;
+        const int code = (valid && !fresh) ? as[k] : 0;
+        int cc = (code >> (2 * e)) & 3;
+        if (valid) {
+            const double uk = I.Ulin[idx], du = I.V[(size_t)k * VREC + V_V + e];
+            const double lb = a.lbu[e] - uk, ub = a.ubu[e] - uk;
+            const double tolu = 1e-12 * (ub - lb);
+            if (cc == 0) {
+                if (!(du >= lb - tolu)) cc = 1;             // written so that a NaN fails
+                else if (!(du <= ub + tolu)) cc = 2;
+            }
+            if (!isfinite(du)) flags |= PC_NAN;
+            if (fmin(du - lb, ub - du) < 1e-3) flags |= PC_ACTIVE;
+        }
+        int word = cc << (2 * e);
+        word |= __shfl_xor_sync(FULL_MASK, word, 1);
+        word |= __shfl_xor_sync(FULL_MASK, word, 2);
+        if (valid) {
+            if (word != code) flags |= PC_CHANGED;
+            if (word) flags |= PC_PINNED;
+            if (e == 0 && (fresh || word != code)) as[k] = word;
+        }
+    }
+    flags = __reduce_or_sync(FULL_MASK, flags);
+    __syncwarp();
+    return flags;
+}
+
 __device__ __forceinline__ double step_to_boundary(double v, double dv)
 {
     return dv < 0.0 ? -v / dv : 2.0;   // 2 = "not blocking" (callers clamp at 1)
 }
 
-// WITH_AS = false is the default build of the kernel (the active-set sweep variants are not even compiled into it, so the
-// option costs nothing when it is off); WITH_AS = true serves option "active_set_path".
-template <bool WITH_AS>
+// Maximum number of pinned-LQR solves of the primal-dual active-set iteration before the interior-point iteration takes over
+#ifndef BR2_MAX_AS
+#define BR2_MAX_AS 6
+#endif
+
 __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(SolveArgs a)
 {
     __shared__ WarpSmem smem[IPM_WARPS];
@@ -1077,16 +1129,25 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
     }
     __syncwarp();
 
-    // Work distribution: the first instance of a warp is its global warp index; further ones come from an atomic queue
-    // that starts behind the statically assigned block.  On the fast path the next index is reserved when the final sweep
-    // of the current instance starts, so the atomic's round trip is off the path between two instances (it was ~4 % of
-    // the kernel).  Only lane 0 holds the reservation.
+    // Work distribution.  Instances are visited in the order the PREVIOUS solve left behind: those that ended with active bounds
+    // (hint = 1: several factorisations, possibly interior-point iterations) first, so that the long jobs start at t = 0 and the
+    // one-factorisation instances fill the tail (longest-processing-time-first).  queue position -> instance through order_cur;
+    // a warp's first position is its global warp index, later ones come from an atomic counter that starts behind the statically
+    // assigned block and is reserved one instance ahead (the atomic's round trip was ~4 % of the kernel).  Only lane 0 holds the
+    // reservation.  The epilogue appends the instance to order_next (hard ones from the front, easy ones from the back).
+    const int par = a.ctr[CTR_PARITY] & 1;
+    const int* order_cur = a.order + (size_t)par * a.B;
+    int* order_next = a.order + (size_t)(par ^ 1) * a.B;
     const int nwarps = gridDim.x * IPM_WARPS;
     int reserved = blockIdx.x * IPM_WARPS + (threadIdx.x >> 5);
+    if (lane == 0) reserved = reserved < a.B ? order_cur[reserved] : a.B;
     bool have = true;
     for (;;) {
         int inst = reserved;
-        if (!have && lane == 0) inst = nwarps + atomicAdd(a.work_counter, 1);
+        if (!have && lane == 0) {
+            const int qpos = nwarps + atomicAdd(a.ctr + CTR_QUEUE, 1);
+            inst = qpos < a.B ? order_cur[qpos] : a.B;
+        }
         have = false;
         inst = __shfl_sync(FULL_MASK, inst, 0);
         if (inst >= a.B) break;
@@ -1095,56 +1156,47 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         int status = 2, it = 0;
         double mu = 0.0, res_stat = 0.0, stat_scale = 1.0, bmax = 0.0;
         bool solved = false;
-        // ---------- interior-solution fast path ----------
-        // If the minimiser of the QP without its box lies inside the box it IS the minimiser of the QP (convexity), and
-        // it costs one Riccati factorisation + one closed-loop roll-out instead of an interior-point iteration sequence.
-        // It is attempted when no bound was active at this instance's previous solution (hint carried between solves; it
-        // only steers which exact method runs first, never the result).
         bool active = false;                    // a bound is (nearly) active at the solution -> hint for the next solve
-        if (a.fast_path && a.hint[inst] == 0) {
-            if (factor_sweep<FS_ABS>(I)) {
-                prefetch_iterate(I);
-                if (lane == 0) reserved = nwarps + atomicAdd(a.work_counter, 1);
-                have = true;
+        // ---------- primal-dual active-set iteration on Riccati solves ----------
+        // Attempt 0 without a guess is the interior-solution fast path: the minimiser of the QP without its box, one factorisation
+        // + one closed-loop roll-out; if it lies inside the box it IS the minimiser of the QP (convexity).  Otherwise the inputs
+        // outside their box are pinned at the violated bound (primal_check) and the LQR is solved again with those inputs fixed
+        // (factor_sweep<FS_AS>); once a candidate respects the box, a costate sweep checks the multiplier signs of the pinned inputs
+        // (costate_check) and releases the wrong ones.  A candidate that passes both tests satisfies the KKT conditions of the strictly
+        // convex QP, so it is its unique minimiser -- the same point the interior-point iteration converges to.  This is the primal-
+        // dual active-set (semismooth Newton) method; on this problem class it needs 2 solves from scratch and 1 from the previous
+        // tick's active set (hint = 1: a.aset holds it).  BR2_MAX_AS solves without acceptance -> interior-point iteration.
+        if (a.fast_path) {
+            const bool guess = a.active_set && a.hint[inst] == 1;
+            const int max_att = a.active_set ? BR2_MAX_AS : 1;
+            for (int att = 0; att < max_att; att++) {
+                const bool okf = (att == 0 && !guess) ? factor_sweep<FS_ABS>(I) : factor_sweep<FS_AS>(I);
+                if (!okf) break;
+                if (att == 0) {
+                    prefetch_iterate(I);
+                    if (lane == 0) {
+                        const int qpos = nwarps + atomicAdd(a.ctr + CTR_QUEUE, 1);
+                        reserved = qpos < a.B ? order_cur[qpos] : a.B;
+                    }
+                    have = true;
+                }
                 bmax = forward_sweep<2>(I);     // leaves (dx, du) in V_X, V_V
-                bool inside = true;
-#pragma unroll 5
-                for (int idx = lane; idx < nb; idx += 32) {
-                    const int e = idx & 3;
-                    const double un = I.Ulin[idx] + I.V[(size_t)(idx >> 2) * VREC + V_V + e];
-                    const double tl = un - a.lbu[e], tu = a.ubu[e] - un;
-                    inside &= (tl >= 0.0) && (tu >= 0.0);
-                    active |= fmin(tl, tu) < 1e-3;
-                }
-                if (__all_sync(FULL_MASK, inside)) { solved = true; status = 0; it = 1; }
-            }
-        }
-        // ---------- active-set fast path ----------
-        // Bounds were active at the previous solution: solve the LQR with the previous active set pinned (one factorisation +
-        // one roll-out), verify the KKT conditions with a costate sweep, repair the guess and retry up to twice; exact whenever
-        // it accepts, interior-point iteration otherwise.
-        bool by_as = false;
-        if (WITH_AS && !solved && a.hint[inst] == 1) {
-            for (int att = 0; att < 3 && !solved; att++) {
-                if (!factor_sweep<FS_AS>(I)) break;
-                if (att == 0) prefetch_iterate(I);
-                bmax = forward_sweep<2>(I);
-                if (costate_check(I)) { solved = true; by_as = true; status = 0; it = att + 1; }
-            }
-            if (by_as) {
-#pragma unroll 5
-                for (int idx = lane; idx < nb; idx += 32) {
-                    const int e = idx & 3;
-                    const double un = I.Ulin[idx] + I.V[(size_t)(idx >> 2) * VREC + V_V + e];
-                    active |= fmin(un - a.lbu[e], a.ubu[e] - un) < 1e-3;
+                it = att + 1;
+                const int fl = primal_check(I, att == 0 && !guess);
+                if (fl & PC_NAN) break;
+                active = (fl & PC_ACTIVE) != 0;
+                if (!(fl & PC_CHANGED)) {
+                    if (!(fl & PC_PINNED)) { solved = true; break; }
+                    if (costate_check(I)) { solved = true; break; }
                 }
             }
+            if (solved) status = 0;
         }
         if (!solved) {
             ipm_init(I);
             bmax = forward_sweep<0>(I);
         }
-        for (it = solved ? 1 : 0; !solved && it < a.max_iter; it++) {
+        for (it = solved ? it : 0; !solved && it < a.max_iter; it++) {
             // ---------- B1: factorisation + predictor rhs ----------
             if (!factor_sweep<FS_IPM>(I)) { status = 4; break; }
             if (it == 0) {
@@ -1261,7 +1313,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         finite = __all_sync(FULL_MASK, finite);
         if (!solved) active = act2;
         active = __any_sync(FULL_MASK, active);
-        if (WITH_AS && !solved && status == 0) {
+        if (a.active_set && !solved && status == 0) {
             // the interior-point solution's active set (slack ~ mu / lam at an active bound) is the next solve's guess
             for (int base = 0; base < nb; base += 32) {
                 const int idx = base + lane;
@@ -1275,7 +1327,13 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
                 if (valid && (lane & 3) == 0) a.aset[(size_t)inst * N + (idx >> 2)] = code;
             }
         }
-        if (lane == 0) a.hint[inst] = (active || status != 0) ? 1 : 0;
+        if (lane == 0) {
+            const int hard = (active || status != 0) ? 1 : 0;
+            a.hint[inst] = hard;
+            // position in the next solve's visiting order: hard instances from the front, easy ones from the back
+            const int pos = hard ? atomicAdd(a.ctr + CTR_HARD, 1) : a.B - 1 - atomicAdd(a.ctr + CTR_EASY, 1);
+            order_next[pos] = inst;
+        }
         if (finite) {
             // X / U were last touched by the lineariser, before ~300 MB of stage records went through L2: without care this is
             // a chain of DRAM round trips (it was 11 % of the kernel).  The lines are prefetched into L2 ahead of the forward
@@ -1292,7 +1350,9 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
 #pragma unroll
                 for (int j = 0; j < 5; j++) {
                     const int idx = base + 32 * j;
-                    if (idx < nb) Uo[idx] = u[j] + d[j];
+                    // (a pinned input lands on its bound up to one rounding of (bound - U) + U, an accepted free input within 1e-12
+                    // of the box width: clamp)
+                    if (idx < nb) Uo[idx] = fmin(fmax(u[j] + d[j], a.lbu[idx & 3]), a.ubu[idx & 3]);
                 }
             }
             const int nxs = 12 * (N + 1);
@@ -1335,22 +1395,22 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
     }
 }
 
+void configure_kernels()
+{
+    // the resident blocks need MINB x WARPS x 11.6 KB of staging buffers: ask for the largest carve-out (function attributes
+    // are per device: called from br2_batch_create with the solver's device current)
+    cudaFuncSetAttribute(ipm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
 {
-    static bool configured = false;
-    if (!configured) {   // the resident blocks need MINB x WARPS x 11.6 KB of staging buffers: ask for the largest carve-out
-        cudaFuncSetAttribute(ipm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(ipm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
-    }
-    cudaMemsetAsync(a.work_counter, 0, sizeof(int), s);
-    // Persistent grid, one warp per instance at a time, instances handed out by an atomic queue.  (Sizing the resident
+    // Persistent grid, one warp per instance at a time, instances handed out by an atomic queue (its counters are reset and
+    // the order buffers flipped by block 0 of the lineariser that precedes this kernel in the stream).  (Sizing the resident
     // set for even waves -- 14 instead of 16 warps/SM at B = 4096 -- measured 8 % slower: throughput grows with the
     // number of resident warps and the queue already evens out the tail; profiles/r01h_ipm_variants.txt.)
     int blocks = (a.B + IPM_WARPS - 1) / IPM_WARPS;
     if (blocks > sm_count * BR2_IPM_MINB) blocks = sm_count * BR2_IPM_MINB;
-    if (a.active_set) ipm_kernel<true><<<blocks, IPM_WARPS * 32, 0, s>>>(a);
-    else ipm_kernel<false><<<blocks, IPM_WARPS * 32, 0, s>>>(a);
+    ipm_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
 }
 
 }  // namespace br2

@@ -47,6 +47,23 @@ BR2_API const char *br2_version(void);
 /* number of CUDA devices visible (0 when none / no driver) */
 BR2_API int br2_device_count(void);
 
+/* The problem data the generated solver bakes in (acados_solver_bluerov2.c / scripts/acados_ocp.json), as this library
+ * bakes them: ONE table used by br2_batch_create and by the acados-ABI shim.  Host-only, needs no CUDA device.
+ *   N, Tf            BLUEROV2_N = 80 shooting intervals over tf = 1.0 s -> time step Tf / N = 0.0125 (:137, :389)
+ *   W, We            diagonals of the stage / terminal least-squares weights (:424-459, :468-479); cost scaling = time step on
+ *                    stages 0..N-1, terminal unscaled (:389-394)
+ *   lbu, ubu         input box on stages 0..N-1 (:547-571)
+ *   x_init           initial guess of every state node and the default stage-0 bounds lbx_0 = ubx_0 (:522-541, :681-708)
+ *   nbxe0            number of stage-0 state bounds flagged as equalities (:228) -- all 12
+ *   qp_iter_max      :668;   erk_stages / erk_steps   integrator: ERK, 4 stages, 1 step per interval (:633, :639)
+ *   qp_warm_start    0 (json solver_options.qp_solver_warm_start): every QP is solved from a cold start */
+typedef struct br2_ocp_defaults {
+    int N, nx, nu, np, ny, ny_e, nbu, nbx0, nbxe0, qp_iter_max, qp_warm_start, erk_stages, erk_steps;
+    double Tf;
+    double W[16], We[12], lbu[4], ubu[4], x_init[12];
+} br2_ocp_defaults;
+BR2_API void br2_get_ocp_defaults(br2_ocp_defaults *out);
+
 /* == bluerov2_acados_create_with_discretization (acados_solver_bluerov2.c:734-783) for `batch` instances on CUDA
  * device `device`.  time_steps[N] may be NULL: N equal steps over Tf = 1 s (generate_c_code.py:17,24).
  * Defaults baked exactly as the generated C: W, W_e (:424-479), |u| <= 50 (:547-571), qp_iter_max 50 (:668),
@@ -121,7 +138,7 @@ BR2_API long long br2_batch_ipm_iterations_total(br2_batch_solver *s, int reset)
  * Optional (NULL to skip): d_dist[B][4] extra disturbance on p[0..3]; d_wave_amp[B][4] + d_wave_tau0[B] the wave wrench of
  * applyBodyWrench mode 0 (bluerov2_dob.cpp:774-797) at tick `tick`; d_body_acc[B][6] out = finite-differenced body
  * velocities (bluerov2_dob.cpp:148-153); d_lines[B] trajectory row counters, incremented (line_number++, :367).
- * Uses the device of the pointers' current context; only enqueues on `stream`. */
+ * Launches on the device that owns d_x (the caller's current device is left untouched); only enqueues on `stream`. */
 BR2_API int br2_plant_step_device(int batch, double *d_x, const double *d_u, const double *d_p, const double *d_dist,
                                   const double *d_wave_amp, const double *d_wave_tau0, int tick, double h,
                                   double *d_body_acc, int *d_lines, void *stream);
