@@ -102,3 +102,35 @@ def test_thrust_allocation(oracle):
     u = np.array([1.0, -2.0, 3.0, 0.5]); rc = 0.026546960744430276
     want = np.array([(-1 - 2 + 0.5), (-1 + 2 - 0.5), (1 - 2 - 0.5), (1 + 2 + 0.5), -3, -3]) / rc
     assert np.allclose(oracle.thrust_alloc(u), want, rtol=1e-15)
+
+
+@pytest.mark.parametrize("N,spread,seed", [(40, 0.5, 0), (40, 3.0, 0), (20, 3.0, 1), (10, 3.0, 2)])
+def test_rti_step_matches_scipy_bvls(oracle, N, spread, seed):
+    """Third-party check of the QP layer.  The Gauss-Newton QP of an RTI step is a bounded linear least-squares problem:
+    with H = L L' (Cholesky of the condensed Hessian), 1/2 du'H du + g'du = 1/2 |L'du + L^-1 g|^2 + const.  scipy's
+    lsq_linear(method="bvls") (Stark & Parker's bounded-variable least squares, an active-set method that shares no code and no
+    algorithm with the oracle's Riccati interior-point iteration) must land on the same du to 1e-7."""
+    from scipy.linalg import cholesky, solve_triangular
+    from scipy.optimize import lsq_linear
+    w = wl.tracking_batch(6, N, seed=seed, pos_spread=spread)
+    n_active = 0
+    for i in range(6):
+        X, U = w["X"][i].copy(), w["U"][i].copy()
+        x0 = w["x0"][i].copy()
+        line = int(w["lines"][i])
+        for tick in range(3):
+            yref = traj.window(w["traj"], line + tick, N)
+            qp, st, info, Xn, Un = _one_step(oracle, N, x0, yref, w["p"][i], X, U)
+            assert st == 0
+            H, g, G, c = condense(qp)
+            L = cholesky(H, lower=True)
+            res = lsq_linear(L.T, -solve_triangular(L, g, lower=True), bounds=(qp["lb"].ravel(), qp["ub"].ravel()),
+                             method="bvls", tol=1e-15, max_iter=2000)
+            assert res.status > 0, res.message
+            du = (Un - U).ravel()
+            assert np.abs(du - res.x).max() < 1e-7, (i, tick, np.abs(du - res.x).max())
+            n_active += int(res.active_mask.astype(bool).sum())
+            x0 = oracle.erk4(x0, Un[0], w["p"][i], 0.05)
+            X, U = Xn, Un
+    if spread >= 3.0 and N == 40:
+        assert n_active > 0, "active-bound set did not activate any bound"
