@@ -34,7 +34,7 @@ struct br2_batch_solver {
     int max_iter, fast_path, ekf_model, active_set;
     double tol;
     // device state
-    double *d_Ts, *d_X, *d_U, *d_G, *d_F, *d_V, *d_u0, *d_thrust, *d_info;
+    double *d_Ts, *d_X, *d_U, *d_S, *d_u0, *d_thrust, *d_info;
     int *d_status, *d_iters, *d_counter, *d_hint, *d_aset, *d_order;
     double *d_x0, *d_yref, *d_p;              // staging for the host API
     double* d_traj;                           // reference trajectory for device-side windowing [traj_rows][16]
@@ -97,7 +97,7 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
 {
     if (!s) return BR2_OK;
     DeviceGuard guard_(s->device);
-    void* ptrs[] = {s->d_Ts, s->d_X, s->d_U, s->d_G, s->d_F, s->d_V, s->d_u0, s->d_thrust, s->d_info, s->d_status,
+    void* ptrs[] = {s->d_Ts, s->d_X, s->d_U, s->d_S, s->d_u0, s->d_thrust, s->d_info, s->d_status,
                     s->d_iters, s->d_counter, s->d_x0, s->d_yref, s->d_p, s->d_ex, s->d_eP, s->d_thr, s->d_meas,
                     s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls, s->d_yaw, s->d_aset, s->d_order};
     for (void* p : ptrs)
@@ -163,7 +163,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
         }                                                                                                 \
     } while (0)
     DA(d_Ts, N); DA(d_X, B * (N + 1) * NX); DA(d_U, B * N * NU);
-    DA(d_G, B * N * GREC); DA(d_F, B * N * FREC); DA(d_V, B * (N + 1) * VREC);
+    DA(d_S, B * (N + 1) * SREC);
     DA(d_u0, B * 4); DA(d_thrust, B * 6); DA(d_info, B * 4); DA(d_status, B); DA(d_iters, B); DA(d_counter, 4); DA(d_order, 2 * B);
     DA(d_x0, B * NX); DA(d_yref, B * (N + 1) * NY); DA(d_p, B * (N + 1) * NP);
     DA(d_ex, B * 18); DA(d_eP, B * 324); DA(d_thr, B * 6); DA(d_meas, B * 12); DA(d_acc, B * 6); DA(d_wf, B * 6);
@@ -199,7 +199,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     configure_kernels();
     configure_ekf();
     CKF(cudaMemset(s->d_info, 0, sizeof(double) * B * 4));
-    CKF(cudaMemset(s->d_V, 0, sizeof(double) * B * (N + 1) * VREC));
+    CKF(cudaMemset(s->d_S, 0, sizeof(double) * B * (N + 1) * SREC));
     *out = s;
     int rc = br2_batch_reset(s, 0);
     if (rc == BR2_OK) rc = br2_batch_ekf_reset(s);
@@ -345,7 +345,7 @@ static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, con
     a.Ts = s->d_Ts;
     memcpy(a.W, s->W, sizeof a.W); memcpy(a.We, s->We, sizeof a.We);
     memcpy(a.lbu, s->lbu, sizeof a.lbu); memcpy(a.ubu, s->ubu, sizeof a.ubu);
-    a.X = s->d_X; a.U = s->d_U; a.G = s->d_G; a.F = s->d_F; a.V = s->d_V;
+    a.X = s->d_X; a.U = s->d_U; a.S = s->d_S;
     a.u0 = d_u0 ? d_u0 : s->d_u0;
     a.thrust = d_thrust ? d_thrust : s->d_thrust;
     a.status = d_status ? d_status : s->d_status;
@@ -490,17 +490,20 @@ extern "C" int br2_batch_get_linearization_host(br2_batch_solver* s, double* AB,
     if (!s) return fail(BR2_EINVAL, "null solver");
     ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
-    const size_t n = (size_t)s->B * s->N;
-    double* h = (double*)malloc(sizeof(double) * n * GREC);
+    const size_t N = s->N, nrec = (size_t)s->B * (N + 1);
+    double* h = (double*)malloc(sizeof(double) * nrec * SREC);
     if (!h) return fail(BR2_ENOMEM, "out of host memory");
-    cudaError_t e = cudaMemcpy(h, s->d_G, sizeof(double) * n * GREC, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(h, s->d_S, sizeof(double) * nrec * SREC, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess)
-        for (size_t i = 0; i < n; i++) {
-            if (AB)   // un-permute the fragment order (layout.h) into row-major 12 x 16
-                for (int r = 0; r < 12; r++)
-                    for (int c = 0; c < 16; c++) AB[i * 192 + r * 16 + c] = h[i * GREC + g_off(r, c)];
-            if (b) memcpy(b + i * 12, h + i * GREC + G_B_OFF, sizeof(double) * 12);
-        }
+        for (size_t b_ = 0; b_ < (size_t)s->B; b_++)
+            for (size_t k = 0; k < N; k++) {
+                const double* g = h + (b_ * (N + 1) + k) * SREC + S_G;
+                const size_t i = b_ * N + k;
+                if (AB)   // un-permute the fragment order (layout.h) into row-major 12 x 16
+                    for (int r = 0; r < 12; r++)
+                        for (int c = 0; c < 16; c++) AB[i * 192 + r * 16 + c] = g[g_off(r, c)];
+                if (b) memcpy(b + i * 12, g + G_B_OFF, sizeof(double) * 12);
+            }
     free(h);
     CK(e);
     return BR2_OK;

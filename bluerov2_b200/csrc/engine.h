@@ -26,9 +26,7 @@ struct SolveArgs {
     double* X;             // [B][N+1][12]
     double* U;             // [B][N][4]
     // workspaces (device)
-    double* G;             // [B][N][GREC]
-    double* F;             // [B][N][FREC]
-    double* V;             // [B][N+1][VREC]
+    double* S;             // [B][N+1][SREC] stage records [V | G | F] (layout.h)
     // outputs (device)
     double* u0;            // [B][4]
     double* thrust;        // [B][6]  (may alias an NCCL / symmetric send buffer)

@@ -154,7 +154,7 @@ __device__ __forceinline__ void lin_phase_a(const SolveArgs& a, LinSmem& sm, int
     cs[15 * LRND] = mc.ju_yaw2; cs[16 * LRND] = mc.ju_yaw4; cs[17 * LRND] = h;
     if (!live) return;
     // tail of the stage record: b_k, qlin_k, rlin_k, Ts_k, pad (32 doubles, 32-byte aligned)
-    double* Gt = a.G + (size_t)gs * GREC + G_B_OFF;
+    double* Gt = a.S + ((size_t)inst * (a.N + 1) + k) * SREC + S_G + G_B_OFF;
     const double* yr = yref_row(a, inst, k);
     const double* Xn = Xk + NX;
     double tl[32];
@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
                 }
             }
             if (gs < total) {
-                double* Gk = a.G + (size_t)gs * GREC;
+                const int gi = gs / a.N;
+                double* Gk = a.S + ((size_t)gi * (a.N + 1) + (gs - gi * a.N)) * SREC + S_G;
                 double* da = Gk + (((zca >> 3)) << 5) + ((zca & 7) << 2);     // g_off(0, zc); row block ki adds 64
                 double* db = Gk + (((zcb >> 3)) << 5) + ((zcb & 7) << 2);
 #pragma unroll
@@ -329,41 +330,106 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 
-// ---- per-warp TMA bulk-copy pipeline: stage records are prefetched HBM -> shared memory NSLOT-1 stages ahead ----
-struct __align__(128) StageBuf { double G[GREC]; double F[FREC]; double V[VREC]; };
+// ---- per-warp staging ring: the stage records of a sweep are copied HBM -> shared memory NSLOT-1 stages ahead of the compute ----
+// cp.async (LDGSTS, 16 bytes per lane, L2 only) with commit / wait groups.  Round 1 used one-lane TMA bulk copies completing on
+// mbarriers: ptxas wraps every cp.async.bulk issued from non-uniform registers in an elect / R2UR / branch loop and the parity
+// bookkeeping came on top -- ~60 of the 150..600 instructions of EVERY stage of EVERY sweep were pipeline mechanics
+// (profiles/r01o_ipm_ncu_summary.txt: IMAD 18.7 %, the kernel is issue-bound).  With the three records of a stage laid end to end
+// (layout.h: S_k = [V | G | F]) a stage costs 4..6 copy instructions, one commit, one wait and one warp barrier.
 constexpr int NSLOT = BR2_NSLOT;     // ring depth: records of NSLOT-1 stages are in flight ahead of the one being computed
+constexpr int REC_BYTES = SREC * 8;
 // xch: per-warp exchange buffer of the factor sweep: H[:, 12..15] (16 rows x 4) + g (4)
-struct __align__(128) WarpSmem { StageBuf st[NSLOT]; double xch[72]; unsigned long long bar[NSLOT]; };
+struct __align__(128) WarpSmem { double st[NSLOT][SREC]; double xch[80]; };
+static_assert(sizeof(WarpSmem) % 128 == 0, "ring slots stay 128-byte aligned");
+enum { P_V = 1, P_G = 2, P_F = 4 };  // which parts of a stage record a sweep reads
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+__device__ __forceinline__ void cp16(uint32_t dst, const char* src)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// One stage record, the parts named by PARTS: 16-byte chunk c = lane + 32 j sits at byte 512 j + 16 lane of the record, so
+//   V = j 0,   G = j 1..3 and lanes < 16 of j 4,   F = lanes >= 16 of j 4 and lanes < 16 of j 5.
+// dst / src are the lane's own addresses (slot base / record base + 16 lane).
+template <int PARTS>
+__device__ __forceinline__ void stage_copy(uint32_t dst, const char* src, int lane)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    if (PARTS & P_V) cp16(dst, src);
+    if (PARTS & P_G) {
+        cp16(dst + 512, src + 512);
+        cp16(dst + 1024, src + 1024);
+        cp16(dst + 1536, src + 1536);
+    }
+    if ((PARTS & P_G) && (PARTS & P_F)) cp16(dst + 2048, src + 2048);
+    else if (PARTS & P_G) { if (lane < 16) cp16(dst + 2048, src + 2048); }
+    else if (PARTS & P_F) { if (lane >= 16) cp16(dst + 2048, src + 2048); }
+    if (PARTS & P_F) { if (lane < 16) cp16(dst + 2560, src + 2560); }
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+
+// Per-instance pointers and the sweep pipeline
+struct Inst {
+    const SolveArgs& a;
+    WarpSmem& sm;
+    int inst, lane, q, t, N;
+    double* S;                  // the instance's stage records S_0 .. S_N (layout.h)
+    double* V;                  // = S + S_V: V record of stage k at V + k * SREC
+    const double* Xlin;
+    const double* Ulin;
+    const char* src;            // pipeline: the lane's global address inside the next record to copy
+    uint32_t dst0;              // pipeline: the lane's shared address inside ring slot 0
+    __device__ Inst(const SolveArgs& a_, WarpSmem& sm_, int inst_, int lane_)
+        : a(a_), sm(sm_), inst(inst_), lane(lane_), q(lane_ >> 2), t(lane_ & 3), N(a_.N)
+    {
+        S = a.S + (size_t)inst * (N + 1) * SREC;
+        V = S + S_V;
+        Xlin = a.X + (size_t)inst * (N + 1) * NX;
+        Ulin = a.U + (size_t)inst * N * NU;
+        dst0 = smem_u32(&sm.st[0][0]) + 16 * lane;
+        src = nullptr;
+    }
+    // Stages are visited in sequence i = 0..N-1 (record k = i forward, k = N-1-i backward); ring slot = i % NSLOT.
+    // begin(): everything this warp wrote to global so far is ordered before the copies (warp barrier), then fill the ring.
+    template <int PARTS, bool BACKWARD>
+    __device__ __forceinline__ void begin()
+    {
+        __syncwarp();
+        src = reinterpret_cast<const char*>(S) + 16 * lane + (BACKWARD ? (size_t)(N - 1) * REC_BYTES : 0);
+#pragma unroll
+        for (int j = 0; j < NSLOT - 1; j++) {
+            if (j < N) stage_copy<PARTS>(dst0 + j * REC_BYTES, src, lane);
+            cp_commit();
+            src += BACKWARD ? -REC_BYTES : REC_BYTES;
+        }
+    }
+    // top of iteration i: wait for this iteration's records (all but the NSLOT-2 youngest groups complete), warp barrier (the
+    // copies of the other lanes become visible, and every lane is past its reads of the slot consumed by iteration i-1), then
+    // refill that slot with the records of stage i + NSLOT - 1.  Returns the slot to read.
+    template <int PARTS, bool BACKWARD>
+    __device__ __forceinline__ const double* advance(int i)
+    {
+        cp_wait<NSLOT - 2>();
+        __syncwarp();
+        const int j = i + NSLOT - 1;
+        if (j < N) stage_copy<PARTS>(dst0 + (j % NSLOT) * REC_BYTES, src, lane);
+        cp_commit();
+        src += BACKWARD ? -REC_BYTES : REC_BYTES;
+        return sm.st[i % NSLOT];
+    }
+};
+
+// pull the instance's iterate (X, U rows) into L2 ahead of the epilogue that updates it
+__device__ __forceinline__ void prefetch_iterate(const Inst& I)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    const char* xb = reinterpret_cast<const char*>(I.Xlin);
+    const char* ub = reinterpret_cast<const char*>(I.Ulin);
+    const int xbytes = (I.N + 1) * NX * 8, ubytes = I.N * NU * 8;
+    for (int o = I.lane * 128; o < xbytes + 128; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + (o < xbytes ? o : xbytes - 8)));
+    for (int o = I.lane * 128; o < ubytes + 128; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ub + (o < ubytes ? o : ubytes - 8)));
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
-{
-    uint32_t done;
-    // non-blocking probe first: with the ring NSLOT-1 stages ahead the phase has normally completed already, and
-    // try_wait costs ~90 cycles even then
-    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (done) return;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-// generic-proxy global writes of this warp (made visible to the issuing lane by __syncwarp) -> async-proxy reads
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // 4x4 Cholesky of the symmetric matrix with lower entries m (row-major lower: 00 10 11 20 21 22 30 31 32 33).
 // Outputs strictly-lower entries and reciprocal diagonal.  Returns false when a pivot is not positive.
@@ -444,86 +510,6 @@ __device__ __forceinline__ void inv4_apply(const Inv4& B, const double* v, doubl
     o[3] = (B.b30 * v[0] + B.b31 * v[1] + B.b32 * v[2] + B.b33 * v[3]) * B.id;
 }
 
-// Per-instance pointers
-struct Inst {
-    const SolveArgs& a;
-    WarpSmem& sm;
-    uint32_t& phase;            // parities of the slot barriers (bit s = next parity to wait for on slot s)
-    int inst, lane, q, t, N;
-    const double* G;
-    double* F;
-    double* V;
-    const double* Xlin;
-    const double* Ulin;
-    __device__ Inst(const SolveArgs& a_, WarpSmem& sm_, uint32_t& phase_, int inst_, int lane_)
-        : a(a_), sm(sm_), phase(phase_), inst(inst_), lane(lane_), q(lane_ >> 2), t(lane_ & 3), N(a_.N)
-    {
-        G = a.G + (size_t)inst * N * GREC;
-        F = a.F + (size_t)inst * N * FREC;
-        V = a.V + (size_t)inst * (N + 1) * VREC;
-        Xlin = a.X + (size_t)inst * (N + 1) * NX;
-        Ulin = a.U + (size_t)inst * N * NU;
-    }
-    // prefetch the records of stage k into slot s (one lane issues; completion lands on the slot's mbarrier)
-    template <bool NEED_F, bool NEED_V>
-    __device__ __forceinline__ void issue(int s, int k)
-    {
-        if (lane == 0) {
-            const uint32_t bar = smem_u32(&sm.bar[s]), dst = smem_u32(&sm.st[s]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                         ::"r"(bar), "r"((uint32_t)((GREC + (NEED_V ? VREC : 0) + (NEED_F ? FREC : 0)) * sizeof(double))) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(G + (size_t)k * GREC), "r"((uint32_t)(GREC * sizeof(double))), "r"(bar) : "memory");
-            if (NEED_V)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(dst + (uint32_t)((GREC + FREC) * sizeof(double))), "l"(V + (size_t)k * VREC),
-                               "r"((uint32_t)(VREC * sizeof(double))), "r"(bar) : "memory");
-            if (NEED_F)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(dst + (uint32_t)(GREC * sizeof(double))), "l"(F + (size_t)k * FREC),
-                               "r"((uint32_t)(FREC * sizeof(double))), "r"(bar) : "memory");
-        }
-    }
-    // Sweep pipeline.  Stages are visited in sequence i = 0..N-1 (k = i forward, k = N-1-i backward); slot = i % NSLOT.
-    // begin(): everything this warp wrote to global so far must be visible to the copy engine, then fill the ring.
-    template <bool NEED_F, bool BACKWARD, bool NEED_V>
-    __device__ __forceinline__ void begin()
-    {
-        __syncwarp();
-        if (lane == 0) fence_proxy_async();
-#pragma unroll
-        for (int j = 0; j < NSLOT - 1; j++)
-            if (j < N) issue<NEED_F, NEED_V>(j, BACKWARD ? N - 1 - j : j);
-    }
-    // top of iteration i: the slot consumed by iteration i-1 is free (after the warp sync) -> refill it with the
-    // records of stage i + NSLOT - 1, then wait for this iteration's records.  Returns the slot to read.
-    template <bool NEED_F, bool BACKWARD, bool NEED_V>
-    __device__ __forceinline__ int advance(int i)
-    {
-        const int s = i % NSLOT;
-        __syncwarp();
-        const int j = i + NSLOT - 1;
-        if (j < N) issue<NEED_F, NEED_V>(j % NSLOT, BACKWARD ? N - 1 - j : j);
-        wait(s);
-        return s;
-    }
-    __device__ __forceinline__ void wait(int s)
-    {
-        mbar_wait(&sm.bar[s], (phase >> s) & 1u);
-        phase ^= 1u << s;
-    }
-};
-
-// pull the instance's iterate (X, U rows) into L2 ahead of the epilogue that updates it
-__device__ __forceinline__ void prefetch_iterate(const Inst& I)
-{
-    const char* xb = reinterpret_cast<const char*>(I.Xlin);
-    const char* ub = reinterpret_cast<const char*>(I.Ulin);
-    const int xbytes = (I.N + 1) * NX * 8, ubytes = I.N * NU * 8;
-    for (int o = I.lane * 128; o < xbytes + 128; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + (o < xbytes ? o : xbytes - 8)));
-    for (int o = I.lane * 128; o < ubytes + 128; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ub + (o < ubytes ? o : ubytes - 8)));
-}
-
 // E0: cold start of the IPM iterate (qp_solver_warm_start 0): du = 0 pushed strictly inside the box, slacks
 // exactly consistent, lam = mu0 / t.
 __device__ void ipm_init(Inst& I)
@@ -537,7 +523,7 @@ __device__ void ipm_init(Inst& I)
         double v = fmin(fmax(0.0, lb + thr), ub - thr);
         if (ub - lb < 2 * thr) v = 0.5 * (lb + ub);
         const double tl = v - lb, tu = ub - v;
-        double* Vk = I.V + (size_t)k * VREC;
+        double* Vk = I.V + (size_t)k * SREC;
         Vk[V_V + e] = v; Vk[V_TL + e] = tl; Vk[V_TU + e] = tu;
         Vk[V_LL + e] = mu0 / tl; Vk[V_LU + e] = mu0 / tu;
     }
@@ -556,7 +542,8 @@ __device__ double forward_sweep(Inst& I)
     const int q = I.q, t = I.t, N = I.N;
     const bool lo = q < 4;                      // quad owns a second state row 8 + q (else: no row 12..15)
     constexpr bool FEEDBACK = MODE != 0, AFFINE = MODE != 1;
-    I.template begin<FEEDBACK, false, !FEEDBACK>();     // records in flight while the start values below are fetched
+    constexpr int PARTS = FEEDBACK ? (P_G | P_F) : (P_V | P_G);
+    I.template begin<PARTS, false>();     // records in flight while the start values below are fetched
     double zr[3];                               // propagated vector, row layout: x[4ki + t]
     double bmax = 0.0;
 #pragma unroll
@@ -568,11 +555,11 @@ __device__ double forward_sweep(Inst& I)
 #pragma unroll
     for (int ki = 0; ki < 4; ki++) { o0[ki] = g_off(q, 4 * ki + t); o1[ki] = g_off(8 + (q & 3), 4 * ki + t); }
     for (int k = 0; k < N; k++) {
-        const int s = I.template advance<FEEDBACK, false, !FEEDBACK>(k);
-        const double* Gs = I.sm.st[s].G;
-        const double* Fs = I.sm.st[s].F;
-        const double* Vs = I.sm.st[s].V;
-        double* Vk = I.V + (size_t)k * VREC;
+        const double* Ss = I.template advance<PARTS, false>(k);
+        const double* Gs = Ss + S_G;
+        const double* Fs = Ss + S_F;
+        const double* Vs = Ss + S_V;
+        double* Vk = I.V + (size_t)k * SREC;
         double z0[4], z1[4];
 #pragma unroll
         for (int ki = 0; ki < 4; ki++) {
@@ -614,7 +601,7 @@ __device__ double forward_sweep(Inst& I)
     }
     if (q == 0) {
 #pragma unroll
-        for (int ki = 0; ki < 3; ki++) I.V[(size_t)N * VREC + xoff + 4 * ki + t] = zr[ki];
+        for (int ki = 0; ki < 3; ki++) I.V[(size_t)N * SREC + xoff + 4 * ki + t] = zr[ki];
     }
     __syncwarp();
     return AFFINE ? warp_max(bmax) : 0.0;
@@ -656,12 +643,13 @@ __device__ bool factor_sweep(Inst& I)
     const int row0 = 2 * t, row1 = 2 * t + 1, row2 = hi2 ? 2 * t + 5 : 8 + 2 * t;
     const int zo0 = g_off(row0, q), zo1 = g_off(row1, q), zo2 = g_off(row2, q);
     // P+ in C layout: h[m][n][j] = P[8m+q][8n+2t+j]; vin[kt] = (q == 4 ? v1 : q == 5 ? v2 : 0)[row(kt)]
-    I.template begin<false, true, KIND == FS_IPM>();    // records in flight while the terminal values are fetched
+    constexpr int PARTS = KIND == FS_IPM ? (P_V | P_G) : P_G;
+    I.template begin<PARTS, true>();    // records in flight while the terminal values are fetched
     double h[2][2][2];
     double vin[3] = {0.0, 0.0, 0.0};
     double pq0 = 0.0, pq1 = 0.0;                // FS_ABS: p+ in quad layout (rows q, 8+q)
     {
-        const double* VN = I.V + (size_t)N * VREC;
+        const double* VN = I.V + (size_t)N * SREC;
         const double* yN = yref_row(a, I.inst, N);
 #pragma unroll
         for (int m = 0; m < 2; m++)
@@ -691,11 +679,11 @@ __device__ bool factor_sweep(Inst& I)
         }
     }
     for (int k = N - 1, it = 0; k >= 0; k--, it++) {
-        const int s = I.template advance<false, true, KIND == FS_IPM>(it);
-        const double* Gs = I.sm.st[s].G;
-        const double* Vs = I.sm.st[s].V;
-        double* Fk = I.F + (size_t)k * FREC;
-        double* Vk = I.V + (size_t)k * VREC;
+        const double* Ss = I.template advance<PARTS, true>(it);
+        const double* Gs = Ss + S_G;
+        const double* Vs = Ss + S_V;
+        double* Fk = I.S + (size_t)k * SREC + S_F;
+        double* Vk = I.V + (size_t)k * SREC;
         // FS_AS: the stage's guessed active set (2 bits per input: 1 = at the lower, 2 = at the upper bound) and the pinned values
         // du_e = bound_e - U_k[e] (uniform over the warp)
         int code = 0;
@@ -944,13 +932,13 @@ __device__ void backward_vec_sweep(Inst& I)
     const bool lo = q < 4;
     const int e = q & 3;
     double pr[3] = {0.0, 0.0, 0.0};             // p+ in row layout
-    I.template begin<true, true, true>();
+    I.template begin<P_V | P_G | P_F, true>();
     for (int k = N - 1, it = 0; k >= 0; k--, it++) {
-        const int s = I.template advance<true, true, true>(it);
-        const double* Gk = I.sm.st[s].G;
-        const double* Fk = I.sm.st[s].F;
-        const double* Vs = I.sm.st[s].V;
-        double* Vk = I.V + (size_t)k * VREC;
+        const double* Ss = I.template advance<P_V | P_G | P_F, true>(it);
+        const double* Gk = Ss + S_G;
+        const double* Fk = Ss + S_F;
+        const double* Vs = Ss + S_V;
+        double* Vk = I.V + (size_t)k * SREC;
         double o0 = 0.0, o1 = 0.0;
 #pragma unroll
         for (int ki = 0; ki < 3; ki++) {
@@ -979,7 +967,7 @@ __device__ void backward_vec_sweep(Inst& I)
         chol4_fwd(L, gt);
         chol4_bwd(L, gt);
         if (lane == 0) {
-            double* Fo = I.F + (size_t)k * FREC + F_KFF;
+            double* Fo = I.S + (size_t)k * SREC + S_F + F_KFF;
             *reinterpret_cast<double2*>(Fo) = make_double2(gt[0], gt[1]);
             *reinterpret_cast<double2*>(Fo + 2) = make_double2(gt[2], gt[3]);
         }
@@ -1001,10 +989,10 @@ __device__ bool costate_check(Inst& I)
     const SolveArgs& a = I.a;
     const bool lo = q < 4;
     const int e = q & 3;
-    I.template begin<false, true, true>();
+    I.template begin<P_V | P_G, true>();
     double pr[3];                               // lam+ in row layout
     {
-        const double* VN = I.V + (size_t)N * VREC;
+        const double* VN = I.V + (size_t)N * SREC;
         const double* yN = yref_row(a, I.inst, N);
 #pragma unroll
         for (int ki = 0; ki < 3; ki++) {
@@ -1014,9 +1002,9 @@ __device__ bool costate_check(Inst& I)
     }
     bool good = true;
     for (int k = N - 1, it = 0; k >= 0; k--, it++) {
-        const int s = I.template advance<false, true, true>(it);
-        const double* Gk = I.sm.st[s].G;
-        const double* Vs = I.sm.st[s].V;
+        const double* Ss = I.template advance<P_V | P_G, true>(it);
+        const double* Gk = Ss + S_G;
+        const double* Vs = Ss + S_V;
         double o0 = 0.0, o1 = 0.0;
 #pragma unroll
         for (int ki = 0; ki < 3; ki++) {
@@ -1081,7 +1069,7 @@ __device__ int primal_check(Inst& I, bool fresh)
         const int code = (valid && !fresh) ? as[k] : 0;
         int cc = (code >> (2 * e)) & 3;
         if (valid) {
-            const double uk = I.Ulin[idx], du = I.V[(size_t)k * VREC + V_V + e];
+            const double uk = I.Ulin[idx], du = I.V[(size_t)k * SREC + V_V + e];
             const double lb = a.lbu[e] - uk, ub = a.ubu[e] - uk;
             const double tolu = 1e-12 * (ub - lb);
             if (cc == 0) {
@@ -1121,14 +1109,6 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
     const int lane = threadIdx.x & 31;
     const int N = a.N, nb = 4 * N;
     WarpSmem& sm = smem[threadIdx.x >> 5];
-    uint32_t phase = 0;
-    if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < NSLOT; j++) mbar_init(&sm.bar[j], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
     // Work distribution.  Instances are visited in the order the PREVIOUS solve left behind: those that ended with active bounds
     // (hint = 1: several factorisations, possibly interior-point iterations) first, so that the long jobs start at t = 0 and the
     // one-factorisation instances fill the tail (longest-processing-time-first).  queue position -> instance through order_cur;
@@ -1151,7 +1131,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         have = false;
         inst = __shfl_sync(FULL_MASK, inst, 0);
         if (inst >= a.B) break;
-        Inst I(a, sm, phase, inst, lane);
+        Inst I(a, sm, inst, lane);
 
         int status = 2, it = 0;
         double mu = 0.0, res_stat = 0.0, stat_scale = 1.0, bmax = 0.0;
@@ -1203,7 +1183,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
                 // mu and stationarity residual of the starting point (later iterations get them from E2)
                 double s = 0.0, rs = 0.0;
                 for (int idx = lane; idx < nb; idx += 32) {
-                    const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                    const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
                     const int e = idx & 3;
                     const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e];
                     s += ll * tl + lu * tu;
@@ -1219,7 +1199,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             // ---------- E1: affine step length, sigma, corrector rhs ----------
             double a_aff = 1.0;
             for (int idx = lane; idx < nb; idx += 32) {
-                const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
                 const int e = idx & 3;
                 const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
                 const double dll = -ll - ll * dv / tl, dlu = -lu + lu * dv / tu;
@@ -1229,7 +1209,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             a_aff = warp_min(a_aff);
             double mu_aff = 0.0;
             for (int idx = lane; idx < nb; idx += 32) {
-                const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
                 const int e = idx & 3;
                 const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
                 const double dll = -ll - ll * dv / tl, dlu = -lu + lu * dv / tu;
@@ -1239,7 +1219,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             double sigma = mu_aff / mu;
             sigma = sigma * sigma * sigma;
             for (int idx = lane; idx < nb; idx += 32) {
-                double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                double* Vk = I.V + (size_t)(idx >> 2) * SREC;
                 const int e = idx & 3;
                 const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
                 const double dll = -ll - ll * dv / tl, dlu = -lu + lu * dv / tu;
@@ -1254,7 +1234,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             // ---------- E2: step lengths and update ----------
             double ap = 2.0, ad = 2.0;
             for (int idx = lane; idx < nb; idx += 32) {
-                const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
                 const int e = idx & 3;
                 const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
                 const double dll = Vk[V_CL + e] / tl - ll - ll * dv / tl, dlu = Vk[V_CU + e] / tu - lu + lu * dv / tu;
@@ -1270,7 +1250,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             // gradient is affine in du and the Newton equation gives  d(gu) = -gh - (ll/tl + lu/tu) ddu  stage-locally.
             double s_mu = 0.0, s_rs = 0.0;
             for (int idx = lane; idx < nb; idx += 32) {
-                double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+                double* Vk = I.V + (size_t)(idx >> 2) * SREC;
                 const int e = idx & 3;
                 const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
                 const double cl = Vk[V_CL + e], cu = Vk[V_CU + e], gu = Vk[V_GU + e];
@@ -1289,7 +1269,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             mu = warp_sum(s_mu) / (2.0 * nb);
             res_stat = warp_max(s_rs);
             for (int idx = lane; idx < 12 * (N + 1); idx += 32) {
-                double* Vk = I.V + (size_t)(idx / 12) * VREC;
+                double* Vk = I.V + (size_t)(idx / 12) * SREC;
                 const int e = idx % 12;
                 Vk[V_X + e] += ap * Vk[V_DX + e];
             }
@@ -1304,12 +1284,12 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         bool act2 = false;
 #pragma unroll 5
         for (int idx = lane; idx < nb; idx += 32) {
-            const double* Vk = I.V + (size_t)(idx >> 2) * VREC;
+            const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
             finite &= isfinite(Vk[V_V + (idx & 3)]);
             if (!solved) act2 |= fmin(Vk[V_TL + (idx & 3)], Vk[V_TU + (idx & 3)]) < 1e-3;
         }
         // the states are the exact roll-out of the inputs: NaN/Inf anywhere reaches x_N
-        if (lane < 12) finite &= isfinite(I.V[(size_t)N * VREC + V_X + lane]);
+        if (lane < 12) finite &= isfinite(I.V[(size_t)N * SREC + V_X + lane]);
         finite = __all_sync(FULL_MASK, finite);
         if (!solved) active = act2;
         active = __any_sync(FULL_MASK, active);
@@ -1318,7 +1298,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             for (int base = 0; base < nb; base += 32) {
                 const int idx = base + lane;
                 const bool valid = idx < nb;
-                const double* Vk = I.V + (size_t)((valid ? idx : 0) >> 2) * VREC;
+                const double* Vk = I.V + (size_t)((valid ? idx : 0) >> 2) * SREC;
                 int cc = 0;
                 if (valid) cc = Vk[V_TL + (idx & 3)] < 1e-7 ? 1 : (Vk[V_TU + (idx & 3)] < 1e-7 ? 2 : 0);
                 int code = cc << (2 * (lane & 3));
@@ -1344,7 +1324,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
                 for (int j = 0; j < 5; j++) {
                     const int idx = base + 32 * j;
                     const bool p = idx < nb;
-                    d[j] = p ? I.V[(size_t)(idx >> 2) * VREC + V_V + (idx & 3)] : 0.0;
+                    d[j] = p ? I.V[(size_t)(idx >> 2) * SREC + V_V + (idx & 3)] : 0.0;
                     u[j] = p ? Uo[idx] : 0.0;
                 }
 #pragma unroll
@@ -1362,7 +1342,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
                 for (int j = 0; j < 8; j++) {
                     const int idx = base + 32 * j;
                     const bool p = idx < nxs;
-                    d[j] = p ? I.V[(size_t)(idx / 12) * VREC + V_X + idx % 12] : 0.0;
+                    d[j] = p ? I.V[(size_t)(idx / 12) * SREC + V_X + idx % 12] : 0.0;
                     x[j] = p ? Xo[idx] : 0.0;
                 }
 #pragma unroll

@@ -56,4 +56,12 @@ constexpr int V_CL = 52;   // complementarity rhs lower: sigma*mu - dt_aff*dlam_
 constexpr int V_CU = 56;   // complementarity rhs upper
 // [60..63] pad
 
+// Stage record S_k of an instance, k = 0..N (the terminal record only uses its V part): the three records of a stage laid
+// end to end, S_k = [V_k | G_k | F_k], so that a sweep addresses everything of a stage from ONE running pointer and the
+// staging copies of a stage are 16-byte chunks at fixed offsets of it.  352 doubles = 2816 B = 22 x 128 B.
+constexpr int SREC = VREC + GREC + FREC;
+constexpr int S_V = 0;
+constexpr int S_G = VREC;
+constexpr int S_F = VREC + GREC;
+
 }  // namespace br2
