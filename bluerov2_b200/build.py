@@ -25,7 +25,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+# BR2_VARIANT=<tag> builds / loads a tuning or instrumentation variant from lib_<tag>/ (with BR2_NVCC_DEFS), leaving lib/ alone
+_VARIANT = os.environ.get("BR2_VARIANT", "")
+LIBDIR = os.path.join(HERE, "lib_" + _VARIANT if _VARIANT else "lib")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(LIBDIR, "libacados_ocp_solver_bluerov2.so")
 SHIMS = ("libacados.so", "libhpipm.so", "libblasfeo.so")

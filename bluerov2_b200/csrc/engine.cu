@@ -170,7 +170,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     DA(d_pout, B * NP);
     DA(d_rls, B * 4 * RLS_STRIDE);
     DA(d_yaw, B * 2);
-    DA(d_iter_total, 1);
+    DA(d_iter_total, 1 + 16);     // [0] iteration counter, [1..16] phase cycle counters of the instrumentation build
     DA(d_hint, B);
     DA(d_aset, B * N);
     DA(d_lines, B);
@@ -181,7 +181,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     CKF(cudaEventCreate(&s->ev0));
     CKF(cudaEventCreate(&s->ev1));
     CKF(cudaEventCreate(&s->ev_mid));
-    CKF(cudaMemset(s->d_iter_total, 0, sizeof(unsigned long long)));
+    CKF(cudaMemset(s->d_iter_total, 0, sizeof(unsigned long long) * 17));
     CKF(cudaMemcpy(s->d_Ts, s->Ts, sizeof(double) * N, cudaMemcpyHostToDevice));
     CKF(cudaMemset(s->d_status, 0, sizeof(int) * B));
     CKF(cudaMemset(s->d_iters, 0, sizeof(int) * B));
@@ -349,7 +349,7 @@ static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, con
     a.u0 = d_u0 ? d_u0 : s->d_u0;
     a.thrust = d_thrust ? d_thrust : s->d_thrust;
     a.status = d_status ? d_status : s->d_status;
-    a.iters = s->d_iters; a.info = s->d_info; a.ctr = s->d_counter; a.order = s->d_order; a.iter_total = s->d_iter_total; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
+    a.iters = s->d_iters; a.info = s->d_info; a.ctr = s->d_counter; a.order = s->d_order; a.iter_total = s->d_iter_total; a.prof = s->d_iter_total + 1; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
     a.max_iter = s->max_iter; a.tol = s->tol;
 }
 
@@ -541,6 +541,17 @@ extern "C" long long br2_batch_ipm_iterations_total(br2_batch_solver* s, int res
     if (cudaMemcpy(&v, s->d_iter_total, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     if (reset) cudaMemset(s->d_iter_total, 0, sizeof v);
     return (long long)v;
+}
+
+// instrumentation build (-DBR2_PROFILE): cycles per kernel phase summed over warps since the last reset; zeros otherwise
+extern "C" int br2_batch_phase_cycles(br2_batch_solver* s, unsigned long long* out16, int reset)
+{
+    if (!s || !out16) return fail(BR2_EINVAL, "null argument");
+    ON_DEVICE(s);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out16, s->d_iter_total + 1, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(s->d_iter_total + 1, 0, sizeof(unsigned long long) * 16));
+    return BR2_OK;
 }
 
 // ---- nominal plant (closed-loop studies on the device) ----

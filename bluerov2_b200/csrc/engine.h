@@ -41,6 +41,7 @@ struct SolveArgs {
     int* aset;             // [B][N] guessed active set per stage, 2 bits per input (0 free, 1 at lbu, 2 at ubu)
     int active_set;        // primal-dual active-set iteration when the interior solution leaves the box (option "active_set_path")
     unsigned long long* iter_total;   // [1] IPM iterations executed, accumulated over instances and solves
+    unsigned long long* prof;         // [16] cycles per kernel phase (instrumentation build -DBR2_PROFILE only), else unused
     // options
     int max_iter;          // qp_solver_iter_max (50)
     double tol;            // IPM tolerance on mu and on the scaled stationarity residual

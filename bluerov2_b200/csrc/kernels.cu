@@ -574,13 +574,14 @@ __device__ double forward_sweep(Inst& I)
         if (!FEEDBACK) {
             ut = Vs[V_V + t];
         } else {
-            // (K x)[q] for q < 4: K[q][4ki+t] = Kt[4ki+t][q]
+            // (K x)[q] for q < 4: K[q][4ki+t] -- MODE 1 (after an interior-point factorisation): Kt[4ki+t][q];  MODE 2 (after an
+            // absolute-form factorisation): K in C-fragment order, kff = its column 12
             double part = 0.0;
 #pragma unroll
-            for (int ki = 0; ki < 3; ki++) part = fma(lo ? Fs[(4 * ki + t) * 4 + q] : 0.0, zr[ki], part);
+            for (int ki = 0; ki < 3; ki++) part = fma(lo ? Fs[MODE == 2 ? f_kc(q, 4 * ki + t) : (4 * ki + t) * 4 + q] : 0.0, zr[ki], part);
             part += shfl_x(part, 1);
             part += shfl_x(part, 2);
-            const double uq = -Fs[F_KFF + (q & 3)] - part;
+            const double uq = -Fs[MODE == 2 ? f_kc(q & 3, 12) : F_KFF + (q & 3)] - part;
             if (lo && t == 0) Vk[uoff + q] = uq;
             ut = shfl(uq, 4 * t);
         }
@@ -642,6 +643,10 @@ __device__ bool factor_sweep(Inst& I)
     // contraction rows held for the three k-tiles, and their offsets inside a G record (column block m adds 32)
     const int row0 = 2 * t, row1 = 2 * t + 1, row2 = hi2 ? 2 * t + 5 : 8 + 2 * t;
     const int zo0 = g_off(row0, q), zo1 = g_off(row1, q), zo2 = g_off(row2, q);
+    // cofactor (a = e, t) of the exchanged 4x4: rows {0..3} \ {e}, columns {0..3} \ {t}; pinned columns of lanes t >= 2
+    const int ro0 = 4 * (0 + (0 >= e)), ro1 = 4 * (1 + (1 >= e)), ro2 = 4 * (2 + (2 >= e));
+    const int co0 = 0 + (0 >= t), co1 = 1 + (1 >= t), co2 = 2 + (2 >= t);
+    const int pc0 = 2 * (t & 1), pc1 = pc0 + 1;
     // P+ in C layout: h[m][n][j] = P[8m+q][8n+2t+j]; vin[kt] = (q == 4 ? v1 : q == 5 ? v2 : 0)[row(kt)]
     constexpr int PARTS = KIND == FS_IPM ? (P_V | P_G) : P_G;
     I.template begin<PARTS, true>();    // records in flight while the terminal values are fetched
@@ -684,16 +689,18 @@ __device__ bool factor_sweep(Inst& I)
         const double* Vs = Ss + S_V;
         double* Fk = I.S + (size_t)k * SREC + S_F;
         double* Vk = I.V + (size_t)k * SREC;
-        // FS_AS: the stage's guessed active set (2 bits per input: 1 = at the lower, 2 = at the upper bound) and the pinned values
-        // du_e = bound_e - U_k[e] (uniform over the warp)
+        // FS_AS: the stage's guessed active set (2 bits per input: 1 = at the lower, 2 = at the upper bound; uniform over the
+        // warp) and the pinned values du_c = bound_c - U_k[c] of the inputs this lane deals with: its two columns c0, c1 of
+        // H[:, 12..15] (lanes t >= 2) and its own input e (quads 4..7)
         int code = 0;
-        double ubar[4] = {0.0, 0.0, 0.0, 0.0};
+        double ub0 = 0.0, ub1 = 0.0, ube = 0.0;
         if (PIN) {
             code = a.aset[(size_t)I.inst * N + k];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int cc = (code >> (2 * c)) & 3;
-                ubar[c] = (cc == 2 ? a.ubu[c] : a.lbu[c]) - I.Ulin[k * NU + c];
+            if (code != 0) {
+                const double* Uk = I.Ulin + k * NU;
+                ub0 = (((code >> (2 * pc0)) & 3) == 2 ? a.ubu[pc0] : a.lbu[pc0]) - Uk[pc0];
+                ub1 = (((code >> (2 * pc1)) & 3) == 2 ? a.ubu[pc1] : a.lbu[pc1]) - Uk[pc1];
+                ube = (((code >> (2 * e)) & 3) == 2 ? a.ubu[e] : a.lbu[e]) - Uk[e];
             }
         }
         double z[3][2];
@@ -749,114 +756,125 @@ __device__ bool factor_sweep(Inst& I)
             dmma(h[0][n], a02, z[2][n]);        dmma(h[1][n], a12, z[2][n]);
         }
         // ---- the vector products sit in columns 12, 13 of W': lane (q,2) holds ([A|B]'v1)[8m+q], ([A|B]'v2)[8m+q] ----
-        double at0 = shfl(w[0][1][0], qb | 2), at1 = shfl(w[1][1][0], qb | 2);
+        double* xch = I.sm.xch;
+        double yg0, yg1;                         // (K'g)[q], (K'g)[8+q]
+        double at0, at1, bt0 = 0.0, bt1 = 0.0;
         if (ABSF) {
-            // Z's+ = Z'p+ + (Z'P+) b_k: lane (q,t) holds columns 2t, 2t+1, 8+2t, 9+2t of rows q / 8+q of Z'P+
+            // ================= absolute-form LQR stage (fast paths): explicit inverse of Lam, distributed =================
+            // Round 1 solved the 4x4 system redundantly on every lane (adjugate + three 4x4 applies: 133 of the stage's 154 fp64
+            // instructions, 266 of its 756 fp64-pipe cycles -- and the factor sweep is fp64-pipe-bound: profiles/r2c_phase_profile.json).
+            // Now lane (q,t) forms ONE entry of Lam^-1 (a 3x3 cofactor of the exchanged matrix), the determinant is a quad
+            // reduction, and K = Lam^-1 [H_ux | g] is two DMMAs whose operands are single shared-memory loads:
+            //   A fragment (row a = q < 4, col t)      = Lam^-1[a][t]
+            //   B fragment (row t, col 8n+q)           = H_xu[8n+q][t] = xch[32 n + lane]   (column 12: g[t])
+            // The same xch values are the A fragment of H_xu in the Riccati update, whose column 12 (K's column 12 = kff) returns
+            // K'g for free.
+            // Z's+ = Z'p+ + (Z'P+) b_k: lane (q,t) holds columns 2t, 2t+1, 8+2t, 9+2t of rows q / 8+q of Z'P+; the p+ part is
+            // column 12 of W', a register of lane (q,2) -- the only lane that needs at0 / at1 from here on
             const double bb0 = Gs[G_B_OFF + row0], bb1 = Gs[G_B_OFF + row1];
             const double bb2 = hi2 ? 0.0 : Gs[G_B_OFF + 8 + 2 * t], bb3 = hi2 ? 0.0 : Gs[G_B_OFF + 9 + 2 * t];
             double s0 = w[0][0][0] * bb0 + w[0][0][1] * bb1 + w[0][1][0] * bb2 + w[0][1][1] * bb3;
             double s1 = w[1][0][0] * bb0 + w[1][0][1] * bb1 + w[1][1][0] * bb2 + w[1][1][1] * bb3;
             s0 += shfl_x(s0, 1); s1 += shfl_x(s1, 1);
             s0 += shfl_x(s0, 2); s1 += shfl_x(s1, 2);
-            at0 += s0; at1 += s1;
-        }
-        double bt0 = 0.0, bt1 = 0.0;
-        if (KIND == FS_IPM) { bt0 = shfl(w[0][1][1], qb | 2); bt1 = shfl(w[1][1][1], qb | 2); }
-        const double gu = gu_loc + at1;          // quads 4..7: IPM: R du + r + B'pi+;  ABS: rlin + B's+ (= g)
-        const double gval = gu + bt1;            // IPM predictor rhs: gh = gu
-        // ---- Lam = B'P+B + R~ : add the diagonal where the diagonal element lives, then broadcast ----
-        if (!lo && t == 2 + (e >> 1)) {
-            if (e & 1) h[1][1][1] += rt; else h[1][1][0] += rt;
-        }
-        // ---- H[:, 12..15] (= H_xu rows and Lam) and g go through the warp's exchange buffer: the lanes t = 2, 3 of every quad
-        //      hold columns 12..15 of rows q and 8+q; one 128-bit store each, then every lane reads what it needs (the 4x4 system
-        //      is solved redundantly per lane) -- 12 shared-memory loads instead of 22 64-bit shuffles ----
-        double* xch = I.sm.xch;
-        if (t >= 2) {
-            *reinterpret_cast<double2*>(xch + q * 4 + 2 * (t - 2)) = make_double2(h[0][1][0], h[0][1][1]);
-            *reinterpret_cast<double2*>(xch + (8 + q) * 4 + 2 * (t - 2)) = make_double2(h[1][1][0], h[1][1][1]);
-            if (!lo && t == 2) xch[64 + e] = gval;
-        }
-        __syncwarp();
-        double m10[10];
-        {
-            const double2 r1 = *reinterpret_cast<const double2*>(xch + 13 * 4);
-            const double2 r2a = *reinterpret_cast<const double2*>(xch + 14 * 4), r3a = *reinterpret_cast<const double2*>(xch + 15 * 4);
-            const double2 r3b = *reinterpret_cast<const double2*>(xch + 15 * 4 + 2);
-            m10[0] = xch[12 * 4];
-            m10[1] = r1.x; m10[2] = r1.y;
-            m10[3] = r2a.x; m10[4] = r2a.y; m10[5] = xch[14 * 4 + 2];
-            m10[6] = r3a.x; m10[7] = r3a.y; m10[8] = r3b.x; m10[9] = r3b.y;
-        }
-        // ---- rows q and 8+q of H_xu ----
-        double y0[4], y1[4], gt[4];
-        {
-            const double2 a0 = *reinterpret_cast<const double2*>(xch + q * 4), a1 = *reinterpret_cast<const double2*>(xch + q * 4 + 2);
-            const double2 b0 = *reinterpret_cast<const double2*>(xch + (8 + q) * 4), b1 = *reinterpret_cast<const double2*>(xch + (8 + q) * 4 + 2);
-            const double2 g0 = *reinterpret_cast<const double2*>(xch + 64), g1 = *reinterpret_cast<const double2*>(xch + 66);
-            y0[0] = a0.x; y0[1] = a0.y; y0[2] = a1.x; y0[3] = a1.y;
-            y1[0] = b0.x; y1[1] = b0.y; y1[2] = b1.x; y1[3] = b1.y;
-            gt[0] = g0.x; gt[1] = g0.y; gt[2] = g1.x; gt[3] = g1.y;       // g on every lane
-        }
-        if (KIND == FS_IPM && !lo && t == 2) Vk[V_GU + e] = gu;
-        if (PIN && code != 0) {
-            // pinned inputs F: b_k <- b_k + B_F ubar_F reaches the vector recursion through H[:, 12+F] (state rows: at, input rows:
-            // g), then their rows / columns leave the 4x4 system (identity row, g_F = -ubar_F so that u_F = -kff_F = ubar_F)
-            double Lm[4][4];
-            Lm[0][0] = m10[0]; Lm[1][0] = Lm[0][1] = m10[1]; Lm[1][1] = m10[2]; Lm[2][0] = Lm[0][2] = m10[3];
-            Lm[2][1] = Lm[1][2] = m10[4]; Lm[2][2] = m10[5]; Lm[3][0] = Lm[0][3] = m10[6]; Lm[3][1] = Lm[1][3] = m10[7];
-            Lm[3][2] = Lm[2][3] = m10[8]; Lm[3][3] = m10[9];
-            double gn[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                double gsum = gt[r];
-#pragma unroll
-                for (int c = 0; c < 4; c++)
-                    if ((code >> (2 * c)) & 3) gsum = fma(Lm[r][c], ubar[c], gsum);
-                gn[r] = gsum;
+            at0 = w[0][1][0] + s0; at1 = w[1][1][0] + s1;            // meaningful on lanes t == 2
+            double gval = gu_loc + at1;                               // lane (4+e, 2): g_e = rlin_e + (B's+)_e
+            // ---- exchange: lanes t >= 2 hold H[8m+q][12 + c], c = 2(t-2) + j; rows 12..15 are Lam (R~ on its diagonal) ----
+            double e0 = h[0][1][0], e1 = h[0][1][1], f0 = h[1][1][0], f1 = h[1][1][1];
+            if (!lo && t == 2 + (e >> 1)) {
+                if (e & 1) f1 += rt; else f0 += rt;
             }
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                if ((code >> (2 * c)) & 3) {
-                    at0 = fma(y0[c], ubar[c], at0);
-                    at1 = fma(y1[c], ubar[c], at1);
-                    y0[c] = 0.0; y1[c] = 0.0;
-                    gn[c] = -ubar[c];
-#pragma unroll
-                    for (int r = 0; r < 4; r++) { Lm[r][c] = 0.0; Lm[c][r] = 0.0; }
-                    Lm[c][c] = 1.0;
-                }
+            if (PIN && code != 0) {
+                // inputs F pinned at ubar_F: their columns act on the states and on the free inputs through H[:, 12+F] ubar_F
+                // (b_k <- b_k + B_F ubar_F), then row / column F leave the system (identity row, g_F = -ubar_F => u_F = ubar_F)
+                const bool p0 = (code >> (2 * pc0)) & 3, p1 = (code >> (2 * pc1)) & 3, pe = (code >> (2 * e)) & 3;
+                double pa0 = (p0 ? e0 * ub0 : 0.0) + (p1 ? e1 * ub1 : 0.0);
+                double pa1 = (p0 ? f0 * ub0 : 0.0) + (p1 ? f1 * ub1 : 0.0);
+                pa0 += shfl_x(pa0, 1); pa1 += shfl_x(pa1, 1);        // lanes 2 <-> 3 of the quad
+                at0 += pa0;
+                if (lo) at1 += pa1; else gval = pe ? -ube : gval + pa1;
+                if (p0) { e0 = 0.0; f0 = lo ? 0.0 : ((e == pc0) ? 1.0 : 0.0); }
+                if (p1) { e1 = 0.0; f1 = lo ? 0.0 : ((e == pc1) ? 1.0 : 0.0); }
+                if (!lo && pe) { f0 = (e == pc0) ? 1.0 : 0.0; f1 = (e == pc1) ? 1.0 : 0.0; }
             }
-#pragma unroll
-            for (int r = 0; r < 4; r++) gt[r] = gn[r];
-            m10[0] = Lm[0][0]; m10[1] = Lm[1][0]; m10[2] = Lm[1][1]; m10[3] = Lm[2][0]; m10[4] = Lm[2][1]; m10[5] = Lm[2][2];
-            m10[6] = Lm[3][0]; m10[7] = Lm[3][1]; m10[8] = Lm[3][2]; m10[9] = Lm[3][3];
-        }
-        double yg0, yg1;                         // (K'g)[q], (K'g)[8+q]
-        if (ABSF) {
-            // Lam = R + B'P+B is well conditioned here: explicit inverse, no dependent rsqrt / substitution chains.
-            //   K = Lam^-1 H_ux,  kff = Lam^-1 g,  P = Q + H_xx - H_xu K
-            Inv4 Bi;
-            ok &= inv4(m10, Bi);
-            double kc[4], kd[4], kf[4];
-            inv4_apply(Bi, y0, kc);              // K[:, q]
-            inv4_apply(Bi, y1, kd);              // K[:, 8+q]   (garbage in quads 4..7, masked below)
-            inv4_apply(Bi, gt, kf);
-            yg0 = y0[0] * kf[0] + y0[1] * kf[1] + y0[2] * kf[2] + y0[3] * kf[3];
-            yg1 = y1[0] * kf[0] + y1[1] * kf[1] + y1[2] * kf[2] + y1[3] * kf[3];
-            const double ys0 = (t == 0) ? y0[0] : (t == 1) ? y0[1] : (t == 2) ? y0[2] : y0[3];
-            double ys1 = (t == 0) ? y1[0] : (t == 1) ? y1[1] : (t == 2) ? y1[2] : y1[3];
-            const double ks0 = (t == 0) ? kc[0] : (t == 1) ? kc[1] : (t == 2) ? kc[2] : kc[3];
-            double ks1 = (t == 0) ? kd[0] : (t == 1) ? kd[1] : (t == 2) ? kd[2] : kd[3];
-            // F record, branch-free: K[t][q] is element 4q + t = lane of Kt (one coalesced 256-byte store), K[t][8+q] element
-            // 32 + lane for the quads that own a second state row, kff[t] from lanes 0..3
-            Fk[lane] = ks0;
-            if (lo) Fk[32 + lane] = ks1;
-            if (lane < 4) Fk[F_KFF + lane] = (t == 0) ? kf[0] : (t == 1) ? kf[1] : (t == 2) ? kf[2] : kf[3];
-            if (!lo) { ys1 = 0.0; ks1 = 0.0; }
-            dmma(h[0][0], -ys0, ks0); dmma(h[0][1], -ys0, ks1);
-            dmma(h[1][0], -ys1, ks0); dmma(h[1][1], -ys1, ks1);
+            if (t >= 2) {
+                *reinterpret_cast<double2*>(xch + q * 4 + 2 * (t - 2)) = make_double2(e0, e1);
+                *reinterpret_cast<double2*>(xch + (8 + q) * 4 + 2 * (t - 2)) = make_double2(f0, f1);
+                if (!lo && t == 2) xch[64 + e] = gval;
+            }
+            __syncwarp();
+            // ---- my entry of Lam^-1: cofactor (a, t) of the 4x4 at xch[48..63], a = q & 3 ----
+            const double* LM = xch + 48;
+            double cof;
+            {
+                const double m00 = LM[ro0 + co0], m01 = LM[ro0 + co1], m02 = LM[ro0 + co2];
+                const double m10_ = LM[ro1 + co0], m11 = LM[ro1 + co1], m12 = LM[ro1 + co2];
+                const double m20 = LM[ro2 + co0], m21 = LM[ro2 + co1], m22 = LM[ro2 + co2];
+                const double d0 = m11 * m22 - m12 * m21, d1 = m10_ * m22 - m12 * m20, d2 = m10_ * m21 - m11 * m20;
+                cof = m00 * d0 - m01 * d1 + m02 * d2;
+                if ((e + t) & 1) cof = -cof;
+            }
+            double det = LM[4 * e + t] * cof;                         // expansion along row a
+            det += shfl_x(det, 1);
+            det += shfl_x(det, 2);
+            ok &= (det > 0.0) && ((e != t) || (cof > 0.0));           // positive definite: det and the principal 3x3 minors
+            const double linv = lo ? cof * (1.0 / det) : 0.0;
+            const double hx0 = xch[lane];
+            const double hx1 = lo ? xch[32 + lane] : (q == 4 ? xch[64 + t] : 0.0);
+            // (xch is rewritten by the next stage only after the warp barrier at the top of its iteration)
+            // ---- K = Lam^-1 [H_ux | g]: C layout, lane (a,t) holds K[a][8n+2t+j]; K[a][12] = kff[a] ----
+            double kc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            dmma(kc[0], linv, hx0);
+            dmma(kc[1], linv, hx1);
+            // F record = K in C-fragment order (layout.h): four coalesced 128-byte rows from lanes 0..15
+            if (lane < 16) {
+                Fk[lane] = kc[0][0]; Fk[16 + lane] = kc[0][1]; Fk[32 + lane] = kc[1][0]; Fk[48 + lane] = kc[1][1];
+            }
+            // ---- B fragment of K for the update: K[t][8n+q] sits in register q&1 of lane (t, q>>1) ----
+            const int sl = 4 * t + (q >> 1);
+            const double k00 = shfl(kc[0][0], sl), k01 = shfl(kc[0][1], sl), k10 = shfl(kc[1][0], sl), k11 = shfl(kc[1][1], sl);
+            const double kb0 = (q & 1) ? k01 : k00, kb1 = (q & 1) ? k11 : k10;
+            // ---- P = Q + H_xx - H_xu K; column 12 of the right tiles (lane t == 2, register 0) collects -(H_xu kff) = -K'g ----
+            if (t == 2) { h[0][1][0] = 0.0; h[1][1][0] = 0.0; }
+            dmma(h[0][0], -hx0, kb0); dmma(h[0][1], -hx0, kb1);
+            dmma(h[1][0], -hx1, kb0); dmma(h[1][1], -hx1, kb1);
+            yg0 = -h[0][1][0]; yg1 = -h[1][1][0];                     // meaningful on lanes t == 2
         } else {
+            at0 = shfl(w[0][1][0], qb | 2); at1 = shfl(w[1][1][0], qb | 2);
+            bt0 = shfl(w[0][1][1], qb | 2); bt1 = shfl(w[1][1][1], qb | 2);
+            const double gu = gu_loc + at1;          // quads 4..7: R du + r + B'pi+
+            const double gval = gu + bt1;            // predictor rhs: gh = gu
+            // ---- Lam = B'P+B + R~ : add the diagonal where the diagonal element lives, then broadcast ----
+            if (!lo && t == 2 + (e >> 1)) {
+                if (e & 1) h[1][1][1] += rt; else h[1][1][0] += rt;
+            }
+            if (t >= 2) {
+                *reinterpret_cast<double2*>(xch + q * 4 + 2 * (t - 2)) = make_double2(h[0][1][0], h[0][1][1]);
+                *reinterpret_cast<double2*>(xch + (8 + q) * 4 + 2 * (t - 2)) = make_double2(h[1][1][0], h[1][1][1]);
+                if (!lo && t == 2) xch[64 + e] = gval;
+            }
+            __syncwarp();
+            double m10[10];
+            {
+                const double2 r1 = *reinterpret_cast<const double2*>(xch + 13 * 4);
+                const double2 r2a = *reinterpret_cast<const double2*>(xch + 14 * 4), r3a = *reinterpret_cast<const double2*>(xch + 15 * 4);
+                const double2 r3b = *reinterpret_cast<const double2*>(xch + 15 * 4 + 2);
+                m10[0] = xch[12 * 4];
+                m10[1] = r1.x; m10[2] = r1.y;
+                m10[3] = r2a.x; m10[4] = r2a.y; m10[5] = xch[14 * 4 + 2];
+                m10[6] = r3a.x; m10[7] = r3a.y; m10[8] = r3b.x; m10[9] = r3b.y;
+            }
+            // ---- rows q and 8+q of H_xu ----
+            double y0[4], y1[4], gt[4];
+            {
+                const double2 a0 = *reinterpret_cast<const double2*>(xch + q * 4), a1 = *reinterpret_cast<const double2*>(xch + q * 4 + 2);
+                const double2 b0 = *reinterpret_cast<const double2*>(xch + (8 + q) * 4), b1 = *reinterpret_cast<const double2*>(xch + (8 + q) * 4 + 2);
+                const double2 g0 = *reinterpret_cast<const double2*>(xch + 64), g1 = *reinterpret_cast<const double2*>(xch + 66);
+                y0[0] = a0.x; y0[1] = a0.y; y0[2] = a1.x; y0[3] = a1.y;
+                y1[0] = b0.x; y1[1] = b0.y; y1[2] = b1.x; y1[3] = b1.y;
+                gt[0] = g0.x; gt[1] = g0.y; gt[2] = g1.x; gt[3] = g1.y;       // g on every lane
+            }
+            if (KIND == FS_IPM && !lo && t == 2) Vk[V_GU + e] = gu;
             Chol4 L;
             ok &= chol4(m10, L);
             chol4_fwd(L, y0);                    // Y[:, q]
@@ -916,7 +934,8 @@ __device__ bool factor_sweep(Inst& I)
         } else {
             pq0 = qx0 + at0 - yg0;               // p = qlin + A's+ - K'g
             pq1 = qx1 + at1 - yg1;
-            const double i0 = shfl(pq0, 8 * t), i1 = shfl(pq0, 8 * t + 4), i2 = shfl(pq1, hi2 ? 4 * (2 * t - 3) : 8 * t);
+            // (p lives on lane t == 2 of each quad)
+            const double i0 = shfl(pq0, 8 * t + 2), i1 = shfl(pq0, 8 * t + 6), i2 = shfl(pq1, (hi2 ? 4 * (2 * t - 3) : 8 * t) + 2);
             vin[0] = (q == 4) ? i0 : 0.0; vin[1] = (q == 4) ? i1 : 0.0; vin[2] = (q == 4) ? i2 : 0.0;
         }
     }
@@ -1098,6 +1117,22 @@ __device__ __forceinline__ double step_to_boundary(double v, double dv)
     return dv < 0.0 ? -v / dv : 2.0;   // 2 = "not blocking" (callers clamp at 1)
 }
 
+// Instrumentation build (-DBR2_PROFILE, scripts/phase_profile.py): cycles per phase of the kernel, summed over warps, in a.prof[]
+#ifdef BR2_PROFILE
+#define PROF_START() long long prof_t0 = clock64()
+#define PROF(idx)                                                                              \
+    do {                                                                                       \
+        const long long prof_t1 = clock64();                                                   \
+        if (lane == 0 && a.prof) atomicAdd(a.prof + (idx), (unsigned long long)(prof_t1 - prof_t0)); \
+        prof_t0 = prof_t1;                                                                     \
+    } while (0)
+#else
+#define PROF_START()
+#define PROF(idx)
+#endif
+enum { PF_FACTOR_ABS = 0, PF_FACTOR_AS, PF_FWD_CL, PF_PRIMAL, PF_COSTATE, PF_IPM_INIT, PF_FACTOR_IPM, PF_FWD_AFF, PF_E1, PF_BVEC,
+       PF_FWD_COR, PF_E2, PF_EPILOGUE, PF_COUNT };
+
 // Maximum number of pinned-LQR solves of the primal-dual active-set iteration before the interior-point iteration takes over
 #ifndef BR2_MAX_AS
 #define BR2_MAX_AS 6
@@ -1132,6 +1167,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         inst = __shfl_sync(FULL_MASK, inst, 0);
         if (inst >= a.B) break;
         Inst I(a, sm, inst, lane);
+        PROF_START();
 
         int status = 2, it = 0;
         double mu = 0.0, res_stat = 0.0, stat_scale = 1.0, bmax = 0.0;
@@ -1151,6 +1187,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             const int max_att = a.active_set ? BR2_MAX_AS : 1;
             for (int att = 0; att < max_att; att++) {
                 const bool okf = (att == 0 && !guess) ? factor_sweep<FS_ABS>(I) : factor_sweep<FS_AS>(I);
+                PROF((att == 0 && !guess) ? PF_FACTOR_ABS : PF_FACTOR_AS);
                 if (!okf) break;
                 if (att == 0) {
                     prefetch_iterate(I);
@@ -1161,13 +1198,17 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
                     have = true;
                 }
                 bmax = forward_sweep<2>(I);     // leaves (dx, du) in V_X, V_V
+                PROF(PF_FWD_CL);
                 it = att + 1;
                 const int fl = primal_check(I, att == 0 && !guess);
+                PROF(PF_PRIMAL);
                 if (fl & PC_NAN) break;
                 active = (fl & PC_ACTIVE) != 0;
                 if (!(fl & PC_CHANGED)) {
                     if (!(fl & PC_PINNED)) { solved = true; break; }
-                    if (costate_check(I)) { solved = true; break; }
+                    const bool okc = costate_check(I);
+                    PROF(PF_COSTATE);
+                    if (okc) { solved = true; break; }
                 }
             }
             if (solved) status = 0;
@@ -1175,10 +1216,13 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
         if (!solved) {
             ipm_init(I);
             bmax = forward_sweep<0>(I);
+            PROF(PF_IPM_INIT);
         }
         for (it = solved ? it : 0; !solved && it < a.max_iter; it++) {
             // ---------- B1: factorisation + predictor rhs ----------
-            if (!factor_sweep<FS_IPM>(I)) { status = 4; break; }
+            const bool okf = factor_sweep<FS_IPM>(I);
+            PROF(PF_FACTOR_IPM);
+            if (!okf) { status = 4; break; }
             if (it == 0) {
                 // mu and stationarity residual of the starting point (later iterations get them from E2)
                 double s = 0.0, rs = 0.0;
@@ -1196,6 +1240,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             }
             // ---------- F1: affine step ----------
             forward_sweep<1>(I);
+            PROF(PF_FWD_AFF);
             // ---------- E1: affine step length, sigma, corrector rhs ----------
             double a_aff = 1.0;
             for (int idx = lane; idx < nb; idx += 32) {
@@ -1227,10 +1272,13 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
                 Vk[V_CU + e] = sigma * mu + dv * dlu;
             }
             __syncwarp();
+            PROF(PF_E1);
             // ---------- B2 / F2: corrector ----------
             prefetch_iterate(I);            // this may be the last iteration: have X, U in L2 for the epilogue
             backward_vec_sweep(I);
+            PROF(PF_BVEC);
             forward_sweep<1>(I);
+            PROF(PF_FWD_COR);
             // ---------- E2: step lengths and update ----------
             double ap = 2.0, ad = 2.0;
             for (int idx = lane; idx < nb; idx += 32) {
@@ -1274,8 +1322,10 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
                 Vk[V_X + e] += ap * Vk[V_DX + e];
             }
             __syncwarp();
+            PROF(PF_E2);
             if (mu < a.tol && res_stat < a.tol * stat_scale) { status = 0; it++; break; }
         }
+        PROF(PF_E2);
 
         // ---------- epilogue: full SQP step, u0, thrust allocation (both paths leave (dx, du) in V_X, V_V) ----------
         double* Xo = a.X + (size_t)inst * (N + 1) * NX;
@@ -1366,6 +1416,7 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             a.status[inst] = status;
             a.iters[inst] = it;
             atomicAdd(a.iter_total, (unsigned long long)it);
+            PROF(PF_EPILOGUE);
             a.info[(size_t)inst * 4 + 0] = mu;
             a.info[(size_t)inst * 4 + 1] = res_stat;
             a.info[(size_t)inst * 4 + 2] = bmax;

@@ -69,6 +69,7 @@ def load_library(path: str | None = None):
         "br2_batch_last_solve_time": (C.c_double, [V]),
         "br2_batch_last_kernel_times": (C.c_int, [V, _D, _D]),
         "br2_batch_ipm_iterations_total": (C.c_longlong, [V, C.c_int]),
+        "br2_batch_phase_cycles": (C.c_int, [V, V, C.c_int]),
         "br2_plant_step_device": (C.c_int, [C.c_int, V, V, V, V, V, V, C.c_int, C.c_double, V, V, V]),
         "br2_batch_ekf_reset": (C.c_int, [V]),
         "br2_batch_ekf_device": (C.c_int, [V, V, V, V, V, V, C.c_int, V]),
@@ -307,6 +308,15 @@ class BatchSolver:
 
     def ipm_iterations_total(self, reset: bool = False) -> int:
         return int(self._L.br2_batch_ipm_iterations_total(self._h, int(reset)))
+
+    PHASES = ("factor_abs", "factor_as", "fwd_closed_loop", "primal_check", "costate_check", "ipm_start", "factor_ipm", "fwd_affine",
+              "e1_centring", "bwd_corrector", "fwd_corrector", "e2_update", "epilogue")
+
+    def phase_cycles(self, reset: bool = False) -> dict:
+        """SM cycles per phase of the IPM kernel summed over warps (library built with -DBR2_PROFILE; zeros otherwise)"""
+        out = np.zeros(16, dtype=np.uint64)
+        self._check(self._L.br2_batch_phase_cycles(self._h, out.ctypes.data_as(C.c_void_p), int(reset)))
+        return {n: int(out[i]) for i, n in enumerate(self.PHASES)}
 
     # -- EKF (BLUEROV2_DOB::EKF) -----------------------------------------------------------------------
     def ekf_reset(self):

@@ -133,6 +133,12 @@ BR2_API int br2_batch_last_kernel_times(br2_batch_solver *s, double *t_linearize
  * the roofline formula bytes_sweep = 4384 * N * n_it) */
 BR2_API long long br2_batch_ipm_iterations_total(br2_batch_solver *s, int reset);
 
+/* Instrumentation (library built with -DBR2_PROFILE only; all zeros otherwise): SM cycles per phase of the IPM kernel, summed
+ * over warps since the last reset -- [0] factor sweep (interior fast path), [1] factor sweep (pinned), [2] closed-loop roll-out,
+ * [3] primal check, [4] costate check, [5] IPM start + roll-out, [6] IPM factor sweep, [7] affine forward sweep, [8] affine step
+ * length / centring, [9] corrector backward sweep, [10] corrector forward sweep, [11] step lengths / update, [12] epilogue. */
+BR2_API int br2_batch_phase_cycles(br2_batch_solver *s, unsigned long long *out16, int reset);
+
 /* Nominal plant for device-resident closed-loop studies: one RK4 step of length h of the OCP model
  * (bluerov2_dobmpc/scripts/bluerov2.py:103-137) per instance, x[B][12] in place, inputs u[B][4], parameters p[B][16].
  * Optional (NULL to skip): d_dist[B][4] extra disturbance on p[0..3]; d_wave_amp[B][4] + d_wave_tau0[B] the wave wrench of
