@@ -35,7 +35,7 @@ struct br2_batch_solver {
     double tol;
     // device state
     double *d_Ts, *d_X, *d_U, *d_S, *d_u0, *d_thrust, *d_info;
-    int *d_status, *d_iters, *d_counter, *d_hint, *d_aset, *d_order;
+    int *d_status, *d_iters, *d_counter, *d_hint, *d_aset, *d_order, *d_fb;
     double *d_x0, *d_yref, *d_p;              // staging for the host API
     double* d_traj;                           // reference trajectory for device-side windowing [traj_rows][16]
     int* d_lines;                             // staging: first trajectory row per instance
@@ -99,7 +99,7 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
     DeviceGuard guard_(s->device);
     void* ptrs[] = {s->d_Ts, s->d_X, s->d_U, s->d_S, s->d_u0, s->d_thrust, s->d_info, s->d_status,
                     s->d_iters, s->d_counter, s->d_x0, s->d_yref, s->d_p, s->d_ex, s->d_eP, s->d_thr, s->d_meas,
-                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls, s->d_yaw, s->d_aset, s->d_order};
+                    s->d_acc, s->d_wf, s->d_pout, s->d_iter_total, s->d_hint, s->d_traj, s->d_lines, s->d_rls, s->d_yaw, s->d_aset, s->d_order, s->d_fb};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -164,7 +164,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     } while (0)
     DA(d_Ts, N); DA(d_X, B * (N + 1) * NX); DA(d_U, B * N * NU);
     DA(d_S, B * (N + 1) * SREC);
-    DA(d_u0, B * 4); DA(d_thrust, B * 6); DA(d_info, B * 4); DA(d_status, B); DA(d_iters, B); DA(d_counter, 4); DA(d_order, 2 * B);
+    DA(d_u0, B * 4); DA(d_thrust, B * 6); DA(d_info, B * 4); DA(d_status, B); DA(d_iters, B); DA(d_counter, CTR_COUNT); DA(d_order, 2 * B); DA(d_fb, B);
     DA(d_x0, B * NX); DA(d_yref, B * (N + 1) * NY); DA(d_p, B * (N + 1) * NP);
     DA(d_ex, B * 18); DA(d_eP, B * 324); DA(d_thr, B * 6); DA(d_meas, B * 12); DA(d_acc, B * 6); DA(d_wf, B * 6);
     DA(d_pout, B * NP);
@@ -187,7 +187,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     CKF(cudaMemset(s->d_iters, 0, sizeof(int) * B));
     CKF(cudaMemset(s->d_hint, 0, sizeof(int) * B));
     CKF(cudaMemset(s->d_aset, 0, sizeof(int) * B * N));
-    CKF(cudaMemset(s->d_counter, 0, sizeof(int) * 4));
+    CKF(cudaMemset(s->d_counter, 0, sizeof(int) * CTR_COUNT));
     {   // visiting order of the IPM kernel: identity in both halves until a solve has ranked the instances
         int* h = (int*)malloc(sizeof(int) * 2 * B);
         if (!h) { br2_batch_free(s); return fail(BR2_ENOMEM, "br2_batch_create: out of host memory"); }
@@ -349,7 +349,7 @@ static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, con
     a.u0 = d_u0 ? d_u0 : s->d_u0;
     a.thrust = d_thrust ? d_thrust : s->d_thrust;
     a.status = d_status ? d_status : s->d_status;
-    a.iters = s->d_iters; a.info = s->d_info; a.ctr = s->d_counter; a.order = s->d_order; a.iter_total = s->d_iter_total; a.prof = s->d_iter_total + 1; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
+    a.iters = s->d_iters; a.info = s->d_info; a.ctr = s->d_counter; a.order = s->d_order; a.fb = s->d_fb; a.iter_total = s->d_iter_total; a.prof = s->d_iter_total + 1; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
     a.max_iter = s->max_iter; a.tol = s->tol;
 }
 

@@ -33,8 +33,9 @@ struct SolveArgs {
     int* status;           // [B]
     int* iters;            // [B]
     double* info;          // [B][4]: mu, res_stat, max|b| (dynamics gap at the linearisation point), max step
-    int* ctr;              // [4] CTR_QUEUE: persistent-kernel work queue; CTR_HARD / CTR_EASY: fill counts of the next solve's
+    int* ctr;              // [CTR_COUNT] CTR_QUEUE: persistent-kernel work queue; CTR_HARD / CTR_EASY: fill counts of the next solve's
                            //     visiting order; CTR_PARITY: which half of `order` is current (reset / flipped by the lineariser)
+    int* fb;               // [B] fallback list: instances the fast paths handed to the interior-point kernel (count in ctr[CTR_FB])
     int* order;            // [2][B] visiting order of the instances (a permutation), double-buffered: hint = 1 instances first
     int* hint;             // [B] 1 = a bound was active at the previous solution (skip the interior fast path)
     int fast_path;         // try the interior-solution fast path (option "fast_path", default 1)
@@ -59,7 +60,7 @@ __device__ __forceinline__ const double* yref_row(const SolveArgs& a, int inst, 
 void launch_linearize(const SolveArgs& a, cudaStream_t s);
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s);
 void configure_kernels();      // per-device function attributes (call with the solver's device current)
-enum { CTR_QUEUE = 0, CTR_HARD = 1, CTR_EASY = 2, CTR_PARITY = 3 };
+enum { CTR_QUEUE = 0, CTR_HARD = 1, CTR_EASY = 2, CTR_PARITY = 3, CTR_FB = 4, CTR_FBQ = 5, CTR_COUNT = 8 };
 
 // EKF (bluerov2_dob.cpp:495-545), one warp per instance
 struct EkfArgs {

@@ -21,13 +21,16 @@
 
 // occupancy knobs (defaults = the measured best; scripts/gpu_tune.sh rebuilds with others)
 #ifndef BR2_NSLOT
-#define BR2_NSLOT 4
+#define BR2_NSLOT 3
 #endif
 #ifndef BR2_IPM_WARPS
 #define BR2_IPM_WARPS 4
 #endif
 #ifndef BR2_IPM_MINB
 #define BR2_IPM_MINB (16 / BR2_IPM_WARPS)
+#endif
+#ifndef BR2_PDAS_MINB
+#define BR2_PDAS_MINB (16 / BR2_IPM_WARPS)
 #endif
 #ifndef BR2_LIN_MINB
 #define BR2_LIN_MINB 12
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
     const int base = blockIdx.x * LRND;
     if (blockIdx.x == 0 && lane == 0) {
         // housekeeping for the IPM kernel that follows in the stream: reset its work-queue counters, flip the order buffers
-        a.ctr[CTR_QUEUE] = 0; a.ctr[CTR_HARD] = 0; a.ctr[CTR_EASY] = 0; a.ctr[CTR_PARITY] ^= 1;
+        a.ctr[CTR_QUEUE] = 0; a.ctr[CTR_HARD] = 0; a.ctr[CTR_EASY] = 0; a.ctr[CTR_PARITY] ^= 1; a.ctr[CTR_FB] = 0; a.ctr[CTR_FBQ] = 0;
     }
     if (lane < LRND) {
         const int gs = base + lane;
@@ -308,6 +311,14 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// reciprocal good to ~1e-7 relative: the hardware seed (MUFU.RCP64H, ~20 bits) and one Newton step
+__device__ __forceinline__ double rcp_approx(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y * fma(-x, y, 2.0);
 }
 
 __device__ __forceinline__ double warp_min(double v)
@@ -530,27 +541,49 @@ __device__ void ipm_init(Inst& I)
     __syncwarp();
 }
 
+// What the interior-point iteration accumulates while its sweeps run (round 1 made six extra passes over the V records per
+// iteration for these -- "E1" / "E2", 23 % of the forced interior-point time, profiles/r2c_phase_profile.json).  Per bound
+// (slack s, multiplier lam, slack step ds = +dv for the lower, -dv for the upper bound) the step lengths are kept as INVERSE
+// step lengths (max instead of min, one division per instance instead of one per bound):
+//   affine step     dlam = -lam (1 + ds/s):   1/alpha >= -ds/s, 1 + ds/s;   sum (lam + a dlam)(s + a ds) = (1 - a) sum lam s + a^2 S2
+//   corrector step  dlam = (c - lam ds)/s - lam:  1/alpha_p >= -ds/s,  1/alpha_d >= -dlam/lam;
+//                   sum (lam + ad dlam)(s + ap ds) = sum lam s + ap A1 + ad A2 + ap ad A3
+//   stationarity residual after the step: r+ = (1 - ad) r + (ap - ad) dgu,  dgu = -gh - (ll/tl + lu/tu) dv  (Newton equation)
+struct IpmAcc {
+    double ia = 0.0, s2 = 0.0;                                  // affine sweep: inverse step length, S2
+    double ia_p = 0.0, ia_d = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, dgmax = 0.0;   // corrector sweep
+};
+// The update of the iterate is applied lazily: by the next factor sweep (which reads every V record anyway) or, after the last
+// iteration, by the epilogue.  dlam of the step sits in V_CL / V_CU (the corrector forward sweep overwrites its rhs with it).
+struct IpmUpd {
+    bool pending = false;
+    double ap = 0.0, ad = 0.0;
+    double mu_sum = 0.0, res_max = 0.0;                         // out: complementarity sum and stationarity residual of the iterate
+};
+
 // Forward sweep.
 //   MODE 0: roll-out of the iterate            x+ = A x + B v + b,            x_0 = x0 - X_0   (reads V_V, writes V_X)
-//   MODE 1: Newton step                        ddu = -kff - K ddx, ddx+ = A ddx + B ddu, ddx_0 = 0 (writes V_DX, V_DV)
+//   MODE 1: affine Newton step                 ddu = -kff - K ddx, ddx+ = A ddx + B ddu, ddx_0 = 0 (writes V_DV; accumulates acc.ia, s2)
 //   MODE 2: closed-loop roll-out (fast path)   u = -kff - K x,     x+ = A x + B u + b,   x_0 = x0 - X_0 (writes V_X, V_V)
+//   MODE 3: corrector Newton step              like MODE 1; writes V_DX, V_DV and dlam -> V_CL / V_CU; accumulates the rest of acc
 // Z = [A|B] is read row-per-quad: lane (q,t) holds Z[q][4ki+t] and Z[8+q][4ki+t]; every product is 4 (3) local
 // FMAs and a reduction over the 4 lanes of a quad.  Returns max |b| in MODE 0 / 2.
 template <int MODE>
-__device__ double forward_sweep(Inst& I)
+__device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr)
 {
     const int q = I.q, t = I.t, N = I.N;
     const bool lo = q < 4;                      // quad owns a second state row 8 + q (else: no row 12..15)
-    constexpr bool FEEDBACK = MODE != 0, AFFINE = MODE != 1;
-    constexpr int PARTS = FEEDBACK ? (P_G | P_F) : (P_V | P_G);
+    constexpr bool FEEDBACK = MODE != 0, AFFINE = (MODE == 0 || MODE == 2), NEWTON = (MODE == 1 || MODE == 3);
+    constexpr int PARTS = NEWTON ? (P_V | P_G | P_F) : FEEDBACK ? (P_G | P_F) : (P_V | P_G);
+    double ia = 0.0, ia_d = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, dgmax = 0.0;     // IpmAcc partials of this lane
     I.template begin<PARTS, false>();     // records in flight while the start values below are fetched
     double zr[3];                               // propagated vector, row layout: x[4ki + t]
     double bmax = 0.0;
 #pragma unroll
     for (int ki = 0; ki < 3; ki++)
         zr[ki] = AFFINE ? I.a.x0[(size_t)I.inst * NX + 4 * ki + t] - I.Xlin[4 * ki + t] : 0.0;
-    constexpr int xoff = (MODE == 1) ? V_DX : V_X;
-    constexpr int uoff = (MODE == 1) ? V_DV : V_V;
+    constexpr int xoff = NEWTON ? V_DX : V_X;
+    constexpr int uoff = NEWTON ? V_DV : V_V;
     int o0[4], o1[4];                           // shared-memory offsets of my rows of Z (constant over the sweep)
 #pragma unroll
     for (int ki = 0; ki < 4; ki++) { o0[ki] = g_off(q, 4 * ki + t); o1[ki] = g_off(8 + (q & 3), 4 * ki + t); }
@@ -566,7 +599,7 @@ __device__ double forward_sweep(Inst& I)
             z0[ki] = Gs[o0[ki]];
             z1[ki] = lo ? Gs[o1[ki]] : 0.0;
         }
-        if (q == 0) {
+        if (q == 0 && MODE != 1) {              // (the state part of the affine step is never read)
 #pragma unroll
             for (int ki = 0; ki < 3; ki++) Vk[xoff + 4 * ki + t] = zr[ki];
         }
@@ -578,12 +611,40 @@ __device__ double forward_sweep(Inst& I)
             // absolute-form factorisation): K in C-fragment order, kff = its column 12
             double part = 0.0;
 #pragma unroll
-            for (int ki = 0; ki < 3; ki++) part = fma(lo ? Fs[MODE == 2 ? f_kc(q, 4 * ki + t) : (4 * ki + t) * 4 + q] : 0.0, zr[ki], part);
+            for (int ki = 0; ki < 3; ki++) part = fma(lo ? Fs[MODE == 2 ? f_kc(q & 3, 4 * ki + t) : (4 * ki + t) * 4 + q] : 0.0, zr[ki], part);
             part += shfl_x(part, 1);
             part += shfl_x(part, 2);
             const double uq = -Fs[MODE == 2 ? f_kc(q & 3, 12) : F_KFF + (q & 3)] - part;
             if (lo && t == 0) Vk[uoff + q] = uq;
             ut = shfl(uq, 4 * t);
+            if (NEWTON) {
+                // Side computation on the lanes that own input q (off the recursion's critical path).  Lane t handles ONE bound of
+                // input q: even t the lower (s = tl, lam = ll, ds = +du), odd t the upper (s = tu, lam = lu, ds = -du) -- the two are
+                // mirror images, and TL/TU, LL/LU, CL/CU are adjacent fields.  Step-length tests use an approximate reciprocal
+                // (rel. error < 1e-6, made conservative by the factor 1 + 2e-6 applied to the inverse step length afterwards).
+                const int fo = (q & 3) + 4 * (t & 1);
+                const double s_b = Vs[V_TL + fo], l_b = Vs[V_LL + fo];
+                const double ds = (t & 1) ? -uq : uq;
+                if (MODE == 1) {
+                    const double r = ds * rcp_approx(s_b);
+                    if (lo) ia = fmax(ia, fmax(-r, 1.0 + r));
+                    if (lo && t < 2) c1 = fma(-l_b * (1.0 + r), ds, c1);                 // S2 += dlam ds
+                } else {
+                    const double is = 1.0 / s_b, c_b = Vs[V_CL + fo];
+                    const double dl = fma(fma(-l_b, ds, c_b), is, -l_b);                 // dlam = (c - lam ds) / s - lam
+                    double piece = (t & 1) ? -(dl + l_b) : (dl + l_b);                     // dgu = -gu + (dll + ll) - (dlu + lu)
+                    piece += shfl_x(piece, 1);
+                    if (lo) {
+                        ia = fmax(ia, -ds * is);
+                        ia_d = fmax(ia_d, -dl * rcp_approx(l_b));
+                        dgmax = fmax(dgmax, fabs(piece - Vs[V_GU + (q & 3)]));
+                    }
+                    if (lo && t < 2) {
+                        c1 = fma(l_b, ds, c1); c2 = fma(dl, s_b, c2); c3 = fma(dl, ds, c3);
+                        Vk[V_CL + fo] = dl;
+                    }
+                }
+            }
         }
         double p0 = z0[3] * ut, p1 = z1[3] * ut;
 #pragma unroll
@@ -600,11 +661,17 @@ __device__ double forward_sweep(Inst& I)
         zr[1] = shfl(p0, 4 * (4 + t));
         zr[2] = shfl(p1, 4 * t);
     }
-    if (q == 0) {
+    if (q == 0 && MODE != 1) {
 #pragma unroll
         for (int ki = 0; ki < 3; ki++) I.V[(size_t)N * SREC + xoff + 4 * ki + t] = zr[ki];
     }
     __syncwarp();
+    constexpr double SAFE = 1.0 + 2e-6;         // covers the error of rcp_approx
+    if (MODE == 1) { acc->ia = SAFE * warp_max(ia); acc->s2 = warp_sum(c1); }
+    if (MODE == 3) {
+        acc->ia_p = warp_max(ia); acc->ia_d = SAFE * warp_max(ia_d); acc->dgmax = warp_max(dgmax);
+        acc->a1 = warp_sum(c1); acc->a2 = warp_sum(c2); acc->a3 = warp_sum(c3);
+    }
     return AFFINE ? warp_max(bmax) : 0.0;
 }
 
@@ -628,7 +695,7 @@ __device__ double forward_sweep(Inst& I)
 enum { FS_IPM = 0, FS_ABS = 1, FS_AS = 2 };    // FS_AS: FS_ABS with the inputs of the guessed active set pinned at their bounds
 
 template <int KIND>
-__device__ bool factor_sweep(Inst& I)
+__device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
 {
     const int q = I.q, t = I.t, N = I.N, lane = I.lane;
     const SolveArgs& a = I.a;
@@ -640,6 +707,7 @@ __device__ bool factor_sweep(Inst& I)
     const bool hi2 = t >= 2;
     const int src2 = hi2 ? lane - 2 : lane;     // where my kt2 element lives
     bool ok = true;
+    double mu_sum = 0.0, res_max = 0.0;         // FS_IPM: accumulated on lanes (4 + e, 2)
     // contraction rows held for the three k-tiles, and their offsets inside a G record (column block m adds 32)
     const int row0 = 2 * t, row1 = 2 * t + 1, row2 = hi2 ? 2 * t + 5 : 8 + 2 * t;
     const int zo0 = g_off(row0, q), zo1 = g_off(row1, q), zo2 = g_off(row2, q);
@@ -666,11 +734,18 @@ __device__ bool factor_sweep(Inst& I)
                     h[m][n][j] = (r == c && r < 12) ? a.We[r < 12 ? r : 0] : 0.0;
                 }
         if (KIND == FS_IPM) {
-            // pi_N = We (x_N + X_N - xref_N) for lanes q == 4; p_N = 0
+            // pi_N = We (x_N + X_N - xref_N) for lanes q == 4; p_N = 0.  A pending update reaches x_N here: the three rows of the
+            // four lanes of quad 4 are the twelve states, each exactly once
             if (q == 4) {
-                vin[0] = a.We[row0] * (VN[V_X + row0] + I.Xlin[N * NX + row0] - yN[row0]);
-                vin[1] = a.We[row1] * (VN[V_X + row1] + I.Xlin[N * NX + row1] - yN[row1]);
-                vin[2] = a.We[row2] * (VN[V_X + row2] + I.Xlin[N * NX + row2] - yN[row2]);
+                double xn0 = VN[V_X + row0], xn1 = VN[V_X + row1], xn2 = VN[V_X + row2];
+                if (upd->pending) {
+                    double* VNw = I.V + (size_t)N * SREC;
+                    xn0 = fma(upd->ap, VN[V_DX + row0], xn0); xn1 = fma(upd->ap, VN[V_DX + row1], xn1); xn2 = fma(upd->ap, VN[V_DX + row2], xn2);
+                    VNw[V_X + row0] = xn0; VNw[V_X + row1] = xn1; VNw[V_X + row2] = xn2;
+                }
+                vin[0] = a.We[row0] * (xn0 + I.Xlin[N * NX + row0] - yN[row0]);
+                vin[1] = a.We[row1] * (xn1 + I.Xlin[N * NX + row1] - yN[row1]);
+                vin[2] = a.We[row2] * (xn2 + I.Xlin[N * NX + row2] - yN[row2]);
             }
         } else {
             // p_N = We (X_N - xref_N)
@@ -716,12 +791,28 @@ __device__ bool factor_sweep(Inst& I)
         const double rd = tsk * a.W[12 + e];
         double rt = rd;
         double gu_loc = Gs[G_RLIN + e];
+        double ll_e = 0.0, lu_e = 0.0, cmp_e = 0.0;     // FS_IPM: multipliers and complementarity products of input e
         if (KIND == FS_IPM) {
+            // the iterate of this stage, with the previous iteration's step applied on the way (and written back)
+            double xq0 = Vs[V_X + q], xq1 = lo ? Vs[V_X + 8 + e] : 0.0;
+            double v = Vs[V_V + e], tl = Vs[V_TL + e], tu = Vs[V_TU + e];
+            ll_e = Vs[V_LL + e]; lu_e = Vs[V_LU + e];
+            if (upd->pending) {
+                const double ap = upd->ap, ad = upd->ad, dv = Vs[V_DV + e];
+                xq0 = fma(ap, Vs[V_DX + q], xq0);
+                if (lo) xq1 = fma(ap, Vs[V_DX + 8 + e], xq1);
+                v = fma(ap, dv, v); tl = fma(ap, dv, tl); tu = fma(-ap, dv, tu);
+                ll_e = fma(ad, Vs[V_CL + e], ll_e); lu_e = fma(ad, Vs[V_CU + e], lu_e);
+                if (t == 0) Vk[V_X + q] = xq0;
+                if (lo && t == 1) Vk[V_X + 8 + q] = xq1;
+                if (!lo && t == 2) { Vk[V_V + e] = v; Vk[V_TL + e] = tl; Vk[V_TU + e] = tu; Vk[V_LL + e] = ll_e; Vk[V_LU + e] = lu_e; }
+            }
             // residual form around the iterate (x, v):  Q (x + X - xref) = Q x + qlin,  R (v + U - uref) = R v + rlin
-            qx0 = fma(qd0, Vs[V_X + q], qx0);
-            if (lo) qx1 = fma(qd1, Vs[V_X + 8 + e], qx1);
-            rt += Vs[V_LL + e] / Vs[V_TL + e] + Vs[V_LU + e] / Vs[V_TU + e];
-            gu_loc = fma(rd, Vs[V_V + e], gu_loc);
+            qx0 = fma(qd0, xq0, qx0);
+            if (lo) qx1 = fma(qd1, xq1, qx1);
+            rt += ll_e / tl + lu_e / tu;
+            gu_loc = fma(rd, v, gu_loc);
+            cmp_e = ll_e * tl + lu_e * tu;
         }
         // kt2 elements of P+ that live in lane t-2
         const double hx0 = shfl(h[0][1][1], src2), hx1 = shfl(h[1][1][1], src2);
@@ -874,7 +965,11 @@ __device__ bool factor_sweep(Inst& I)
                 y1[0] = b0.x; y1[1] = b0.y; y1[2] = b1.x; y1[3] = b1.y;
                 gt[0] = g0.x; gt[1] = g0.y; gt[2] = g1.x; gt[3] = g1.y;       // g on every lane
             }
-            if (KIND == FS_IPM && !lo && t == 2) Vk[V_GU + e] = gu;
+            if (!lo && t == 2) {
+                Vk[V_GU + e] = gu;
+                mu_sum += cmp_e;
+                res_max = fmax(res_max, fabs(gu - ll_e + lu_e));
+            }
             Chol4 L;
             ok &= chol4(m10, L);
             chol4_fwd(L, y0);                    // Y[:, q]
@@ -940,12 +1035,15 @@ __device__ bool factor_sweep(Inst& I)
         }
     }
     __syncwarp();
+    if (KIND == FS_IPM) { upd->mu_sum = warp_sum(mu_sum); upd->res_max = warp_max(res_max); upd->pending = false; }
     return __all_sync(FULL_MASK, ok);
 }
 
-// Backward vector sweep (corrector): rhs gh = gu - cl/tl + cu/tu;  g = gh + B'p+,  kff = Lam^-1 g,  p = A'p+ - K'g.
+// Backward vector sweep (corrector): rhs gh = gu - cl/tl + cu/tu with the second-order terms cl = sigma mu - dv_aff dll_aff,
+// cu = sigma mu + dv_aff dlu_aff formed here from the affine step in V_DV (and stored for the corrector forward sweep);
+// g = gh + B'p+,  kff = Lam^-1 g,  p = A'p+ - K'g.
 // Z is read in fragment order; lane (q,t) forms its part of column q and column 8+q of Z'p and the quad reduces over t.
-__device__ void backward_vec_sweep(Inst& I)
+__device__ void backward_vec_sweep(Inst& I, double sigmu)
 {
     const int q = I.q, t = I.t, N = I.N, lane = I.lane;
     const bool lo = q < 4;
@@ -964,8 +1062,12 @@ __device__ void backward_vec_sweep(Inst& I)
             o0 = fma(Gk[((ki * 2 + 0) << 5) + lane], pr[ki], o0);
             o1 = fma(Gk[((ki * 2 + 1) << 5) + lane], pr[ki], o1);
         }
-        const double tl = Vs[V_TL + e], tu = Vs[V_TU + e];
-        const double gh = Vs[V_GU + e] - Vs[V_CL + e] / tl + Vs[V_CU + e] / tu;
+        const double itl = 1.0 / Vs[V_TL + e], itu = 1.0 / Vs[V_TU + e];
+        const double ll = Vs[V_LL + e], lu = Vs[V_LU + e], dva = Vs[V_DV + e];
+        const double cl = fma(dva, fma(ll * dva, itl, ll), sigmu);       // sigma mu - dv dll,  dll = -ll - ll dv / tl
+        const double cu = fma(dva, fma(lu * dva, itu, -lu), sigmu);      // sigma mu + dv dlu,  dlu = -lu + lu dv / tu
+        const double gh = Vs[V_GU + e] - cl * itl + cu * itu;
+        if (!lo && t == 2) { Vk[V_CL + e] = cl; Vk[V_CU + e] = cu; }
         const double2 ka = *reinterpret_cast<const double2*>(Fk + q * 4), kb = *reinterpret_cast<const double2*>(Fk + q * 4 + 2);
         double2 kc = make_double2(0.0, 0.0), kd = make_double2(0.0, 0.0);
         if (lo) { kc = *reinterpret_cast<const double2*>(Fk + (8 + q) * 4); kd = *reinterpret_cast<const double2*>(Fk + (8 + q) * 4 + 2); }
@@ -1133,12 +1235,201 @@ __device__ __forceinline__ double step_to_boundary(double v, double dv)
 enum { PF_FACTOR_ABS = 0, PF_FACTOR_AS, PF_FWD_CL, PF_PRIMAL, PF_COSTATE, PF_IPM_INIT, PF_FACTOR_IPM, PF_FWD_AFF, PF_E1, PF_BVEC,
        PF_FWD_COR, PF_E2, PF_EPILOGUE, PF_COUNT };
 
+// The interior-point iteration.  (Tried as a function that is never inlined, to shield the register allocation of the fast
+// paths from this code: the generic-space accesses to the kernel parameters and the spills at the call cost 40 % on the forced
+// interior-point run and gained nothing on the fast path -- gpurun_out r2g.)
+struct IpmOut { int status, it; double mu, res_stat, stat_scale, bmax; };
+__device__ __forceinline__ void ipm_solve(Inst& I, IpmOut& out)
+{
+    const SolveArgs& a = I.a;
+    const int lane = I.lane, N = I.N, nb = 4 * N;
+    int status = 2, it = 0;
+    double mu = 0.0, res_stat = 0.0, stat_scale = 1.0, bmax = 0.0;
+    PROF_START();
+    // ---------- interior-point iteration (Mehrotra predictor-corrector), the fallback ----------
+    // Four sweeps per iteration and nothing else: the factor sweep applies the previous iteration's step on the way and returns
+    // mu and the stationarity residual of the iterate; the two forward sweeps accumulate the step lengths and the sums that
+    // centring and the stopping test need (IpmAcc).
+    IpmUpd upd;
+    IpmAcc acc;
+    ipm_init(I);
+    bmax = forward_sweep<0>(I);
+    PROF(PF_IPM_INIT);
+    const double inv2nb = 1.0 / (2.0 * nb);
+    for (it = 0; it < a.max_iter; it++) {
+        // ---------- B1: (pending update,) factorisation, predictor rhs, mu and residual of the iterate ----------
+        const bool okf = factor_sweep<FS_IPM>(I, &upd);
+        PROF(PF_FACTOR_IPM);
+        if (!okf) { status = 4; break; }
+        mu = upd.mu_sum * inv2nb;
+        res_stat = upd.res_max;
+        if (it == 0) stat_scale = fmax(1.0, res_stat);
+        if (mu < a.tol && res_stat < a.tol * stat_scale) { status = 0; break; }
+        // ---------- F1: affine step, its step length and complementarity -> sigma ----------
+        forward_sweep<1>(I, &acc);
+        PROF(PF_FWD_AFF);
+        const double a_aff = acc.ia > 1.0 ? 1.0 / acc.ia : 1.0;
+        const double mu_aff = ((1.0 - a_aff) * upd.mu_sum + a_aff * a_aff * acc.s2) * inv2nb;
+        double sigma = mu_aff / mu;
+        sigma = sigma * sigma * sigma;
+        // ---------- B2 / F2: corrector ----------
+        prefetch_iterate(I);            // this may be the last iteration: have X, U in L2 for the epilogue
+        backward_vec_sweep(I, sigma * mu);
+        PROF(PF_BVEC);
+        forward_sweep<3>(I, &acc);
+        PROF(PF_FWD_COR);
+        // ---------- step lengths; the update itself is left to the next factor sweep / the epilogue ----------
+        double ap = acc.ia_p > 1.0 ? 1.0 / acc.ia_p : 1.0, ad = acc.ia_d > 1.0 ? 1.0 / acc.ia_d : 1.0;
+        const double tau = fmin(fmax(0.995, 1.0 - mu), 1.0 - 1e-8);
+        ap = fmin(1.0, tau * ap);
+        ad = fmin(1.0, tau * ad);
+        upd.pending = true; upd.ap = ap; upd.ad = ad;
+        // mu of the new iterate in closed form, its stationarity residual bounded by |1 - ad| |r| + |ap - ad| |dgu| (exact when
+        // ap == ad): if that already meets the tolerance the next factor sweep is not needed
+        const double mu_new = (upd.mu_sum + ap * acc.a1 + ad * acc.a2 + ap * ad * acc.a3) * inv2nb;
+        const double res_new = (1.0 - ad) * res_stat + fabs(ap - ad) * acc.dgmax;
+        if (mu_new < a.tol && res_new < a.tol * stat_scale) { mu = mu_new; res_stat = res_new; status = 0; it++; break; }
+    }
+    PROF(PF_E2);
+    if (upd.pending) {
+        // the last step is still pending: apply it to the iterate in place (primal part; the multipliers are not used again)
+        const double app = upd.ap;
+        for (int idx = lane; idx < nb; idx += 32) {
+            double* Vk = I.V + (size_t)(idx >> 2) * SREC;
+            const int e = idx & 3;
+            const double dvp = app * Vk[V_DV + e];
+            Vk[V_V + e] += dvp; Vk[V_TL + e] += dvp; Vk[V_TU + e] -= dvp;
+        }
+        for (int idx = lane; idx < 12 * (N + 1); idx += 32) {
+            double* Vk = I.V + (size_t)(idx / 12) * SREC;
+            Vk[V_X + idx % 12] = fma(app, Vk[V_DX + idx % 12], Vk[V_X + idx % 12]);
+        }
+        __syncwarp();
+    }
+    out.status = status; out.it = it; out.mu = mu; out.res_stat = res_stat; out.stat_scale = stat_scale; out.bmax = bmax;
+}
+
 // Maximum number of pinned-LQR solves of the primal-dual active-set iteration before the interior-point iteration takes over
 #ifndef BR2_MAX_AS
 #define BR2_MAX_AS 6
 #endif
 
-__global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(SolveArgs a)
+// Epilogue of an instance (both kernels): full SQP step on (X, U), u0, thrust allocation (bluerov2_dob.cpp:388-395), status,
+// statistics, the hint and the place in the next solve's visiting order.  Both solution paths leave (dx, du) in V_X, V_V.
+struct SolveOut { int status, it; double mu, res_stat, stat_scale, bmax; bool solved, active; };
+__device__ __forceinline__ void finish_instance(Inst& I, const SolveOut& r, int* order_next)
+{
+    const SolveArgs& a = I.a;
+    const int lane = I.lane, N = I.N, nb = 4 * N, inst = I.inst;
+    int status = r.status;
+    const int it = r.it;
+    const bool solved = r.solved;
+    bool active = r.active;
+    const double mu = r.mu, res_stat = r.res_stat, stat_scale = r.stat_scale, bmax = r.bmax;
+    // ---------- epilogue: full SQP step, u0, thrust allocation (both paths leave (dx, du) in V_X, V_V) ----------
+    double* Xo = a.X + (size_t)inst * (N + 1) * NX;
+    double* Uo = a.U + (size_t)inst * N * NU;
+    bool finite = true;
+    bool act2 = false;
+#pragma unroll 5
+    for (int idx = lane; idx < nb; idx += 32) {
+        const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
+        finite &= isfinite(Vk[V_V + (idx & 3)]);
+        if (!solved) act2 |= fmin(Vk[V_TL + (idx & 3)], Vk[V_TU + (idx & 3)]) < 1e-3;
+    }
+    // the states are the exact roll-out of the inputs: NaN/Inf anywhere reaches x_N
+    if (lane < 12) finite &= isfinite(I.V[(size_t)N * SREC + V_X + lane]);
+    finite = __all_sync(FULL_MASK, finite);
+    if (!solved) active = act2;
+    active = __any_sync(FULL_MASK, active);
+    if (a.active_set && !solved && status == 0) {
+        // the interior-point solution's active set (slack ~ mu / lam at an active bound) is the next solve's guess
+        for (int base = 0; base < nb; base += 32) {
+            const int idx = base + lane;
+            const bool valid = idx < nb;
+            const double* Vk = I.V + (size_t)((valid ? idx : 0) >> 2) * SREC;
+            int cc = 0;
+            if (valid) cc = Vk[V_TL + (idx & 3)] < 1e-7 ? 1 : (Vk[V_TU + (idx & 3)] < 1e-7 ? 2 : 0);
+            int code = cc << (2 * (lane & 3));
+            code |= __shfl_xor_sync(FULL_MASK, code, 1);
+            code |= __shfl_xor_sync(FULL_MASK, code, 2);
+            if (valid && (lane & 3) == 0) a.aset[(size_t)inst * N + (idx >> 2)] = code;
+        }
+    }
+    if (lane == 0) {
+        const int hard = (active || status != 0) ? 1 : 0;
+        a.hint[inst] = hard;
+        // position in the next solve's visiting order: hard instances from the front, easy ones from the back
+        const int pos = hard ? atomicAdd(a.ctr + CTR_HARD, 1) : a.B - 1 - atomicAdd(a.ctr + CTR_EASY, 1);
+        order_next[pos] = inst;
+    }
+    if (finite) {
+        // X / U were last touched by the lineariser, before ~300 MB of stage records went through L2: without care this is
+        // a chain of DRAM round trips (it was 11 % of the kernel).  The lines are prefetched into L2 ahead of the forward
+        // sweep (prefetch_iterate) and each batch issues all of its loads before its first store.
+        for (int base = lane; base < nb; base += 32 * 5) {
+            double d[5], u[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const int idx = base + 32 * j;
+                const bool p = idx < nb;
+                d[j] = p ? I.V[(size_t)(idx >> 2) * SREC + V_V + (idx & 3)] : 0.0;
+                u[j] = p ? Uo[idx] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const int idx = base + 32 * j;
+                // (a pinned input lands on its bound up to one rounding of (bound - U) + U, an accepted free input within 1e-12
+                // of the box width: clamp)
+                if (idx < nb) Uo[idx] = fmin(fmax(u[j] + d[j], a.lbu[idx & 3]), a.ubu[idx & 3]);
+            }
+        }
+        const int nxs = 12 * (N + 1);
+        for (int base = lane; base < nxs; base += 32 * 8) {
+            double d[8], x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = base + 32 * j;
+                const bool p = idx < nxs;
+                d[j] = p ? I.V[(size_t)(idx / 12) * SREC + V_X + idx % 12] : 0.0;
+                x[j] = p ? Xo[idx] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int idx = base + 32 * j;
+                if (idx < nxs) Xo[idx] = x[j] + d[j];
+            }
+        }
+    } else {
+        status = 1;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        double u0[4] = {Uo[0], Uo[1], Uo[2], Uo[3]};
+        double th[6];
+        thrust_alloc(u0, th);
+#pragma unroll
+        for (int i = 0; i < 4; i++) a.u0[(size_t)inst * 4 + i] = u0[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) a.thrust[(size_t)inst * 6 + i] = th[i];
+        a.status[inst] = status;
+        a.iters[inst] = it;
+        atomicAdd(a.iter_total, (unsigned long long)it);
+        PROF(PF_EPILOGUE);
+        a.info[(size_t)inst * 4 + 0] = mu;
+        a.info[(size_t)inst * 4 + 1] = res_stat;
+        a.info[(size_t)inst * 4 + 2] = bmax;
+        a.info[(size_t)inst * 4 + 3] = stat_scale;
+    }
+    __syncwarp();
+}
+
+// Kernel 1 of the QP solve: the fast paths.  One warp per instance at a time, persistent over the batch.  What it cannot solve
+// (no acceptance after BR2_MAX_AS attempts, a failed factorisation, option fast_path = 0) goes to the fallback list of kernel 2.
+// (Without the interior-point code this kernel fits 96 / 80 registers with 32 / 48 bytes of spills, i.e. 20 / 24 resident warps per
+// SM instead of 16 -- and gets SLOWER, 0.240 / 0.248 ms against 0.216 ms: the factor sweep is bound by the fp64 pipe, not by
+// latency, and the tighter allocation costs instructions.  gpurun_out r2h, profiles/r02_pdas_occupancy.txt.)
+__global__ void __launch_bounds__(IPM_WARPS * 32, BR2_PDAS_MINB) pdas_kernel(const __grid_constant__ SolveArgs a)
 {
     __shared__ WarpSmem smem[IPM_WARPS];
     const int lane = threadIdx.x & 31;
@@ -1214,233 +1505,64 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(Solve
             if (solved) status = 0;
         }
         if (!solved) {
-            ipm_init(I);
-            bmax = forward_sweep<0>(I);
-            PROF(PF_IPM_INIT);
+            // hand the instance to the interior-point kernel
+            if (lane == 0) a.fb[atomicAdd(a.ctr + CTR_FB, 1)] = inst;
+            continue;
         }
-        for (it = solved ? it : 0; !solved && it < a.max_iter; it++) {
-            // ---------- B1: factorisation + predictor rhs ----------
-            const bool okf = factor_sweep<FS_IPM>(I);
-            PROF(PF_FACTOR_IPM);
-            if (!okf) { status = 4; break; }
-            if (it == 0) {
-                // mu and stationarity residual of the starting point (later iterations get them from E2)
-                double s = 0.0, rs = 0.0;
-                for (int idx = lane; idx < nb; idx += 32) {
-                    const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
-                    const int e = idx & 3;
-                    const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e];
-                    s += ll * tl + lu * tu;
-                    rs = fmax(rs, fabs(Vk[V_GU + e] - ll + lu));
-                }
-                mu = warp_sum(s) / (2.0 * nb);
-                res_stat = warp_max(rs);
-                stat_scale = fmax(1.0, res_stat);
-                if (mu < a.tol && res_stat < a.tol * stat_scale) { status = 0; break; }
-            }
-            // ---------- F1: affine step ----------
-            forward_sweep<1>(I);
-            PROF(PF_FWD_AFF);
-            // ---------- E1: affine step length, sigma, corrector rhs ----------
-            double a_aff = 1.0;
-            for (int idx = lane; idx < nb; idx += 32) {
-                const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
-                const int e = idx & 3;
-                const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
-                const double dll = -ll - ll * dv / tl, dlu = -lu + lu * dv / tu;
-                a_aff = fmin(a_aff, fmin(fmin(step_to_boundary(tl, dv), step_to_boundary(tu, -dv)),
-                                         fmin(step_to_boundary(ll, dll), step_to_boundary(lu, dlu))));
-            }
-            a_aff = warp_min(a_aff);
-            double mu_aff = 0.0;
-            for (int idx = lane; idx < nb; idx += 32) {
-                const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
-                const int e = idx & 3;
-                const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
-                const double dll = -ll - ll * dv / tl, dlu = -lu + lu * dv / tu;
-                mu_aff += (ll + a_aff * dll) * (tl + a_aff * dv) + (lu + a_aff * dlu) * (tu - a_aff * dv);
-            }
-            mu_aff = warp_sum(mu_aff) / (2.0 * nb);
-            double sigma = mu_aff / mu;
-            sigma = sigma * sigma * sigma;
-            for (int idx = lane; idx < nb; idx += 32) {
-                double* Vk = I.V + (size_t)(idx >> 2) * SREC;
-                const int e = idx & 3;
-                const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
-                const double dll = -ll - ll * dv / tl, dlu = -lu + lu * dv / tu;
-                Vk[V_CL + e] = sigma * mu - dv * dll;
-                Vk[V_CU + e] = sigma * mu + dv * dlu;
-            }
-            __syncwarp();
-            PROF(PF_E1);
-            // ---------- B2 / F2: corrector ----------
-            prefetch_iterate(I);            // this may be the last iteration: have X, U in L2 for the epilogue
-            backward_vec_sweep(I);
-            PROF(PF_BVEC);
-            forward_sweep<1>(I);
-            PROF(PF_FWD_COR);
-            // ---------- E2: step lengths and update ----------
-            double ap = 2.0, ad = 2.0;
-            for (int idx = lane; idx < nb; idx += 32) {
-                const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
-                const int e = idx & 3;
-                const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
-                const double dll = Vk[V_CL + e] / tl - ll - ll * dv / tl, dlu = Vk[V_CU + e] / tu - lu + lu * dv / tu;
-                ap = fmin(ap, fmin(step_to_boundary(tl, dv), step_to_boundary(tu, -dv)));
-                ad = fmin(ad, fmin(step_to_boundary(ll, dll), step_to_boundary(lu, dlu)));
-            }
-            ap = fmin(1.0, warp_min(ap));
-            ad = fmin(1.0, warp_min(ad));
-            const double tau = fmin(fmax(0.995, 1.0 - mu), 1.0 - 1e-8);
-            ap = fmin(1.0, tau * ap);
-            ad = fmin(1.0, tau * ad);
-            // update; mu and the stationarity residual of the NEW iterate follow without another sweep: the reduced
-            // gradient is affine in du and the Newton equation gives  d(gu) = -gh - (ll/tl + lu/tu) ddu  stage-locally.
-            double s_mu = 0.0, s_rs = 0.0;
-            for (int idx = lane; idx < nb; idx += 32) {
-                double* Vk = I.V + (size_t)(idx >> 2) * SREC;
-                const int e = idx & 3;
-                const double tl = Vk[V_TL + e], tu = Vk[V_TU + e], ll = Vk[V_LL + e], lu = Vk[V_LU + e], dv = Vk[V_DV + e];
-                const double cl = Vk[V_CL + e], cu = Vk[V_CU + e], gu = Vk[V_GU + e];
-                const double dll = cl / tl - ll - ll * dv / tl, dlu = cu / tu - lu + lu * dv / tu;
-                const double gh = gu - cl / tl + cu / tu;
-                const double dgu = -gh - (ll / tl + lu / tu) * dv;
-                const double tln = tl + ap * dv, tun = tu - ap * dv, lln = ll + ad * dll, lun = lu + ad * dlu;
-                Vk[V_V + e] += ap * dv;
-                Vk[V_TL + e] = tln;
-                Vk[V_TU + e] = tun;
-                Vk[V_LL + e] = lln;
-                Vk[V_LU + e] = lun;
-                s_mu += lln * tln + lun * tun;
-                s_rs = fmax(s_rs, fabs(gu + ap * dgu - lln + lun));
-            }
-            mu = warp_sum(s_mu) / (2.0 * nb);
-            res_stat = warp_max(s_rs);
-            for (int idx = lane; idx < 12 * (N + 1); idx += 32) {
-                double* Vk = I.V + (size_t)(idx / 12) * SREC;
-                const int e = idx % 12;
-                Vk[V_X + e] += ap * Vk[V_DX + e];
-            }
-            __syncwarp();
-            PROF(PF_E2);
-            if (mu < a.tol && res_stat < a.tol * stat_scale) { status = 0; it++; break; }
-        }
-        PROF(PF_E2);
+        SolveOut r;
+        r.status = status; r.it = it; r.mu = mu; r.res_stat = res_stat; r.stat_scale = stat_scale; r.bmax = bmax;
+        r.solved = true; r.active = active;
+        finish_instance(I, r, order_next);
+        PROF(PF_EPILOGUE);
+    }
+}
 
-        // ---------- epilogue: full SQP step, u0, thrust allocation (both paths leave (dx, du) in V_X, V_V) ----------
-        double* Xo = a.X + (size_t)inst * (N + 1) * NX;
-        double* Uo = a.U + (size_t)inst * N * NU;
-        bool finite = true;
-        bool act2 = false;
-#pragma unroll 5
-        for (int idx = lane; idx < nb; idx += 32) {
-            const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
-            finite &= isfinite(Vk[V_V + (idx & 3)]);
-            if (!solved) act2 |= fmin(Vk[V_TL + (idx & 3)], Vk[V_TU + (idx & 3)]) < 1e-3;
-        }
-        // the states are the exact roll-out of the inputs: NaN/Inf anywhere reaches x_N
-        if (lane < 12) finite &= isfinite(I.V[(size_t)N * SREC + V_X + lane]);
-        finite = __all_sync(FULL_MASK, finite);
-        if (!solved) active = act2;
-        active = __any_sync(FULL_MASK, active);
-        if (a.active_set && !solved && status == 0) {
-            // the interior-point solution's active set (slack ~ mu / lam at an active bound) is the next solve's guess
-            for (int base = 0; base < nb; base += 32) {
-                const int idx = base + lane;
-                const bool valid = idx < nb;
-                const double* Vk = I.V + (size_t)((valid ? idx : 0) >> 2) * SREC;
-                int cc = 0;
-                if (valid) cc = Vk[V_TL + (idx & 3)] < 1e-7 ? 1 : (Vk[V_TU + (idx & 3)] < 1e-7 ? 2 : 0);
-                int code = cc << (2 * (lane & 3));
-                code |= __shfl_xor_sync(FULL_MASK, code, 1);
-                code |= __shfl_xor_sync(FULL_MASK, code, 2);
-                if (valid && (lane & 3) == 0) a.aset[(size_t)inst * N + (idx >> 2)] = code;
-            }
-        }
-        if (lane == 0) {
-            const int hard = (active || status != 0) ? 1 : 0;
-            a.hint[inst] = hard;
-            // position in the next solve's visiting order: hard instances from the front, easy ones from the back
-            const int pos = hard ? atomicAdd(a.ctr + CTR_HARD, 1) : a.B - 1 - atomicAdd(a.ctr + CTR_EASY, 1);
-            order_next[pos] = inst;
-        }
-        if (finite) {
-            // X / U were last touched by the lineariser, before ~300 MB of stage records went through L2: without care this is
-            // a chain of DRAM round trips (it was 11 % of the kernel).  The lines are prefetched into L2 ahead of the forward
-            // sweep (prefetch_iterate) and each batch issues all of its loads before its first store.
-            for (int base = lane; base < nb; base += 32 * 5) {
-                double d[5], u[5];
-#pragma unroll
-                for (int j = 0; j < 5; j++) {
-                    const int idx = base + 32 * j;
-                    const bool p = idx < nb;
-                    d[j] = p ? I.V[(size_t)(idx >> 2) * SREC + V_V + (idx & 3)] : 0.0;
-                    u[j] = p ? Uo[idx] : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < 5; j++) {
-                    const int idx = base + 32 * j;
-                    // (a pinned input lands on its bound up to one rounding of (bound - U) + U, an accepted free input within 1e-12
-                    // of the box width: clamp)
-                    if (idx < nb) Uo[idx] = fmin(fmax(u[j] + d[j], a.lbu[idx & 3]), a.ubu[idx & 3]);
-                }
-            }
-            const int nxs = 12 * (N + 1);
-            for (int base = lane; base < nxs; base += 32 * 8) {
-                double d[8], x[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int idx = base + 32 * j;
-                    const bool p = idx < nxs;
-                    d[j] = p ? I.V[(size_t)(idx / 12) * SREC + V_X + idx % 12] : 0.0;
-                    x[j] = p ? Xo[idx] : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int idx = base + 32 * j;
-                    if (idx < nxs) Xo[idx] = x[j] + d[j];
-                }
-            }
-        } else {
-            status = 1;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            double u0[4] = {Uo[0], Uo[1], Uo[2], Uo[3]};
-            double th[6];
-            thrust_alloc(u0, th);
-#pragma unroll
-            for (int i = 0; i < 4; i++) a.u0[(size_t)inst * 4 + i] = u0[i];
-#pragma unroll
-            for (int i = 0; i < 6; i++) a.thrust[(size_t)inst * 6 + i] = th[i];
-            a.status[inst] = status;
-            a.iters[inst] = it;
-            atomicAdd(a.iter_total, (unsigned long long)it);
-            PROF(PF_EPILOGUE);
-            a.info[(size_t)inst * 4 + 0] = mu;
-            a.info[(size_t)inst * 4 + 1] = res_stat;
-            a.info[(size_t)inst * 4 + 2] = bmax;
-            a.info[(size_t)inst * 4 + 3] = stat_scale;
-        }
-        __syncwarp();
+// Kernel 2: Mehrotra predictor-corrector interior-point iteration for the instances on the fallback list (normally empty: the
+// blocks read the count and leave).
+__global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(const __grid_constant__ SolveArgs a)
+{
+    __shared__ WarpSmem smem[IPM_WARPS];
+    const int lane = threadIdx.x & 31;
+    WarpSmem& sm = smem[threadIdx.x >> 5];
+    const int nfb = a.ctr[CTR_FB];
+    int* order_next = a.order + (size_t)((a.ctr[CTR_PARITY] & 1) ^ 1) * a.B;
+    int pos = blockIdx.x * IPM_WARPS + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * IPM_WARPS;
+    while (pos < nfb) {
+        const int inst = a.fb[pos];
+        Inst I(a, sm, inst, lane);
+        PROF_START();
+        prefetch_iterate(I);
+        IpmOut o;
+        ipm_solve(I, o);
+        SolveOut r;
+        r.status = o.status; r.it = o.it; r.mu = o.mu; r.res_stat = o.res_stat; r.stat_scale = o.stat_scale; r.bmax = o.bmax;
+        r.solved = false; r.active = false;
+        finish_instance(I, r, order_next);
+        PROF(PF_EPILOGUE);
+        if (lane == 0) pos = nwarps + atomicAdd(a.ctr + CTR_FBQ, 1);
+        pos = __shfl_sync(FULL_MASK, pos, 0);
     }
 }
 
 void configure_kernels()
 {
-    // the resident blocks need MINB x WARPS x 11.6 KB of staging buffers: ask for the largest carve-out (function attributes
+    // the resident blocks need MINB x WARPS x 9 KB of staging buffers: ask for the largest carve-out (function attributes
     // are per device: called from br2_batch_create with the solver's device current)
+    cudaFuncSetAttribute(pdas_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(ipm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
 {
-    // Persistent grid, one warp per instance at a time, instances handed out by an atomic queue (its counters are reset and
-    // the order buffers flipped by block 0 of the lineariser that precedes this kernel in the stream).  (Sizing the resident
+    // Persistent grids, one warp per instance at a time, instances handed out by atomic queues (their counters are reset and
+    // the order buffers flipped by block 0 of the lineariser that precedes these kernels in the stream).  (Sizing the resident
     // set for even waves -- 14 instead of 16 warps/SM at B = 4096 -- measured 8 % slower: throughput grows with the
     // number of resident warps and the queue already evens out the tail; profiles/r01h_ipm_variants.txt.)
-    int blocks = (a.B + IPM_WARPS - 1) / IPM_WARPS;
-    if (blocks > sm_count * BR2_IPM_MINB) blocks = sm_count * BR2_IPM_MINB;
+    const int need = (a.B + IPM_WARPS - 1) / IPM_WARPS;
+    int blocks = need < sm_count * BR2_PDAS_MINB ? need : sm_count * BR2_PDAS_MINB;
+    pdas_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
+    blocks = need < sm_count * BR2_IPM_MINB ? need : sm_count * BR2_IPM_MINB;
     ipm_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
 }
 

@@ -246,3 +246,61 @@ def test_public_headers_compile_standalone(tmp_path, lang):
     std = "-std=c99" if lang == "c" else "-std=c++14"
     out = subprocess.run([cc, std, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", INCLUDE, str(src)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-3000:]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# behaviour of the generated-ABI functions around the solve, tests/abi/a10_behaviour.c
+def _a10(mode, timeout=120):
+    exe = os.path.join(ABI_BIN, "a10_behaviour")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "abi"), exe], check=True)
+    return subprocess.run([exe, mode], capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.mark.parametrize("mode,needle", [
+    ("cond_N", "acados_update_qp_solver_cond_N() failed, since no partial condensing solver is used!"),   # gen.c:788-794
+    ("params_np", "trying to set 15 parameters for external functions. External function has 16 parameters. Exiting."),   # :839-844
+    ("sparse_np", "trying to set 17 parameters for external functions. External function has 16 parameters. Exiting."),   # :890-896
+])
+def test_misuse_prints_and_exits_1(lib_path, mode, needle):
+    """fatal misuse -> the reference's message and exit(1), before anything needs a CUDA device"""
+    out = _a10(mode)
+    assert out.returncode == 1, (out.returncode, out.stdout, out.stderr)
+    assert needle in out.stdout and "returned" not in out.stdout
+
+
+def test_custom_update_returns_1(lib_path):
+    """acados_solver_bluerov2.c:1030-1036: prints its two lines and returns 1"""
+    out = _a10("custom_update")
+    assert out.returncode == 0 and "custom_update_rc 1" in out.stdout
+    assert "dummy function that can be called in between solver calls" in out.stdout and "nothing set yet.." in out.stdout
+
+
+@pytest.mark.gpu
+def test_reset_and_sparse_params_behaviour(lib_path, oracle):
+    """_reset zeroes the iterate (acados_solver_bluerov2.c:797-830) and the next solve is the cold solve from zeros;
+    _update_params_sparse (:886-943) fed index by index equals dense _update_params; both against the oracle"""
+    out = _a10("gpu")
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    kv = {}
+    for line in out.stdout.splitlines():
+        parts = line.split()
+        if len(parts) >= 2 and parts[0].replace("_", "").isalnum():
+            try:
+                kv[parts[0]] = [float(v) for v in parts[1:]]
+            except ValueError:
+                pass
+    assert kv["status_A"] == [0] and kv["status_after_reset"] == [0] and kv["status_B"] == [0]
+    assert kv["reset_rc"] == [0] and kv["sparse_rc"] == [0] and kv["free_rc"] == [0] and kv["custom_update_rc"] == [1]
+    assert kv["iterate_before_reset"][0] > 1.0 and kv["iterate_after_reset"] == [0.0]
+    assert kv["reset_vs_cold"][0] == 0.0            # same engine, same inputs: bit-identical
+    assert kv["reset_vs_warm"][0] > 1e-3            # and it is a different linearisation point than the warm start
+    # the oracle from the zero iterate with the same data
+    from bluerov2_b200 import workloads as wl
+    N = 20
+    x0 = np.zeros(12); x0[[0, 1, 2, 5, 6]] = [0.3, -0.2, -19.6, 0.25, 0.1]
+    p = wl.NOMINAL_P.copy(); p[:4] = [1.5, -0.7, 0.4, 0.05]
+    yref = np.zeros((N + 1, 16)); yref[:, 0] = 0.05 * np.arange(N + 1); yref[:, 2] = -20.0; yref[:, 6] = 1.0
+    X, U = np.zeros((N + 1, 12)), np.zeros((N, 4))
+    st, _ = oracle.rti_step(wl.time_steps(N), x0, yref, p, X, U)
+    assert st == 0 and np.abs(U[0] - np.array(kv["u_after_reset"])).max() < 1e-6
