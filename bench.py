@@ -4,24 +4,23 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--horizon N]
 
 A "step" is one control tick of the hot path over one batch: for every instance the call sequence of
-BLUEROV2_DOB::solve (bluerov2_dob.cpp:307-395) -- x0, parameters, yref window, one SQP-RTI iteration
-(linearisation + Riccati IPM), u0 and the 4->6 thrust allocation.  Like the node, which keeps the trajectory file in
-memory and advances a line counter (bluerov2_dob.cpp:367), the solver holds the trajectory on the device and a tick
-passes one row index per instance (reference windowing on the device, ref_cb).  Workload = BASELINE config 2 (batch 4096 per GPU,
-random x0 around the circle reference, N = 40, fp64): closed loop, plant = nominal ERK4 at 0.05 s, iterate carried
-between ticks.  The closed-loop input sequence (x0_t, yref_t) is generated ONCE before the timed region (untimed
-pass through the same CUDA solver + a numpy plant) and then replayed from the same initial iterate, so the timed
-ticks see exactly the warm-started problems of ticks W..W+K-1.
+BLUEROV2_DOB::solve (bluerov2_dob.cpp:307-395) -- x0, parameters, yref window, one SQP-RTI iteration (linearisation + QP), u0 and
+the 4->6 thrust allocation.  Like the node, which keeps the trajectory file in memory and advances a line counter
+(bluerov2_dob.cpp:367), the solver holds the trajectory on the device and a tick names one row per instance (ref_cb).
 
-  value : whole-job steps/s, inputs resident in HBM, device time (CUDA events), max over ranks.
-  e2e   : the same ticks through the public host API (BatchSolver.solve_windowed -> br2_batch_solve_windowed_host) with
-          pinned HOST buffers: H2D of x0 / row indices / p and D2H of u0/thrust/status inside the timed region.
-  roofline / cpu_baseline: see DESIGN.md "Measurement".
+Headline workload = BASELINE config 2 (batch 4096 per GPU -- 8192 per GPU at 8 GPUs = config 4 --, random x0 around the circle
+reference, N = 40, fp64), closed loop with the nominal ERK4 plant at 0.05 s, iterate carried between ticks.
 
---impl reference times the reference's CPU algorithm for the same metric: acados/HPIPM cannot be built here, so it
-is the oracle port (oracle/bluerov2_oracle.c, ERK routed through the reference's own CasADi-generated VDE from
-oracle/_ref when that was built), OpenMP over instances on all host cores.  That leg and the cpu_baseline leg are
-the only places this file touches oracle/.
+  value : whole-job steps/s, device-resident closed loop: one br2_batch_tick_device per tick (lineariser -> QP kernels -> plant
+          step on the device state, replayed as one CUDA graph), CUDA events on the launching stream, max over ranks.
+  e2e   : the same closed-loop ticks through the host API (BatchSolver.tick -> br2_batch_tick_host) with pinned HOST buffers:
+          H2D of x0 / row indices / p and D2H of u0 / thrust / status inside the timed region, a distinct input buffer per tick.
+  roofline / cpu_baseline / sub-records (forced interior-point iteration, saturated start, config 3, config 5, explicit-yref
+  host path): see DESIGN.md "Measurement".
+
+--impl reference times the reference's CPU algorithm for the same metric: acados/HPIPM cannot be built here, so it is the oracle
+port (oracle/bluerov2_oracle.c, ERK routed through the reference's own CasADi-generated VDE from oracle/_ref when that was
+built), OpenMP over instances on all host cores.  That leg and the cpu_baseline leg are the only places this file touches oracle/.
 """
 from __future__ import annotations
 
@@ -42,15 +41,27 @@ from bluerov2_b200 import traj, workloads as wl  # noqa: E402
 
 METRIC = "SQP-RTI steps/sec (batched 6-DOF OCP, N=40)"
 UNIT = "steps/s"
-BYTES_PER_STAGE_ITER = 4384          # 548 doubles per instance, stage and IPM iteration
+BYTES_PER_STAGE_ITER = 4384          # 548 doubles per instance, stage and QP iteration (factorisation + solve)
 
 
-def measured_traffic(B, N, fast_path):
-    """DRAM bytes per ipm_kernel launch from the committed ncu capture of the same configuration, else None"""
+def config_of(B: int, world: int, N: int, pos_spread: float) -> dict:
+    """the workload description BOTH arms print (identical keys and strings)"""
+    return {"workload": f"config {4 if world * B == 65536 else 2}: batch {B} per GPU, random x0 around the circle reference (pos spread "
+                        f"{pos_spread} m), N={N}, Ts={1.0 / N:g} s, fp64, closed loop (nominal ERK4 plant at 0.05 s), iterate carried "
+                        f"between ticks, seed 0",
+            "batch_per_gpu": B, "global_batch": world * B, "horizon": N, "pos_spread": pos_spread}
+
+
+def default_batch(world: int) -> int:
+    return 8192 if world >= 8 else 4096      # config 4 = 65536 = 8 x 8192; configs 2 / 3 = 4096 on one GPU
+
+
+def measured_traffic(kind: str, B: int, N: int):
+    """DRAM bytes per launch from the committed ncu capture of the same configuration (profiles/ipm_traffic.json), else None"""
     try:
         with open(os.path.join(ROOT, "profiles", "ipm_traffic.json")) as f:
             for e in json.load(f)["entries"]:
-                if e["batch"] == B and e["horizon"] == N and bool(e["fast_path"]) == bool(fast_path):
+                if e.get("kernel", "ipm_kernel") == kind and e["batch"] == B and e["horizon"] == N:
                     return float(e["dram_bytes_per_launch"]), e["source"]
     except Exception:
         pass
@@ -110,63 +121,6 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def make_workload(B: int, N: int, seed: int, pos_spread: float):
-    w = wl.tracking_batch(B, N, seed=seed, reference="circle", pos_spread=pos_spread)
-    return w
-
-
-def record_closed_loop(solver, w, ticks: int, N: int):
-    """untimed: run `ticks` closed-loop ticks through the CUDA solver, return the per-tick inputs (host arrays)"""
-    x0, lines = w["x0"].copy(), w["lines"].copy()
-    solver.set_iterate(w["X"], w["U"])
-    x0s, lns = [], []
-    solver.set_trajectory(w["traj"])
-    for _ in range(ticks):
-        x0s.append(x0.copy()); lns.append(lines.astype(np.int32))
-        u0, _, st = solver.solve_windowed(x0, lns[-1], w["p"])
-        if (st != 0).any():
-            raise RuntimeError(f"solver status != 0 while recording the workload: {np.unique(st, return_counts=True)}")
-        x0 = wl.plant_step(x0, u0, w["p"], 0.05)
-        lines = lines + 1
-    return x0s, lns
-
-
-def record_closed_loop_dob(solver, w, ticks: int, N: int, seed: int, settle: int = 60):
-    """untimed, BASELINE config 3: inputs of DOB-MPC ticks (thruster forces, pose/velocity measurement, finite-differenced
-    body acceleration, trajectory row) from a plant driven by sampled wave disturbances (mode 0 of applyBodyWrench,
-    bluerov2_dob.cpp:774-797).  The loop is first settled for `settle` ticks (the filter of the reference is explicit
-    RK4 at 50 ms on roll/pitch dynamics with |lambda dt| > 2.8: it only lives in the gentle regime |u| < 1), and the
-    plant is driven by the UNCOMPENSATED command: the node's compensation gain 1/0.0325 (bluerov2_dob.cpp:326-338) over-
-    compensates ~30x on any plant whose thrust scale is the OCP model's, so the compensated command is computed (timed
-    path) but not fed back.  Returns the per-tick inputs and the state to restart the replay from."""
-    B = w["x0"].shape[0]
-    amp, tau0 = wl.wave_disturbance(B, seed=seed + 1)
-    x, lines = w["x0"].copy(), w["lines"].copy()
-    solver.set_trajectory(w["traj"])
-    solver.set_iterate(w["X"], w["U"])
-    vel_prev, thr = x[:, 6:12].copy(), np.zeros((B, 6))
-    rec = {"thr": [], "meas": [], "acc": [], "lines": []}
-    start = None
-    for t in range(settle + ticks):
-        if t == settle:
-            X0, U0 = solver.get_iterate()
-            solver.ekf_reset()
-            ex, eP = solver.ekf_state()
-            ex[:, :12] = x                  # filter starts at the true pose
-            start = (X0, U0, ex, eP)
-        if t >= settle:
-            rec["thr"].append(thr.copy()); rec["meas"].append(x.copy())
-            rec["acc"].append((x[:, 6:12] - vel_prev) / 0.05); rec["lines"].append(lines.astype(np.int32))
-        vel_prev = x[:, 6:12].copy()
-        u0, th, st = solver.solve_windowed(x, lines.astype(np.int32), w["p"])
-        if (st != 0).any():
-            raise RuntimeError(f"solver status != 0 while recording the DOB workload: {np.unique(st, return_counts=True)}")
-        thr = th.copy()                                   # thrust feedback = previous command
-        x = wl.plant_step(x, u0, w["p"], 0.05, dist=wl.wave_at(amp, tau0, t))
-        lines = lines + 1
-    return rec, start
-
-
 def cpu_leg(N: int, budget_s: float, ticks_wanted: int, threads: int = 0, seed: int = 0, pos_spread: float = 0.5):
     """the oracle port timed on the host cores over a bounded closed-loop sample of the same workload"""
     from oracle import Oracle, CasadiRef
@@ -205,25 +159,27 @@ def cpu_leg(N: int, budget_s: float, ticks_wanted: int, threads: int = 0, seed: 
     return dict(batch=Bs, times=times, iters=iters, cores=int(used), note=kind_note)
 
 
-# ---------------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     K, W, N = args.steps, args.warmup, args.horizon
+    B = args.batch or default_batch(world)
     r = cpu_leg(N, budget_s=args.cpu_budget, ticks_wanted=K + W, seed=0, pos_spread=args.pos_spread)
     t = float(np.sum(r["times"][W:]))
     value = r["batch"] * K / t
-    sample = (f"{r['batch']} instances x {K} closed-loop ticks (after {W} warm-up ticks) of config 2 "
-              f"(same generator and seed as the GPU arm, first {r['batch']} instances); {r['note']}")
+    sample = (f"{r['batch']} instances x {K} closed-loop ticks (after {W} warm-up ticks): the first {r['batch']} instances of the "
+              f"workload (same generator and seed as the GPU arm); {r['note']}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": f"config 2: random x0 around the circle reference, N={N}, Ts={1.0 / N:g} s, fp64; CPU arm on a "
-                               f"bounded sample (batch {r['batch']})", "batch_per_step": r["batch"], "horizon": N,
-                   "mean_ipm_iterations": float(np.mean(r["iters"][W:]))},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "config": config_of(B, world, N, args.pos_spread),
+        "mean_ipm_iterations": float(np.mean(r["iters"][W:])),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
+                         "algorithm": "interior-point iteration on every instance (no interior / active-set shortcut): compare with "
+                                      "the GPU arm's sub-record forced_ipm for like-for-like, with its headline for the product path"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "acados/HPIPM/BLASFEO are un-vendored and not installable here; this is the acados-equivalent restatement "
                 "(same RTI step, Riccati IPM -- ~10x fewer flops than the reference's full condensing + dense HPIPM).",
@@ -231,6 +187,286 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------
+class DeviceLoop:
+    """device-resident closed loop: state, row counters and parameters stay in fixed device buffers, one tick() per control tick
+    (solve + plant step in place), thrusts written straight into the rank's slot of the tick's gather buffer"""
+
+    def __init__(self, S, sol, w, dev, world=1):
+        import torch
+        from bluerov2_b200.sharding import PipelinedThrustGather
+        self.torch, self.sol, self.w, self.dev = torch, sol, w, dev
+        B = w["x0"].shape[0]
+        self.B = B
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+        self.x_init, self.lines_init = d(w["x0"]), d(w["lines"].astype(np.int32))
+        self.x, self.lines, self.p = self.x_init.clone(), self.lines_init.clone(), d(w["p"])
+        self.acc = torch.zeros((B, 6), dtype=torch.float64, device=dev)
+        self.u0 = torch.empty((B, 4), dtype=torch.float64, device=dev)
+        self.st = torch.empty((B,), dtype=torch.int32, device=dev)
+        # all ranks' thrust vectors, double-buffered: the all-gather of tick t overlaps the lineariser of tick t + 1
+        self.gather = PipelinedThrustGather(world * B, dev, depth=int(os.environ.get("BR2_GATHER_DEPTH", "2")))
+        self.distributed = world > 1
+        sol.set_trajectory(w["traj"])
+
+    def restart(self):
+        self.sol.set_iterate(self.w["X"], self.w["U"])
+        self.x.copy_(self.x_init); self.lines.copy_(self.lines_init)
+        self.sol.set_tick_index(0)
+
+    def tick(self, t):
+        self.sol.tick(self.x, p=self.p, lines=self.lines, body_acc=self.acc, out=(self.u0, self.gather.slot(t), self.st), plant_h=0.05)
+        if self.distributed:
+            self.gather.all_gather_async(t)     # ONE all-gather per tick, enqueued behind the solve
+
+    def finish(self):
+        self.gather.wait_all()                  # the last ticks' collectives belong to the timed region
+
+
+def timed_device_loop(torch, dist, loop, W, K, dev, distributed, sampler=None, per_tick=False):
+    """W warm-up ticks, then K ticks bracketed by barrier + synchronize, CUDA events on the launching stream.
+    Returns (seconds, mean QP iterations per instance and tick, non-zero statuses, [per-tick ms])"""
+    sol = loop.sol
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        loop.finish()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    loop.restart()
+    for t in range(W):
+        loop.tick(t)
+    barrier()
+    sol.ipm_iterations_total(reset=True); sol.nonzero_status_total(reset=True)
+    n_ev = K + 1 if per_tick else 2
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_ev)]
+    if sampler is not None:
+        sampler.start()
+    ev[0].record(stream)
+    for t in range(W, W + K):
+        loop.tick(t)
+        if per_tick:
+            ev[t - W + 1].record(stream)
+    loop.finish()
+    if not per_tick:
+        ev[1].record(stream)
+    barrier()
+    dt = ev[0].elapsed_time(ev[-1]) * 1e-3
+    ticks_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)] if per_tick else None
+    return dt, sol.ipm_iterations_total(reset=True) / (loop.B * K), sol.nonzero_status_total(reset=True), ticks_ms
+
+
+def kernel_times(torch, loop, W, K, dev):
+    """per-kernel device times (CUDA events recorded by the library on the launching stream between its kernels): the timed
+    ticks replayed once more with option kernel_timing on, reading the events after each tick (outside the steps/s measurement)"""
+    sol = loop.sol
+    sol.set_option("kernel_timing", 1)
+    loop.restart()
+    t_lin, t_qp = [], []
+    for t in range(W + K):
+        loop.tick(t)
+        if t >= W:
+            torch.cuda.synchronize(dev)
+            a, b = sol.last_kernel_times()
+            t_lin.append(a); t_qp.append(b)
+    loop.finish()
+    sol.set_option("kernel_timing", 0)
+    return float(np.mean(t_lin)), float(np.mean(t_qp))
+
+
+def record_states(torch, loop, T, dev):
+    """untimed: the closed loop's per-tick inputs (x0, row index) as host arrays, for the host-API loops"""
+    loop.restart()
+    xs, ls = [], []
+    for t in range(T):
+        xs.append(loop.x.cpu().numpy().copy()); ls.append(loop.lines.cpu().numpy().copy())
+        loop.tick(t)
+    loop.finish()
+    torch.cuda.synchronize(dev)
+    return xs, ls
+
+
+def roofline_of(B, N, iters_mean, t_qp, kernel):
+    peak, peak_src = peaks()
+    alg = B * BYTES_PER_STAGE_ITER * N * iters_mean
+    achieved = alg / t_qp / 1e9
+    traffic, src = measured_traffic(kernel, B, N)
+    return {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": src, "algorithmic_bytes": alg, "peak_source": peak_src,
+            "formula": f"B*{BYTES_PER_STAGE_ITER}*N*mean_qp_iterations / t_qp"}
+
+
+def host_loop(torch, sol, w, xs, ls, W, K, explicit_yref, N):
+    """closed-loop ticks through the host API with pinned host buffers, a distinct input buffer per tick; wall clock around K ticks.
+    explicit_yref: upload the (N+1) x 16 reference window per instance like ocp_nlp_cost_model_set("yref") x (N+1) does
+    (bluerov2_dob.cpp:370-372) instead of naming a trajectory row"""
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    B = w["x0"].shape[0]
+    h_x0 = [pin(a) for a in xs[:W + K]]
+    h_p = pin(w["p"])
+    out = (pin(np.empty((B, 4))), pin(np.empty((B, 6))), pin(np.empty((B,), dtype=np.int32)))
+    if explicit_yref:
+        h_ref = [pin(traj.window_batch(w["traj"], l.astype(np.int64), N)) for l in ls[:W + K]]
+        call = lambda t: sol.tick(h_x0[t], p=h_p, yref=h_ref[t], out=out)   # noqa: E731
+        h2d = (B * 12 + B * 16 + B * (N + 1) * 16) * 8
+    else:
+        h_ref = [pin(l.astype(np.int32)) for l in ls[:W + K]]
+        call = lambda t: sol.tick(h_x0[t], p=h_p, lines=h_ref[t], out=out)  # noqa: E731
+        h2d = (B * 12 + B * 16) * 8 + B * 4      # x0, p (fp64) and one trajectory row index per instance (int32)
+    sol.set_iterate(w["X"], w["U"])
+    ok = True
+    for t in range(W):
+        call(t)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(W, W + K):
+        call(t)
+        ok = ok and bool((out[2] == 0).all())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ok = ok and bool(np.isfinite(out[0]).all())
+    return dt, ok, h2d, (B * 4 + B * 6) * 8 + B * 4
+
+
+# ---------------------------------------------------------------------------------------------------------
+def sub_records(torch, S, dev, args, N, cpu):
+    """the regimes the headline does not time (rank 0, one GPU): nested records of the one JSON line"""
+    out = {}
+    W, K = 5, 30
+
+    def solver_for(B, Nh, spread, **opts):
+        w = wl.tracking_batch(B, Nh, seed=0, reference="circle", pos_spread=spread)
+        sol = S.BatchSolver(B, Nh, device=dev.index)
+        sol.set_option("kernel_timing", 0)
+        for k, v in opts.items():
+            sol.set_option(k, v)
+        return sol, w, DeviceLoop(S, sol, w, dev)
+
+    # ---- forced interior-point iteration (the reference's algorithm on every instance): like for like with the CPU arm ----
+    sol, w, loop = solver_for(args.batch_sub, N, args.pos_spread, fast_path=0)
+    dt, itm, bad, _ = timed_device_loop(torch, None, loop, W, K, dev, False)
+    tl, tq = kernel_times(torch, loop, W, K, dev)
+    out["forced_ipm"] = {"value": args.batch_sub * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K, "mean_ipm_iterations": itm,
+                         "nonzero_status": bad, "kernels": {"linearize_ms": 1e3 * tl, "qp_ms": 1e3 * tq},
+                         "roofline": roofline_of(args.batch_sub, N, itm, tq, "ipm_kernel"),
+                         "what": "option fast_path = 0: Mehrotra predictor-corrector Riccati IPM on every instance, cold-started every tick"}
+    sol.close()
+    # ---- saturated start: 3 m position spread, thrusters saturated during the first ticks; timed FROM TICK 0 ----
+    sol, w, loop = solver_for(args.batch_sub, N, 3.0)
+    timed_device_loop(torch, None, loop, 0, 8, dev, False)              # throw-away pass: graphs built, code paths warm
+    dt, itm, bad, ticks = timed_device_loop(torch, None, loop, 0, 12, dev, False, per_tick=True)
+    tq_ticks = []
+    sol.set_option("kernel_timing", 1)
+    loop.restart()
+    for t in range(12):
+        loop.tick(t); torch.cuda.synchronize(dev)
+        tq_ticks.append(1e3 * sol.last_kernel_times()[1])
+    it0, _ = sol.stats()
+    out["saturated_start"] = {"value": args.batch_sub * 12 / dt, "unit": UNIT, "tick_ms": [round(x, 4) for x in ticks],
+                              "qp_ms_per_tick": [round(x, 4) for x in tq_ticks], "mean_qp_iterations": itm, "nonzero_status": bad,
+                              "what": "pos spread 3.0 m, ticks 0..11 timed from tick 0 (about a third of the instances start with "
+                                      "saturated thrusters): interior fast path + primal-dual active-set iteration, IPM fallback"}
+    sol.close()
+    # ---- config 5: horizon sweep at batch 8192 ----
+    sweep = []
+    for Nh in (10, 20, 40, 80):
+        sol, w, loop = solver_for(8192, Nh, args.pos_spread)
+        dt, itm, bad, _ = timed_device_loop(torch, None, loop, W, K, dev, False)
+        tl, tq = kernel_times(torch, loop, W, K, dev)
+        rf = roofline_of(8192, Nh, itm, tq, "pdas_kernel")
+        sweep.append({"horizon": Nh, "value": 8192 * K / dt, "ms_per_step": 1e3 * dt / K, "linearize_ms": 1e3 * tl, "qp_ms": 1e3 * tq,
+                      "roofline_frac": rf["frac"], "achieved_gbs": rf["achieved"], "nonzero_status": bad})
+        sol.close()
+    out["config5_horizon_sweep"] = {"batch": 8192, "unit": UNIT, "points": sweep}
+    # ---- config 3: DOB-MPC (EKF -> parameters -> solve as ONE tick), sampled wave disturbances, lemniscate reference ----
+    out["config3_dob"] = dob_record(torch, S, dev, args, N)
+    return out
+
+
+def dob_record(torch, S, dev, args, N):
+    """BASELINE config 3.  Inputs recorded from the settled closed loop driven by the UNCOMPENSATED command (the node's compensation
+    gain 1/0.0325, bluerov2_dob.cpp:326-338, over-compensates ~30x on any plant whose thrust scale is the OCP model's, so the
+    compensated command is computed -- the timed path -- but not fed back); the timed loop replays them through fixed device
+    buffers (four small device-to-device copies per tick, inside the timed region) into br2_batch_tick_device(ekf = 1)."""
+    B, W, K, settle = args.batch_sub, 5, 30, 60
+    w = wl.tracking_batch(B, N, seed=0, reference="lemniscate", pos_spread=min(args.pos_spread, 0.2), level=True)
+    sol = S.BatchSolver(B, N, device=dev.index)
+    sol.set_option("kernel_timing", 0)
+    sol.set_trajectory(w["traj"]); sol.set_iterate(w["X"], w["U"])
+    amp, tau0 = wl.wave_disturbance(B, seed=1)
+    x, lines = w["x0"].copy(), w["lines"].copy()
+    vel_prev, thr = x[:, 6:12].copy(), np.zeros((B, 6))
+    rec = {"thr": [], "meas": [], "acc": [], "lines": []}
+    start = None
+    for t in range(settle + W + K):
+        if t == settle:
+            X0, U0 = sol.get_iterate()
+            sol.ekf_reset()
+            ex, eP = sol.ekf_state()
+            ex[:, :12] = x                  # filter starts at the true pose
+            start = (X0, U0, ex, eP)
+        if t >= settle:
+            rec["thr"].append(thr.copy()); rec["meas"].append(x.copy())
+            rec["acc"].append((x[:, 6:12] - vel_prev) / 0.05); rec["lines"].append(lines.astype(np.int32))
+        vel_prev = x[:, 6:12].copy()
+        u0, th, st = sol.solve_windowed(x, lines.astype(np.int32), w["p"])
+        if (st != 0).any():
+            return {"error": f"solver status != 0 while recording the DOB workload at tick {t}"}
+        thr = th.copy()                                   # thrust feedback = previous command
+        x = wl.plant_step(x, u0, w["p"], 0.05, dist=wl.wave_at(amp, tau0, t))
+        lines = lines + 1
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    src = [tuple(d(rec[k][t]) for k in ("meas", "thr", "acc", "lines")) for t in range(W + K)]
+    bx, bt, ba, bl = (torch.empty_like(a) for a in src[0])
+    out = (torch.empty((B, 4), dtype=torch.float64, device=dev), torch.empty((B, 6), dtype=torch.float64, device=dev),
+           torch.empty((B,), dtype=torch.int32, device=dev))
+    wf = torch.empty((B, 6), dtype=torch.float64, device=dev)
+
+    def tick(t):
+        bx.copy_(src[t][0]); bt.copy_(src[t][1]); ba.copy_(src[t][2]); bl.copy_(src[t][3])
+        sol.tick(bx, lines=bl, thrusts=bt, body_acc=ba, ekf=1, compensate=True, out=out, wf_dist=wf)
+
+    def restart():
+        sol.set_iterate(start[0], start[1]); sol.set_ekf_state(start[2], start[3])
+
+    stream = torch.cuda.current_stream(dev)
+    restart()
+    for t in range(W):
+        tick(t)
+    torch.cuda.synchronize(dev)
+    sol.ipm_iterations_total(reset=True); sol.nonzero_status_total(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(W, W + K):
+        tick(t)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    dt = e0.elapsed_time(e1) * 1e-3
+    itm, bad = sol.ipm_iterations_total(reset=True) / (B * K), sol.nonzero_status_total(reset=True)
+    # host path: the tick through br2_batch_tick_host (EKF inputs up, u0 / thrust / status / disturbance down)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    hsrc = [tuple(pin(rec[k][t]) for k in ("meas", "thr", "acc", "lines")) for t in range(W + K)]
+    hout = (pin(np.empty((B, 4))), pin(np.empty((B, 6))), pin(np.empty((B,), dtype=np.int32)))
+    hwf = pin(np.empty((B, 6)))
+    restart()
+    for t in range(W):
+        sol.tick(hsrc[t][0], lines=hsrc[t][3], thrusts=hsrc[t][1], body_acc=hsrc[t][2], ekf=1, out=hout, wf_dist=hwf)
+    t0 = time.perf_counter()
+    for t in range(W, W + K):
+        sol.tick(hsrc[t][0], lines=hsrc[t][3], thrusts=hsrc[t][1], body_acc=hsrc[t][2], ekf=1, out=hout, wf_dist=hwf)
+    dth = time.perf_counter() - t0
+    sol.close()
+    return {"value": B * K / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / K, "mean_qp_iterations": itm, "nonzero_status": bad,
+            "gpu_launches_per_tick": 4, "kernels": ["ekf_kernel", "linearize_kernel", "pdas_kernel", "ipm_kernel"],
+            "e2e": {"value": B * K / dth, "unit": UNIT, "ms_per_step": 1e3 * dth / K,
+                    "h2d_bytes_per_step": (B * 12 + B * 6 + B * 6) * 8 + B * 4, "d2h_bytes_per_step": (B * 4 + B * 6 + B * 6) * 8 + B * 4},
+            "what": f"batch {B} DOB-MPC: 18-state EKF -> OCP parameters -> RTI solve as one br2_batch_tick_device (one CUDA graph), sampled wave "
+                    f"disturbances, lemniscate reference, N={N}; inputs recorded from the settled closed loop (see dob_record)"}
+
+
+# ---------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -246,179 +482,93 @@ def run_ours(args):
     distributed = world > 1
     if distributed:
         dist.init_process_group("nccl", device_id=dev)
-    K, W, N, B = args.steps, args.warmup, args.horizon, args.batch
+    K, W, N = args.steps, args.warmup, args.horizon
+    B = args.batch or default_batch(world)
+    args.batch_sub = args.batch or 4096
     if W < 3:
         raise SystemExit("--warmup must be >= 3")
 
     sampler = ClockSampler(local)
-    dob = args.workload == "dob"
-    w = wl.tracking_batch(B, N, seed=1000 * rank, reference="lemniscate" if dob else "circle",
-                          pos_spread=min(args.pos_spread, 0.2) if dob else args.pos_spread, level=dob)
+    # every rank draws the same generator with its own seed offset: shards of one job
+    w = wl.tracking_batch(B, N, seed=1000 * rank, reference="circle", pos_spread=args.pos_spread)
     sol = S.BatchSolver(B, N, device=local)
+    sol.set_option("kernel_timing", 0)
     if args.no_fast_path:
         sol.set_option("fast_path", 0)
     if args.active_set_path is not None:
         sol.set_option("active_set_path", args.active_set_path)
-    if dob:
-        rec, dob0 = record_closed_loop_dob(sol, w, W + K, N, seed=1000 * rank)
-        x0s, lns = rec["meas"], rec["lines"]
-        d_thr = [torch.from_numpy(a).to(dev) for a in rec["thr"]]
-        d_acc = [torch.from_numpy(a).to(dev) for a in rec["acc"]]
-        ekf_out = (torch.empty((B, 6), dtype=torch.float64, device=dev), torch.empty((B, 16), dtype=torch.float64, device=dev))
-    else:
-        x0s, lns = record_closed_loop(sol, w, W + K, N)
+    loop = DeviceLoop(S, sol, w, dev, world)
 
-    # ---- device-resident inputs, one distinct buffer per tick ----
-    d_x0 = [torch.from_numpy(a).to(dev) for a in x0s]
-    d_lines = [torch.from_numpy(a).to(dev) for a in lns]
-    d_p = torch.from_numpy(w["p"]).to(dev)
-
-    def restart():
-        if dob:
-            sol.set_iterate(dob0[0], dob0[1])
-            sol.set_ekf_state(dob0[2], dob0[3])
-        else:
-            sol.set_iterate(w["X"], w["U"])
-    from bluerov2_b200.sharding import PipelinedThrustGather
-    # all ranks' thrust vectors, double-buffered: the all-gather of tick t overlaps the lineariser of tick t + 1
-    gather = PipelinedThrustGather(world * B, dev, depth=int(os.environ.get("BR2_GATHER_DEPTH", "2")))
-    out_u0, out_st = torch.empty((B, 4), dtype=torch.float64, device=dev), torch.empty((B,), dtype=torch.int32, device=dev)
-    out = (out_u0, gather.slot(0), out_st)
-    stream = torch.cuda.current_stream(dev)
-
-    def tick(t):
-        o = (out_u0, gather.slot(t), out_st)    # thrusts land directly in this rank's slot of the tick's gather buffer
-        if dob:     # EKF writes the OCP parameters on the device; the solve reads them there (same stream, no host hop)
-            sol.ekf(d_thr[t], d_x0[t], d_acc[t], compensate=True, out=ekf_out)
-            sol.solve_windowed(d_x0[t], d_lines[t], ekf_out[1], out=o)
-        else:
-            sol.solve_windowed(d_x0[t], d_lines[t], d_p, out=o)
-        if distributed:
-            gather.all_gather_async(t)          # ONE all-gather per tick, enqueued behind the solve
-
-    def barrier():
-        gather.wait_all()                       # the last ticks' collectives belong to the timed region
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    restart()
-    for t in range(W):
-        tick(t)
-    barrier()
-    sol.ipm_iterations_total(reset=True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    t_lin, t_ipm = [], []
-    sampler.start()
-    ev[0].record(stream)
-    for t in range(W, W + K):
-        tick(t)
-    gather.wait_all()                           # the stream waits for the collectives still in flight before the end event
-    ev[1].record(stream)
-    barrier()
+    dt, iters_mean, n_bad, _ = timed_device_loop(torch, dist, loop, W, K, dev, distributed, sampler)
     clocks = sampler.stop()
-    dt = ev[0].elapsed_time(ev[1]) * 1e-3
-    iters_total = sol.ipm_iterations_total(reset=True)
-    st = out[2].cpu().numpy()
-    n_bad = int((st != 0).sum())
+    t_lin, t_qp = kernel_times(torch, loop, W, K, dev)
+    graphs = sol.graphs_built()
 
-    # per-kernel device times (CUDA events recorded by the library on the launching stream around each kernel):
-    # replay the timed ticks once more, reading the events after each tick (outside the steps/s measurement)
-    restart()
-    for t in range(W + K):
-        tick(t)
-        if t >= W:
-            torch.cuda.synchronize(dev)
-            a, b = sol.last_kernel_times()
-            t_lin.append(a); t_ipm.append(b)
-
-    # ---- e2e: host buffers through the public host API ----
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
-    h_x0 = [pin(a) for a in x0s]
-    h_lines = [torch.from_numpy(a).pin_memory().numpy() for a in lns]
-    h_p = pin(w["p"])
-    h_out = (pin(np.empty((B, 4))), pin(np.empty((B, 6))), torch.empty((B,), dtype=torch.int32).pin_memory().numpy())
-    if dob:
-        h_thr = [pin(a) for a in rec["thr"]]
-        h_acc = [pin(a) for a in rec["acc"]]
-        h_ekf = (pin(np.empty((B, 6))), pin(np.empty((B, 16))))
-
-    def host_tick(t):
-        if dob:     # the two public host calls of a DOB-MPC tick; p makes the round trip through the host like in the node
-            sol.ekf(h_thr[t], h_x0[t], h_acc[t], compensate=True, out=h_ekf)
-            sol.solve_windowed(h_x0[t], h_lines[t], h_ekf[1], out=h_out)
-        else:
-            sol.solve_windowed(h_x0[t], h_lines[t], h_p, out=h_out)
-
-    restart()
-    for t in range(W):
-        host_tick(t)
-    barrier()
-    t0 = time.perf_counter()
-    for t in range(W, W + K):
-        host_tick(t)
-    barrier()
-    dt_e2e = time.perf_counter() - t0
-    e2e_ok = bool((h_out[2] == 0).all()) and bool(np.isfinite(h_out[0]).all())
-    if dob:     # thrusts, measurement (= x0), body acceleration, row index up; disturbance, p, u0, thrust, status down; p up again
-        h2d = (B * 6 + B * 12 + B * 6 + B * 16) * 8 + B * 4
-        d2h = (B * 6 + B * 16 + B * 4 + B * 6) * 8 + B * 4
-    else:
-        h2d = (B * 12 + B * 16) * 8 + B * 4      # x0, p (fp64) and one trajectory row index per instance (int32)
-        d2h = (B * 4 + B * 6) * 8 + B * 4
+    # ---- e2e: the same closed-loop ticks through the host API ----
+    xs, ls = record_states(torch, loop, W + K, dev)
+    dt_e2e, e2e_ok, h2d, d2h = host_loop(torch, sol, w, xs, ls, W, K, False, N)
+    dt_exp = None
+    if world == 1 and not args.quick:
+        dt_exp, exp_ok, h2d_exp, _ = host_loop(torch, sol, w, xs, ls, W, min(K, 50), True, N)
 
     if distributed:
         tt = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt, dt_e2e = float(tt[0]), float(tt[1])
-        cnt = torch.tensor([float(iters_total), float(n_bad)], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([float(iters_mean), float(n_bad)], dtype=torch.float64, device=dev)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        iters_total, n_bad = float(cnt[0]), int(cnt[1])
-        iters_mean = iters_total / (world * B * K)
-    else:
-        iters_mean = iters_total / (B * K)
+        iters_mean, n_bad = float(cnt[0]) / world, int(cnt[1])
 
     if rank == 0:
-        peak, peak_src = peaks()
-        t_ipm_avg = float(np.mean(t_ipm))
-        alg_bytes = B * BYTES_PER_STAGE_ITER * N * iters_mean
-        achieved = alg_bytes / t_ipm_avg / 1e9
-        traffic, traffic_src = measured_traffic(B, N, not args.no_fast_path)
         line = {
             "metric": METRIC, "value": world * B * K / dt, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": (f"config 3: batch {B} per GPU DOB-MPC (18-state EKF -> parameters -> RTI solve, back to back on "
-                                    f"one stream), sampled wave disturbances, lemniscate reference, N={N}, fp64; inputs recorded from the settled "
-                                    f"closed loop driven by the uncompensated command (see record_closed_loop_dob)"
-                                    if dob else
-                                    f"config 2: batch {B} per GPU, random x0 around the circle reference (pos spread "
-                                    f"{args.pos_spread} m), N={N}, Ts={1.0 / N:g} s, fp64, closed loop (nominal ERK4 plant at 0.05 s), "
-                                    f"iterate carried between ticks"), "batch_per_gpu": B, "global_batch": world * B, "horizon": N,
-                       "mean_ipm_iterations": iters_mean, "nonzero_status": n_bad, "fast_path": not args.no_fast_path,
-                       "l2": "per-tick working set (stage records + factors + iterates) "
-                             f"{B * N * (208 + 64 + 64) * 8 / 1e6:.0f} MB > 126 MB L2; distinct input buffers per step",
-                       "parallelism": f"{world} x independent shards" + (", one NCCL all-gather of the thrust vectors per tick (double-buffered: it overlaps the next tick's lineariser)" if distributed else "")},
+            "config": config_of(B, world, N, args.pos_spread),
+            "mean_qp_iterations": iters_mean, "nonzero_status": n_bad, "fast_path": not args.no_fast_path,
+            "l2": "per-tick working set (stage records + iterates) "
+                  f"{B * (N + 1) * 352 * 8 / 1e6:.0f} MB > 126 MB L2",
+            "parallelism": f"{world} x independent shards" + (", one NCCL all-gather of the thrust vectors per tick (double-buffered: it "
+                                                              "overlaps the next tick's lineariser)" if distributed else ""),
             "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ok": e2e_ok,
-                    "ms_per_step": 1e3 * dt_e2e / K},
-            "gpu_launches": (3 if dob else 2) * K,
-            "kernels": {"linearize_ms": 1e3 * float(np.mean(t_lin)), "ipm_ms": 1e3 * t_ipm_avg,
-                        "ipm_share_of_step": t_ipm_avg / (dt / K)},
-            "roofline": {"kernel": "ipm_kernel (Riccati sweeps)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
-                         "peak_source": peak_src,
-                         "formula": f"B*{BYTES_PER_STAGE_ITER}*N*mean_ipm_iterations / t_ipm"},
+                    "ms_per_step": 1e3 * dt_e2e / K, "api": "br2_batch_tick_host (windowed reference: one trajectory row index per instance)",
+                    "overhead_over_device_time": dt_e2e / dt - 1.0},
+            "gpu_launches": 4 * K,
+            "gpu_launches_per_tick": {"count": 4, "kernels": ["linearize_kernel", "pdas_kernel", "ipm_kernel (fallback list, normally empty)",
+                                                              "plant_kernel"], "graphs_instantiated": graphs,
+                                      "how": "one cudaGraphLaunch per tick (br2_batch_tick_device)"},
+            "kernels": {"linearize_ms": 1e3 * t_lin, "qp_ms": 1e3 * t_qp, "qp_share_of_step": t_qp / (dt / K)},
+            "roofline": roofline_of(B, N, iters_mean, t_qp, "ipm_kernel" if args.no_fast_path else "pdas_kernel"),
             "clocks": clocks,
         }
-        # ---- CPU baseline on this box's host cores (bounded sample) ----
-        if world == 1 and not args.no_cpu and not dob:
+        if dt_exp is not None:
+            Ke = min(K, 50)
+            line["e2e_explicit_yref"] = {"value": B * Ke / dt_exp, "unit": UNIT, "ms_per_step": 1e3 * dt_exp / Ke, "h2d_bytes_per_step": h2d_exp,
+                                         "d2h_bytes_per_step": d2h, "ok": exp_ok, "fraction_of_windowed_e2e": (B * Ke / dt_exp) / (B * K / dt_e2e),
+                                         "api": "br2_batch_tick_host with the explicit (N+1) x 16 reference window per instance "
+                                                "(ocp_nlp_cost_model_set \"yref\" x (N+1), bluerov2_dob.cpp:370-372)"}
+        if world == 1 and not args.no_cpu:
             r = cpu_leg(N, budget_s=args.cpu_budget, ticks_wanted=3 + 2, seed=0, pos_spread=args.pos_spread)
             tcpu = float(np.sum(r["times"][2:]))
             line["cpu_baseline"] = {"value": r["batch"] * 3 / tcpu, "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": f"{r['batch']} instances x 3 closed-loop ticks (after 2 warm-up ticks) of the same workload; {r['note']}",
                                     "mean_ipm_iterations": float(np.mean(r["iters"][2:]))}
+        if world == 1 and not args.quick:
+            sol.close()
+            sub = sub_records(torch, S, dev, args, N, line.get("cpu_baseline"))
+            line["sub_records"] = sub
+            if "cpu_baseline" in line and "forced_ipm" in sub:
+                cb = line["cpu_baseline"]
+                cb["like_for_like"] = {
+                    "gpu_forced_ipm_over_cpu": sub["forced_ipm"]["value"] / cb["value"],
+                    "gpu_default_over_cpu": line["value"] / cb["value"],
+                    "note": "the CPU arm runs the interior-point iteration on every instance; forced_ipm is the GPU doing the same, the "
+                            "headline additionally uses the exact interior / active-set shortcuts (same minimiser, fewer factorisations)"}
         print(json.dumps(line), flush=True)
-    sol.close()
+    try:
+        sol.close()
+    except Exception:
+        pass
     if distributed:
         dist.destroy_process_group()
 
@@ -429,16 +579,15 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="instances per GPU (default 4096; 8192 at 8 GPUs = BASELINE config 4)")
     ap.add_argument("--horizon", type=int, default=40)
     ap.add_argument("--pos-spread", type=float, default=0.5)
-    ap.add_argument("--workload", default="tracking", choices=["tracking", "dob"],
-                    help="tracking = BASELINE config 2 (default, the headline); dob = config 3 (EKF + solve per tick)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline / reference arm")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline + e2e only (no sub-records)")
     ap.add_argument("--no-fast-path", action="store_true", help="always run the interior-point iteration (diagnostic)")
     ap.add_argument("--active-set-path", type=int, default=None, choices=[0, 1],
-                    help="override the library default of the active-set fast path (diagnostic)")
+                    help="override the library default of the primal-dual active-set iteration (diagnostic)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -755,20 +755,64 @@ BR2_MODEL_API const int* bluerov2_expl_vde_adj_sparsity_out(int i) { return i ==
 BR2_MODEL_API int bluerov2_expl_vde_adj_n_in(void) { return 4; }
 BR2_MODEL_API int bluerov2_expl_vde_adj_n_out(void) { return 1; }
 
-// NLS residual y = [x; u] (terminal y = x): bluerov2.py:144,153-154
-BR2_MODEL_API int bluerov2_cost_y_fun(const real_t** arg, real_t** res, int*, real_t*, void*)
+// ---- cost functions: NLS residual y = [x; u] (terminal y = x), bluerov2.py:144,153-154 -------------------------------------
+// The nine functions of c_generated_code/bluerov2_cost/bluerov2_cost.h:45-114 with CasADi's six entry points each.  A null
+// input reads as zeros and a null output is skipped, like the generated code.  The engine never calls them (its Gauss-Newton
+// Hessian Ts*W is baked into the kernels); they complete the drop-in's symbol table and are checked against the reference's own
+// generated C in tests/test_abi.py.
+//   _fun            (x, u, z, p)        -> y
+//   _fun_jac_ut_xt  (x, u, z, p)        -> y, d y / d [u; x] transposed ((nu+nx) x ny, one unit entry per column), (ny x 0)
+//   _hess           (x, u, z, lam_y, p) -> (nu+nx) x (nu+nx), structurally empty: the residual is linear
+static const int kSpEmpty[] = {0, 0, 0};
+static const int kSpJacUtXt[] = {16, 16, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16,
+                                 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 0, 1, 2, 3};        // column j = y_j: row of x_j is 4 + j, of u_a is a
+static const int kSpNy0[] = {16, 0, 0};
+static const int kSpHess[] = {16, 16, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+static const int kSpJacE[] = {12, 12, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+static const int kSpNyE0[] = {12, 0, 0};
+static const int kSpHessE[] = {12, 12, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+static void cost_y(const real_t** arg, real_t* y, bool terminal)
 {
-    if (res[0]) { memcpy(res[0], arg[0], sizeof(double) * 12); memcpy(res[0] + 12, arg[1], sizeof(double) * 4); }
+    for (int i = 0; i < 12; i++) y[i] = arg[0] ? arg[0][i] : 0.0;
+    if (!terminal)
+        for (int i = 0; i < 4; i++) y[12 + i] = arg[1] ? arg[1][i] : 0.0;
+}
+#define BR2_COST_HELPERS(f, n_in, n_out, SP_IN, SP_OUT)                                                                       \
+    BR2_MODEL_API int f##_work(int* a, int* b, int* c, int* d) { if (a) *a = n_in; if (b) *b = n_out; if (c) *c = 0; if (d) *d = 0; return 0; } \
+    BR2_MODEL_API const int* f##_sparsity_in(int i) { static const int* const t[] = SP_IN; return (i >= 0 && i < n_in) ? t[i] : nullptr; }     \
+    BR2_MODEL_API const int* f##_sparsity_out(int i) { static const int* const t[] = SP_OUT; return (i >= 0 && i < n_out) ? t[i] : nullptr; }  \
+    BR2_MODEL_API int f##_n_in(void) { return n_in; }                                                                          \
+    BR2_MODEL_API int f##_n_out(void) { return n_out; }
+#define BR2_LIST(...) {__VA_ARGS__}
+#define BR2_COST_STAGE(pre)                                                                                                    \
+    BR2_MODEL_API int pre##_fun(const real_t** arg, real_t** res, int*, real_t*, void*) { if (res[0]) cost_y(arg, res[0], false); return 0; } \
+    BR2_COST_HELPERS(pre##_fun, 4, 1, BR2_LIST(kSpX, kSpU, kSpEmpty, kSpP), BR2_LIST(kSpP))                                   \
+    BR2_MODEL_API int pre##_fun_jac_ut_xt(const real_t** arg, real_t** res, int*, real_t*, void*)                              \
+    {                                                                                                                          \
+        if (res[0]) cost_y(arg, res[0], false);                                                                                \
+        if (res[1]) for (int i = 0; i < 16; i++) res[1][i] = 1.0;                                                              \
+        return 0;                                                                                                              \
+    }                                                                                                                          \
+    BR2_COST_HELPERS(pre##_fun_jac_ut_xt, 4, 3, BR2_LIST(kSpX, kSpU, kSpEmpty, kSpP), BR2_LIST(kSpP, kSpJacUtXt, kSpNy0))     \
+    BR2_MODEL_API int pre##_hess(const real_t**, real_t**, int*, real_t*, void*) { return 0; }                                \
+    BR2_COST_HELPERS(pre##_hess, 5, 1, BR2_LIST(kSpX, kSpU, kSpEmpty, kSpP, kSpP), BR2_LIST(kSpHess))
+BR2_COST_STAGE(bluerov2_cost_y_0)      // bluerov2_cost.h:45-66
+BR2_COST_STAGE(bluerov2_cost_y)        // :70-91
+// terminal node: y = x, no input (bluerov2_cost.h:95-116)
+BR2_MODEL_API int bluerov2_cost_y_e_fun(const real_t** arg, real_t** res, int*, real_t*, void*) { if (res[0]) cost_y(arg, res[0], true); return 0; }
+BR2_COST_HELPERS(bluerov2_cost_y_e_fun, 4, 1, BR2_LIST(kSpX, kSpEmpty, kSpEmpty, kSpP), BR2_LIST(kSpX))
+BR2_MODEL_API int bluerov2_cost_y_e_fun_jac_ut_xt(const real_t** arg, real_t** res, int*, real_t*, void*)
+{
+    if (res[0]) cost_y(arg, res[0], true);
+    if (res[1]) for (int i = 0; i < 12; i++) res[1][i] = 1.0;
     return 0;
 }
-BR2_MODEL_API int bluerov2_cost_y_0_fun(const real_t** arg, real_t** res, int* iw, real_t* w, void* mem)
-{
-    return bluerov2_cost_y_fun(arg, res, iw, w, mem);
-}
-BR2_MODEL_API int bluerov2_cost_y_e_fun(const real_t** arg, real_t** res, int*, real_t*, void*)
-{
-    if (res[0]) memcpy(res[0], arg[0], sizeof(double) * 12);
-    return 0;
-}
+BR2_COST_HELPERS(bluerov2_cost_y_e_fun_jac_ut_xt, 4, 3, BR2_LIST(kSpX, kSpEmpty, kSpEmpty, kSpP), BR2_LIST(kSpX, kSpJacE, kSpNyE0))
+BR2_MODEL_API int bluerov2_cost_y_e_hess(const real_t**, real_t**, int*, real_t*, void*) { return 0; }
+BR2_COST_HELPERS(bluerov2_cost_y_e_hess, 5, 1, BR2_LIST(kSpX, kSpEmpty, kSpEmpty, kSpX, kSpP), BR2_LIST(kSpHessE))
+#undef BR2_COST_STAGE
+#undef BR2_COST_HELPERS
+#undef BR2_LIST
 
 }  // extern "C"

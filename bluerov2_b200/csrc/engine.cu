@@ -48,6 +48,15 @@ struct br2_batch_solver {
     cudaEvent_t ev_x0;              // x0 upload complete (the IPM kernel is its first reader)
     unsigned long long* d_iter_total;   // IPM iterations executed, summed over instances and solves
     bool timed;
+    // tick graphs: the kernels (and, for host buffers, the copies) of one control tick instantiated as a CUDA graph, keyed on the
+    // caller's buffers and on a generation counter that every change of options / weights / bounds / trajectory bumps
+    struct TickGraph { br2_tick_io io; int host; unsigned gen; unsigned long long stamp; cudaGraphExec_t exec; } tg[4];
+    unsigned gen;
+    unsigned long long tick_stamp;
+    int graphs_built, kernel_timing, tick_graph;
+    cudaEvent_t ev_fork;
+    struct Miss { br2_tick_io io; int host; unsigned gen; bool valid; } miss[4];   // the last keys that missed the graph cache
+    unsigned miss_next;
 };
 
 // generated-C defaults: acados_solver_bluerov2.c:424-459 (W), :468-479 (W_e), :547-571 (bounds), :522-541 / :681-708 (x init);
@@ -106,6 +115,9 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev_mid) cudaEventDestroy(s->ev_mid);
     if (s->ev_x0) cudaEventDestroy(s->ev_x0);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    for (auto& g : s->tg)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->stream_x0) cudaStreamDestroy(s->stream_x0);
     free(s);
@@ -153,6 +165,8 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     s->fast_path = 1;
     s->active_set = 1;      // primal-dual active-set iteration on by default (option "active_set_path")
     s->tol = 1e-12;
+    s->kernel_timing = 1;
+    s->tick_graph = 1;
     const size_t B = batch;
 #define DA(p, n)                                                                                          \
     do {                                                                                                  \
@@ -170,7 +184,7 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     DA(d_pout, B * NP);
     DA(d_rls, B * 4 * RLS_STRIDE);
     DA(d_yaw, B * 2);
-    DA(d_iter_total, 1 + 16);     // [0] iteration counter, [1..16] phase cycle counters of the instrumentation build
+    DA(d_iter_total, 1 + 16 + 1); // [0] iteration counter, [1..16] phase cycle counters of the instrumentation build, [17] non-zero statuses
     DA(d_hint, B);
     DA(d_aset, B * N);
     DA(d_lines, B);
@@ -178,10 +192,11 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     CKF(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CKF(cudaStreamCreateWithFlags(&s->stream_x0, cudaStreamNonBlocking));
     CKF(cudaEventCreateWithFlags(&s->ev_x0, cudaEventDisableTiming));
+    CKF(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     CKF(cudaEventCreate(&s->ev0));
     CKF(cudaEventCreate(&s->ev1));
     CKF(cudaEventCreate(&s->ev_mid));
-    CKF(cudaMemset(s->d_iter_total, 0, sizeof(unsigned long long) * 17));
+    CKF(cudaMemset(s->d_iter_total, 0, sizeof(unsigned long long) * 18));
     CKF(cudaMemcpy(s->d_Ts, s->Ts, sizeof(double) * N, cudaMemcpyHostToDevice));
     CKF(cudaMemset(s->d_status, 0, sizeof(int) * B));
     CKF(cudaMemset(s->d_iters, 0, sizeof(int) * B));
@@ -227,6 +242,7 @@ extern "C" int br2_batch_set_weights(br2_batch_solver* s, const double* W16, con
             if (!(We12[i] >= 0)) return fail(BR2_EINVAL, "We[%d] = %g: need >= 0", i, We12[i]);
         memcpy(s->We, We12, sizeof(double) * 12);
     }
+    s->gen++;
     return BR2_OK;
 }
 
@@ -237,6 +253,7 @@ extern "C" int br2_batch_set_bounds(br2_batch_solver* s, const double* lbu4, con
         if (!(lbu4[i] < ubu4[i])) return fail(BR2_EINVAL, "bounds %d: lbu %g >= ubu %g", i, lbu4[i], ubu4[i]);
     memcpy(s->lbu, lbu4, sizeof(double) * 4);
     memcpy(s->ubu, ubu4, sizeof(double) * 4);
+    s->gen++;
     return BR2_OK;
 }
 
@@ -254,6 +271,9 @@ extern "C" int br2_batch_set_time_steps(br2_batch_solver* s, const double* ts)
 extern "C" int br2_batch_set_option_int(br2_batch_solver* s, const char* name, int v)
 {
     if (!s || !name) return fail(BR2_EINVAL, "null argument");
+    s->gen++;
+    if (!strcmp(name, "kernel_timing")) { s->kernel_timing = v != 0; return BR2_OK; }
+    if (!strcmp(name, "tick_graph")) { s->tick_graph = v != 0; return BR2_OK; }
     if (!strcmp(name, "qp_iter_max")) {
         if (v < 1) return fail(BR2_EINVAL, "qp_iter_max = %d", v);
         s->max_iter = v;
@@ -277,6 +297,7 @@ extern "C" int br2_batch_set_option_int(br2_batch_solver* s, const char* name, i
 extern "C" int br2_batch_set_option_double(br2_batch_solver* s, const char* name, double v)
 {
     if (!s || !name) return fail(BR2_EINVAL, "null argument");
+    s->gen++;
     if (!strcmp(name, "qp_tol")) {
         if (!(v > 0)) return fail(BR2_EINVAL, "qp_tol = %g", v);
         s->tol = v;
@@ -349,7 +370,7 @@ static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, con
     a.u0 = d_u0 ? d_u0 : s->d_u0;
     a.thrust = d_thrust ? d_thrust : s->d_thrust;
     a.status = d_status ? d_status : s->d_status;
-    a.iters = s->d_iters; a.info = s->d_info; a.ctr = s->d_counter; a.order = s->d_order; a.fb = s->d_fb; a.iter_total = s->d_iter_total; a.prof = s->d_iter_total + 1; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
+    a.iters = s->d_iters; a.info = s->d_info; a.ctr = s->d_counter; a.order = s->d_order; a.fb = s->d_fb; a.iter_total = s->d_iter_total; a.prof = s->d_iter_total + 1; a.bad_total = s->d_iter_total + 17; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
     a.max_iter = s->max_iter; a.tol = s->tol;
 }
 
@@ -384,7 +405,7 @@ static int solve_host_common(br2_batch_solver* s, const double* x0, const double
     fill_args(s, a, s->d_x0, d_yref, d_lines, s->d_p, p_per_stage, nullptr, nullptr, nullptr);
     CK(cudaEventRecord(s->ev0, st));
     launch_linearize(a, st);
-    CK(cudaEventRecord(s->ev_mid, st));
+    if (s->kernel_timing) CK(cudaEventRecord(s->ev_mid, st));
     CK(cudaMemcpyAsync(s->d_x0, x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, s->stream_x0));
     CK(cudaEventRecord(s->ev_x0, s->stream_x0));
     double* a_u0 = mapped_alias(u0);
@@ -422,6 +443,7 @@ extern "C" int br2_batch_set_trajectory(br2_batch_solver* s, const double* traj,
     if (e != cudaSuccess) return fail(BR2_ENOMEM, "cudaMalloc(trajectory, %d rows) failed: %s", rows, cudaGetErrorString(e));
     CK(cudaMemcpy(s->d_traj, traj, sizeof(double) * (size_t)rows * NY, cudaMemcpyHostToDevice));
     s->traj_rows = rows;
+    s->gen++;
     return BR2_OK;
 }
 
@@ -454,7 +476,7 @@ static int solve_enqueue(br2_batch_solver* s, const double* d_x0, const double* 
     fill_args(s, a, d_x0, d_yref, d_lines, d_p, p_per_stage, d_u0, d_thrust, d_status);
     CK(cudaEventRecord(s->ev0, st));
     launch_linearize(a, st);
-    CK(cudaEventRecord(s->ev_mid, st));
+    if (s->kernel_timing) CK(cudaEventRecord(s->ev_mid, st));
     if (before_ipm) CK(cudaStreamWaitEvent(st, before_ipm, 0));
     launch_ipm(a, s->sm_count, st);
     CK(cudaEventRecord(s->ev1, st));
@@ -522,6 +544,7 @@ extern "C" double br2_batch_last_solve_time(br2_batch_solver* s)
 extern "C" int br2_batch_last_kernel_times(br2_batch_solver* s, double* t_linearize, double* t_ipm)
 {
     if (!s || !s->timed) return fail(BR2_EINVAL, "no solve recorded");
+    if (!s->kernel_timing) return fail(BR2_EINVAL, "option kernel_timing is 0: no event between the kernels");
     ON_DEVICE(s);
     CK(cudaEventSynchronize(s->ev1));
     float a = 0.f, b = 0.f;
@@ -540,6 +563,222 @@ extern "C" long long br2_batch_ipm_iterations_total(br2_batch_solver* s, int res
     unsigned long long v = 0;
     if (cudaMemcpy(&v, s->d_iter_total, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     if (reset) cudaMemset(s->d_iter_total, 0, sizeof v);
+    return (long long)v;
+}
+
+// ---- one control tick as one call / one CUDA graph -----------------------------------------------------------------
+static bool pinned_host(const void* p)
+{
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Everything of a tick, issued on `st` (plus stream_x0 for the forked x0 upload of the host path).  Runs either inside a
+// stream capture (graph construction) or directly.
+static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cudaStream_t st)
+{
+    const size_t B = s->B, N = s->N;
+    const size_t psz = sizeof(double) * B * (io.p_per_stage ? (N + 1) * NP : NP);
+    const double *d_x0 = io.x0, *d_yref = io.yref, *d_p = io.p, *d_thr = io.thrusts, *d_acc = io.body_acc;
+    const int* d_lines = io.lines;
+    bool forked = false;
+    if (host) {
+        if (io.ekf) {
+            CK(cudaMemcpyAsync(s->d_x0, io.x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(s->d_thr, io.thrusts, sizeof(double) * B * 6, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(s->d_acc, io.body_acc, sizeof(double) * B * 6, cudaMemcpyHostToDevice, st));
+            d_thr = s->d_thr; d_acc = s->d_acc;
+        } else {
+            CK(cudaMemcpyAsync(s->d_p, io.p, psz, cudaMemcpyHostToDevice, st));
+            d_p = s->d_p;
+        }
+        if (io.lines) { CK(cudaMemcpyAsync(s->d_lines, io.lines, sizeof(int) * B, cudaMemcpyHostToDevice, st)); d_lines = s->d_lines; }
+        else { CK(cudaMemcpyAsync(s->d_yref, io.yref, sizeof(double) * B * (N + 1) * NY, cudaMemcpyHostToDevice, st)); d_yref = s->d_yref; }
+        d_x0 = s->d_x0;
+        if (!io.ekf) {
+            // x0 rides a second stream past the lineariser: the QP kernel is its first reader
+            CK(cudaEventRecord(s->ev_fork, st));
+            CK(cudaStreamWaitEvent(s->stream_x0, s->ev_fork, 0));
+            CK(cudaMemcpyAsync(s->d_x0, io.x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, s->stream_x0));
+            CK(cudaEventRecord(s->ev_x0, s->stream_x0));
+            forked = true;
+        }
+    }
+    // outputs: device buffers, or -- host path -- the caller's buffers themselves when the device can write them (mapped)
+    double* o_u0 = host ? nullptr : io.u0;
+    double* o_th = host ? nullptr : io.thrust;
+    int* o_st = host ? nullptr : io.status;
+    if (host) { o_u0 = mapped_alias(io.u0); o_th = mapped_alias(io.thrust); o_st = mapped_alias(io.status); }
+    if (io.ekf) {
+        EkfArgs e;
+        e.B = s->B; e.esti_x = s->d_ex; e.esti_P = s->d_eP; e.thrusts = d_thr; e.meas = d_x0; e.body_acc = d_acc;
+        e.wf_dist = host ? s->d_wf : io.wf_dist; e.p_out = s->d_pout; e.compensate = io.compensate; e.model = s->ekf_model;
+        launch_ekf(e, st);
+        if (io.ekf == 2) {
+            RlsArgs r;
+            r.B = s->B; r.state = s->d_rls; r.esti_x = s->d_ex; r.body_acc = d_acc; r.meas = d_x0; r.p_out = s->d_pout;
+            r.compensate = io.compensate;
+            launch_rls(r, st);
+        }
+        d_p = s->d_pout;
+    }
+    SolveArgs a;
+    fill_args(s, a, d_x0, d_yref, d_lines, d_p, io.ekf ? 0 : io.p_per_stage, o_u0, o_th, o_st);
+    CK(cudaEventRecord(s->ev0, st));
+    launch_linearize(a, st);
+    if (s->kernel_timing) CK(cudaEventRecord(s->ev_mid, st));
+    if (forked) CK(cudaStreamWaitEvent(st, s->ev_x0, 0));
+    launch_ipm(a, s->sm_count, st);
+    CK(cudaEventRecord(s->ev1, st));
+    if (!host && io.plant_h > 0) {
+        PlantArgs pl;
+        pl.B = s->B; pl.x = const_cast<double*>(io.x0); pl.u = a.u0; pl.p = d_p; pl.dist = nullptr;
+        pl.wave_amp = io.wave_amp; pl.wave_tau0 = io.wave_tau0; pl.body_acc = io.body_acc; pl.lines = const_cast<int*>(io.lines);
+        pl.h = io.plant_h; pl.tick = -1; pl.tick_ctr = s->d_counter + CTR_TICK;
+        launch_plant(pl, st);
+    }
+    if (host) {
+        if (io.u0 && !o_u0) CK(cudaMemcpyAsync(io.u0, s->d_u0, sizeof(double) * B * 4, cudaMemcpyDeviceToHost, st));
+        if (io.thrust && !o_th) CK(cudaMemcpyAsync(io.thrust, s->d_thrust, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
+        if (io.status && !o_st) CK(cudaMemcpyAsync(io.status, s->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+        if (io.ekf && io.wf_dist) CK(cudaMemcpyAsync(io.wf_dist, s->d_wf, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
+    }
+    s->timed = true;
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+
+static int tick_validate(br2_batch_solver* s, const br2_tick_io* io, int host, const char* who)
+{
+    if (!s || !io) return fail(BR2_EINVAL, "%s: null argument", who);
+    if (!io->x0) return fail(BR2_EINVAL, "%s: x0 is NULL", who);
+    if (!io->yref == !io->lines) return fail(BR2_EINVAL, "%s: exactly one of yref / lines must be given", who);
+    if (io->lines && !s->d_traj) return fail(BR2_EINVAL, "%s: lines given but no trajectory set (br2_batch_set_trajectory)", who);
+    if (io->ekf < 0 || io->ekf > 2) return fail(BR2_EINVAL, "%s: ekf = %d", who, io->ekf);
+    if (io->ekf && (!io->thrusts || !io->body_acc)) return fail(BR2_EINVAL, "%s: ekf needs thrusts and body_acc", who);
+    if (!io->ekf && !io->p) return fail(BR2_EINVAL, "%s: p is NULL (and no filter produces it)", who);
+    if (host && io->plant_h > 0) return fail(BR2_EINVAL, "%s: the plant step is a device-path option", who);
+    if ((io->wave_amp == nullptr) != (io->wave_tau0 == nullptr)) return fail(BR2_EINVAL, "%s: wave_amp and wave_tau0 go together", who);
+    return BR2_OK;
+}
+
+// cached graph of this (io, host) or a newly captured one; nullptr (and rc == BR2_OK) when graphs are not to be used
+static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, cudaGraphExec_t* out)
+{
+    *out = nullptr;
+    if (!s->tick_graph) return BR2_OK;
+    br2_batch_solver::TickGraph* slot = &s->tg[0];
+    for (auto& g : s->tg) {
+        if (g.exec && g.host == host && g.gen == s->gen && !memcmp(&g.io, &io, sizeof io)) {
+            g.stamp = ++s->tick_stamp;
+            *out = g.exec;
+            return BR2_OK;
+        }
+        if (!g.exec) { if (slot->exec) slot = &g; }
+        else if (slot->exec && g.stamp < slot->stamp) slot = &g;      // least recently used
+    }
+    // a graph is worth building only for a caller that comes back with the same buffers: the first sighting of a key goes the
+    // stream path and is remembered (the last four: double-buffered callers alternate), the second one instantiates -- so a
+    // caller that cycles through many distinct buffers never thrashes the cache
+    bool seen = false;
+    for (auto& m : s->miss)
+        if (m.valid && m.host == host && m.gen == s->gen && !memcmp(&m.io, &io, sizeof io)) { seen = true; m.valid = false; }
+    if (!seen) {
+        auto& m = s->miss[s->miss_next++ % 4];
+        m.io = io; m.host = host; m.gen = s->gen; m.valid = true;
+        return BR2_OK;
+    }
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = tick_issue(s, io, host, s->stream);
+    cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    if (rc != BR2_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc != BR2_OK ? rc : fail(BR2_ECUDA, "tick graph capture failed: %s", cudaGetErrorString(e));
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(BR2_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    if (slot->exec) cudaGraphExecDestroy(slot->exec);
+    slot->io = io; slot->host = host; slot->gen = s->gen; slot->stamp = ++s->tick_stamp; slot->exec = exec;
+    s->graphs_built++;
+    *out = exec;
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_graphs_built(const br2_batch_solver* s) { return s ? s->graphs_built : 0; }
+
+extern "C" int br2_batch_set_tick_index(br2_batch_solver* s, int next_tick)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    ON_DEVICE(s);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(s->d_counter + CTR_TICK, &next_tick, sizeof(int), cudaMemcpyHostToDevice));
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_tick_device(br2_batch_solver* s, const br2_tick_io* io_in, void* stream)
+{
+    int rc = tick_validate(s, io_in, 0, "br2_batch_tick_device");
+    if (rc != BR2_OK) return rc;
+    ON_DEVICE(s);
+    br2_tick_io io;
+    memset(&io, 0, sizeof io);                          // (padding bytes take part in the cache comparison)
+    io.x0 = io_in->x0; io.yref = io_in->yref; io.p = io_in->p; io.thrusts = io_in->thrusts; io.lines = io_in->lines;
+    io.body_acc = io_in->body_acc; io.u0 = io_in->u0; io.thrust = io_in->thrust; io.wf_dist = io_in->wf_dist; io.status = io_in->status;
+    io.wave_amp = io_in->wave_amp; io.wave_tau0 = io_in->wave_tau0; io.plant_h = io_in->plant_h;
+    io.p_per_stage = io_in->p_per_stage; io.ekf = io_in->ekf; io.compensate = io_in->compensate;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    cudaGraphExec_t exec = nullptr;
+    if (cap == cudaStreamCaptureStatusNone) {
+        rc = tick_graph_for(s, io, 0, &exec);
+        if (rc != BR2_OK) return rc;
+    }
+    if (exec) { CK(cudaGraphLaunch(exec, st)); s->timed = true; return BR2_OK; }
+    return tick_issue(s, io, 0, st);                    // the caller is capturing its own graph, or graphs are switched off
+}
+
+extern "C" int br2_batch_tick_host(br2_batch_solver* s, const br2_tick_io* io_in)
+{
+    int rc = tick_validate(s, io_in, 1, "br2_batch_tick_host");
+    if (rc != BR2_OK) return rc;
+    ON_DEVICE(s);
+    br2_tick_io io;
+    memset(&io, 0, sizeof io);
+    io.x0 = io_in->x0; io.yref = io_in->yref; io.p = io_in->p; io.thrusts = io_in->thrusts; io.lines = io_in->lines;
+    io.body_acc = io_in->body_acc; io.u0 = io_in->u0; io.thrust = io_in->thrust; io.wf_dist = io_in->wf_dist; io.status = io_in->status;
+    io.p_per_stage = io_in->p_per_stage; io.ekf = io_in->ekf; io.compensate = io_in->compensate;
+    cudaGraphExec_t exec = nullptr;
+    // copies from / to pageable memory are staged by the driver at enqueue time: only pinned buffers go into a graph
+    const bool pinned = pinned_host(io.x0) && pinned_host(io.yref) && pinned_host(io.p) && pinned_host(io.thrusts) && pinned_host(io.lines) &&
+                        pinned_host(io.body_acc) && pinned_host(io.u0) && pinned_host(io.thrust) && pinned_host(io.wf_dist) && pinned_host(io.status);
+    if (pinned) {
+        rc = tick_graph_for(s, io, 1, &exec);
+        if (rc != BR2_OK) return rc;
+    }
+    if (exec) { CK(cudaGraphLaunch(exec, s->stream)); s->timed = true; }
+    else {
+        rc = tick_issue(s, io, 1, s->stream);
+        if (rc != BR2_OK) return rc;
+    }
+    CK(cudaStreamSynchronize(s->stream));
+    return BR2_OK;
+}
+
+extern "C" long long br2_batch_nonzero_status_total(br2_batch_solver* s, int reset)
+{
+    if (!s) return -1;
+    DeviceGuard guard_(s->device);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, s->d_iter_total + 17, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset) cudaMemset(s->d_iter_total + 17, 0, sizeof v);
     return (long long)v;
 }
 
@@ -571,7 +810,7 @@ extern "C" int br2_plant_step_device(int batch, double* d_x, const double* d_u, 
     CK(guard_.err);
     PlantArgs a;
     a.B = batch; a.x = d_x; a.u = d_u; a.p = d_p; a.dist = d_dist; a.wave_amp = d_wave_amp; a.wave_tau0 = d_wave_tau0;
-    a.body_acc = d_body_acc; a.lines = d_lines; a.h = h; a.tick = tick;
+    a.body_acc = d_body_acc; a.lines = d_lines; a.h = h; a.tick = tick; a.tick_ctr = nullptr;
     launch_plant(a, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return BR2_OK;

@@ -42,6 +42,7 @@ struct SolveArgs {
     int* aset;             // [B][N] guessed active set per stage, 2 bits per input (0 free, 1 at lbu, 2 at ubu)
     int active_set;        // primal-dual active-set iteration when the interior solution leaves the box (option "active_set_path")
     unsigned long long* iter_total;   // [1] IPM iterations executed, accumulated over instances and solves
+    unsigned long long* bad_total;    // [1] instances that ended with a non-zero status, accumulated over solves
     unsigned long long* prof;         // [16] cycles per kernel phase (instrumentation build -DBR2_PROFILE only), else unused
     // options
     int max_iter;          // qp_solver_iter_max (50)
@@ -60,7 +61,7 @@ __device__ __forceinline__ const double* yref_row(const SolveArgs& a, int inst, 
 void launch_linearize(const SolveArgs& a, cudaStream_t s);
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s);
 void configure_kernels();      // per-device function attributes (call with the solver's device current)
-enum { CTR_QUEUE = 0, CTR_HARD = 1, CTR_EASY = 2, CTR_PARITY = 3, CTR_FB = 4, CTR_FBQ = 5, CTR_COUNT = 8 };
+enum { CTR_QUEUE = 0, CTR_HARD = 1, CTR_EASY = 2, CTR_PARITY = 3, CTR_FB = 4, CTR_FBQ = 5, CTR_TICK = 6, CTR_COUNT = 8 };
 
 // EKF (bluerov2_dob.cpp:495-545), one warp per instance
 struct EkfArgs {
@@ -109,7 +110,8 @@ struct PlantArgs {
     double* body_acc;        // [B][6] out, or null
     int* lines;              // [B] in/out trajectory row counters, or null
     double h;
-    int tick;
+    int tick;                // wave phase index; < 0: read it from *tick_ctr - 1 (the solver's tick counter: graph replays)
+    const int* tick_ctr;
 };
 void launch_plant(const PlantArgs& a, cudaStream_t s);
 

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
     const int base = blockIdx.x * LRND;
     if (blockIdx.x == 0 && lane == 0) {
         // housekeeping for the IPM kernel that follows in the stream: reset its work-queue counters, flip the order buffers
-        a.ctr[CTR_QUEUE] = 0; a.ctr[CTR_HARD] = 0; a.ctr[CTR_EASY] = 0; a.ctr[CTR_PARITY] ^= 1; a.ctr[CTR_FB] = 0; a.ctr[CTR_FBQ] = 0;
+        a.ctr[CTR_QUEUE] = 0; a.ctr[CTR_HARD] = 0; a.ctr[CTR_EASY] = 0; a.ctr[CTR_PARITY] ^= 1; a.ctr[CTR_FB] = 0; a.ctr[CTR_FBQ] = 0; a.ctr[CTR_TICK] += 1;
     }
     if (lane < LRND) {
         const int gs = base + lane;
@@ -1415,7 +1415,7 @@ __device__ __forceinline__ void finish_instance(Inst& I, const SolveOut& r, int*
         a.status[inst] = status;
         a.iters[inst] = it;
         atomicAdd(a.iter_total, (unsigned long long)it);
-        PROF(PF_EPILOGUE);
+        if (status != 0) atomicAdd(a.bad_total, 1ULL);
         a.info[(size_t)inst * 4 + 0] = mu;
         a.info[(size_t)inst * 4 + 1] = res_stat;
         a.info[(size_t)inst * 4 + 2] = bmax;

@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(128) plant_kernel(PlantArgs a)
     for (int j = 0; j < NP; j++) p[j] = a.p[(size_t)i * NP + j];
     if (a.wave_amp) {
         // F = sin(tau) * A,  tau = tau0 + 0.125 * tick  (bluerov2_dob.cpp:774-797: tau advances 0.05 * 2.5 per tick)
-        const double sn = sin(a.wave_tau0[i] + 0.125 * a.tick);
+        const int tick = a.tick >= 0 ? a.tick : *a.tick_ctr - 1;
+        const double sn = sin(a.wave_tau0[i] + 0.125 * tick);
 #pragma unroll
         for (int j = 0; j < 4; j++) p[j] += sn * a.wave_amp[(size_t)i * 4 + j];
     }

@@ -70,6 +70,11 @@ def load_library(path: str | None = None):
         "br2_batch_last_kernel_times": (C.c_int, [V, _D, _D]),
         "br2_batch_ipm_iterations_total": (C.c_longlong, [V, C.c_int]),
         "br2_batch_phase_cycles": (C.c_int, [V, V, C.c_int]),
+        "br2_batch_nonzero_status_total": (C.c_longlong, [V, C.c_int]),
+        "br2_batch_tick_device": (C.c_int, [V, V, V]),
+        "br2_batch_tick_host": (C.c_int, [V, V]),
+        "br2_batch_graphs_built": (C.c_int, [V]),
+        "br2_batch_set_tick_index": (C.c_int, [V, C.c_int]),
         "br2_plant_step_device": (C.c_int, [C.c_int, V, V, V, V, V, V, C.c_int, C.c_double, V, V, V]),
         "br2_batch_ekf_reset": (C.c_int, [V]),
         "br2_batch_ekf_device": (C.c_int, [V, V, V, V, V, V, C.c_int, V]),
@@ -114,6 +119,14 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
+class _TickIO(C.Structure):
+    """struct br2_tick_io (include/bluerov2_b200.h)"""
+    _fields_ = [("x0", C.c_void_p), ("yref", C.c_void_p), ("p", C.c_void_p), ("thrusts", C.c_void_p), ("lines", C.c_void_p),
+                ("body_acc", C.c_void_p), ("u0", C.c_void_p), ("thrust", C.c_void_p), ("wf_dist", C.c_void_p), ("status", C.c_void_p),
+                ("wave_amp", C.c_void_p), ("wave_tau0", C.c_void_p), ("plant_h", C.c_double),
+                ("p_per_stage", C.c_int), ("ekf", C.c_int), ("compensate", C.c_int)]
+
+
 class _HostArgs:
     """Host-array marshalling for the hot calls.  Callers pass the same numpy buffers tick after tick; checking layout and
     building a ctypes pointer costs ~2.5 us per array per call, 15 us per solve -- 4 % of a 0.4 ms tick.  An array object
@@ -149,6 +162,7 @@ class BatchSolver:
         self._L = load_library(lib_path)
         self._h = C.c_void_p()
         self._hostargs = _HostArgs()
+        self._tick_cache = {}
         ts = None if time_steps is None else _np(time_steps, (N,))
         self._check(self._L.br2_batch_create(C.byref(self._h), int(batch), int(N), _ptr(ts), int(device)))
         self.B, self.N, self.device = int(batch), int(N), int(device)
@@ -283,6 +297,62 @@ class BatchSolver:
         self._check(self._L.br2_batch_solve_windowed_host(self._h, a0, a1, a2, per_stage, o0, o1, o2))
         return u0, th, st
 
+    def tick(self, x0, p=None, yref=None, lines=None, thrusts=None, body_acc=None, ekf: int = 0, compensate: bool = True,
+             out=None, wf_dist=None, plant_h: float = 0.0, wave=None):
+        """One control tick as ONE call (br2_batch_tick_device / _host): [EKF (-> RLS) -> p ->] RTI step [-> plant step on x0 in
+        place].  All arrays torch CUDA tensors (enqueue on torch's current stream) or all numpy arrays (synchronous).  A caller
+        that passes the same buffers every tick replays one cached CUDA graph.  Returns (u0, thrust, status)."""
+        dev = _is_torch(x0)
+        if out is None:
+            if dev:
+                import torch
+                out = (torch.empty((self.B, NU), dtype=torch.float64, device=x0.device),
+                       torch.empty((self.B, NTHRUST), dtype=torch.float64, device=x0.device),
+                       torch.empty((self.B,), dtype=torch.int32, device=x0.device))
+            else:
+                out = (np.empty((self.B, NU)), np.empty((self.B, NTHRUST)), np.empty((self.B,), dtype=np.int32))
+        args = (x0, p, yref, lines, thrusts, body_acc, out[0], out[1], out[2], wf_dist) + (tuple(wave) if wave is not None else (None, None))
+        key = tuple(id(a) for a in args) + (int(ekf), bool(compensate), float(plant_h))
+        ent = self._tick_cache.get(key)
+        if ent is None or any(a is not b for a, b in zip(ent[1], args)):
+            per_stage = int(p is not None and len(p.shape) == 3)
+            shapes = ((self.B, NX), (self.B, self.N + 1, NP) if per_stage else (self.B, NP), (self.B, self.N + 1, NY), (self.B,),
+                      (self.B, 6), (self.B, 6), (self.B, NU), (self.B, NTHRUST), (self.B,), (self.B, 6), (self.B, 4), (self.B,))
+            ints = (3, 8)       # lines, status
+            ptrs = []
+            for i, (a, shp) in enumerate(zip(args, shapes)):
+                if a is None:
+                    ptrs.append(None)
+                    continue
+                if dev:
+                    import torch
+                    self._dev_check(a, shp, torch.int32 if i in ints else torch.float64)
+                    ptrs.append(a.data_ptr())
+                else:
+                    want = np.int32 if i in ints else np.float64
+                    if not (isinstance(a, np.ndarray) and a.dtype == want and a.flags.c_contiguous and a.shape == tuple(shp)):
+                        raise ValueError(f"tick(): argument {i} must be a contiguous {want.__name__} array of shape {tuple(shp)}")
+                    ptrs.append(a.ctypes.data)
+            io = _TickIO(ptrs[0], ptrs[2], ptrs[1], ptrs[4], ptrs[3], ptrs[5], ptrs[6], ptrs[7], ptrs[9], ptrs[8], ptrs[10], ptrs[11],
+                         float(plant_h), per_stage, int(ekf), int(bool(compensate)))
+            if len(self._tick_cache) > 32:
+                self._tick_cache.clear()
+            ent = self._tick_cache[key] = (io, args, C.byref(io))
+        if dev:
+            import torch
+            stream = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)
+            self._check(self._L.br2_batch_tick_device(self._h, ent[2], stream))
+        else:
+            self._check(self._L.br2_batch_tick_host(self._h, ent[2]))
+        return out
+
+    def graphs_built(self) -> int:
+        return int(self._L.br2_batch_graphs_built(self._h))
+
+    def set_tick_index(self, next_tick: int = 0):
+        """index the next tick's plant step uses for the wave phase (tau = tau0 + 0.125 * index); counts up by itself"""
+        self._check(self._L.br2_batch_set_tick_index(self._h, int(next_tick)))
+
     def stats(self):
         """(ipm_iterations[B], info[B,4] = (mu, stationarity residual, max |dynamics gap|, stationarity scale))."""
         it = np.empty((self.B,), dtype=np.int32)
@@ -308,6 +378,9 @@ class BatchSolver:
 
     def ipm_iterations_total(self, reset: bool = False) -> int:
         return int(self._L.br2_batch_ipm_iterations_total(self._h, int(reset)))
+
+    def nonzero_status_total(self, reset: bool = False) -> int:
+        return int(self._L.br2_batch_nonzero_status_total(self._h, int(reset)))
 
     PHASES = ("factor_abs", "factor_as", "fwd_closed_loop", "primal_check", "costate_check", "ipm_start", "factor_ipm", "fwd_affine",
               "e1_centring", "bwd_corrector", "fwd_corrector", "e2_update", "epilogue")

@@ -86,7 +86,9 @@ BR2_API int br2_batch_set_time_steps(br2_batch_solver *s, const double *time_ste
  * solution had active input bounds is first solved as the LQR with that active set pinned; a costate sweep checks the KKT
  * conditions -- free inputs inside the box, multipliers of the pinned inputs of the right sign --, repairs the guess and
  * retries up to twice; accepted solutions are exact, everything else falls through to the interior-point iteration),
- * "ekf_model" (int, 0 = DOB filter, 1 = AMPC filter) */
+ * "ekf_model" (int, 0 = DOB filter, 1 = AMPC filter), "kernel_timing" (int, default 1: an event between the lineariser and the QP
+ * kernels feeds br2_batch_last_kernel_times; 0 removes it from the tick), "tick_graph" (int, default 1: br2_batch_tick_* replay
+ * cached CUDA graphs; 0 = always enqueue kernel by kernel) */
 BR2_API int br2_batch_set_option_int(br2_batch_solver *s, const char *name, int v);
 BR2_API int br2_batch_set_option_double(br2_batch_solver *s, const char *name, double v);
 
@@ -108,6 +110,40 @@ BR2_API int br2_batch_solve_device(br2_batch_solver *s, const double *d_x0, cons
  * makes the copies asynchronous; pageable memory works too. */
 BR2_API int br2_batch_solve_host(br2_batch_solver *s, const double *x0, const double *yref, const double *p,
                          int p_per_stage, double *u0, double *thrust, int *status);
+
+/* One control tick as ONE call == the body of the node's loop, `EKF(); solve();` (bluerov2_dobmpc/src/bluerov2_dob_node.cpp:13-31):
+ *   [EKF (-> RLS, AMPC) -> parameters] -> SQP-RTI step -> u0, thrusts [-> nominal plant step, device closed loops].
+ * The kernels of a tick are instantiated as one CUDA graph per distinct set of buffers (a small cache keyed on this struct):
+ * a caller that reuses its buffers from tick to tick -- every closed loop does -- pays one graph launch per tick instead of
+ * four to six kernel launches, events and copies.  Pointers are device pointers for _device and host pointers for _host
+ * (pinned host buffers are captured into the graph, copies included; pageable ones take the stream path).
+ *   x0        [B][12]  measured state; with ekf != 0 also the filter's measurement (meas_y, bluerov2_dob.cpp:501-503)
+ *   yref      [B][N+1][16] explicit reference, or NULL with lines != NULL: windowed from br2_batch_set_trajectory
+ *   lines     [B] first trajectory row per instance (int)
+ *   p         [B][16] ([B][N+1][16] when p_per_stage) OCP parameters; ignored when ekf != 0 (the filter writes them)
+ *   ekf       0: no filter.  1: BLUEROV2_DOB::EKF -> p (bluerov2_dob.cpp:324-355).  2: EKF -> RLSFF -> p (BLUEROV2_AMPC::solve,
+ *             bluerov2_ampc.cpp:340-382).  thrusts[B][6], body_acc[B][6] are the filter's inputs; compensate = COMPENSATE_D
+ *   u0 [B][4], thrust [B][6], status [B] outputs (any may be NULL: internal buffers); wf_dist [B][6] world-frame disturbance (or NULL)
+ *   plant_h   > 0 (device only): after the solve, one nominal plant step of length plant_h on x0 IN PLACE with the new u0
+ *             (br2_plant_step_device: optional wave_amp[B][4] / wave_tau0[B] wrench, body_acc out, lines++), so that a device-resident
+ *             closed loop is a sequence of identical calls. */
+typedef struct br2_tick_io {
+    const double *x0, *yref, *p, *thrusts;
+    const int *lines;
+    double *body_acc;            /* EKF input; also the plant's output when plant_h > 0 */
+    double *u0, *thrust, *wf_dist;
+    int *status;
+    const double *wave_amp, *wave_tau0;
+    double plant_h;
+    int p_per_stage, ekf, compensate;
+} br2_tick_io;
+BR2_API int br2_batch_tick_device(br2_batch_solver *s, const br2_tick_io *io, void *stream);
+BR2_API int br2_batch_tick_host(br2_batch_solver *s, const br2_tick_io *io);
+/* number of CUDA graphs instantiated so far (diagnostic: stays constant in a steady closed loop) */
+BR2_API int br2_batch_graphs_built(const br2_batch_solver *s);
+/* index the next tick's plant step uses for the wave phase (tau = tau0 + 0.125 * index, bluerov2_dob.cpp:774-797); the solver
+ * counts ticks by itself from 0 at creation */
+BR2_API int br2_batch_set_tick_index(br2_batch_solver *s, int next_tick);
 
 /* Reference windowing on the device == BLUEROV2_DOB::ref_cb (bluerov2_dob.cpp:218-265) / BLUEROV2_PATH::read_N_pub
  * (bluerov2_path/src/bluerov2_path.cpp:79-118): the trajectory file's rows (16 columns each, readDataFromFile
@@ -132,6 +168,8 @@ BR2_API int br2_batch_last_kernel_times(br2_batch_solver *s, double *t_linearize
 /* IPM iterations executed, summed over all instances and all solves since creation / the last reset (the n_it of
  * the roofline formula bytes_sweep = 4384 * N * n_it) */
 BR2_API long long br2_batch_ipm_iterations_total(br2_batch_solver *s, int reset);
+/* instances that ended a solve with a non-zero status, summed over all solves since creation / the last reset */
+BR2_API long long br2_batch_nonzero_status_total(br2_batch_solver *s, int reset);
 
 /* Instrumentation (library built with -DBR2_PROFILE only; all zeros otherwise): SM cycles per phase of the IPM kernel, summed
  * over warps since the last reset -- [0] factor sweep (interior fast path), [1] factor sweep (pinned), [2] closed-loop roll-out,

@@ -304,3 +304,89 @@ def test_reset_and_sparse_params_behaviour(lib_path, oracle):
     X, U = np.zeros((N + 1, 12)), np.zeros((N, 4))
     st, _ = oracle.rti_step(wl.time_steps(N), x0, yref, p, X, U)
     assert st == 0 and np.abs(U[0] - np.array(kv["u_after_reset"])).max() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the nine cost functions with CasADi's six entry points each (bluerov2_cost.h:45-116)
+COST_FUNCS = [pre + suf for pre in ("bluerov2_cost_y_0", "bluerov2_cost_y", "bluerov2_cost_y_e") for suf in ("_fun", "_fun_jac_ut_xt", "_hess")]
+
+
+def _casadi_api(lib, name, int_t):
+    """evaluate `name` with random dense inputs sized by its own sparsity_in / sparsity_out, plus all helper results.
+    int_t: the library's casadi_int (int on both sides: bluerov2_cost_y_fun.c:27)."""
+    DP = C.POINTER(C.c_double)
+    IP = C.POINTER(int_t)
+
+    def sp(kind, i):
+        fn = getattr(lib, f"{name}_sparsity_{kind}"); fn.argtypes = [int_t]; fn.restype = IP
+        p = fn(i)
+        if not p:
+            return None
+        rows, cols = p[0], p[1]
+        colind = [p[2 + j] for j in range(cols + 1)]
+        return (rows, cols, colind, [p[2 + cols + 1 + k] for k in range(colind[-1])])
+
+    n = {}
+    for k in ("n_in", "n_out"):
+        fn = getattr(lib, f"{name}_{k}"); fn.argtypes = []; fn.restype = int_t
+        n[k] = int(fn())
+    sz = [int_t() for _ in range(4)]
+    wk = getattr(lib, name + "_work"); wk.argtypes = [IP] * 4; wk.restype = C.c_int
+    assert wk(*[C.byref(v) for v in sz]) == 0
+    sp_in = [sp("in", i) for i in range(n["n_in"])]
+    sp_out = [sp("out", i) for i in range(n["n_out"])]
+    assert sp("in", n["n_in"]) is None and sp("out", n["n_out"]) is None
+    rng = np.random.default_rng(abs(hash(name)) % 1000)
+    ins = [rng.uniform(-2, 2, max(len(s[3]), 1)) for s in sp_in]
+    outs = [np.full(max(len(s[3]), 1), np.nan) for s in sp_out]
+    fn = getattr(lib, name); fn.argtypes = [C.POINTER(DP), C.POINTER(DP), C.c_void_p, C.c_void_p, C.c_void_p]; fn.restype = C.c_int
+    arg = (DP * len(ins))(*[a.ctypes.data_as(DP) for a in ins])
+    res = (DP * len(outs))(*[a.ctypes.data_as(DP) for a in outs])
+    assert fn(arg, res, None, None, None) == 0
+    vals = [o[:len(s[3])].copy() for o, s in zip(outs, sp_out)]
+    # a null input reads as zeros
+    arg0 = (DP * len(ins))(*[None for _ in ins])
+    outs0 = [np.full(max(len(s[3]), 1), np.nan) for s in sp_out]
+    res0 = (DP * len(outs0))(*[a.ctypes.data_as(DP) for a in outs0])
+    assert fn(arg0, res0, None, None, None) == 0
+    return dict(n=n, work=[int(v.value) for v in sz], sp_in=sp_in, sp_out=sp_out, ins=ins, vals=vals,
+                vals_null=[o[:len(s[3])].copy() for o, s in zip(outs0, sp_out)])
+
+
+@pytest.mark.parametrize("name", COST_FUNCS)
+def test_cost_functions_known_answers(lib_path, name):
+    """y = [x; u] (terminal y = x), Jacobian = one unit entry per column at the row of that variable in [u; x], empty Hessian"""
+    r = _casadi_api(C.CDLL(lib_path), name, C.c_int)
+    terminal = "_y_e_" in name
+    ny = 12 if terminal else 16
+    x, u = r["ins"][0], r["ins"][1]
+    if name.endswith("_hess"):
+        assert r["n"] == {"n_in": 5, "n_out": 1} and r["work"] == [5, 1, 0, 0]
+        assert r["sp_out"][0] == (ny, ny, [0] * (ny + 1), []) and r["vals"][0].size == 0
+        return
+    want_y = x[:12] if terminal else np.concatenate([x[:12], u[:4]])
+    assert np.array_equal(r["vals"][0], want_y) and np.array_equal(r["vals_null"][0], np.zeros(ny))
+    if name.endswith("_fun"):
+        assert r["n"] == {"n_in": 4, "n_out": 1} and r["work"] == [4, 1, 0, 0]
+    else:
+        assert r["n"] == {"n_in": 4, "n_out": 3} and r["work"] == [4, 3, 0, 0]
+        rows = list(range(12)) if terminal else list(range(4, 16)) + [0, 1, 2, 3]
+        assert r["sp_out"][1] == (ny, ny, list(range(ny + 1)), rows) and np.array_equal(r["vals"][1], np.ones(ny))
+        assert r["sp_out"][2] == (ny, 0, [0], [])
+
+
+@pytest.mark.parametrize("name", COST_FUNCS)
+def test_cost_functions_match_reference_generated_c(lib_path, name):
+    """all six entry points of every cost function against the reference's own CasADi-generated C (oracle/_ref, compiled
+    from /root/reference/.../bluerov2_cost/*.c): n_in / n_out / work sizes, every sparsity pattern, and the values"""
+    from oracle.oracle import REF_SO
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ours = _casadi_api(C.CDLL(lib_path), name, C.c_int)
+    ref = _casadi_api(C.CDLL(REF_SO), name, C.c_int)            # casadi_int is int in the acados-generated code (bluerov2_cost_y_fun.c:27)
+    assert ours["n"] == ref["n"] and ours["work"] == ref["work"]
+    assert ours["sp_in"] == ref["sp_in"] and ours["sp_out"] == ref["sp_out"]
+    for a, b in zip(ours["vals"], ref["vals"]):
+        assert np.array_equal(a, b)
+    for a, b in zip(ours["vals_null"], ref["vals_null"]):
+        assert np.array_equal(a, b)

@@ -1,0 +1,141 @@
+"""One control tick as one call / one CUDA graph (br2_batch_tick_device / _host == `EKF(); solve();`, the body of the node's loop,
+bluerov2_dobmpc/src/bluerov2_dob_node.cpp:13-31): the graph replays must be indistinguishable from the kernel-by-kernel entry
+points they bundle, and a steady closed loop must build exactly one graph."""
+import numpy as np
+import pytest
+
+from bluerov2_b200 import traj, workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def solver_mod():
+    from bluerov2_b200 import solver
+    if solver.device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu-marked tests must run on the B200 box")
+    return solver
+
+
+def _pin(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+
+def test_device_closed_loop_tick_graph_equals_separate_calls(solver_mod):
+    """solve -> plant (wave wrench, body acceleration, row counter) as ONE graph launch per tick against the same loop issued
+    call by call: bit-identical states, one graph built; from a saturated start so that all three QP paths run"""
+    import torch
+    dev = torch.device("cuda", 0)
+    N, B, T = 20, 256, 14
+    w = wl.tracking_batch(B, N, seed=5, reference="lemniscate", pos_spread=2.5)
+    amp, tau0 = wl.wave_disturbance(B, seed=3)
+    d = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a if dt is None else a.astype(dt))).to(dev)   # noqa: E731
+    res = []
+    for graph in (1, 0):
+        s = solver_mod.BatchSolver(B, N)
+        s.set_trajectory(w["traj"]); s.set_iterate(w["X"], w["U"])
+        x, lines, p = d(w["x0"]), d(w["lines"], np.int32), d(w["p"])
+        wave = (d(amp), d(tau0))
+        acc = torch.zeros((B, 6), dtype=torch.float64, device=dev)
+        out = None
+        sts = []
+        for t in range(T):
+            if graph:
+                out = s.tick(x, p=p, lines=lines, body_acc=acc, out=out, plant_h=0.05, wave=wave)
+            else:
+                out = s.solve_windowed(x, lines, p, out=out)
+                solver_mod.plant_step(x, out[0], p, 0.05, wave=wave, tick=t, body_acc=acc, lines=lines)
+            sts.append(out[2].cpu().numpy().copy())
+        torch.cuda.synchronize()
+        it, _ = s.stats()
+        res.append((x.cpu().numpy(), lines.cpu().numpy(), acc.cpu().numpy(), out[0].cpu().numpy(), np.array(sts), it, s.graphs_built()))
+        s.close()
+    for a, b in zip(res[0][:5], res[1][:5]):
+        assert np.array_equal(a, b)
+    assert (res[0][4] == 0).all()
+    assert res[0][6] == 1 and res[1][6] == 0          # one graph for the whole loop; none without tick()
+
+
+def test_dob_tick_equals_ekf_then_solve(solver_mod):
+    """ekf = 1: EKF -> parameters -> solve in one graph == br2_batch_ekf_device + br2_batch_solve_windowed_device"""
+    import torch
+    dev = torch.device("cuda", 0)
+    N, B, T = 20, 128, 6
+    w = wl.tracking_batch(B, N, seed=6, reference="lemniscate", pos_spread=0.2, level=True)
+    rng = np.random.default_rng(1)
+    thr = rng.uniform(-5, 5, (T, B, 6)); acc = rng.uniform(-0.3, 0.3, (T, B, 6))
+    meas = w["x0"][None] + rng.uniform(-0.02, 0.02, (T, B, 12))
+    d = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a if dt is None else a.astype(dt))).to(dev)   # noqa: E731
+    outs = []
+    for fused in (1, 0):
+        s = solver_mod.BatchSolver(B, N)
+        s.set_trajectory(w["traj"]); s.set_iterate(w["X"], w["U"])
+        lines = d(w["lines"], np.int32)
+        x, th_in, ac = d(meas[0]), d(thr[0]), d(acc[0])          # fixed device buffers, refilled every tick
+        wf = torch.empty((B, 6), dtype=torch.float64, device=dev)
+        out = None
+        us = []
+        for t in range(T):
+            x.copy_(d(meas[t])); th_in.copy_(d(thr[t])); ac.copy_(d(acc[t]))
+            if fused:
+                out = s.tick(x, lines=lines, thrusts=th_in, body_acc=ac, ekf=1, compensate=True, out=out, wf_dist=wf)
+            else:
+                wf2, pp = s.ekf(th_in, x, ac, compensate=True, out=(wf, torch.empty((B, 16), dtype=torch.float64, device=dev)))
+                out = s.solve_windowed(x, lines, pp, out=out)
+            us.append(out[0].cpu().numpy().copy())
+        torch.cuda.synchronize()
+        ex, eP = s.ekf_state()
+        outs.append((np.array(us), wf.cpu().numpy(), ex, eP, out[2].cpu().numpy(), s.graphs_built()))
+        s.close()
+    for a, b in zip(outs[0][:5], outs[1][:5]):
+        assert np.array_equal(a, b)
+    assert (outs[0][4] == 0).all() and outs[0][5] == 1
+
+
+def test_host_tick_equals_host_solve(solver_mod):
+    """pinned host buffers: copies + kernels of a tick as one graph == br2_batch_solve_host / _windowed_host (+ ekf_host);
+    pageable buffers take the stream path and give the same numbers"""
+    N, B = 20, 96
+    w = wl.tracking_batch(B, N, seed=8, pos_spread=2.0)
+    ref = solver_mod.BatchSolver(B, N); ref.set_trajectory(w["traj"]); ref.set_iterate(w["X"], w["U"])
+    u_ref, th_ref, st_ref = ref.solve(w["x0"], w["yref"], w["p"])
+    for pinned in (True, False):
+        f = _pin if pinned else (lambda a: np.ascontiguousarray(a).copy())
+        s = solver_mod.BatchSolver(B, N); s.set_trajectory(w["traj"]); s.set_iterate(w["X"], w["U"])
+        x0, yref, p = f(w["x0"]), f(w["yref"]), f(w["p"])
+        out = (f(np.zeros((B, 4))), f(np.zeros((B, 6))), f(np.zeros(B, dtype=np.int32)))
+        u0, th, st = s.tick(x0, p=p, yref=yref, out=out)
+        assert np.array_equal(u0, u_ref) and np.array_equal(th, th_ref) and np.array_equal(st, st_ref)
+        assert s.graphs_built() == 0                       # first sighting of these buffers: stream path
+        # the second consecutive tick with the same buffers instantiates the graph, the third replays it
+        s.tick(x0, p=p, yref=yref, out=out)
+        assert s.graphs_built() == (1 if pinned else 0)
+        s.tick(x0, p=p, yref=yref, out=out)
+        assert s.graphs_built() == (1 if pinned else 0)
+        lines = f(w["lines"].astype(np.int32))
+        s.set_iterate(w["X"], w["U"])
+        u1, _, _ = s.tick(x0, p=p, lines=lines, out=out)
+        assert np.array_equal(u1, u_ref)                   # window of the same rows == the explicit yref
+        s.set_iterate(w["X"], w["U"])
+        u2, _, _ = s.tick(x0, p=p, lines=lines, out=out)   # ... and through its graph
+        assert np.array_equal(u2, u_ref)
+        assert s.graphs_built() == (2 if pinned else 0)
+        s.close()
+    ref.close()
+
+
+def test_tick_argument_errors(solver_mod):
+    s = solver_mod.BatchSolver(4, 10)
+    x0 = np.zeros((4, 12)); p = np.zeros((4, 16)); yref = np.zeros((4, 11, 16))
+    with pytest.raises(solver_mod.SolverError):
+        s.tick(x0, p=p)                                     # neither yref nor lines
+    with pytest.raises(solver_mod.SolverError):
+        s.tick(x0, p=p, lines=np.zeros(4, dtype=np.int32))  # no trajectory set
+    with pytest.raises(solver_mod.SolverError):
+        s.tick(x0, yref=yref)                               # no p and no filter
+    with pytest.raises(solver_mod.SolverError):
+        s.tick(x0, yref=yref, ekf=1)                        # filter without its inputs
+    with pytest.raises(solver_mod.SolverError):
+        s.tick(x0, p=p, yref=yref, plant_h=0.05)            # plant is a device-path option
+    s.close()
