@@ -43,6 +43,8 @@ struct br2_batch_solver {
     double *d_ex, *d_eP, *d_thr, *d_meas, *d_acc, *d_wf, *d_pout;   // EKF state + staging
     double* d_rls;                            // RLS-VFF state [B][4][RLS_STRIDE] (AMPC)
     float* d_yaw;                             // continuous-yaw accumulators [B][2] = (pre_yaw, yaw_sum), floats as in the node
+    cudaStream_t stream_c[4];          // compute streams of the ranges of a pipelined tick
+    cudaEvent_t ev_done[4];
     cudaStream_t stream, stream_x0;   // host API: main stream; second stream carrying the x0 upload past the lineariser
     cudaEvent_t ev0, ev1, ev_mid;   // solve start / end / between linearisation and IPM
     cudaEvent_t ev_x0;              // x0 upload complete (the IPM kernel is its first reader)
@@ -50,11 +52,14 @@ struct br2_batch_solver {
     bool timed;
     // tick graphs: the kernels (and, for host buffers, the copies) of one control tick instantiated as a CUDA graph, keyed on the
     // caller's buffers and on a generation counter that every change of options / weights / bounds / trajectory bumps
-    struct TickGraph { br2_tick_io io; int host; unsigned gen; unsigned long long stamp; cudaGraphExec_t exec; } tg[4];
+    struct H2DNode { cudaGraphNode_t node; int which; size_t off, bytes; void* dst; };   // upload node: input index, offset inside it
+    struct TickGraph { br2_tick_io io; int host; unsigned gen; unsigned long long stamp; cudaGraphExec_t exec; cudaGraph_t graph;
+                       H2DNode up[12]; int nup; } tg[4];
+    int graph_updates;      // replays of a host graph on NEW input buffers (upload nodes re-pointed, nothing re-instantiated)
     unsigned gen;
     unsigned long long tick_stamp;
     int graphs_built, kernel_timing, tick_graph;
-    cudaEvent_t ev_fork;
+    cudaEvent_t ev_fork, ev_chunk[4];
     struct Miss { br2_tick_io io; int host; unsigned gen; bool valid; } miss[4];   // the last keys that missed the graph cache
     unsigned miss_next;
 };
@@ -116,8 +121,16 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
     if (s->ev_mid) cudaEventDestroy(s->ev_mid);
     if (s->ev_x0) cudaEventDestroy(s->ev_x0);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-    for (auto& g : s->tg)
+    for (auto e : s->ev_chunk)
+        if (e) cudaEventDestroy(e);
+    for (auto e : s->ev_done)
+        if (e) cudaEventDestroy(e);
+    for (auto c : s->stream_c)
+        if (c) cudaStreamDestroy(c);
+    for (auto& g : s->tg) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->stream_x0) cudaStreamDestroy(s->stream_x0);
     free(s);
@@ -193,6 +206,9 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     CKF(cudaStreamCreateWithFlags(&s->stream_x0, cudaStreamNonBlocking));
     CKF(cudaEventCreateWithFlags(&s->ev_x0, cudaEventDisableTiming));
     CKF(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    for (auto& e : s->ev_chunk) CKF(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : s->ev_done) CKF(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& c : s->stream_c) CKF(cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking));
     CKF(cudaEventCreate(&s->ev0));
     CKF(cudaEventCreate(&s->ev1));
     CKF(cudaEventCreate(&s->ev_mid));
@@ -358,7 +374,7 @@ extern "C" int br2_batch_iterate_device(br2_batch_solver* s, double** X, double*
 static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, const double* d_yref, const int* d_lines,
                       const double* d_p, int p_per_stage, double* d_u0, double* d_thrust, int* d_status)
 {
-    a.B = s->B; a.N = s->N;
+    a.B = s->B; a.N = s->N; a.lo = 0; a.hi = s->B; a.housekeeping = 2; a.qidx = 0;
     a.x0 = d_x0; a.yref = d_yref; a.p = d_p;
     a.traj = s->d_traj; a.lines = d_lines; a.traj_rows = s->traj_rows;
     a.p_inst_stride = p_per_stage ? (s->N + 1) * NP : NP;
@@ -580,10 +596,15 @@ static bool pinned_host(const void* p)
 static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cudaStream_t st)
 {
     const size_t B = s->B, N = s->N;
+    // the timing events must stay usable from outside a graph: inside a capture they are recorded as EXTERNAL event nodes
+    cudaStreamCaptureStatus capst = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &capst) != cudaSuccess) { cudaGetLastError(); capst = cudaStreamCaptureStatusNone; }
+    const unsigned evflag = capst == cudaStreamCaptureStatusNone ? cudaEventRecordDefault : cudaEventRecordExternal;
     const size_t psz = sizeof(double) * B * (io.p_per_stage ? (N + 1) * NP : NP);
     const double *d_x0 = io.x0, *d_yref = io.yref, *d_p = io.p, *d_thr = io.thrusts, *d_acc = io.body_acc;
     const int* d_lines = io.lines;
-    bool forked = false;
+    bool forked = false, chunked = false;
+    int nchunk = 4;
     if (host) {
         if (io.ekf) {
             CK(cudaMemcpyAsync(s->d_x0, io.x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
@@ -594,16 +615,32 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
             CK(cudaMemcpyAsync(s->d_p, io.p, psz, cudaMemcpyHostToDevice, st));
             d_p = s->d_p;
         }
+        // explicit reference windows are the big upload (B x (N+1) x 16 doubles: 21.5 MB at B = 4096, N = 40 -- longer on the wire
+        // than the kernels of the tick): for large batches without a filter it is cut into four instance ranges and
+        // pipelined, range c being linearised and solved while ranges c+1.. are still in flight (below)
+        static const int kChunks = [] { const char* e = getenv("BR2_YREF_CHUNKS"); int v = e ? atoi(e) : 4; return v == 1 || v == 2 || v == 4 ? v : 4; }();
+        nchunk = kChunks;
+        chunked = !io.lines && !io.ekf && B >= 1024 && nchunk > 1;
         if (io.lines) { CK(cudaMemcpyAsync(s->d_lines, io.lines, sizeof(int) * B, cudaMemcpyHostToDevice, st)); d_lines = s->d_lines; }
-        else { CK(cudaMemcpyAsync(s->d_yref, io.yref, sizeof(double) * B * (N + 1) * NY, cudaMemcpyHostToDevice, st)); d_yref = s->d_yref; }
+        else if (!chunked) { CK(cudaMemcpyAsync(s->d_yref, io.yref, sizeof(double) * B * (N + 1) * NY, cudaMemcpyHostToDevice, st)); }
+        if (!io.lines) d_yref = s->d_yref;
         d_x0 = s->d_x0;
         if (!io.ekf) {
             // x0 rides a second stream past the lineariser: the QP kernel is its first reader
+            if (chunked) launch_tick_begin(s->d_counter, st);    // the ranges' kernels do no housekeeping of their own
             CK(cudaEventRecord(s->ev_fork, st));
             CK(cudaStreamWaitEvent(s->stream_x0, s->ev_fork, 0));
             CK(cudaMemcpyAsync(s->d_x0, io.x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, s->stream_x0));
             CK(cudaEventRecord(s->ev_x0, s->stream_x0));
             forked = true;
+            if (chunked) {
+                const size_t row = (N + 1) * NY;
+                for (int c = 0; c < nchunk; c++) {
+                    const size_t lo = B * c / nchunk, hi = B * (c + 1) / nchunk;
+                    CK(cudaMemcpyAsync(s->d_yref + lo * row, io.yref + lo * row, sizeof(double) * (hi - lo) * row, cudaMemcpyHostToDevice, s->stream_x0));
+                    CK(cudaEventRecord(s->ev_chunk[c], s->stream_x0));
+                }
+            }
         }
     }
     // outputs: device buffers, or -- host path -- the caller's buffers themselves when the device can write them (mapped)
@@ -626,12 +663,30 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
     }
     SolveArgs a;
     fill_args(s, a, d_x0, d_yref, d_lines, d_p, io.ekf ? 0 : io.p_per_stage, o_u0, o_th, o_st);
-    CK(cudaEventRecord(s->ev0, st));
-    launch_linearize(a, st);
-    if (s->kernel_timing) CK(cudaEventRecord(s->ev_mid, st));
-    if (forked) CK(cudaStreamWaitEvent(st, s->ev_x0, 0));
-    launch_ipm(a, s->sm_count, st);
-    CK(cudaEventRecord(s->ev1, st));
+    CK(cudaEventRecordWithFlags(s->ev0, st, evflag));
+    if (chunked) {
+        // range c on its own stream: waits for its part of the upload (and for x0), then lineariser -> pdas_kernel; the ranges
+        // overlap each other and the rest of the upload (a range alone leaves most of the chip idle: its time is the latency of
+        // one instance, not its share of the batch)
+        for (int c = 0; c < nchunk; c++) {
+            SolveArgs ac = a;
+            ac.lo = (int)(B * c / nchunk); ac.hi = (int)(B * (c + 1) / nchunk); ac.housekeeping = 0; ac.qidx = c;
+            cudaStream_t sc = s->stream_c[c];
+            CK(cudaStreamWaitEvent(sc, s->ev_chunk[c], 0));      // (recorded after ev_x0 and after the fork: joins the capture)
+            launch_linearize(ac, sc);
+            launch_pdas(ac, s->sm_count, sc);
+            CK(cudaEventRecord(s->ev_done[c], sc));
+            CK(cudaStreamWaitEvent(st, s->ev_done[c], 0));
+        }
+        if (s->kernel_timing) CK(cudaEventRecordWithFlags(s->ev_mid, st, evflag));     // (no lineariser / QP split in this mode)
+        launch_ipm_fallback(a, s->sm_count, st);
+    } else {
+        launch_linearize(a, st);
+        if (s->kernel_timing) CK(cudaEventRecordWithFlags(s->ev_mid, st, evflag));
+        if (forked) CK(cudaStreamWaitEvent(st, s->ev_x0, 0));
+        launch_ipm(a, s->sm_count, st);
+    }
+    CK(cudaEventRecordWithFlags(s->ev1, st, evflag));
     if (!host && io.plant_h > 0) {
         PlantArgs pl;
         pl.B = s->B; pl.x = const_cast<double*>(io.x0); pl.u = a.u0; pl.p = d_p; pl.dist = nullptr;
@@ -664,6 +719,27 @@ static int tick_validate(br2_batch_solver* s, const br2_tick_io* io, int host, c
     return BR2_OK;
 }
 
+// the host INPUT buffers of a tick (index = H2DNode::which) and their sizes: a host graph can be replayed on other input buffers
+// by re-pointing its upload nodes (cudaGraphExecMemcpyNodeSetParams1D), everything else of the key must match
+static int tick_inputs(const br2_batch_solver* s, const br2_tick_io& io, const void* ptr[5], size_t bytes[5])
+{
+    const size_t B = s->B, N = s->N;
+    ptr[0] = io.x0; bytes[0] = sizeof(double) * B * NX;
+    ptr[1] = io.yref; bytes[1] = sizeof(double) * B * (N + 1) * NY;
+    ptr[2] = io.lines; bytes[2] = sizeof(int) * B;
+    ptr[3] = io.ekf ? (const void*)io.thrusts : (const void*)io.p; bytes[3] = io.ekf ? sizeof(double) * B * 6 : sizeof(double) * B * (io.p_per_stage ? (N + 1) * NP : NP);
+    ptr[4] = io.ekf ? io.body_acc : nullptr; bytes[4] = sizeof(double) * B * 6;
+    return 5;
+}
+static bool same_but_inputs(const br2_tick_io& a, const br2_tick_io& b)
+{
+    if ((a.yref == nullptr) != (b.yref == nullptr) || (a.lines == nullptr) != (b.lines == nullptr)) return false;
+    br2_tick_io x = a, y = b;
+    x.x0 = y.x0 = nullptr; x.yref = y.yref = nullptr; x.lines = y.lines = nullptr;
+    if (a.ekf) { x.thrusts = y.thrusts = nullptr; x.body_acc = y.body_acc = nullptr; } else { x.p = y.p = nullptr; }
+    return !memcmp(&x, &y, sizeof x);
+}
+
 // cached graph of this (io, host) or a newly captured one; nullptr (and rc == BR2_OK) when graphs are not to be used
 static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, cudaGraphExec_t* out)
 {
@@ -682,9 +758,27 @@ static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, 
     // a graph is worth building only for a caller that comes back with the same buffers: the first sighting of a key goes the
     // stream path and is remembered (the last four: double-buffered callers alternate), the second one instantiates -- so a
     // caller that cycles through many distinct buffers never thrashes the cache
+    if (host) {
+        // same tick on other input buffers: re-point the upload nodes of a cached graph
+        for (auto& g : s->tg) {
+            if (!(g.exec && g.host == 1 && g.gen == s->gen && g.nup > 0 && same_but_inputs(g.io, io))) continue;
+            const void* np_[5]; size_t nb_[5];
+            tick_inputs(s, io, np_, nb_);
+            bool okk = true;
+            for (int i = 0; i < g.nup && okk; i++) {
+                const auto& u = g.up[i];
+                okk = cudaGraphExecMemcpyNodeSetParams1D(g.exec, u.node, u.dst, (const char*)np_[u.which] + u.off, u.bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+            }
+            if (!okk) { cudaGetLastError(); break; }
+            g.io = io; g.stamp = ++s->tick_stamp;
+            s->graph_updates++;
+            *out = g.exec;
+            return BR2_OK;
+        }
+    }
     bool seen = false;
     for (auto& m : s->miss)
-        if (m.valid && m.host == host && m.gen == s->gen && !memcmp(&m.io, &io, sizeof io)) { seen = true; m.valid = false; }
+        if (m.valid && m.host == host && m.gen == s->gen && (host ? same_but_inputs(m.io, io) : !memcmp(&m.io, &io, sizeof io))) { seen = true; m.valid = false; }
     if (!seen) {
         auto& m = s->miss[s->miss_next++ % 4];
         m.io = io; m.host = host; m.gen = s->gen; m.valid = true;
@@ -701,16 +795,41 @@ static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, 
     }
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { cudaGetLastError(); return fail(BR2_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); return fail(BR2_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
     if (slot->exec) cudaGraphExecDestroy(slot->exec);
-    slot->io = io; slot->host = host; slot->gen = s->gen; slot->stamp = ++s->tick_stamp; slot->exec = exec;
+    if (slot->graph) cudaGraphDestroy(slot->graph);
+    slot->io = io; slot->host = host; slot->gen = s->gen; slot->stamp = ++s->tick_stamp; slot->exec = exec; slot->graph = graph; slot->nup = 0;
+    if (host) {
+        // remember the upload nodes: which input each reads and where inside it
+        const void* ip[5]; size_t ib[5];
+        tick_inputs(s, io, ip, ib);
+        cudaGraphNode_t nodes[64];
+        size_t nn = 64;
+        bool complete = cudaGraphGetNodes(graph, nodes, &nn) == cudaSuccess && nn <= 64;
+        for (size_t i = 0; complete && i < nn; i++) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess) { complete = false; break; }
+            if (ty != cudaGraphNodeTypeMemcpy) continue;
+            cudaMemcpy3DParms mp;
+            if (cudaGraphMemcpyNodeGetParams(nodes[i], &mp) != cudaSuccess) { complete = false; break; }
+            if (mp.kind != cudaMemcpyHostToDevice) continue;
+            const char* src = (const char*)mp.srcPtr.ptr;
+            const size_t bytes = mp.extent.width * mp.extent.height * mp.extent.depth;
+            int which = -1;
+            for (int k = 0; k < 5; k++)
+                if (ip[k] && src >= (const char*)ip[k] && src + bytes <= (const char*)ip[k] + ib[k]) which = k;
+            if (which < 0 || slot->nup >= 12) { complete = false; break; }
+            slot->up[slot->nup++] = {nodes[i], which, (size_t)(src - (const char*)ip[which]), bytes, mp.dstPtr.ptr};
+        }
+        if (!complete) { cudaGetLastError(); slot->nup = 0; }      // this graph is replayed on its own buffers only
+    }
     s->graphs_built++;
     *out = exec;
     return BR2_OK;
 }
 
 extern "C" int br2_batch_graphs_built(const br2_batch_solver* s) { return s ? s->graphs_built : 0; }
+extern "C" int br2_batch_graph_updates(const br2_batch_solver* s) { return s ? s->graph_updates : 0; }
 
 extern "C" int br2_batch_set_tick_index(br2_batch_solver* s, int next_tick)
 {

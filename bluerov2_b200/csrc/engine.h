@@ -11,6 +11,10 @@ constexpr int NMAX = 256;   // maximum horizon supported by the engine
 // Everything a launch needs; passed by value (fits the 4 KB kernel parameter space).
 struct SolveArgs {
     int B, N;
+    int lo, hi;            // instance range of this launch (lineariser / pdas_kernel): the whole batch, or one chunk of a pipelined tick
+    int housekeeping;      // what block 0 of the lineariser resets: 2 = everything a tick needs (the normal case: this launch opens
+                           // the tick), 0 = nothing (ranges of a pipelined tick: tick_begin_kernel has done it for all of them)
+    int qidx;              // which work-queue counter (CTR_QUEUE + qidx) this range's pdas_kernel uses: ranges run concurrently
     // problem data (device)
     const double* x0;      // [B][12]
     const double* yref;    // [B][N+1][16], or null when the reference is windowed on the device:
@@ -59,9 +63,12 @@ __device__ __forceinline__ const double* yref_row(const SolveArgs& a, int inst, 
 }
 
 void launch_linearize(const SolveArgs& a, cudaStream_t s);
-void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s);
+void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s);          // = launch_pdas + launch_ipm_fallback
+void launch_pdas(const SolveArgs& a, int sm_count, cudaStream_t s);
+void launch_ipm_fallback(const SolveArgs& a, int sm_count, cudaStream_t s);
+void launch_tick_begin(int* ctr, cudaStream_t s);     // per-tick housekeeping as a kernel of its own (pipelined ticks)
 void configure_kernels();      // per-device function attributes (call with the solver's device current)
-enum { CTR_QUEUE = 0, CTR_HARD = 1, CTR_EASY = 2, CTR_PARITY = 3, CTR_FB = 4, CTR_FBQ = 5, CTR_TICK = 6, CTR_COUNT = 8 };
+enum { CTR_HARD = 1, CTR_EASY = 2, CTR_PARITY = 3, CTR_FB = 4, CTR_FBQ = 5, CTR_TICK = 6, CTR_QUEUE = 8, CTR_COUNT = 12 };   // CTR_QUEUE .. +3: one per range
 
 // EKF (bluerov2_dob.cpp:495-545), one warp per instance
 struct EkfArgs {

@@ -114,7 +114,7 @@ __device__ __forceinline__ void jac_load(Jac& J, const double* src)
 // phase A for one stage (lane-private)
 __device__ __forceinline__ void lin_phase_a(const SolveArgs& a, LinSmem& sm, int slot, int gs, bool live)
 {
-    const int inst = gs / a.N, k = gs - inst * a.N;
+    const int il = gs / a.N, k = gs - il * a.N, inst = a.lo + il;
     const double* p = a.p + (size_t)inst * a.p_inst_stride + (size_t)k * a.p_stage_stride;
     ModelConst mc;
     {
@@ -174,15 +174,24 @@ __device__ __forceinline__ void lin_phase_a(const SolveArgs& a, LinSmem& sm, int
 }
 static_assert(G_B_OFF == 192 && G_QLIN == 204 && G_RLIN == 216 && G_TS == 220 && GREC == 224, "tail layout");
 
+// per-tick reset of the work queues, the order / fallback counters, the order parity and the tick index
+__device__ __forceinline__ void tick_housekeeping(int* ctr)
+{
+    ctr[CTR_QUEUE] = 0; ctr[CTR_QUEUE + 1] = 0; ctr[CTR_QUEUE + 2] = 0; ctr[CTR_QUEUE + 3] = 0;
+    ctr[CTR_HARD] = 0; ctr[CTR_EASY] = 0; ctr[CTR_PARITY] ^= 1; ctr[CTR_FB] = 0; ctr[CTR_FBQ] = 0; ctr[CTR_TICK] += 1;
+}
+__global__ void tick_begin_kernel(int* ctr) { tick_housekeeping(ctr); }
+void launch_tick_begin(int* ctr, cudaStream_t s) { tick_begin_kernel<<<1, 1, 0, s>>>(ctr); }
+
 __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a)
 {
     __shared__ LinSmem sm;
     const int lane = threadIdx.x;
-    const int total = a.B * a.N;
+    const int total = (a.hi - a.lo) * a.N;
     const int base = blockIdx.x * LRND;
     if (blockIdx.x == 0 && lane == 0) {
         // housekeeping for the IPM kernel that follows in the stream: reset its work-queue counters, flip the order buffers
-        a.ctr[CTR_QUEUE] = 0; a.ctr[CTR_HARD] = 0; a.ctr[CTR_EASY] = 0; a.ctr[CTR_PARITY] ^= 1; a.ctr[CTR_FB] = 0; a.ctr[CTR_FBQ] = 0; a.ctr[CTR_TICK] += 1;
+        if (a.housekeeping) tick_housekeeping(a.ctr);
     }
     if (lane < LRND) {
         const int gs = base + lane;
@@ -265,7 +274,7 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
             }
             if (gs < total) {
                 const int gi = gs / a.N;
-                double* Gk = a.S + ((size_t)gi * (a.N + 1) + (gs - gi * a.N)) * SREC + S_G;
+                double* Gk = a.S + ((size_t)(a.lo + gi) * (a.N + 1) + (gs - gi * a.N)) * SREC + S_G;
                 double* da = Gk + (((zca >> 3)) << 5) + ((zca & 7) << 2);     // g_off(0, zc); row block ki adds 64
                 double* db = Gk + (((zcb >> 3)) << 5) + ((zcb & 7) << 2);
 #pragma unroll
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
 
 void launch_linearize(const SolveArgs& a, cudaStream_t s)
 {
-    const long long total = (long long)a.B * a.N;
+    const long long total = (long long)(a.hi - a.lo) * a.N;
     const int grid = (int)((total + LRND - 1) / LRND);
     linearize_kernel<<<grid, 32, 0, s>>>(a);
 }
@@ -1445,14 +1454,18 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_PDAS_MINB) pdas_kernel(con
     const int* order_cur = a.order + (size_t)par * a.B;
     int* order_next = a.order + (size_t)(par ^ 1) * a.B;
     const int nwarps = gridDim.x * IPM_WARPS;
+    // queue position -> instance: through the visiting order for the whole batch, lo + position for an instance range
+    const int nq = a.hi - a.lo;
+    const bool ranged = nq != a.B;
+    auto inst_of = [&](int qpos) { return qpos < nq ? (ranged ? a.lo + qpos : order_cur[qpos]) : a.B; };
     int reserved = blockIdx.x * IPM_WARPS + (threadIdx.x >> 5);
-    if (lane == 0) reserved = reserved < a.B ? order_cur[reserved] : a.B;
+    if (lane == 0) reserved = inst_of(reserved);
     bool have = true;
     for (;;) {
         int inst = reserved;
         if (!have && lane == 0) {
-            const int qpos = nwarps + atomicAdd(a.ctr + CTR_QUEUE, 1);
-            inst = qpos < a.B ? order_cur[qpos] : a.B;
+            const int qpos = nwarps + atomicAdd(a.ctr + CTR_QUEUE + a.qidx, 1);
+            inst = inst_of(qpos);
         }
         have = false;
         inst = __shfl_sync(FULL_MASK, inst, 0);
@@ -1483,8 +1496,8 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_PDAS_MINB) pdas_kernel(con
                 if (att == 0) {
                     prefetch_iterate(I);
                     if (lane == 0) {
-                        const int qpos = nwarps + atomicAdd(a.ctr + CTR_QUEUE, 1);
-                        reserved = qpos < a.B ? order_cur[qpos] : a.B;
+                        const int qpos = nwarps + atomicAdd(a.ctr + CTR_QUEUE + a.qidx, 1);
+                        reserved = inst_of(qpos);
                     }
                     have = true;
                 }
@@ -1553,17 +1566,28 @@ void configure_kernels()
     cudaFuncSetAttribute(ipm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
+void launch_pdas(const SolveArgs& a, int sm_count, cudaStream_t s)
 {
-    // Persistent grids, one warp per instance at a time, instances handed out by atomic queues (their counters are reset and
-    // the order buffers flipped by block 0 of the lineariser that precedes these kernels in the stream).  (Sizing the resident
+    // Persistent grid, one warp per instance at a time, instances handed out by an atomic queue (its counter is reset and the
+    // order buffers flipped by block 0 of the lineariser that precedes this kernel in the stream).  (Sizing the resident
     // set for even waves -- 14 instead of 16 warps/SM at B = 4096 -- measured 8 % slower: throughput grows with the
     // number of resident warps and the queue already evens out the tail; profiles/r01h_ipm_variants.txt.)
-    const int need = (a.B + IPM_WARPS - 1) / IPM_WARPS;
-    int blocks = need < sm_count * BR2_PDAS_MINB ? need : sm_count * BR2_PDAS_MINB;
+    const int need = (a.hi - a.lo + IPM_WARPS - 1) / IPM_WARPS;
+    const int blocks = need < sm_count * BR2_PDAS_MINB ? need : sm_count * BR2_PDAS_MINB;
     pdas_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
-    blocks = need < sm_count * BR2_IPM_MINB ? need : sm_count * BR2_IPM_MINB;
+}
+
+void launch_ipm_fallback(const SolveArgs& a, int sm_count, cudaStream_t s)
+{
+    const int need = (a.B + IPM_WARPS - 1) / IPM_WARPS;
+    const int blocks = need < sm_count * BR2_IPM_MINB ? need : sm_count * BR2_IPM_MINB;
     ipm_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
+}
+
+void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s)
+{
+    launch_pdas(a, sm_count, s);
+    launch_ipm_fallback(a, sm_count, s);
 }
 
 }  // namespace br2

@@ -74,6 +74,7 @@ def load_library(path: str | None = None):
         "br2_batch_tick_device": (C.c_int, [V, V, V]),
         "br2_batch_tick_host": (C.c_int, [V, V]),
         "br2_batch_graphs_built": (C.c_int, [V]),
+        "br2_batch_graph_updates": (C.c_int, [V]),
         "br2_batch_set_tick_index": (C.c_int, [V, C.c_int]),
         "br2_plant_step_device": (C.c_int, [C.c_int, V, V, V, V, V, V, C.c_int, C.c_double, V, V, V]),
         "br2_batch_ekf_reset": (C.c_int, [V]),
@@ -348,6 +349,9 @@ class BatchSolver:
 
     def graphs_built(self) -> int:
         return int(self._L.br2_batch_graphs_built(self._h))
+
+    def graph_updates(self) -> int:
+        return int(self._L.br2_batch_graph_updates(self._h))
 
     def set_tick_index(self, next_tick: int = 0):
         """index the next tick's plant step uses for the wave phase (tau = tau0 + 0.125 * index); counts up by itself"""

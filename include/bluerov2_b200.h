@@ -141,6 +141,8 @@ BR2_API int br2_batch_tick_device(br2_batch_solver *s, const br2_tick_io *io, vo
 BR2_API int br2_batch_tick_host(br2_batch_solver *s, const br2_tick_io *io);
 /* number of CUDA graphs instantiated so far (diagnostic: stays constant in a steady closed loop) */
 BR2_API int br2_batch_graphs_built(const br2_batch_solver *s);
+/* host path: replays of a cached graph on NEW (pinned) input buffers -- its upload nodes are re-pointed, nothing is re-instantiated */
+BR2_API int br2_batch_graph_updates(const br2_batch_solver *s);
 /* index the next tick's plant step uses for the wave phase (tau = tau0 + 0.125 * index, bluerov2_dob.cpp:774-797); the solver
  * counts ticks by itself from 0 at creation */
 BR2_API int br2_batch_set_tick_index(br2_batch_solver *s, int next_tick);

@@ -139,3 +139,53 @@ def test_tick_argument_errors(solver_mod):
     with pytest.raises(solver_mod.SolverError):
         s.tick(x0, p=p, yref=yref, plant_h=0.05)            # plant is a device-path option
     s.close()
+
+
+def test_pipelined_explicit_yref_upload_equals_plain_host_solve(solver_mod):
+    """B >= 1024 with explicit reference windows: the upload is cut into four instance ranges, range c linearised and solved
+    while the later ranges are still on the wire; instances are independent, so the result is bit-identical to the one-piece
+    host solve -- over several closed-loop ticks from a saturated start (hints, visiting order and fallback list cross the ranges)"""
+    N, B, T = 10, 1024 + 7, 5
+    w = wl.tracking_batch(B, N, seed=9, pos_spread=2.5)
+    a = solver_mod.BatchSolver(B, N); a.set_iterate(w["X"], w["U"])
+    b = solver_mod.BatchSolver(B, N); b.set_iterate(w["X"], w["U"])
+    x0, lines = w["x0"].copy(), w["lines"].copy()
+    pin = lambda v: _pin(v)   # noqa: E731
+    hx, hp = pin(x0), pin(w["p"])
+    hy = pin(np.zeros((B, N + 1, 16)))
+    out = (pin(np.zeros((B, 4))), pin(np.zeros((B, 6))), pin(np.zeros(B, dtype=np.int32)))
+    for t in range(T):
+        yref = traj.window_batch(w["traj"], lines, N)
+        ua, tha, sta = a.solve(x0, yref, w["p"])                      # br2_batch_solve_host: one piece
+        hx[:] = x0; hy[:] = yref
+        ub, thb, stb = b.tick(hx, p=hp, yref=hy, out=out)             # br2_batch_tick_host: pipelined ranges (a graph from tick 1 on)
+        assert np.array_equal(ua, ub) and np.array_equal(tha, thb) and np.array_equal(sta, stb), t
+        assert (sta == 0).all()
+        x0 = wl.plant_step(x0, ua, w["p"], 0.05)
+        lines = lines + 1
+    Xa, Ua = a.get_iterate(); Xb, Ub = b.get_iterate()
+    assert np.array_equal(Xa, Xb) and np.array_equal(Ua, Ub)
+    assert b.graphs_built() == 1
+    a.close(); b.close()
+
+
+def test_host_graph_replayed_on_new_input_buffers(solver_mod):
+    """a caller that hands in a fresh pinned input buffer every tick (messages arriving) still replays ONE graph: its upload nodes
+    are re-pointed; results equal the stream path tick by tick"""
+    N, B, T = 10, 1024, 6
+    w = wl.tracking_batch(B, N, seed=10, pos_spread=1.0)
+    a = solver_mod.BatchSolver(B, N); a.set_iterate(w["X"], w["U"]); a.set_option("tick_graph", 0)
+    b = solver_mod.BatchSolver(B, N); b.set_iterate(w["X"], w["U"])
+    hp = _pin(w["p"])
+    outa = (_pin(np.zeros((B, 4))), _pin(np.zeros((B, 6))), _pin(np.zeros(B, dtype=np.int32)))
+    outb = (_pin(np.zeros((B, 4))), _pin(np.zeros((B, 6))), _pin(np.zeros(B, dtype=np.int32)))
+    x0, lines = w["x0"].copy(), w["lines"].copy()
+    for t in range(T):
+        hx, hy = _pin(x0), _pin(traj.window_batch(w["traj"], lines, N))       # new buffers every tick
+        ua, _, sta = a.tick(hx, p=hp, yref=hy, out=outa)
+        ub, _, stb = b.tick(hx, p=hp, yref=hy, out=outb)
+        assert np.array_equal(ua, ub) and np.array_equal(sta, stb) and (sta == 0).all(), t
+        x0 = wl.plant_step(x0, ua.copy(), w["p"], 0.05)
+        lines = lines + 1
+    assert a.graphs_built() == 0 and b.graphs_built() == 1 and b.graph_updates() == T - 2
+    a.close(); b.close()
