@@ -204,23 +204,41 @@ class DeviceLoop:
         self.acc = torch.zeros((B, 6), dtype=torch.float64, device=dev)
         self.u0 = torch.empty((B, 4), dtype=torch.float64, device=dev)
         self.st = torch.empty((B,), dtype=torch.int32, device=dev)
-        # all ranks' thrust vectors, double-buffered: the all-gather of tick t overlaps the lineariser of tick t + 1
-        self.gather = PipelinedThrustGather(world * B, dev, depth=int(os.environ.get("BR2_GATHER_DEPTH", "2")))
+        # Every rank ends a tick with all ranks' thrust vectors.  Default: peer-to-peer, fused into the solve (the QP epilogue stores
+        # into every rank's gather buffer over NVLink, PeerThrustExchange) -- no collective kernel on the tick's path.
+        # BR2_GATHER=nccl: one NCCL all-gather per tick instead (double-buffered: it overlaps the next tick's lineariser).
         self.distributed = world > 1
+        self.mode = os.environ.get("BR2_GATHER", "peer") if self.distributed else "none"
+        self.gather = PipelinedThrustGather(world * B, dev, depth=int(os.environ.get("BR2_GATHER_DEPTH", "2")))
+        self.thr = torch.empty((B, 6), dtype=torch.float64, device=dev)
+        self.peer = None
+        if self.mode == "peer":
+            from bluerov2_b200.sharding import PeerThrustExchange
+            self.peer = PeerThrustExchange(sol, B)
         sol.set_trajectory(w["traj"])
 
     def restart(self):
+        import torch.distributed as dist
         self.sol.set_iterate(self.w["X"], self.w["U"])
         self.x.copy_(self.x_init); self.lines.copy_(self.lines_init)
+        if self.peer is not None:
+            self.torch.cuda.synchronize(self.dev); dist.barrier()      # every rank's stores have landed before the flags restart
         self.sol.set_tick_index(0)
+        if self.peer is not None:
+            dist.barrier()
 
     def tick(self, t):
-        self.sol.tick(self.x, p=self.p, lines=self.lines, body_acc=self.acc, out=(self.u0, self.gather.slot(t), self.st), plant_h=0.05)
-        if self.distributed:
+        if self.mode == "nccl":
+            self.sol.tick(self.x, p=self.p, lines=self.lines, body_acc=self.acc, out=(self.u0, self.gather.slot(t), self.st), plant_h=0.05)
             self.gather.all_gather_async(t)     # ONE all-gather per tick, enqueued behind the solve
+        else:
+            self.sol.tick(self.x, p=self.p, lines=self.lines, body_acc=self.acc, out=(self.u0, self.thr, self.st), plant_h=0.05)
 
     def finish(self):
-        self.gather.wait_all()                  # the last ticks' collectives belong to the timed region
+        if self.mode == "nccl":
+            self.gather.wait_all()              # the last ticks' collectives belong to the timed region
+        elif self.peer is not None:
+            self.peer.wait()                    # ... and so does the arrival of every rank's last tick
 
 
 def timed_device_loop(torch, dist, loop, W, K, dev, distributed, sampler=None, per_tick=False):
@@ -528,8 +546,11 @@ def run_ours(args):
             "mean_qp_iterations": iters_mean, "nonzero_status": n_bad, "fast_path": not args.no_fast_path,
             "l2": "per-tick working set (stage records + iterates) "
                   f"{B * (N + 1) * 352 * 8 / 1e6:.0f} MB > 126 MB L2",
-            "parallelism": f"{world} x independent shards" + (", one NCCL all-gather of the thrust vectors per tick (double-buffered: it "
-                                                              "overlaps the next tick's lineariser)" if distributed else ""),
+            "parallelism": f"{world} x independent shards" + ("" if not distributed else
+                                                              ", thrust vectors exchanged peer-to-peer from the QP epilogue (stores into every rank's gather "
+                                                              "buffer over NVLink, one flag per rank and tick; no collective kernel)" if loop.mode == "peer" else
+                                                              ", one NCCL all-gather of the thrust vectors per tick (double-buffered: it overlaps the next "
+                                                              "tick's lineariser)"),
             "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ok": e2e_ok,
                     "ms_per_step": 1e3 * dt_e2e / K, "api": "br2_batch_tick_host (windowed reference: one trajectory row index per instance)",
                     "overhead_over_device_time": dt_e2e / dt - 1.0},

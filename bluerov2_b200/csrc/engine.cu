@@ -43,6 +43,7 @@ struct br2_batch_solver {
     double *d_ex, *d_eP, *d_thr, *d_meas, *d_acc, *d_wf, *d_pout;   // EKF state + staging
     double* d_rls;                            // RLS-VFF state [B][4][RLS_STRIDE] (AMPC)
     float* d_yaw;                             // continuous-yaw accumulators [B][2] = (pre_yaw, yaw_sum), floats as in the node
+    cudaStream_t stream_xchg; cudaEvent_t ev_xfork, ev_xdone;   // side branch that ships the previous tick's thrusts to the peers
     cudaStream_t stream_c[4];          // compute streams of the ranges of a pipelined tick
     cudaEvent_t ev_done[4];
     cudaStream_t stream, stream_x0;   // host API: main stream; second stream carrying the x0 upload past the lineariser
@@ -53,14 +54,20 @@ struct br2_batch_solver {
     // tick graphs: the kernels (and, for host buffers, the copies) of one control tick instantiated as a CUDA graph, keyed on the
     // caller's buffers and on a generation counter that every change of options / weights / bounds / trajectory bumps
     struct H2DNode { cudaGraphNode_t node; int which; size_t off, bytes; void* dst; };   // upload node: input index, offset inside it
-    struct TickGraph { br2_tick_io io; int host; unsigned gen; unsigned long long stamp; cudaGraphExec_t exec; cudaGraph_t graph;
+    struct TickGraph { br2_tick_io io; int host; int xchg; unsigned gen; unsigned long long stamp; cudaGraphExec_t exec; cudaGraph_t graph;
                        H2DNode up[12]; int nup; } tg[4];
+    // sharding: local gather buffer + flags (one allocation, exported through CUDA IPC), mapped peers
+    ShardView shard;
+    double* d_shard;          // [2][world * B][6] doubles, then [world] int flags, then [1] int time-out marker
+    void* peer_base[MAX_SHARDS];   // cudaIpcOpenMemHandle mappings (to close)
+    long long ticks_host;     // ticks enqueued so far (host-side mirror of ctr[CTR_TICK])
+    long long xchg_host;      // exchanges enqueued so far (mirror of ctr[CTR_XTICK]): tick t is shipped as a side branch of tick t + 1
     int graph_updates;      // replays of a host graph on NEW input buffers (upload nodes re-pointed, nothing re-instantiated)
     unsigned gen;
     unsigned long long tick_stamp;
     int graphs_built, kernel_timing, tick_graph;
     cudaEvent_t ev_fork, ev_chunk[4];
-    struct Miss { br2_tick_io io; int host; unsigned gen; bool valid; } miss[4];   // the last keys that missed the graph cache
+    struct Miss { br2_tick_io io; int host; int xchg; unsigned gen; bool valid; } miss[4];   // the last keys that missed the graph cache
     unsigned miss_next;
 };
 
@@ -127,6 +134,12 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
         if (e) cudaEventDestroy(e);
     for (auto c : s->stream_c)
         if (c) cudaStreamDestroy(c);
+    if (s->stream_xchg) cudaStreamDestroy(s->stream_xchg);
+    if (s->ev_xfork) cudaEventDestroy(s->ev_xfork);
+    if (s->ev_xdone) cudaEventDestroy(s->ev_xdone);
+    for (int r = 0; r < MAX_SHARDS; r++)
+        if (s->peer_base[r]) cudaIpcCloseMemHandle(s->peer_base[r]);
+    if (s->d_shard) cudaFree(s->d_shard);
     for (auto& g : s->tg) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
         if (g.graph) cudaGraphDestroy(g.graph);
@@ -209,6 +222,9 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     for (auto& e : s->ev_chunk) CKF(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : s->ev_done) CKF(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& c : s->stream_c) CKF(cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking));
+    CKF(cudaStreamCreateWithFlags(&s->stream_xchg, cudaStreamNonBlocking));
+    CKF(cudaEventCreateWithFlags(&s->ev_xfork, cudaEventDisableTiming));
+    CKF(cudaEventCreateWithFlags(&s->ev_xdone, cudaEventDisableTiming));
     CKF(cudaEventCreate(&s->ev0));
     CKF(cudaEventCreate(&s->ev1));
     CKF(cudaEventCreate(&s->ev_mid));
@@ -386,7 +402,7 @@ static void fill_args(br2_batch_solver* s, SolveArgs& a, const double* d_x0, con
     a.u0 = d_u0 ? d_u0 : s->d_u0;
     a.thrust = d_thrust ? d_thrust : s->d_thrust;
     a.status = d_status ? d_status : s->d_status;
-    a.iters = s->d_iters; a.info = s->d_info; a.ctr = s->d_counter; a.order = s->d_order; a.fb = s->d_fb; a.iter_total = s->d_iter_total; a.prof = s->d_iter_total + 1; a.bad_total = s->d_iter_total + 17; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
+    a.iters = s->d_iters; a.info = s->d_info; a.ctr = s->d_counter; a.order = s->d_order; a.fb = s->d_fb; a.shard = s->shard; a.iter_total = s->d_iter_total; a.prof = s->d_iter_total + 1; a.bad_total = s->d_iter_total + 17; a.hint = s->d_hint; a.fast_path = s->fast_path; a.aset = s->d_aset; a.active_set = s->active_set;
     a.max_iter = s->max_iter; a.tol = s->tol;
 }
 
@@ -434,6 +450,7 @@ static int solve_host_common(br2_batch_solver* s, const double* x0, const double
     launch_ipm(a, s->sm_count, st);
     CK(cudaEventRecord(s->ev1, st));
     s->timed = true;
+    s->ticks_host++;
     CK(cudaGetLastError());
     if (u0 && !a_u0) CK(cudaMemcpyAsync(u0, s->d_u0, sizeof(double) * B * 4, cudaMemcpyDeviceToHost, st));
     if (thrust && !a_th) CK(cudaMemcpyAsync(thrust, s->d_thrust, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
@@ -497,6 +514,7 @@ static int solve_enqueue(br2_batch_solver* s, const double* d_x0, const double* 
     launch_ipm(a, s->sm_count, st);
     CK(cudaEventRecord(s->ev1, st));
     s->timed = true;
+    s->ticks_host++;
     CK(cudaGetLastError());
     return BR2_OK;
 }
@@ -591,15 +609,31 @@ static bool pinned_host(const void* p)
     return at.type == cudaMemoryTypeHost;
 }
 
+// sharded and fully connected, with a finished tick whose thrust block has not been shipped yet?
+static int shard_pending(const br2_batch_solver* s)
+{
+    if (s->shard.world <= 1 || s->ticks_host <= s->xchg_host) return 0;
+    for (int r = 0; r < s->shard.world; r++)
+        if (!s->shard.buf[r]) return 0;
+    return 1;
+}
+
 // Everything of a tick, issued on `st` (plus stream_x0 for the forked x0 upload of the host path).  Runs either inside a
 // stream capture (graph construction) or directly.
-static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cudaStream_t st)
+static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cudaStream_t st, int xchg)
 {
     const size_t B = s->B, N = s->N;
     // the timing events must stay usable from outside a graph: inside a capture they are recorded as EXTERNAL event nodes
     cudaStreamCaptureStatus capst = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &capst) != cudaSuccess) { cudaGetLastError(); capst = cudaStreamCaptureStatusNone; }
     const unsigned evflag = capst == cudaStreamCaptureStatusNone ? cudaEventRecordDefault : cudaEventRecordExternal;
+    if (xchg) {
+        // sharded: the thrust block of the PREVIOUS tick leaves for the peers on a side branch, concurrently with this tick
+        CK(cudaEventRecord(s->ev_xfork, st));
+        CK(cudaStreamWaitEvent(s->stream_xchg, s->ev_xfork, 0));
+        launch_exchange(s->shard, s->B, s->d_counter, s->stream_xchg);
+        CK(cudaEventRecord(s->ev_xdone, s->stream_xchg));
+    }
     const size_t psz = sizeof(double) * B * (io.p_per_stage ? (N + 1) * NP : NP);
     const double *d_x0 = io.x0, *d_yref = io.yref, *d_p = io.p, *d_thr = io.thrusts, *d_acc = io.body_acc;
     const int* d_lines = io.lines;
@@ -700,6 +734,7 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
         if (io.status && !o_st) CK(cudaMemcpyAsync(io.status, s->d_status, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
         if (io.ekf && io.wf_dist) CK(cudaMemcpyAsync(io.wf_dist, s->d_wf, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
     }
+    if (xchg) CK(cudaStreamWaitEvent(st, s->ev_xdone, 0));
     s->timed = true;
     CK(cudaGetLastError());
     return BR2_OK;
@@ -741,13 +776,13 @@ static bool same_but_inputs(const br2_tick_io& a, const br2_tick_io& b)
 }
 
 // cached graph of this (io, host) or a newly captured one; nullptr (and rc == BR2_OK) when graphs are not to be used
-static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, cudaGraphExec_t* out)
+static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, int xchg, cudaGraphExec_t* out)
 {
     *out = nullptr;
     if (!s->tick_graph) return BR2_OK;
     br2_batch_solver::TickGraph* slot = &s->tg[0];
     for (auto& g : s->tg) {
-        if (g.exec && g.host == host && g.gen == s->gen && !memcmp(&g.io, &io, sizeof io)) {
+        if (g.exec && g.host == host && g.xchg == xchg && g.gen == s->gen && !memcmp(&g.io, &io, sizeof io)) {
             g.stamp = ++s->tick_stamp;
             *out = g.exec;
             return BR2_OK;
@@ -761,7 +796,7 @@ static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, 
     if (host) {
         // same tick on other input buffers: re-point the upload nodes of a cached graph
         for (auto& g : s->tg) {
-            if (!(g.exec && g.host == 1 && g.gen == s->gen && g.nup > 0 && same_but_inputs(g.io, io))) continue;
+            if (!(g.exec && g.host == 1 && g.xchg == xchg && g.gen == s->gen && g.nup > 0 && same_but_inputs(g.io, io))) continue;
             const void* np_[5]; size_t nb_[5];
             tick_inputs(s, io, np_, nb_);
             bool okk = true;
@@ -778,15 +813,15 @@ static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, 
     }
     bool seen = false;
     for (auto& m : s->miss)
-        if (m.valid && m.host == host && m.gen == s->gen && (host ? same_but_inputs(m.io, io) : !memcmp(&m.io, &io, sizeof io))) { seen = true; m.valid = false; }
+        if (m.valid && m.host == host && m.xchg == xchg && m.gen == s->gen && (host ? same_but_inputs(m.io, io) : !memcmp(&m.io, &io, sizeof io))) { seen = true; m.valid = false; }
     if (!seen) {
         auto& m = s->miss[s->miss_next++ % 4];
-        m.io = io; m.host = host; m.gen = s->gen; m.valid = true;
+        m.io = io; m.host = host; m.xchg = xchg; m.gen = s->gen; m.valid = true;
         return BR2_OK;
     }
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = tick_issue(s, io, host, s->stream);
+    int rc = tick_issue(s, io, host, s->stream, xchg);
     cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
     if (rc != BR2_OK || e != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
@@ -798,7 +833,7 @@ static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, 
     if (e != cudaSuccess) { cudaGraphDestroy(graph); cudaGetLastError(); return fail(BR2_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
     if (slot->exec) cudaGraphExecDestroy(slot->exec);
     if (slot->graph) cudaGraphDestroy(slot->graph);
-    slot->io = io; slot->host = host; slot->gen = s->gen; slot->stamp = ++s->tick_stamp; slot->exec = exec; slot->graph = graph; slot->nup = 0;
+    slot->io = io; slot->host = host; slot->xchg = xchg; slot->gen = s->gen; slot->stamp = ++s->tick_stamp; slot->exec = exec; slot->graph = graph; slot->nup = 0;
     if (host) {
         // remember the upload nodes: which input each reads and where inside it
         const void* ip[5]; size_t ib[5];
@@ -828,6 +863,78 @@ static int tick_graph_for(br2_batch_solver* s, const br2_tick_io& io, int host, 
     return BR2_OK;
 }
 
+// ---- sharding: peer-to-peer exchange of the thrust vectors (kernel side: finish_instance in kernels.cu) -----------------------
+extern "C" int br2_batch_shard_init(br2_batch_solver* s, int rank, int world)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    if (world < 1 || world > MAX_SHARDS || rank < 0 || rank >= world) return fail(BR2_EINVAL, "br2_batch_shard_init: rank %d of %d (max %d)", rank, world, MAX_SHARDS);
+    if (s->d_shard) return fail(BR2_EINVAL, "br2_batch_shard_init: already initialised");
+    ON_DEVICE(s);
+    const size_t nd = (size_t)2 * world * s->B * 6;
+    const size_t bytes = nd * sizeof(double) + (MAX_SHARDS + 8) * sizeof(int);
+    CK(cudaMalloc((void**)&s->d_shard, bytes));
+    CK(cudaMemset(s->d_shard, 0, bytes));
+    memset(&s->shard, 0, sizeof s->shard);
+    s->shard.world = world; s->shard.rank = rank;
+    s->shard.buf[rank] = s->d_shard;
+    s->shard.flag[rank] = (int*)(s->d_shard + nd);
+    s->gen++;
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_shard_handle(br2_batch_solver* s, void* handle64)
+{
+    if (!s || !handle64 || !s->d_shard) return fail(BR2_EINVAL, "br2_batch_shard_handle: not initialised");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    ON_DEVICE(s);
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, s->d_shard));
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_shard_connect(br2_batch_solver* s, int peer, const void* handle64)
+{
+    if (!s || !handle64 || !s->d_shard) return fail(BR2_EINVAL, "br2_batch_shard_connect: not initialised");
+    if (peer < 0 || peer >= s->shard.world || peer == s->shard.rank) return fail(BR2_EINVAL, "br2_batch_shard_connect: peer %d", peer);
+    if (s->peer_base[peer]) return fail(BR2_EINVAL, "br2_batch_shard_connect: peer %d already connected", peer);
+    ON_DEVICE(s);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    void* base = nullptr;
+    CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_base[peer] = base;
+    const size_t nd = (size_t)2 * s->shard.world * s->B * 6;
+    s->shard.buf[peer] = (double*)base;
+    s->shard.flag[peer] = (int*)((double*)base + nd);
+    s->gen++;
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_shard_gathered(br2_batch_solver* s, int parity, double** d_buf)
+{
+    if (!s || !d_buf || !s->d_shard) return fail(BR2_EINVAL, "br2_batch_shard_gathered: not initialised");
+    *d_buf = s->d_shard + (size_t)(parity & 1) * s->shard.world * s->B * 6;
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_tick_count(br2_batch_solver* s) { return s ? (int)s->ticks_host : 0; }
+
+extern "C" int br2_batch_shard_wait(br2_batch_solver* s, void* stream)
+{
+    if (!s || !s->d_shard) return fail(BR2_EINVAL, "br2_batch_shard_wait: not initialised");
+    for (int r = 0; r < s->shard.world; r++)
+        if (!s->shard.buf[r]) return fail(BR2_EINVAL, "br2_batch_shard_wait: rank %d is not connected", r);
+    ON_DEVICE(s);
+    const size_t nd = (size_t)2 * s->shard.world * s->B * 6;
+    int* flags = (int*)(s->d_shard + nd);
+    while (s->xchg_host < s->ticks_host) {       // (normally one: the last tick's block)
+        launch_exchange(s->shard, s->B, s->d_counter, (cudaStream_t)stream);
+        s->xchg_host++;
+    }
+    launch_shard_wait(flags, s->shard.world, (int)s->ticks_host, flags + MAX_SHARDS, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+
 extern "C" int br2_batch_graphs_built(const br2_batch_solver* s) { return s ? s->graphs_built : 0; }
 extern "C" int br2_batch_graph_updates(const br2_batch_solver* s) { return s ? s->graph_updates : 0; }
 
@@ -837,6 +944,11 @@ extern "C" int br2_batch_set_tick_index(br2_batch_solver* s, int next_tick)
     ON_DEVICE(s);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(s->d_counter + CTR_TICK, &next_tick, sizeof(int), cudaMemcpyHostToDevice));
+    s->ticks_host = next_tick;
+    s->xchg_host = next_tick;
+    CK(cudaMemcpy(s->d_counter + CTR_XTICK, &next_tick, sizeof(int), cudaMemcpyHostToDevice));
+    // sharded: the local flag array restarts with the tick index (every rank does this between two barriers)
+    if (s->d_shard) CK(cudaMemset(s->d_shard + (size_t)2 * s->shard.world * s->B * 6, 0, (MAX_SHARDS + 8) * sizeof(int)));
     return BR2_OK;
 }
 
@@ -855,12 +967,15 @@ extern "C" int br2_batch_tick_device(br2_batch_solver* s, const br2_tick_io* io_
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
     cudaGraphExec_t exec = nullptr;
+    const int xchg = shard_pending(s);
     if (cap == cudaStreamCaptureStatusNone) {
-        rc = tick_graph_for(s, io, 0, &exec);
+        rc = tick_graph_for(s, io, 0, xchg, &exec);
         if (rc != BR2_OK) return rc;
     }
+    s->ticks_host++;
+    s->xchg_host += xchg;
     if (exec) { CK(cudaGraphLaunch(exec, st)); s->timed = true; return BR2_OK; }
-    return tick_issue(s, io, 0, st);                    // the caller is capturing its own graph, or graphs are switched off
+    return tick_issue(s, io, 0, st, xchg);                    // the caller is capturing its own graph, or graphs are switched off
 }
 
 extern "C" int br2_batch_tick_host(br2_batch_solver* s, const br2_tick_io* io_in)
@@ -877,13 +992,16 @@ extern "C" int br2_batch_tick_host(br2_batch_solver* s, const br2_tick_io* io_in
     // copies from / to pageable memory are staged by the driver at enqueue time: only pinned buffers go into a graph
     const bool pinned = pinned_host(io.x0) && pinned_host(io.yref) && pinned_host(io.p) && pinned_host(io.thrusts) && pinned_host(io.lines) &&
                         pinned_host(io.body_acc) && pinned_host(io.u0) && pinned_host(io.thrust) && pinned_host(io.wf_dist) && pinned_host(io.status);
+    const int xchg = shard_pending(s);
     if (pinned) {
-        rc = tick_graph_for(s, io, 1, &exec);
+        rc = tick_graph_for(s, io, 1, xchg, &exec);
         if (rc != BR2_OK) return rc;
     }
+    s->ticks_host++;
+    s->xchg_host += xchg;
     if (exec) { CK(cudaGraphLaunch(exec, s->stream)); s->timed = true; }
     else {
-        rc = tick_issue(s, io, 1, s->stream);
+        rc = tick_issue(s, io, 1, s->stream, xchg);
         if (rc != BR2_OK) return rc;
     }
     CK(cudaStreamSynchronize(s->stream));

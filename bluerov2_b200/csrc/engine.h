@@ -8,6 +8,14 @@ namespace br2 {
 
 constexpr int NMAX = 256;   // maximum horizon supported by the engine
 
+// Sharded batch (one solver per GPU / process): where the epilogue delivers the thrust vectors of this rank's instances
+constexpr int MAX_SHARDS = 8;
+struct ShardView {
+    int world, rank;               // world <= 1: not sharded
+    double* buf[MAX_SHARDS];       // gather buffer of every rank: [2 (tick parity)][world * B][6]; [rank] is the local one
+    int* flag[MAX_SHARDS];         // flag array of every rank: [world] last tick index published by each rank
+};
+
 // Everything a launch needs; passed by value (fits the 4 KB kernel parameter space).
 struct SolveArgs {
     int B, N;
@@ -48,6 +56,7 @@ struct SolveArgs {
     unsigned long long* iter_total;   // [1] IPM iterations executed, accumulated over instances and solves
     unsigned long long* bad_total;    // [1] instances that ended with a non-zero status, accumulated over solves
     unsigned long long* prof;         // [16] cycles per kernel phase (instrumentation build -DBR2_PROFILE only), else unused
+    ShardView shard;
     // options
     int max_iter;          // qp_solver_iter_max (50)
     double tol;            // IPM tolerance on mu and on the scaled stationarity residual
@@ -66,9 +75,11 @@ void launch_linearize(const SolveArgs& a, cudaStream_t s);
 void launch_ipm(const SolveArgs& a, int sm_count, cudaStream_t s);          // = launch_pdas + launch_ipm_fallback
 void launch_pdas(const SolveArgs& a, int sm_count, cudaStream_t s);
 void launch_ipm_fallback(const SolveArgs& a, int sm_count, cudaStream_t s);
-void launch_tick_begin(int* ctr, cudaStream_t s);     // per-tick housekeeping as a kernel of its own (pipelined ticks)
+void launch_tick_begin(int* ctr, cudaStream_t s);
+void launch_exchange(const ShardView& sh, int B, int* ctr, cudaStream_t s);
+void launch_shard_wait(const int* flag, int world, int tick, int* timed_out, cudaStream_t s);     // per-tick housekeeping as a kernel of its own (pipelined ticks)
 void configure_kernels();      // per-device function attributes (call with the solver's device current)
-enum { CTR_HARD = 1, CTR_EASY = 2, CTR_PARITY = 3, CTR_FB = 4, CTR_FBQ = 5, CTR_TICK = 6, CTR_QUEUE = 8, CTR_COUNT = 12 };   // CTR_QUEUE .. +3: one per range
+enum { CTR_HARD = 1, CTR_EASY = 2, CTR_PARITY = 3, CTR_FB = 4, CTR_FBQ = 5, CTR_TICK = 6, CTR_QUEUE = 8, CTR_XTICK = 12, CTR_XDONE = 13, CTR_COUNT = 16 };   // CTR_QUEUE .. +3: one per range
 
 // EKF (bluerov2_dob.cpp:495-545), one warp per instance
 struct EkfArgs {

@@ -1430,6 +1430,14 @@ __device__ __forceinline__ void finish_instance(Inst& I, const SolveOut& r, int*
         a.info[(size_t)inst * 4 + 2] = bmax;
         a.info[(size_t)inst * 4 + 3] = stat_scale;
     }
+    if (a.shard.world > 1 && lane == 0) {
+        // sharded batch: a second copy of the thrust vector goes into this rank's block of the LOCAL gather buffer (slot = tick
+        // parity); exchange_kernel ships the block to the peers while the next tick is already linearising
+        double* dst = a.shard.buf[a.shard.rank] + ((size_t)(a.ctr[CTR_TICK] & 1) * a.shard.world * a.B + (size_t)a.shard.rank * a.B + inst) * 6;
+        const double* src = a.thrust + (size_t)inst * 6;
+#pragma unroll
+        for (int i = 0; i < 6; i++) dst[i] = src[i];
+    }
     __syncwarp();
 }
 
@@ -1556,6 +1564,57 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(const
         if (lane == 0) pos = nwarps + atomicAdd(a.ctr + CTR_FBQ, 1);
         pos = __shfl_sync(FULL_MASK, pos, 0);
     }
+}
+
+// Sharded batch: ship this rank's block of the gather buffer (the thrust vectors of the tick that has just finished) to every
+// peer's gather buffer over NVLink -- peer stores, no collective -- then publish the tick index in every rank's flag array.
+// grid = (world - 1) x XCHG_CTAS blocks; block (p, j) copies slice j of the block to the p-th peer.  The exchange counter
+// ctr[CTR_XTICK] counts the ticks shipped so far (tick index = count + 1, its parity selects the slot): the kernel of tick t
+// runs as a side branch of tick t + 1's graph, concurrently with that tick's lineariser, so it cannot read the tick counter.
+constexpr int XCHG_CTAS = 4;
+__global__ void __launch_bounds__(256) exchange_kernel(ShardView sh, int B, int* ctr)
+{
+    const int tick = ctr[CTR_XTICK] + 1;
+    int peer = blockIdx.x / XCHG_CTAS;
+    if (peer >= sh.rank) peer++;                                         // skip myself
+    const size_t row0 = ((size_t)(tick & 1) * sh.world * B + (size_t)sh.rank * B) * 6;
+    const double2* src = reinterpret_cast<const double2*>(sh.buf[sh.rank] + row0);
+    double2* dst = reinterpret_cast<double2*>(sh.buf[peer] + row0);
+    const int n2 = B * 3;                                                // 6 doubles per instance = 3 double2
+    for (int i = (blockIdx.x % XCHG_CTAS) * blockDim.x + threadIdx.x; i < n2; i += XCHG_CTAS * blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(ctr + CTR_XDONE, 1);
+        if (done == (int)gridDim.x - 1) {                                // the last block: every slice is on its way and fenced
+            ctr[CTR_XDONE] = 0;
+            ctr[CTR_XTICK] = tick;
+            __threadfence_system();
+            for (int r = 0; r < sh.world; r++) *reinterpret_cast<volatile int*>(sh.flag[r] + sh.rank) = tick;
+        }
+    }
+}
+void launch_exchange(const ShardView& sh, int B, int* ctr, cudaStream_t s)
+{
+    if (sh.world > 1) exchange_kernel<<<(sh.world - 1) * XCHG_CTAS, 256, 0, s>>>(sh, B, ctr);
+}
+
+// consumer side of the sharded exchange: returns when every rank has published tick index >= `tick` (bounded spin)
+__global__ void shard_wait_kernel(const int* flag, int world, int tick, int* timed_out)
+{
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const volatile int* f = flag + r;
+    long long spins = 0;
+    while (*f < tick) {
+        __nanosleep(200);
+        if (++spins > 20000000LL) { *timed_out = 1; break; }      // ~4 s: a peer died
+    }
+    __threadfence_system();
+}
+void launch_shard_wait(const int* flag, int world, int tick, int* timed_out, cudaStream_t s)
+{
+    shard_wait_kernel<<<1, 32, 0, s>>>(flag, world, tick, timed_out);
 }
 
 void configure_kernels()

@@ -102,3 +102,46 @@ class PipelinedThrustGather:
         for i in range(self.depth):
             self._wait(i)
 
+
+
+class PeerThrustExchange:
+    """The per-tick exchange of the thrust vectors without a collective (include/bluerov2_b200.h "Sharding"): every
+    rank's solver owns a gather buffer [2][world * B][6]; the QP epilogue stores each instance's thrusts into the same row of
+    every rank's buffer over NVLink (CUDA IPC mappings), the last warp of a tick publishes the tick index in every rank's flags.
+    This class is the rendezvous: it exchanges the 64-byte IPC handles through torch.distributed (any backend: the handles are
+    host bytes) and connects the peers.  Afterwards the ticks deliver by themselves; ``wait()`` enqueues the consumer-side wait,
+    ``result(tick)`` views the local buffer of that tick's parity as a tensor.
+
+    ``solver`` needs ``shard_init / shard_handle / shard_connect / shard_wait / shard_gathered_ptr`` (BatchSolver has them; the
+    CPU tests pass a recording stand-in)."""
+
+    def __init__(self, solver, batch_per_rank: int, group=None):
+        self.solver, self.group = solver, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.B = int(batch_per_rank)
+        self.bounds = [(r * self.B, (r + 1) * self.B) for r in range(self.world)]
+        solver.shard_init(self.rank, self.world)
+        mine = solver.shard_handle()
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, mine, group=group)
+        else:
+            handles[0] = mine
+        self.handles = handles
+        for r, h in enumerate(handles):
+            if r != self.rank:
+                solver.shard_connect(r, h)
+        if self.world > 1:
+            dist.barrier(group=group)          # nobody ticks before everybody is mapped
+
+    def wait(self, stream=None):
+        self.solver.shard_wait(stream)
+
+    def result(self, tick_index: int, device=None):
+        """[world * B, 6] tensor view of the local gather buffer holding tick `tick_index` (1-based count of ticks solved)"""
+        ptr = self.solver.shard_gathered_ptr(tick_index & 1)
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (self.world * self.B, NTHRUST), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_View(), device=device if device is not None else torch.device("cuda", torch.cuda.current_device()))

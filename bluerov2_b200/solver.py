@@ -75,6 +75,12 @@ def load_library(path: str | None = None):
         "br2_batch_tick_host": (C.c_int, [V, V]),
         "br2_batch_graphs_built": (C.c_int, [V]),
         "br2_batch_graph_updates": (C.c_int, [V]),
+        "br2_batch_shard_init": (C.c_int, [V, C.c_int, C.c_int]),
+        "br2_batch_shard_handle": (C.c_int, [V, V]),
+        "br2_batch_shard_connect": (C.c_int, [V, C.c_int, V]),
+        "br2_batch_shard_wait": (C.c_int, [V, V]),
+        "br2_batch_shard_gathered": (C.c_int, [V, C.c_int, C.POINTER(V)]),
+        "br2_batch_tick_count": (C.c_int, [V]),
         "br2_batch_set_tick_index": (C.c_int, [V, C.c_int]),
         "br2_plant_step_device": (C.c_int, [C.c_int, V, V, V, V, V, V, C.c_int, C.c_double, V, V, V]),
         "br2_batch_ekf_reset": (C.c_int, [V]),
@@ -349,6 +355,35 @@ class BatchSolver:
 
     def graphs_built(self) -> int:
         return int(self._L.br2_batch_graphs_built(self._h))
+
+    # -- sharding: peer-to-peer exchange of the thrust vectors, see bluerov2_b200.sharding.PeerThrustExchange --------
+    def shard_init(self, rank: int, world: int):
+        self._check(self._L.br2_batch_shard_init(self._h, int(rank), int(world)))
+
+    def shard_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._L.br2_batch_shard_handle(self._h, buf))
+        return buf.raw
+
+    def shard_connect(self, peer: int, handle: bytes):
+        if len(handle) != 64:
+            raise ValueError("a CUDA IPC handle has 64 bytes")
+        self._check(self._L.br2_batch_shard_connect(self._h, int(peer), C.create_string_buffer(handle, 64)))
+
+    def shard_wait(self, stream=None):
+        """enqueue a wait until every rank has published the ticks enqueued so far"""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._L.br2_batch_shard_wait(self._h, C.c_void_p(stream)))
+
+    def shard_gathered_ptr(self, parity: int) -> int:
+        p = C.c_void_p()
+        self._check(self._L.br2_batch_shard_gathered(self._h, int(parity), C.byref(p)))
+        return int(p.value)
+
+    def tick_count(self) -> int:
+        return int(self._L.br2_batch_tick_count(self._h))
 
     def graph_updates(self) -> int:
         return int(self._L.br2_batch_graph_updates(self._h))

@@ -179,6 +179,26 @@ BR2_API long long br2_batch_nonzero_status_total(br2_batch_solver *s, int reset)
  * length / centring, [9] corrector backward sweep, [10] corrector forward sweep, [11] step lengths / update, [12] epilogue. */
 BR2_API int br2_batch_phase_cycles(br2_batch_solver *s, unsigned long long *out16, int reset);
 
+/* Sharding across GPUs: instances are independent, so the global batch is cut into contiguous blocks, one solver
+ * (one process, one GPU) per block, and there is no data-path collective inside the solve.  What a tick exchanges is its output:
+ * every rank ends the tick holding the thrust vectors of ALL instances.  The exchange is peer-to-peer and fused into the solve:
+ * the QP epilogue stores each instance's six thrusts into the same row of every rank's gather buffer over NVLink (CUDA IPC
+ * mappings between the processes), and the warp that finishes a rank's last instance publishes the tick index in every rank's
+ * flag array -- no collective kernel, no extra launch.
+ *   br2_batch_shard_init     allocate this rank's gather buffer [2][world * batch][6] (two tick parities) + flags; rank in [0, world)
+ *   br2_batch_shard_handle   64-byte CUDA IPC handle of it: send it to the other ranks (MPI / torch.distributed / a pipe)
+ *   br2_batch_shard_connect  map rank `peer`'s buffer from its handle; after all peers are connected the ticks deliver
+ *   br2_batch_shard_wait     enqueue on `stream` a wait until every rank has published the current tick (tick = ticks solved so far)
+ *   br2_batch_shard_gathered device pointer of the local gather buffer of tick parity `parity` ([world * batch][6], rank-major)
+ * world <= 8 (one NVSwitch domain).  All ranks must run the same number of ticks. */
+BR2_API int br2_batch_shard_init(br2_batch_solver *s, int rank, int world);
+BR2_API int br2_batch_shard_handle(br2_batch_solver *s, void *handle64);
+BR2_API int br2_batch_shard_connect(br2_batch_solver *s, int peer, const void *handle64);
+BR2_API int br2_batch_shard_wait(br2_batch_solver *s, void *stream);
+BR2_API int br2_batch_shard_gathered(br2_batch_solver *s, int parity, double **d_buf);
+/* ticks solved so far (the index the NEXT tick will publish is this value + 1) */
+BR2_API int br2_batch_tick_count(br2_batch_solver *s);
+
 /* Nominal plant for device-resident closed-loop studies: one RK4 step of length h of the OCP model
  * (bluerov2_dobmpc/scripts/bluerov2.py:103-137) per instance, x[B][12] in place, inputs u[B][4], parameters p[B][16].
  * Optional (NULL to skip): d_dist[B][4] extra disturbance on p[0..3]; d_wave_amp[B][4] + d_wave_tau0[B] the wave wrench of

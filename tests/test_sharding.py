@@ -94,3 +94,59 @@ def test_two_rank_pipelined_all_gather_gloo(total):
         assert p.exitcode == 0
     assert all(ok for _, ok in res), res
 
+
+
+# ---- PeerThrustExchange: the rendezvous of the peer-to-peer exchange (handles through torch.distributed, then connect) ----
+class _RecordingSolver:
+    """stands in for BatchSolver on a box without GPUs: records what the rendezvous does"""
+
+    def __init__(self, rank):
+        self.rank, self.calls = rank, []
+
+    def shard_init(self, rank, world):
+        self.calls.append(("init", rank, world))
+
+    def shard_handle(self):
+        return bytes([self.rank]) * 64
+
+    def shard_connect(self, peer, handle):
+        assert len(handle) == 64
+        self.calls.append(("connect", peer, handle[0]))
+
+
+def _peer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bluerov2_b200.sharding import PeerThrustExchange
+        s = _RecordingSolver(rank)
+        ex = PeerThrustExchange(s, batch_per_rank=5)
+        q.put((rank, s.calls, ex.bounds, [h[0] for h in ex.handles]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_rendezvous_gloo():
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, calls, bounds, handles in res:
+        assert calls[0] == ("init", rank, world)
+        # every OTHER rank is connected exactly once, with that rank's own handle
+        assert sorted(calls[1:]) == [("connect", r, r) for r in range(world) if r != rank]
+        assert bounds == [(0, 5), (5, 10)] and handles == [0, 1]
+
+
+def test_peer_exchange_single_rank_needs_no_process_group():
+    from bluerov2_b200.sharding import PeerThrustExchange
+    s = _RecordingSolver(0)
+    ex = PeerThrustExchange(s, batch_per_rank=3)
+    assert s.calls == [("init", 0, 1)] and ex.world == 1 and ex.bounds == [(0, 3)]
