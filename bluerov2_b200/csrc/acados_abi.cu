@@ -31,6 +31,7 @@ struct Ctx {
     br2_batch_solver* eng;
     int N;
     double* Ts;        // [N]
+    double* scaling;   // [N] cost scaling per stage as set through ocp_nlp_cost_model_set("scaling"); the engine ties it to Ts
     double* yref;      // [N+1][16]
     double* p;         // [N+1][16]
     double* X;         // [N+1][12] host mirror of the iterate
@@ -165,7 +166,8 @@ int ocp_nlp_cost_model_set(ocp_nlp_config* config, ocp_nlp_dims*, ocp_nlp_in*, i
         c->weights_dirty = true;
     } else if (!strcmp(field, "scaling")) {
         // cost scaling == time step on stages 0..N-1 (gen.c:389-394, :126-129); the engine ties the two together
-        if (stage < c->N) { c->Ts[stage] = *(const double*)value; c->ts_dirty = true; }
+        // -- kept separately and checked against Ts when the solve starts: a caller that sets the two apart gets a diagnostic
+        if (stage < c->N) c->scaling[stage] = *(const double*)value;
     } else {
         die("ocp_nlp_cost_model_set", field);
     }
@@ -290,6 +292,21 @@ int ocp_nlp_solve(ocp_nlp_solver* solver, ocp_nlp_in*, ocp_nlp_out* out)
         c->status = ACADOS_READY;
         return c->status;
     }
+    // what this solver cannot represent is refused loudly, like every other unsupported setting of this ABI:
+    // the stage-0 state bounds must be equalities (lbx_0 == ubx_0 = x0: all 12 are flagged idxbxe, gen.c:501-543) ...
+    for (int i = 0; i < NX; i++)
+        if (!(c->lbx0[i] == c->ubx0[i])) {
+            fprintf(stderr, "\nerror: bluerov2_acados_solve: lbx_0[%d] = %g differs from ubx_0[%d] = %g; the bluerov2 B200 solver fixes the "
+                            "initial state (all stage-0 state bounds are equalities in the generated problem)\n", i, c->lbx0[i], i, c->ubx0[i]);
+            exit(1);
+        }
+    // ... and the cost scaling of a stage is its time step (acados_solver_bluerov2.c:126-129, 389-394)
+    for (int k = 0; k < c->N; k++)
+        if (!(c->scaling[k] == c->Ts[k])) {
+            fprintf(stderr, "\nerror: bluerov2_acados_solve: cost scaling %g of stage %d differs from its time step %g; the bluerov2 B200 "
+                            "solver ties the two together\n", c->scaling[k], k, c->Ts[k]);
+            exit(1);
+        }
     const auto t0 = std::chrono::steady_clock::now();
     int rc = push_config(c);
     if (rc == BR2_OK && c->iterate_dirty) {
@@ -422,13 +439,14 @@ int bluerov2_acados_create_with_discretization(bluerov2_solver_capsule* capsule,
     Ctx* c = (Ctx*)calloc(1, sizeof(Ctx));
     c->N = N;
     c->Ts = (double*)calloc(N, sizeof(double));
+    c->scaling = (double*)calloc(N, sizeof(double));
     c->yref = (double*)calloc((size_t)(N + 1) * NY, sizeof(double));      // yref defaults to zero (gen.c:403-421)
     c->p = (double*)calloc((size_t)(N + 1) * NP, sizeof(double));         // parameters default to zero (gen.c:355-364)
     c->X = (double*)calloc((size_t)(N + 1) * NX, sizeof(double));
     c->U = (double*)calloc((size_t)N * NU, sizeof(double));
     br2_ocp_defaults dflt;                                  // the one table of baked problem data (include/bluerov2_b200.h)
     br2_get_ocp_defaults(&dflt);
-    for (int k = 0; k < N; k++) c->Ts[k] = new_time_steps ? new_time_steps[k] : dflt.Tf / dflt.N;   // gen.c:389 (0.0125)
+    for (int k = 0; k < N; k++) c->scaling[k] = c->Ts[k] = new_time_steps ? new_time_steps[k] : dflt.Tf / dflt.N;   // gen.c:389-394 (0.0125)
     memcpy(c->W, dflt.W, sizeof c->W);                                                     // gen.c:424-459
     memcpy(c->We, dflt.We, sizeof c->We);                                                  // gen.c:468-479
     memcpy(c->lbu, dflt.lbu, sizeof c->lbu); memcpy(c->ubu, dflt.ubu, sizeof c->ubu);      // gen.c:547-571
@@ -620,7 +638,7 @@ int bluerov2_acados_free(bluerov2_solver_capsule* capsule)
     free(plan->nlp_cost); free(plan->nlp_dynamics); free(plan->nlp_constraints); free(plan->sim_solver_plan);
     free(plan);
     br2_batch_free(c->eng);
-    free(c->Ts); free(c->yref); free(c->p); free(c->X); free(c->U);
+    free(c->Ts); free(c->scaling); free(c->yref); free(c->p); free(c->X); free(c->U);
     free(c);
     memset(capsule, 0, sizeof *capsule);
     return 0;

@@ -725,7 +725,7 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
         PlantArgs pl;
         pl.B = s->B; pl.x = const_cast<double*>(io.x0); pl.u = a.u0; pl.p = d_p; pl.dist = nullptr;
         pl.wave_amp = io.wave_amp; pl.wave_tau0 = io.wave_tau0; pl.body_acc = io.body_acc; pl.lines = const_cast<int*>(io.lines);
-        pl.h = io.plant_h; pl.tick = -1; pl.tick_ctr = s->d_counter + CTR_TICK;
+        pl.h = io.plant_h; pl.tick = -1; pl.tick_ctr = s->d_counter + CTR_TICK; pl.table = nullptr; pl.table_rows = 0; pl.table_phase = nullptr;
         launch_plant(pl, st);
     }
     if (host) {
@@ -1047,6 +1047,26 @@ extern "C" int br2_plant_step_device(int batch, double* d_x, const double* d_u, 
     CK(guard_.err);
     PlantArgs a;
     a.B = batch; a.x = d_x; a.u = d_u; a.p = d_p; a.dist = d_dist; a.wave_amp = d_wave_amp; a.wave_tau0 = d_wave_tau0;
+    a.body_acc = d_body_acc; a.lines = d_lines; a.h = h; a.tick = tick; a.tick_ctr = nullptr; a.table = nullptr; a.table_rows = 0; a.table_phase = nullptr;
+    launch_plant(a, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+
+extern "C" int br2_plant_step_replay_device(int batch, double* d_x, const double* d_u, const double* d_p, const double* d_table, int rows,
+                                            const int* d_phase, int tick, double h, double* d_body_acc, int* d_lines, void* stream)
+{
+    if (batch < 1 || !d_x || !d_u || !d_p || !d_table || rows < 1 || tick < 0 || !(h > 0)) return fail(BR2_EINVAL, "br2_plant_step_replay_device: bad argument");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, d_x) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return fail(BR2_EINVAL, "br2_plant_step_replay_device: d_x is not a device pointer");
+    }
+    DeviceGuard guard_(at.device);
+    CK(guard_.err);
+    PlantArgs a;
+    a.B = batch; a.x = d_x; a.u = d_u; a.p = d_p; a.dist = nullptr; a.wave_amp = nullptr; a.wave_tau0 = nullptr;
+    a.table = d_table; a.table_rows = rows; a.table_phase = d_phase;
     a.body_acc = d_body_acc; a.lines = d_lines; a.h = h; a.tick = tick; a.tick_ctr = nullptr;
     launch_plant(a, (cudaStream_t)stream);
     CK(cudaGetLastError());

@@ -125,6 +125,9 @@ struct PlantArgs {
     const double* dist;      // [B][4] extra disturbance on p[0..3], or null
     const double* wave_amp;  // [B][4] wave amplitudes (A_x, A_y, A_z, A_y/3), or null
     const double* wave_tau0; // [B]    wave phases
+    const double* table;     // [table_rows][4] wrench series (fx, fy, fz, tz) replayed row by row (mode 2 of applyBodyWrench), or null
+    int table_rows;
+    const int* table_phase;  // [B] first row of each instance (or null: 0)
     double* body_acc;        // [B][6] out, or null
     int* lines;              // [B] in/out trajectory row counters, or null
     double h;

@@ -32,6 +32,9 @@
 #ifndef BR2_PDAS_MINB
 #define BR2_PDAS_MINB (16 / BR2_IPM_WARPS)
 #endif
+#ifndef BR2_PF_DIST
+#define BR2_PF_DIST 0
+#endif
 #ifndef BR2_LIN_MINB
 #define BR2_LIN_MINB 12
 #endif
@@ -436,6 +439,17 @@ struct Inst {
         const int j = i + NSLOT - 1;
         if (j < N) stage_copy<PARTS>(dst0 + (j % NSLOT) * REC_BYTES, src, lane);
         cp_commit();
+        if (BR2_PF_DIST > 0) {
+            // experiment (off: BR2_PF_DIST = 0): the copy above runs NSLOT-1 stages ahead and 21 % of the stall samples are the wait
+            // on it (profiles/r02c_pdas_ncu_summary.txt), so pull the record of stage i + BR2_PF_DIST into L2 first, one
+            // 128-byte line per lane.  Measured SLOWER: 0.215 ms without, 0.222 / 0.225 / 0.231 ms at distance 5 / 8 / 12
+            // (profiles/r02_pdas_occupancy.txt): the waits are not DRAM latency the L2 could hide
+            constexpr int L0 = (PARTS & P_V) ? 0 : ((PARTS & P_G) ? 4 : 18), L1 = (PARTS & P_F) ? 22 : ((PARTS & P_G) ? 18 : 4);
+            if (i + BR2_PF_DIST < N && lane >= L0 && lane < L1) {
+                const char* pf = src + (BACKWARD ? -1 : 1) * (BR2_PF_DIST - (NSLOT - 1)) * REC_BYTES + 112 * lane;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            }
+        }
         src += BACKWARD ? -REC_BYTES : REC_BYTES;
         return sm.st[i % NSLOT];
     }

@@ -3,7 +3,7 @@
 // One classical RK4 step of the OCP model (bluerov2_dobmpc/scripts/bluerov2.py:103-137, the same csrc/model.cuh the
 // lineariser integrates) per instance, with an optional true disturbance (X, Y, Z, N) added to p[0..3] -- the "wave"
 // wrench of applyBodyWrench mode 0 (bluerov2_dob.cpp:774-797) is produced on the fly from per-instance amplitudes and
-// phases.  Also emits what the node's pose callback derives for the EKF (bluerov2_dob.cpp:148-153): the body
+// phases; mode 1 (:813-816) is the constant `dist`; mode 2 (:818-874) replays an uploaded series row by row.  Also emits what the node's pose callback derives for the EKF (bluerov2_dob.cpp:148-153): the body
 // acceleration as the finite difference of the body velocities.  One thread per instance: 12 states, ~0.4 kflop.
 #include "engine.h"
 
@@ -26,6 +26,16 @@ __global__ void __launch_bounds__(128) plant_kernel(PlantArgs a)
         const double sn = sin(a.wave_tau0[i] + 0.125 * tick);
 #pragma unroll
         for (int j = 0; j < 4; j++) p[j] += sn * a.wave_amp[(size_t)i * 4 + j];
+    }
+    if (a.table) {
+        // mode 2 (bluerov2_dob.cpp:818-874): the wrench of this tick is a row of the series read from config/force{x,y,z}.txt and
+        // torquez.txt, all four at the same counter (fx_counter++); past the end of the series the last row holds (the reference
+        // reads beyond its vectors there)
+        const int tick = a.tick >= 0 ? a.tick : *a.tick_ctr - 1;
+        int row = tick + (a.table_phase ? a.table_phase[i] : 0);
+        row = row < 0 ? 0 : (row < a.table_rows ? row : a.table_rows - 1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) p[j] += a.table[(size_t)row * 4 + j];
     }
     if (a.dist) {
 #pragma unroll

@@ -527,6 +527,26 @@ class BatchSolver:
         self._check(self._L.br2_batch_rls_set_state_host(self._h, _ptr(_np(st, (self.B, 4, self.RLS_STRIDE)))))
 
 
+def plant_step_replay(x, u, p, table, phase=None, tick: int = 0, h: float = 0.05, body_acc=None, lines=None):
+    """Nominal plant on the device with the wrench series of applyBodyWrench mode 2 (bluerov2_dob.cpp:818-874): ``table`` [rows,4]
+    CUDA tensor (fx, fy, fz, tz), row min(tick + phase[b], rows - 1) per instance.  In place on ``x``; torch's current stream."""
+    import torch
+    L = load_library()
+    B = x.shape[0]
+    for t, shp, dt in ((x, (B, NX), torch.float64), (u, (B, NU), torch.float64), (p, (B, NP), torch.float64), (table, (table.shape[0], 4), torch.float64)):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous() or tuple(t.shape) != shp:
+            raise ValueError(f"expected contiguous CUDA {dt} tensor of shape {shp}")
+    L.br2_plant_step_replay_device.restype = C.c_int
+    L.br2_plant_step_replay_device.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]
+    stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    rc = L.br2_plant_step_replay_device(int(B), _ptr(x), _ptr(u), _ptr(p), _ptr(table), int(table.shape[0]), _ptr(phase), int(tick), float(h),
+                                        _ptr(body_acc), _ptr(lines), stream)
+    if rc != 0:
+        raise SolverError(f"bluerov2_b200 error {rc}: {L.br2_last_error().decode()}")
+    return x
+
+
 def plant_step(x, u, p, h: float = 0.05, dist=None, wave=None, tick: int = 0, body_acc=None, lines=None):
     """Nominal plant on the device (torch CUDA tensors, in place on ``x``): one RK4 step of the OCP model per instance.
     ``wave`` = (amp[B,4], tau0[B]) adds the sampled wave wrench at ``tick``; ``body_acc`` [B,6] receives the finite-

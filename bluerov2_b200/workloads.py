@@ -73,6 +73,20 @@ def wave_at(amp: np.ndarray, tau0: np.ndarray, tick: int) -> np.ndarray:
     return np.sin(tau)[:, None] * amp
 
 
+def wrench_table() -> np.ndarray:
+    """The wrench series of applyBodyWrench mode 2 (bluerov2_dob.cpp:818-874): [496, 4] = (fx, fy, fz, tz), the reference's
+    config/force{x,y,z}.txt and torquez.txt column-stacked (fixture tests/golden/wrench_table.npz, made by make_wrench_table.py)."""
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "wrench_table.npz"))["table"]
+
+
+def wrench_at(table: np.ndarray, tick: int, phase: np.ndarray | None = None, B: int | None = None) -> np.ndarray:
+    """mode 2: row min(tick + phase[b], rows - 1) of the series for every instance -> dist [B, 4] (all four columns at the same
+    counter, fx_counter++ per tick)"""
+    ph = np.zeros(B, dtype=np.int64) if phase is None else np.asarray(phase, dtype=np.int64)
+    return table[np.clip(tick + ph, 0, table.shape[0] - 1)]
+
+
 def dob_params(esti_x: np.ndarray, compensate: bool = True) -> np.ndarray:
     """OCP parameter fill of BLUEROV2_DOB::solve (bluerov2_dob.cpp:324-355) from EKF states [B,18]."""
     B = esti_x.shape[0]

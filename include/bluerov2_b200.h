@@ -209,6 +209,12 @@ BR2_API int br2_plant_step_device(int batch, double *d_x, const double *d_u, con
                                   const double *d_wave_amp, const double *d_wave_tau0, int tick, double h,
                                   double *d_body_acc, int *d_lines, void *stream);
 
+/* Same plant step with the disturbance of applyBodyWrench mode 2 (bluerov2_dob.cpp:818-874): the wrench (fx, fy, fz, tz) is row
+ * min(tick + phase[b], rows - 1) of d_table[rows][4] -- the reference's config/force{x,y,z}.txt and torquez.txt stacked column-wise,
+ * all four read at the same counter.  d_phase[B] (int, may be NULL: 0) lets the instances start at different rows. */
+BR2_API int br2_plant_step_replay_device(int batch, double *d_x, const double *d_u, const double *d_p, const double *d_table, int rows,
+                                         const int *d_phase, int tick, double h, double *d_body_acc, int *d_lines, void *stream);
+
 /* == BLUEROV2_DOB::EKF (bluerov2_dob.cpp:495-545) for every instance, on the solver's stream order.
  * esti_x[B][18], esti_P[B][18][18] live in the solver (br2_batch_ekf_reset sets x = (0,0,-20,0..,6,6,6,0,0,0),
  * P = I: bluerov2_dob.cpp:64-65).  thrusts[B][6] = measured thruster forces, meas[B][12] = pose + body velocities,

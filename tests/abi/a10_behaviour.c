@@ -96,6 +96,19 @@ int main(int argc, char **argv)
         printf("custom_update_rc %d\n", rc);
         return 0;
     }
+    if (!strcmp(mode, "lbx_ne_ubx") || !strcmp(mode, "scaling_ne_ts")) {
+        /* settings acados accepts but this solver cannot represent: refused with a message and exit(1) when the solve starts */
+        bluerov2_solver_capsule *c = make();
+        double ub[BLUEROV2_NX];
+        memcpy(ub, x0, sizeof ub);
+        ocp_nlp_constraints_model_set(c->nlp_config, c->nlp_dims, c->nlp_in, 0, "lbx", x0);
+        if (!strcmp(mode, "lbx_ne_ubx")) ub[3] += 0.5;
+        ocp_nlp_constraints_model_set(c->nlp_config, c->nlp_dims, c->nlp_in, 0, "ubx", ub);
+        if (!strcmp(mode, "scaling_ne_ts")) { double sc = 0.123; ocp_nlp_cost_model_set(c->nlp_config, c->nlp_dims, c->nlp_in, 2, "scaling", &sc); }
+        bluerov2_acados_solve(c);
+        printf("returned\n");
+        return 0;
+    }
     if (strcmp(mode, "gpu")) { fprintf(stderr, "usage: %s cond_N|params_np|sparse_np|custom_update|gpu\n", argv[0]); return 2; }
 
     /* ---- A: dense parameters, two ticks; then _reset and a solve from the zeroed iterate ---- */

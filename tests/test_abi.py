@@ -390,3 +390,13 @@ def test_cost_functions_match_reference_generated_c(lib_path, name):
         assert np.array_equal(a, b)
     for a, b in zip(ours["vals_null"], ref["vals_null"]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,needle", [("lbx_ne_ubx", "differs from ubx_0[3]"), ("scaling_ne_ts", "cost scaling 0.123 of stage 2 differs from its time step")])
+def test_unrepresentable_settings_are_refused_loudly(lib_path, mode, needle):
+    """lbx_0 != ubx_0 and cost scaling != time step are accepted by acados; this solver fixes x0 and ties scaling to Ts, so it
+    says so and exits like it does for every other unsupported setting (no silent different problem)"""
+    out = _a10(mode)
+    assert out.returncode == 1, (out.returncode, out.stdout[-500:], out.stderr[-500:])
+    assert needle in out.stderr and "returned" not in out.stdout

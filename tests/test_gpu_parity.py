@@ -660,3 +660,61 @@ def test_active_set_fast_path_equals_ipm(solver_mod, oracle):
         X, U = Xi, Ui                # (each solver carries its own iterate: set_iterate would clear the active-set history)
     s_as.close(); s_ip.close()
     assert took_sat > 0 and took_as > 0.5 * took_sat, (took_as, took_sat)     # the guess was accepted on most saturated instances
+
+
+def test_plant_wrench_replay_matches_host(solver_mod):
+    """applyBodyWrench mode 2 (bluerov2_dob.cpp:818-874): the device plant replaying the reference's wrench series (fixture
+    tests/golden/wrench_table.npz) row by row, per-instance start rows, clamped at the end, against the numpy plant"""
+    import torch
+    dev = torch.device("cuda", 0)
+    B = 300
+    table = wl.wrench_table()
+    assert table.shape == (496, 4)
+    rng = np.random.default_rng(3)
+    phase = rng.integers(0, 520, B).astype(np.int32)          # some instances run off the end of the series
+    w = wl.tracking_batch(B, 10, seed=2)
+    x = w["x0"].copy()
+    u = rng.uniform(-20, 20, (B, 4))
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    dx, du, dp, dt_, dph = d(x), d(u), d(w["p"]), d(table), d(phase)
+    acc = torch.zeros((B, 6), dtype=torch.float64, device=dev)
+    for tick in (0, 1, 7, 495, 600):
+        solver_mod.plant_step_replay(dx, du, dp, dt_, phase=dph, tick=tick, h=0.05, body_acc=acc)
+        dist = wl.wrench_at(table, tick, phase)
+        assert np.array_equal(dist[phase + tick >= 495], np.tile(table[-1], (int((phase + tick >= 495).sum()), 1)))
+        xn = wl.plant_step(x, u, w["p"], 0.05, dist=dist)
+        assert np.abs(dx.cpu().numpy() - xn).max() < 1e-10, tick
+        assert np.abs(acc.cpu().numpy() - (xn[:, 6:] - x[:, 6:]) / 0.05).max() < 1e-7
+        x = xn
+        dx.copy_(d(x))
+
+
+def test_consolidated_node_fill_matches_oracle(solver_mod, oracle):
+    """BLUEROV2_CTRL (src/ctrller/mpc.cpp:139-187, 199-262): DOMPC parameters (/disturbance divided by the hard-coded 0.0325...,
+    p3 = 0) and a per-tick reference preview whose input columns stay 0, through the explicit-yref entry point, against the oracle
+    fed the same fill; closed loop over a few ticks (the reference arrives per tick, not from a resident trajectory)"""
+    N, B, T = 20, 96, 5
+    Ts = wl.time_steps(N)
+    w = wl.tracking_batch(B, N, seed=21, pos_spread=1.5)
+    rng = np.random.default_rng(5)
+    s = solver_mod.BatchSolver(B, N); s.set_iterate(w["X"], w["U"])
+    X, U = w["X"].copy(), w["U"].copy()
+    x0, lines = w["x0"].copy(), w["lines"].copy()
+    for t in range(T):
+        disturb = rng.uniform(-0.3, 0.3, (B, 3))                       # the /disturbance message of this tick
+        p = wl.ctrl_params(disturb, dompc=True)
+        assert np.array_equal(p[:, 3], np.zeros(B)) and np.allclose(p[:, 0], disturb[:, 0] / 0.032546960744430276)
+        preview = traj.window_batch(w["traj"], lines, N)[:, :, :12]    # the /ref_traj preview: 12 state references per stage
+        yref = wl.ctrl_yref(preview)
+        assert np.array_equal(yref[:, :, 12:], np.zeros((B, N + 1, 4)))
+        u0, th, st = s.solve(x0, yref, p)
+        so, _, _ = oracle.rti_step_batch(Ts, x0, yref, p, X, U)
+        assert (st == 0).all() and (so == 0).all()
+        assert np.abs(u0 - U[:, 0]).max() < TOL_U, t
+        x0 = wl.plant_step(x0, U[:, 0].copy(), w["p"], 0.05)
+        lines = lines + 1
+    Xg, Ug = s.get_iterate()
+    assert np.abs(Ug - U).max() < TOL_U and np.abs(Xg - X).max() < TOL_U
+    # controller type MPC: p[0..3] = 0, nominal hydrodynamics
+    assert np.array_equal(wl.ctrl_params(disturb, dompc=False), np.tile(wl.NOMINAL_P, (B, 1)))
+    s.close()
