@@ -1254,3 +1254,144 @@ extern "C" int br2_batch_yaw_set_state_host(br2_batch_solver* s, const float* st
     return BR2_OK;
 }
 
+
+// ---- IMU error-state Kalman filter (eskf.cu) --------------------------------------------------------------------------------
+struct br2_eskf {
+    int B, device;
+    double *d_state, *d_P, *d_in, *d_out;      // d_in: staging for the host entry points (39 doubles / instance), d_out: 15
+    EskfArgs base;
+    cudaStream_t stream;
+};
+
+extern "C" int br2_eskf_free(br2_eskf* f)
+{
+    if (!f) return BR2_OK;
+    DeviceGuard guard_(f->device);
+    for (void* p : {(void*)f->d_state, (void*)f->d_P, (void*)f->d_in, (void*)f->d_out})
+        if (p) cudaFree(p);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    free(f);
+    return BR2_OK;
+}
+
+extern "C" int br2_eskf_create(br2_eskf** out, int batch, const br2_eskf_params* prm, int device)
+{
+    if (!out) return fail(BR2_EINVAL, "br2_eskf_create: out is NULL");
+    *out = nullptr;
+    if (batch < 1) return fail(BR2_EINVAL, "br2_eskf_create: batch = %d", batch);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BR2_ECUDA, "br2_eskf_create: no CUDA device (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= ndev) return fail(BR2_EINVAL, "br2_eskf_create: device %d of %d", device, ndev);
+    DeviceGuard guard_(device);
+    CK(guard_.err);
+    br2_eskf* f = (br2_eskf*)calloc(1, sizeof(br2_eskf));
+    if (!f) return fail(BR2_ENOMEM, "out of host memory");
+    f->B = batch; f->device = device;
+    // launch/config/imudo.yaml
+    br2_eskf_params d = {0.001, 0.001, 0.001, 0.001, 0.001, 0.01, 0.02, 0.0006, 0.012,
+                         {-4.342596682195816e-07, -3.581072716118436e-18, -0.009999999990570729},
+                         {-2.66013609366142e-20, -1.933924486945935e-19, -3.870624673211354e-16}};
+    if (prm) d = *prm;
+    EskfArgs& a = f->base;
+    memset(&a, 0, sizeof a);
+    a.B = batch;
+    for (int i = 0; i < 21; i++) a.Qd[i] = i < 3 ? d.q_p : i < 6 ? d.q_v : i < 9 ? d.q_r : i < 18 ? d.q_q : d.q_xi;      // Config.cpp:128-139
+    for (int i = 0; i < 12; i++) a.Rd[i] = i < 3 ? d.r_p : i < 6 ? d.r_v : i < 9 ? d.r_r : d.r_th;                          // :147-155
+    memcpy(a.b_a, d.b_a, sizeof a.b_a); memcpy(a.b_g, d.b_g, sizeof a.b_g);
+    const size_t B = batch;
+    bool ok = cudaMalloc((void**)&f->d_state, sizeof(double) * B * 18) == cudaSuccess && cudaMalloc((void**)&f->d_P, sizeof(double) * B * 441) == cudaSuccess &&
+              cudaMalloc((void**)&f->d_in, sizeof(double) * B * 39) == cudaSuccess && cudaMalloc((void**)&f->d_out, sizeof(double) * B * 15) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) {
+        double* h = (double*)calloc(B * 18, sizeof(double));
+        ok = h != nullptr;
+        if (ok) {
+            for (size_t i = 0; i < B; i++) h[i * 18 + 6] = h[i * 18 + 10] = h[i * 18 + 14] = 1.0;      // R = I
+            ok = cudaMemcpy(f->d_state, h, sizeof(double) * B * 18, cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemset(f->d_P, 0, sizeof(double) * B * 441) == cudaSuccess;
+            free(h);
+        }
+    }
+    if (!ok) { cudaError_t le = cudaGetLastError(); br2_eskf_free(f); return fail(BR2_ENOMEM, "br2_eskf_create: allocation failed (%s)", cudaGetErrorString(le)); }
+    a.state = f->d_state; a.P = f->d_P;
+    configure_eskf();
+    *out = f;
+    return BR2_OK;
+}
+
+extern "C" int br2_eskf_set_state_host(br2_eskf* f, const double* state, const double* P)
+{
+    if (!f) return fail(BR2_EINVAL, "null filter");
+    DeviceGuard guard_(f->device); CK(guard_.err);
+    CK(cudaDeviceSynchronize());
+    if (state) CK(cudaMemcpy(f->d_state, state, sizeof(double) * f->B * 18, cudaMemcpyHostToDevice));
+    if (P) CK(cudaMemcpy(f->d_P, P, sizeof(double) * f->B * 441, cudaMemcpyHostToDevice));
+    return BR2_OK;
+}
+extern "C" int br2_eskf_get_state_host(br2_eskf* f, double* state, double* P)
+{
+    if (!f) return fail(BR2_EINVAL, "null filter");
+    DeviceGuard guard_(f->device); CK(guard_.err);
+    CK(cudaDeviceSynchronize());
+    if (state) CK(cudaMemcpy(state, f->d_state, sizeof(double) * f->B * 18, cudaMemcpyDeviceToHost));
+    if (P) CK(cudaMemcpy(P, f->d_P, sizeof(double) * f->B * 441, cudaMemcpyDeviceToHost));
+    return BR2_OK;
+}
+
+extern "C" int br2_eskf_predict_device(br2_eskf* f, const double* d_imu, void* stream)
+{
+    if (!f || !d_imu) return fail(BR2_EINVAL, "br2_eskf_predict_device: null argument");
+    DeviceGuard guard_(f->device); CK(guard_.err);
+    EskfArgs a = f->base;
+    a.imu = d_imu;
+    launch_eskf_predict(a, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+extern "C" int br2_eskf_update_device(br2_eskf* f, const double* d_gps_p, const double* d_gps_v, const double* d_R_meas, const double* d_thrusts,
+                                      const double* d_imu_raw, const double* d_R_gt, double* d_xi_world, double* d_innov, void* stream)
+{
+    if (!f || !d_gps_p || !d_gps_v || !d_R_meas || !d_thrusts || !d_imu_raw || !d_R_gt) return fail(BR2_EINVAL, "br2_eskf_update_device: null argument");
+    DeviceGuard guard_(f->device); CK(guard_.err);
+    EskfArgs a = f->base;
+    a.gps_p = d_gps_p; a.gps_v = d_gps_v; a.R_meas = d_R_meas; a.thrusts = d_thrusts; a.imu = d_imu_raw; a.R_gt = d_R_gt;
+    a.xi_world = d_xi_world; a.innov = d_innov;
+    launch_eskf_update(a, (cudaStream_t)stream);
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+extern "C" int br2_eskf_predict_host(br2_eskf* f, const double* imu)
+{
+    if (!f || !imu) return fail(BR2_EINVAL, "br2_eskf_predict_host: null argument");
+    DeviceGuard guard_(f->device); CK(guard_.err);
+    CK(cudaMemcpyAsync(f->d_in, imu, sizeof(double) * f->B * 6, cudaMemcpyHostToDevice, f->stream));
+    int rc = br2_eskf_predict_device(f, f->d_in, f->stream);
+    if (rc != BR2_OK) return rc;
+    CK(cudaStreamSynchronize(f->stream));
+    return BR2_OK;
+}
+extern "C" int br2_eskf_update_host(br2_eskf* f, const double* gps_p, const double* gps_v, const double* R_meas, const double* thrusts,
+                                    const double* imu_raw, const double* R_gt, double* xi_world, double* innov)
+{
+    if (!f || !gps_p || !gps_v || !R_meas || !thrusts || !imu_raw || !R_gt) return fail(BR2_EINVAL, "br2_eskf_update_host: null argument");
+    DeviceGuard guard_(f->device); CK(guard_.err);
+    const size_t B = f->B;
+    double* d = f->d_in;        // [gps_p 3 | gps_v 3 | R_meas 9 | thrusts 6 | imu 6 | R_gt 9] x B, section by section
+    double *dp = d, *dv = d + 3 * B, *dRm = d + 6 * B, *dth = d + 15 * B, *dimu = d + 21 * B, *dRg = d + 27 * B;
+    CK(cudaMemcpyAsync(dp, gps_p, sizeof(double) * B * 3, cudaMemcpyHostToDevice, f->stream));
+    CK(cudaMemcpyAsync(dv, gps_v, sizeof(double) * B * 3, cudaMemcpyHostToDevice, f->stream));
+    CK(cudaMemcpyAsync(dRm, R_meas, sizeof(double) * B * 9, cudaMemcpyHostToDevice, f->stream));
+    CK(cudaMemcpyAsync(dth, thrusts, sizeof(double) * B * 6, cudaMemcpyHostToDevice, f->stream));
+    CK(cudaMemcpyAsync(dimu, imu_raw, sizeof(double) * B * 6, cudaMemcpyHostToDevice, f->stream));
+    CK(cudaMemcpyAsync(dRg, R_gt, sizeof(double) * B * 9, cudaMemcpyHostToDevice, f->stream));
+    int rc = br2_eskf_update_device(f, dp, dv, dRm, dth, dimu, dRg, f->d_out, f->d_out + 3 * B, f->stream);
+    if (rc != BR2_OK) return rc;
+    if (xi_world) CK(cudaMemcpyAsync(xi_world, f->d_out, sizeof(double) * B * 3, cudaMemcpyDeviceToHost, f->stream));
+    if (innov) CK(cudaMemcpyAsync(innov, f->d_out + 3 * B, sizeof(double) * B * 12, cudaMemcpyDeviceToHost, f->stream));
+    CK(cudaStreamSynchronize(f->stream));
+    return BR2_OK;
+}

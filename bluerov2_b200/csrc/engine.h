@@ -112,6 +112,26 @@ struct RlsArgs {
 };
 void launch_rls(const RlsArgs& a, cudaStream_t s);
 
+// IMU error-state Kalman filter (eskf.cu; bluerov2_states/src/Eskf.cpp:97-331), one warp per instance
+struct EskfArgs {
+    int B;
+    double* state;           // [B][18] nominal state: p[3] v[3] R[9] (row-major) xi[3]
+    double* P;               // [B][21][21] error covariance
+    double Qd[21], Rd[12];   // diagonals of Q_process / R_meas (Config.cpp:128-155)
+    double b_a[3], b_g[3];   // accelerometer / gyro bias (launch/config/imudo.yaml)
+    const double* imu;       // [B][6] specific force + angular rate (predict: the IMU sample; update: imu_raw_B)
+    const double* gps_p;     // [B][3] update: position measurement
+    const double* gps_v;     // [B][3] update: velocity measurement
+    const double* R_meas;    // [B][9] update: attitude measurement
+    const double* R_gt;      // [B][9] update: attitude that gives dynamics_Ma its gravity direction
+    const double* thrusts;   // [B][6] update: thruster forces
+    double* xi_world;        // [B][3] out (may be null): R xi, what the nodelet publishes on /xi
+    double* innov;           // [B][12] out (may be null): the innovation y
+};
+void launch_eskf_predict(const EskfArgs& a, cudaStream_t s);
+void launch_eskf_update(const EskfArgs& a, cudaStream_t s);
+void configure_eskf();
+
 // continuous-yaw accumulator of the node glue (glue.cu; bluerov2_dob.cpp:272-304): state[B][2] = (pre_yaw, yaw_sum) floats,
 // x0[B][12] in place on column 5
 void launch_yaw_unwrap(int B, float* state, double* x0, cudaStream_t s);

@@ -566,5 +566,75 @@ def plant_step(x, u, p, h: float = 0.05, dist=None, wave=None, tick: int = 0, bo
     return x
 
 
+# bluerov2_states/launch/config/imudo.yaml (the library bakes the same values when no parameters are passed)
+ESKF_DEFAULTS = dict(q_p=0.001, q_v=0.001, q_r=0.001, q_q=0.001, q_xi=0.001, r_p=0.01, r_v=0.02, r_r=0.0006, r_th=0.012,
+                     b_a=(-4.342596682195816e-07, -3.581072716118436e-18, -0.009999999990570729),
+                     b_g=(-2.66013609366142e-20, -1.933924486945935e-19, -3.870624673211354e-16))
+
+
+class _EskfParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("q_p", "q_v", "q_r", "q_q", "q_xi", "r_p", "r_v", "r_r", "r_th")] + [("b_a", C.c_double * 3), ("b_g", C.c_double * 3)]
+
+
+class BatchEskf:
+    """B independent IMU error-state Kalman filters (include/bluerov2_b200.h br2_eskf_*; reference: bluerov2_states/src/Eskf.cpp).
+    numpy arrays in, numpy arrays out (host entry points); state [B,18] = p, v, R (row-major), xi; covariance [B,21,21]."""
+
+    def __init__(self, batch: int, device: int = 0, **prm):
+        self._L = L = load_library()
+        V = C.c_void_p
+        for name, args in (("br2_eskf_create", [C.POINTER(V), C.c_int, V, C.c_int]), ("br2_eskf_free", [V]),
+                           ("br2_eskf_set_state_host", [V, V, V]), ("br2_eskf_get_state_host", [V, V, V]), ("br2_eskf_predict_host", [V, V]),
+                           ("br2_eskf_update_host", [V] * 9)):
+            getattr(L, name).restype = C.c_int
+            getattr(L, name).argtypes = args
+        self._h = V()
+        par = None
+        if prm:
+            d = dict(ESKF_DEFAULTS); d.update(prm)
+            par = _EskfParams(d["q_p"], d["q_v"], d["q_r"], d["q_q"], d["q_xi"], d["r_p"], d["r_v"], d["r_r"], d["r_th"],
+                              (C.c_double * 3)(*d["b_a"]), (C.c_double * 3)(*d["b_g"]))
+        rc = L.br2_eskf_create(C.byref(self._h), int(batch), C.byref(par) if par is not None else None, int(device))
+        if rc != 0:
+            raise SolverError(f"bluerov2_b200 error {rc}: {L.br2_last_error().decode()}")
+        self.B = int(batch)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SolverError(f"bluerov2_b200 error {rc}: {self._L.br2_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.br2_eskf_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, state=None, P=None):
+        state = None if state is None else _np(state, (self.B, 18))
+        P = None if P is None else _np(P, (self.B, 21, 21))
+        self._check(self._L.br2_eskf_set_state_host(self._h, _ptr(state), _ptr(P)))
+
+    def get_state(self):
+        state, P = np.empty((self.B, 18)), np.empty((self.B, 21, 21))
+        self._check(self._L.br2_eskf_get_state_host(self._h, _ptr(state), _ptr(P)))
+        return state, P
+
+    def predict(self, imu):
+        self._check(self._L.br2_eskf_predict_host(self._h, _ptr(_np(imu, (self.B, 6)))))
+
+    def update(self, gps_p, gps_v, R_meas, thrusts, imu_raw, R_gt):
+        """-> (xi_world [B,3], innovation [B,12])"""
+        xi, y = np.empty((self.B, 3)), np.empty((self.B, 12))
+        a = [_np(gps_p, (self.B, 3)), _np(gps_v, (self.B, 3)), _np(np.reshape(R_meas, (self.B, 9)), (self.B, 9)), _np(thrusts, (self.B, 6)),
+             _np(imu_raw, (self.B, 6)), _np(np.reshape(R_gt, (self.B, 9)), (self.B, 9))]
+        self._check(self._L.br2_eskf_update_host(self._h, *[_ptr(v) for v in a], _ptr(xi), _ptr(y)))
+        return xi, y
+
+
 def device_count() -> int:
     return int(load_library().br2_device_count())

@@ -258,6 +258,31 @@ BR2_API int br2_batch_yaw_unwrap_host(br2_batch_solver *s, double *x0);
 BR2_API int br2_batch_yaw_get_state_host(br2_batch_solver *s, float *state /* [B][2] */);
 BR2_API int br2_batch_yaw_set_state_host(br2_batch_solver *s, const float *state);
 
+/* == BLUEROV2_STATES::ImuDoNodelet::predict / update (bluerov2_states/src/Eskf.cpp:97-141, 197-331): the IMU error-state Kalman
+ * filter that is the consolidated node's alternative disturbance source (ctrller_type DOMPC reads its /disturbance).  B independent
+ * filters.  Nominal state per instance: p[3], v[3], R[9] (row-major rotation, body -> inertial), xi[3] (disturbance force, body
+ * frame); error covariance P[21][21] over [dp, dv, dtheta, db_g, db_a, dg, dxi].  dt = 1/50 s (:103).
+ *   br2_eskf_params   diagonals of Q_process / R_meas and the biases: q_p, q_v, q_r, q_q (the nine bias / gravity states), q_xi;
+ *                     r_p, r_v, r_r, r_th; b_a[3], b_g[3] (Config.cpp:119-161; NULL = launch/config/imudo.yaml)
+ *   predict           imu[B][6] = (specific force, angular rate) of the newest IMU sample
+ *   update            gps_p[B][3], gps_v[B][3], R_meas[B][9] (the attitude measurement; ground truth in the reference, :170-176),
+ *                     thrusts[B][6], imu_raw[B][6], R_gt[B][9] (attitude giving dynamics_Ma its gravity direction, Dynamics.cpp:180);
+ *                     xi_world[B][3] (may be NULL) = R xi as published on /xi, innov[B][12] (may be NULL) = the innovation
+ * Quirks kept: the velocity correction is injected twice (:320); biases and gravity are never injected. */
+typedef struct br2_eskf br2_eskf;
+typedef struct br2_eskf_params { double q_p, q_v, q_r, q_q, q_xi, r_p, r_v, r_r, r_th, b_a[3], b_g[3]; } br2_eskf_params;
+BR2_API int br2_eskf_create(br2_eskf **out, int batch, const br2_eskf_params *prm, int device);
+BR2_API int br2_eskf_free(br2_eskf *f);
+/* state[B][18] = p, v, R, xi and P[B][441]; either may be NULL (left as is).  Creation leaves p = v = xi = 0, R = I, P = 0 */
+BR2_API int br2_eskf_set_state_host(br2_eskf *f, const double *state, const double *P);
+BR2_API int br2_eskf_get_state_host(br2_eskf *f, double *state, double *P);
+BR2_API int br2_eskf_predict_device(br2_eskf *f, const double *d_imu, void *stream);
+BR2_API int br2_eskf_update_device(br2_eskf *f, const double *d_gps_p, const double *d_gps_v, const double *d_R_meas, const double *d_thrusts,
+                                   const double *d_imu_raw, const double *d_R_gt, double *d_xi_world, double *d_innov, void *stream);
+BR2_API int br2_eskf_predict_host(br2_eskf *f, const double *imu);
+BR2_API int br2_eskf_update_host(br2_eskf *f, const double *gps_p, const double *gps_v, const double *R_meas, const double *thrusts,
+                                 const double *imu_raw, const double *R_gt, double *xi_world, double *innov);
+
 #ifdef __cplusplus
 }
 #endif
