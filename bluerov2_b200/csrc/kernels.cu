@@ -1570,6 +1570,9 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(const
         prefetch_iterate(I);
         IpmOut o;
         ipm_solve(I, o);
+#ifdef BR2_PROFILE
+        prof_t0 = clock64();            // (ipm_solve accounts for its own phases)
+#endif
         SolveOut r;
         r.status = o.status; r.it = o.it; r.mu = o.mu; r.res_stat = o.res_stat; r.stat_scale = o.stat_scale; r.bmax = o.bmax;
         r.solved = false; r.active = false;
