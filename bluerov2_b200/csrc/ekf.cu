@@ -5,13 +5,21 @@
 //   state  [eta(6), nu(6), d(6)];  process model f (:637-695) with rigid-body Coriolis terms and invM(i,i) of the
 //   COUPLED mass matrix;  RK4 with k3 = f(x + k2/3) (sic, :630);  F and H by forward differences, d = 1e-6
 //   (:722-752);  gain through an explicit 18x18 inverse (:535);  Joseph-form covariance update (:537).
-// Lane mapping: the 19 RK4 / 19 h() evaluations of the two finite-difference Jacobians run on lanes 0..18 in
-// parallel (lane 0 = unperturbed); the ten 18x18x18 products use 3 x 4 register tiles on 30 lanes (operands in shared
-// memory, five 18x18 buffers per warp); the Gauss-Jordan inverse keeps one row of [S | I] per lane in registers, finds
-// the pivot with three warp reductions and exchanges row POSITIONS instead of rows.  16 warps/SM (128 registers,
-// 13.4 KB of shared memory per warp): the kernel is latency-bound and its time falls with every resident warp
-// (8 / 12 / 16 warps/SM: 0.24 / 0.18 / 0.15 ms at B = 4096, profiles/r01k_ekf_variants.txt).  Output: esti_x, esti_P, world-frame disturbance (:540-545) and the OCP parameter
-// vector handed to the solver (bluerov2_dob.cpp:324-355).
+//
+// Mapping.  (1) The 19 RK4 / 19 h() evaluations of the two finite-difference Jacobians run on lanes 0..18 in parallel
+// (lane 0 = unperturbed, lane c + 1 perturbs component c); only the 12 components with dynamics are integrated (the
+// disturbance states are constants of f), divisions by constants are multiplications.  (2) The ten 18 x 18 x 18 products
+// of the covariance algebra run on the fp64 tensor-core instruction (DMMA m8n8k4) as four fused chains per tile row,
+//      P_pred = (F P) F' + Q,   S = (H P_pred) H' + R,   K = (P_pred H') S^-1,  A = I - K H,   P = (A P_pred) A' + K R K',
+// every operand a fragment read straight from the row-major matrix in shared memory: with the contraction index
+// enumerated in accumulator-fragment order (even columns, then odd columns of an 8-tile) the accumulator of one product
+// IS the A operand of the next, and X M' needs the same fragment of M as of X -- no re-layout anywhere.  18 = 8 + 8 + 2:
+// fragments are zero-padded by predication; tile products whose operand tile is structurally zero (F = [* * *; * * *;
+// 0 0 D], H = [D 0 0; * * 0; * * *] in 8-tiles) are skipped at compile time: 444 DMMA per instance instead of 540 (and
+// instead of 2160 DFMA + 900 shared-memory loads of the round-1 kernel).  (3) The Gauss-Jordan inverse keeps one row of
+// S per lane in registers, finds the pivot with three warp reductions and exchanges row POSITIONS instead of rows.
+// 16 warps/SM (13.6 KB of shared memory per warp).  Output: esti_x, esti_P, world-frame disturbance (:540-545) and
+// the OCP parameter vector handed to the solver (bluerov2_dob.cpp:324-355).
 #include "engine.h"
 
 namespace br2 {
@@ -38,6 +46,8 @@ constexpr double C = M * Zg;
 constexpr double IM0 = M4 / (M0 * M4 - C * C), IM4 = M0 / (M0 * M4 - C * C);
 constexpr double IM1 = M3 / (M1 * M3 - C * C), IM3 = M1 / (M1 * M3 - C * C);
 constexpr double IM2 = 1.0 / M2, IM5 = 1.0 / M5;
+constexpr double QP = (DT * DT * DT * DT) / 4, QV = DT * DT;      // Q = diag(QP x 6, QV x 12), R = QP I (bluerov2_dob.cpp:49-65)
+constexpr double FD = 1e-6, RFD = 1e6;                            // forward-difference step and its reciprocal
 }  // namespace ekfc
 
 __constant__ double c_K[36] = {
@@ -52,115 +62,140 @@ __constant__ double c_K[36] = {
 __constant__ double c_DlM[2][6] = {{-11.7391, -20, -31.8678, -25, -44.9085, -5}, {0, 0, 0, 0, 0, 0}};
 __constant__ double c_DnlM[2][6] = {{-18.18, -21.66, -36.99, -1.55, -1.55, -1.55}, {0, 0, 0, 0, 0, 0}};
 
-// process model, bluerov2_dob.cpp:637-695 (tau = K * thrusts precomputed)
-__device__ void ekf_f(const double* x, const double* tau, double* xd, const double* c_Dl, const double* c_Dnl)
+// ---- models -------------------------------------------------------------------------------------------------------
+// process model, bluerov2_dob.cpp:637-695, on the 9 components it reads (ang = x[3..5], nu = x[6..11]) plus the
+// disturbance states dd = x[12..17] (constants of f: their derivative is zero, :689-694) and tau = K * thrusts
+__device__ __forceinline__ void ekf_f12(const double (&ang)[3], const double (&nu)[6], const double (&dd)[6], const double* tau,
+                                        double (&xd)[12], const double* c_Dl, const double* c_Dnl)
 {
     using namespace ekfc;
     double s3, c3, s4, c4, s5, c5;
-    sincos(x[3], &s3, &c3); sincos(x[4], &s4, &c4); sincos(x[5], &s5, &c5);
-    xd[0] = (c5 * c4) * x[6] + (-s5 * c3 + c5 * s4 * s3) * x[7] + (s5 * s3 + c5 * c3 * s4) * x[8];
-    xd[1] = (s5 * c4) * x[6] + (c5 * c3 + s3 * s4 * s5) * x[7] + (-c5 * s3 + s4 * s5 * c3) * x[8];
-    xd[2] = (-s4) * x[6] + (c4 * s3) * x[7] + (c4 * c3) * x[8];
-    xd[3] = x[9] + (s5 * s4 / c4) * x[10] + c3 * s4 / c4 * x[11];
-    xd[4] = (c3) * x[10] + (s3) * x[11];
-    xd[5] = (s3 / c4) * x[10] + (c3 / c4) * x[11];
-    xd[6] = IM0 * (tau[0] + M * x[11] * x[7] - M * x[10] * x[8] - EBUOY * s4 + x[12] + c_Dl[0] * x[6] + c_Dnl[0] * fabs(x[6]) * x[6]);
-    xd[7] = IM1 * (tau[1] - M * x[11] * x[6] + M * x[9] * x[8] + EBUOY * c4 * s3 + x[13] + c_Dl[1] * x[7] + c_Dnl[1] * fabs(x[7]) * x[7]);
-    xd[8] = IM2 * (tau[2] + M * x[10] * x[6] - M * x[9] * x[7] + EBUOY * c4 * c3 + x[14] + c_Dl[2] * x[8] + c_Dnl[2] * fabs(x[8]) * x[8]);
-    xd[9] = IM3 * (tau[3] + (Iy - Iz) * x[10] * x[11] - M * Zg * G * c4 * s3 + x[15] + c_Dl[3] * x[9] + c_Dnl[3] * fabs(x[9]) * x[9]);
-    xd[10] = IM4 * (tau[4] + (Iz - Ix) * x[9] * x[11] - M * Zg * G * s4 + x[16] + c_Dl[4] * x[10] + c_Dnl[4] * fabs(x[10]) * x[10]);
-    xd[11] = IM5 * (tau[5] - (Iy - Ix) * x[9] * x[10] + x[17] + c_Dl[5] * x[11] + c_Dnl[5] * fabs(x[11]) * x[11]);
-#pragma unroll
-    for (int i = 12; i < EN; i++) xd[i] = 0.0;
+    sincos(ang[0], &s3, &c3); sincos(ang[1], &s4, &c4); sincos(ang[2], &s5, &c5);
+    const double r4 = 1.0 / c4;
+    xd[0] = (c5 * c4) * nu[0] + (-s5 * c3 + c5 * s4 * s3) * nu[1] + (s5 * s3 + c5 * c3 * s4) * nu[2];
+    xd[1] = (s5 * c4) * nu[0] + (c5 * c3 + s3 * s4 * s5) * nu[1] + (-c5 * s3 + s4 * s5 * c3) * nu[2];
+    xd[2] = (-s4) * nu[0] + (c4 * s3) * nu[1] + (c4 * c3) * nu[2];
+    xd[3] = nu[3] + (s5 * s4 * r4) * nu[4] + c3 * s4 * r4 * nu[5];
+    xd[4] = (c3) * nu[4] + (s3) * nu[5];
+    xd[5] = (s3 * r4) * nu[4] + (c3 * r4) * nu[5];
+    xd[6] = IM0 * (tau[0] + M * nu[5] * nu[1] - M * nu[4] * nu[2] - EBUOY * s4 + dd[0] + c_Dl[0] * nu[0] + c_Dnl[0] * fabs(nu[0]) * nu[0]);
+    xd[7] = IM1 * (tau[1] - M * nu[5] * nu[0] + M * nu[3] * nu[2] + EBUOY * c4 * s3 + dd[1] + c_Dl[1] * nu[1] + c_Dnl[1] * fabs(nu[1]) * nu[1]);
+    xd[8] = IM2 * (tau[2] + M * nu[4] * nu[0] - M * nu[3] * nu[1] + EBUOY * c4 * c3 + dd[2] + c_Dl[2] * nu[2] + c_Dnl[2] * fabs(nu[2]) * nu[2]);
+    xd[9] = IM3 * (tau[3] + (Iy - Iz) * nu[4] * nu[5] - M * Zg * G * c4 * s3 + dd[3] + c_Dl[3] * nu[3] + c_Dnl[3] * fabs(nu[3]) * nu[3]);
+    xd[10] = IM4 * (tau[4] + (Iz - Ix) * nu[3] * nu[5] - M * Zg * G * s4 + dd[4] + c_Dl[4] * nu[4] + c_Dnl[4] * fabs(nu[4]) * nu[4]);
+    xd[11] = IM5 * (tau[5] - (Iy - Ix) * nu[3] * nu[4] + dd[5] + c_Dl[5] * nu[5] + c_Dnl[5] * fabs(nu[5]) * nu[5]);
 }
 
-// measurement model, bluerov2_dob.cpp:698-719
-__device__ void ekf_h(const double* x, const double* acc, double* y, const double* c_Dl, const double* c_Dnl)
+// rows 12..17 of the measurement model, bluerov2_dob.cpp:698-719 (rows 0..11 are y = x)
+__device__ __forceinline__ void ekf_h6(double a3, double a4, const double (&nu)[6], const double (&dd)[6], const double* acc,
+                                       double (&y)[6], const double* c_Dl, const double* c_Dnl)
 {
     using namespace ekfc;
     double s3, c3, s4, c4;
-    sincos(x[3], &s3, &c3); sincos(x[4], &s4, &c4);
-#pragma unroll
-    for (int i = 0; i < 12; i++) y[i] = x[i];
-    y[12] = M0 * acc[0] - M * x[11] * x[7] + M * x[10] * x[8] + EBUOY * s4 - x[12] - c_Dl[0] * x[6] - c_Dnl[0] * fabs(x[6]) * x[6];
-    y[13] = M1 * acc[1] + M * x[11] * x[6] - M * x[9] * x[8] - EBUOY * c4 * s3 - x[13] - c_Dl[1] * x[7] - c_Dnl[1] * fabs(x[7]) * x[7];
-    y[14] = M2 * acc[2] - M * x[10] * x[6] + M * x[9] * x[7] - EBUOY * c4 * c3 - x[14] - c_Dl[2] * x[8] - c_Dnl[2] * fabs(x[8]) * x[8];
-    y[15] = M3 * acc[3] - (Iy - Iz) * x[10] * x[11] + M * Zg * G * c4 * s3 - x[15] - c_Dl[3] * x[9] - c_Dnl[3] * fabs(x[9]) * x[9];
-    y[16] = M4 * acc[4] - (Iz - Ix) * x[9] * x[11] + M * Zg * G * s4 - x[16] - c_Dl[4] * x[10] - c_Dnl[4] * fabs(x[10]) * x[10];
-    y[17] = M5 * acc[5] + (Iy - Ix) * x[9] * x[10] - x[17] - c_Dl[5] * x[11] - c_Dnl[5] * fabs(x[11]) * x[11];
+    sincos(a3, &s3, &c3); sincos(a4, &s4, &c4);
+    y[0] = M0 * acc[0] - M * nu[5] * nu[1] + M * nu[4] * nu[2] + EBUOY * s4 - dd[0] - c_Dl[0] * nu[0] - c_Dnl[0] * fabs(nu[0]) * nu[0];
+    y[1] = M1 * acc[1] + M * nu[5] * nu[0] - M * nu[3] * nu[2] - EBUOY * c4 * s3 - dd[1] - c_Dl[1] * nu[1] - c_Dnl[1] * fabs(nu[1]) * nu[1];
+    y[2] = M2 * acc[2] - M * nu[4] * nu[0] + M * nu[3] * nu[1] - EBUOY * c4 * c3 - dd[2] - c_Dl[2] * nu[2] - c_Dnl[2] * fabs(nu[2]) * nu[2];
+    y[3] = M3 * acc[3] - (Iy - Iz) * nu[4] * nu[5] + M * Zg * G * c4 * s3 - dd[3] - c_Dl[3] * nu[3] - c_Dnl[3] * fabs(nu[3]) * nu[3];
+    y[4] = M4 * acc[4] - (Iz - Ix) * nu[3] * nu[5] + M * Zg * G * s4 - dd[4] - c_Dl[4] * nu[4] - c_Dnl[4] * fabs(nu[4]) * nu[4];
+    y[5] = M5 * acc[5] + (Iy - Ix) * nu[3] * nu[4] - dd[5] - c_Dl[5] * nu[5] - c_Dnl[5] * fabs(nu[5]) * nu[5];
 }
 
-__device__ void ekf_rk4(const double* x, const double* tau, double* xn, const double* c_Dl, const double* c_Dnl)
+// ---- fp64 tensor-core products on row-major 18 x 18 matrices in shared memory -------------------------------------------
+// Lane (q = lane >> 2, t = lane & 3).  Accumulator fragment of tile (I, J): {C[8I+q][8J+2t], C[8I+q][8J+2t+1]}.  With the
+// contraction index of a k-tile enumerated as (0, 2, 4, 6) then (1, 3, 5, 7), the A operand of the two DMMA of k-tile K is
+// the .x / .y of "row fragment" {X[8I+q][8K+2t], X[8I+q][8K+2t+1]} -- the accumulator layout --, and the B operand of
+// C = X M' is the row fragment of M at (J, K).  C = X Y (no transpose) takes the "column fragment" of Y instead.
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
 {
-    using namespace ekfc;
-    // x + (k1 + 2 k2 + 2 k3 + k4) / 6 with the sum accumulated left to right as the reference's expression evaluates it
-    double k[EN], xs[EN], acc[EN];
-    ekf_f(x, tau, k, c_Dl, c_Dnl);
-#pragma unroll
-    for (int i = 0; i < EN; i++) { k[i] *= DT; acc[i] = k[i]; xs[i] = x[i] + k[i] / 2; }
-    ekf_f(xs, tau, k, c_Dl, c_Dnl);
-#pragma unroll
-    for (int i = 0; i < EN; i++) { k[i] *= DT; acc[i] = acc[i] + 2 * k[i]; xs[i] = x[i] + k[i] / 3; }   // sic: /3 (bluerov2_dob.cpp:630)
-    ekf_f(xs, tau, k, c_Dl, c_Dnl);
-#pragma unroll
-    for (int i = 0; i < EN; i++) { k[i] *= DT; acc[i] = acc[i] + 2 * k[i]; xs[i] = x[i] + k[i]; }
-    ekf_f(xs, tau, k, c_Dl, c_Dnl);
-#pragma unroll
-    for (int i = 0; i < EN; i++) { k[i] *= DT; xn[i] = x[i] + (acc[i] + k[i]) / 6; }
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
-
-// C = A * B or A * B' (18x18, shared memory, leading dimension LD).  30 lanes each own a 3 x 4 tile of C (row group
-// lane / 5, column group lane % 5; the last column group is two columns wide): 12 independent accumulators per lane,
-// each summed over k = 0..17 in order with fma -- the order of the oracle's matmul.
-__device__ __forceinline__ void mm18(const double* A, const double* B, double* C, bool transB, int lane)
+// {X[8R+q][8K+2t], X[8R+q][8K+2t+1]}, zero outside 18 x 18 (R, K compile-time after unrolling)
+__device__ __forceinline__ double2 rowfrag(const double* X, int R, int K, int q, int t)
 {
-    if (lane < 30) {
-        const int r0 = 3 * (lane / 5), c0 = 4 * (lane % 5);
-        const bool edge = c0 == 16;
-        double acc[3][4];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-        if (!transB) {
-#pragma unroll 6
-            for (int k = 0; k < EN; k++) {
-                const double2 b01 = *reinterpret_cast<const double2*>(B + k * LD + c0);
-                const double2 b23 = edge ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(B + k * LD + c0 + 2);
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    const double av = A[(r0 + i) * LD + k];
-                    acc[i][0] = fma(av, b01.x, acc[i][0]); acc[i][1] = fma(av, b01.y, acc[i][1]);
-                    acc[i][2] = fma(av, b23.x, acc[i][2]); acc[i][3] = fma(av, b23.y, acc[i][3]);
-                }
-            }
-        } else {
-            const int j2 = edge ? c0 : c0 + 2, j3 = edge ? c0 : c0 + 3;     // clamped: the extra products are discarded
-#pragma unroll 6
-            for (int k = 0; k < EN; k++) {
-                const double b0 = B[c0 * LD + k], b1 = B[(c0 + 1) * LD + k], b2 = B[j2 * LD + k], b3 = B[j3 * LD + k];
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    const double av = A[(r0 + i) * LD + k];
-                    acc[i][0] = fma(av, b0, acc[i][0]); acc[i][1] = fma(av, b1, acc[i][1]);
-                    acc[i][2] = fma(av, b2, acc[i][2]); acc[i][3] = fma(av, b3, acc[i][3]);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            *reinterpret_cast<double2*>(C + (r0 + i) * LD + c0) = make_double2(acc[i][0], acc[i][1]);
-            if (!edge) *reinterpret_cast<double2*>(C + (r0 + i) * LD + c0 + 2) = make_double2(acc[i][2], acc[i][3]);
-        }
+    double2 v = make_double2(0.0, 0.0);
+    if ((R < 2 || q < 2) && (K < 2 || t == 0)) v = *reinterpret_cast<const double2*>(X + (8 * R + q) * LD + 8 * K + 2 * t);
+    return v;
+}
+// {Y[8K+2t][8J+q], Y[8K+2t+1][8J+q]}: the row fragment of Y'
+__device__ __forceinline__ double2 colfrag(const double* Y, int J, int K, int q, int t)
+{
+    double2 v = make_double2(0.0, 0.0);
+    if ((J < 2 || q < 2) && (K < 2 || t == 0)) {
+        v.x = Y[(8 * K + 2 * t) * LD + 8 * J + q];
+        v.y = Y[(8 * K + 2 * t + 1) * LD + 8 * J + q];
     }
-    __syncwarp();
+    return v;
 }
+// structural non-zero tiles, bit (R * 3 + K): F = [* * *; * * *; 0 0 D] (the disturbance rows of the transition matrix are
+// the identity), H = [D 0 0; * * 0; * * *] (rows 0..11 of the measurement are the state)
+constexpr unsigned TM_ALL = 0x1ff;
+constexpr unsigned TM_F = 0x07 | (0x07 << 3) | (0x04 << 6);
+constexpr unsigned TM_H = 0x01 | (0x03 << 3) | (0x07 << 6);
+constexpr unsigned TM_HT = 0x07 | (0x06 << 3) | (0x04 << 6);      // column fragments of H: tile (J, K) <-> H tile (K, J)
+// c[J] += sum_K a[K] * frag(M; J, K) for J = 0..2; amask = the non-zero k-tiles of a (3 bits), mmask = tiles of the fragment
+template <bool TRANS, unsigned MMASK>
+__device__ __forceinline__ void tile_row_product(double (&c)[3][2], const double2 (&a)[3], unsigned amask_const, const double* Mx, int q, int t)
+{
+#pragma unroll
+    for (int J = 0; J < 3; J++)
+#pragma unroll
+        for (int K = 0; K < 3; K++)
+            if (((MMASK >> (J * 3 + K)) & 1u) && ((amask_const >> K) & 1u)) {
+                const double2 m = TRANS ? colfrag(Mx, J, K, q, t) : rowfrag(Mx, J, K, q, t);
+                dmma(c[J], a[K].x, m.x);
+                dmma(c[J], a[K].y, m.y);
+            }
+}
+__device__ __forceinline__ void load_tile_row(double2 (&a)[3], const double* X, int I, int q, int t)
+{
+#pragma unroll
+    for (int K = 0; K < 3; K++) a[K] = rowfrag(X, I, K, q, t);
+}
+__device__ __forceinline__ void acc_to_frag(double2 (&a)[3], const double (&c)[3][2])
+{
+#pragma unroll
+    for (int K = 0; K < 3; K++) a[K] = make_double2(c[K][0], c[K][1]);
+}
+__device__ __forceinline__ void zero_acc(double (&c)[3][2])
+{
+#pragma unroll
+    for (int J = 0; J < 3; J++) c[J][0] = c[J][1] = 0.0;
+}
+// tile row I of an accumulator -> row-major matrix (shared or global), entries outside 18 x 18 dropped
+__device__ __forceinline__ void store_tile_row(double* X, const double (&c)[3][2], int I, int q, int t)
+{
+#pragma unroll
+    for (int J = 0; J < 3; J++)
+        if ((I < 2 || q < 2) && (J < 2 || t == 0))
+            *reinterpret_cast<double2*>(X + (8 * I + q) * LD + 8 * J + 2 * t) = make_double2(c[J][0], c[J][1]);
+}
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+#ifdef BR2_PROFILE
+// SM cycles per phase summed over warps (profile build only; scripts/ekf_phase_profile.py)
+__device__ unsigned long long g_ekf_prof[12];
+#define EPROF(i) do { const long long t_ = clock64(); if (lane == 0) atomicAdd(&g_ekf_prof[i], (unsigned long long)(t_ - eprof_t0)); eprof_t0 = clock64(); } while (0)
+#else
+#define EPROF(i) do { } while (0)
+#endif
 
 struct __align__(16) EkfSmem {
-    double Fm[EN * LD], Hm[EN * LD], Pp[EN * LD], T1[EN * LD], T2[EN * LD];   // Fm doubles as Kal once P_pred is formed
+    double Fm[EN * LD];          // F; the gain once P_pred is formed
+    double Pp[EN * LD];          // P_pred
+    double Hm[EN * LD];          // H
+    double Sm[EN * LD];          // S, then its inverse
+    double Am[EN * LD];          // esti_P on entry; I - K H later
+    double x[EN];                // esti_x on entry
+    double xp[EN];               // x_pred
+    double inn[EN];              // innovation
+    double tau[6], acc[6];       // K * thrusts, body acceleration
     double prow[EN + 2];         // scaled pivot row of the Gauss-Jordan inverse
-    double vec[EN + 2];          // innovation
-    double xpv[2 * EN];          // x_pred | measurement vector y = [pose, body velocity, tau]
 };
 
 __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfArgs a)
@@ -168,77 +203,145 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
     using namespace ekfc;
     extern __shared__ __align__(16) unsigned char smraw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int q = lane >> 2, t = lane & 3;
     EkfSmem& sm = reinterpret_cast<EkfSmem*>(smraw)[wib];
     const int inst = blockIdx.x * EKF_WARPS + wib;
     if (inst >= a.B) return;
-    const double d = 1e-6;
+#ifdef BR2_PROFILE
+    long long eprof_t0 = clock64();
+#endif
     const double* c_Dl = c_DlM[a.model & 1];
     const double* c_Dnl = c_DnlM[a.model & 1];
     double* ex = a.esti_x + (size_t)inst * EN;
     double* eP = a.esti_P + (size_t)inst * EN * EN;
 
-    // meas_y = [pose, body velocity, tau = K * thrusts] (:499-504)
-    double tau[6], acc[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
+    // esti_P -> shared memory, asynchronously (162 chunks of 16 bytes): first read after the two Jacobians
+    for (int ch = lane; ch < EN * EN / 2; ch += 32) cp16(sm.Am + 2 * ch, eP + 2 * ch);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (lane < EN) sm.x[lane] = ex[lane];
+    if (lane < 6) {
+        // tau = K * thrusts (meas_y rows 12..17, :499-504)
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < 6; j++) s += c_K[i * 6 + j] * a.thrusts[(size_t)inst * 6 + j];
-        tau[i] = s;
-        acc[i] = a.body_acc[(size_t)inst * 6 + i];
+        for (int j = 0; j < 6; j++) s += c_K[lane * 6 + j] * a.thrusts[(size_t)inst * 6 + j];
+        sm.tau[lane] = s;
+        sm.acc[lane] = a.body_acc[(size_t)inst * 6 + lane];
     }
-    double x[EN], f1[EN];
-#pragma unroll
-    for (int i = 0; i < EN; i++) x[i] = ex[i];
-    // esti_P -> shared (T2 as staging)
-    for (int idx = lane; idx < EN * EN; idx += 32) sm.T2[(idx / EN) * LD + idx % EN] = eP[idx];
+    __syncwarp();
+    EPROF(0);
 
-    // ---- F = d RK4 / dx by forward differences: lane 0 unperturbed, lane c+1 perturbs component c ----
-    if (lane >= 1 && lane <= EN) {
+    // ---- F = d RK4 / dx by forward differences (:722-736): lane 0 unperturbed, lane c + 1 perturbs component c ----
+    const int pc = lane - 1;                 // (lanes >= 19 repeat the unperturbed evaluation; nothing of theirs is stored)
+    double dd[6];                            // disturbance states of this lane's evaluation
 #pragma unroll
-        for (int i = 0; i < EN; i++)
-            if (i == lane - 1) x[i] += d;
-    }
-    ekf_rk4(x, tau, f1, c_Dl, c_Dnl);
-    double xp[EN];   // x_pred = RK4(esti_x) on every lane
-#pragma unroll
-    for (int i = 0; i < EN; i++) {
-        xp[i] = __shfl_sync(FULL_MASK, f1[i], 0);
-        if (lane >= 1 && lane <= EN) sm.Fm[i * LD + lane - 1] = (f1[i] - xp[i]) / d;
-        if (lane == 0) sm.xpv[i] = f1[i];          // x_pred, read back by component for the state update
-    }
-    if (lane < 6) {
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-            if (i == lane) sm.xpv[EN + 12 + i] = tau[i];     // measurement vector: tau part (pose / velocities added below)
-    }
-    if (lane < 12) sm.xpv[EN + lane] = a.meas[(size_t)inst * 12 + lane];
-    __syncwarp();
-    // ---- P_pred = F P F' + Q (:529) ----
-    mm18(sm.Fm, sm.T2, sm.T1, false, lane);
-    mm18(sm.T1, sm.Fm, sm.Pp, true, lane);
-    if (lane < EN) sm.Pp[lane * LD + lane] += (lane < 6) ? (DT * DT * DT * DT) / 4 : DT * DT;
-    __syncwarp();
-    // ---- H = dh/dx at x_pred by forward differences (:738-752) ----
-#pragma unroll
-    for (int i = 0; i < EN; i++) {
-        x[i] = xp[i];
-        if (lane >= 1 && lane <= EN && i == lane - 1) x[i] += d;
-    }
+    for (int i = 0; i < 6; i++) dd[i] = sm.x[12 + i] + (pc == 12 + i ? FD : 0.0);
+    double xn[12];                           // RK4(x (+ d e_c)), components 0..11
     {
-        double y1[EN];
-        ekf_h(x, acc, y1, c_Dl, c_Dnl);
+        // x + (k1 + 2 k2 + 2 k3 + k4) / 6 with the sum accumulated left to right as the reference's expression evaluates it
+        // (:621-635); k3 is evaluated at x + k2 / 3 (sic, :630)
+        double x0[12], k[12], sum[12], ang[3], nu[6];
 #pragma unroll
-        for (int i = 0; i < EN; i++) {
-            const double yp = __shfl_sync(FULL_MASK, y1[i], 0);
-            if (lane >= 1 && lane <= EN) sm.Hm[i * LD + lane - 1] = (y1[i] - yp) / d;
-            if (lane == 0) sm.vec[i] = sm.xpv[EN + i] - y1[i];      // innovation y - y_pred
-        }
+        for (int i = 0; i < 12; i++) x0[i] = sm.x[i] + (pc == i ? FD : 0.0);
+#pragma unroll
+        for (int i = 0; i < 3; i++) ang[i] = x0[3 + i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) nu[i] = x0[6 + i];
+        ekf_f12(ang, nu, dd, sm.tau, k, c_Dl, c_Dnl);
+#pragma unroll
+        for (int i = 0; i < 12; i++) { k[i] *= DT; sum[i] = k[i]; }
+#pragma unroll
+        for (int i = 0; i < 3; i++) ang[i] = x0[3 + i] + k[3 + i] * 0.5;
+#pragma unroll
+        for (int i = 0; i < 6; i++) nu[i] = x0[6 + i] + k[6 + i] * 0.5;
+        ekf_f12(ang, nu, dd, sm.tau, k, c_Dl, c_Dnl);
+#pragma unroll
+        for (int i = 0; i < 12; i++) { k[i] *= DT; sum[i] = sum[i] + 2 * k[i]; }
+#pragma unroll
+        for (int i = 0; i < 3; i++) ang[i] = x0[3 + i] + k[3 + i] * (1.0 / 3.0);
+#pragma unroll
+        for (int i = 0; i < 6; i++) nu[i] = x0[6 + i] + k[6 + i] * (1.0 / 3.0);
+        ekf_f12(ang, nu, dd, sm.tau, k, c_Dl, c_Dnl);
+#pragma unroll
+        for (int i = 0; i < 12; i++) { k[i] *= DT; sum[i] = sum[i] + 2 * k[i]; }
+#pragma unroll
+        for (int i = 0; i < 3; i++) ang[i] = x0[3 + i] + k[3 + i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) nu[i] = x0[6 + i] + k[6 + i];
+        ekf_f12(ang, nu, dd, sm.tau, k, c_Dl, c_Dnl);
+#pragma unroll
+        for (int i = 0; i < 12; i++) xn[i] = x0[i] + (sum[i] + k[i] * DT) * (1.0 / 6.0);
+    }
+    double xp[12];                           // x_pred = RK4(esti_x), components 0..11, on every lane
+    const bool fdl = lane >= 1 && lane <= EN;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        xp[i] = __shfl_sync(FULL_MASK, xn[i], 0);
+        if (fdl) sm.Fm[i * LD + pc] = (xn[i] - xp[i]) * RFD;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if (fdl) sm.Fm[(12 + i) * LD + pc] = (dd[i] - sm.x[12 + i]) * RFD;      // disturbance rows: RK4 leaves them where they were
+    if (lane >= 12 && lane < EN) sm.xp[lane] = sm.x[lane];
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) sm.xp[i] = xn[i];
     }
     __syncwarp();
-    // ---- S = H Pp H' + R ; explicit inverse by Gauss-Jordan with partial pivoting (:535) ----
-    mm18(sm.Hm, sm.Pp, sm.T1, false, lane);
-    mm18(sm.T1, sm.Hm, sm.T2, true, lane);
+    EPROF(1);
+    // ---- H = dh/dx at x_pred by forward differences (:738-752), innovation ----
+    {
+        double nu[6], y6[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) nu[i] = xp[6 + i] + (pc == 6 + i ? FD : 0.0);
+        const double a3 = xp[3] + (pc == 3 ? FD : 0.0), a4 = xp[4] + (pc == 4 ? FD : 0.0);
+        ekf_h6(a3, a4, nu, dd, sm.acc, y6, c_Dl, c_Dnl);
+#pragma unroll
+        for (int i = 0; i < 12; i++)
+            if (fdl) sm.Hm[i * LD + pc] = pc == i ? ((xp[i] + FD) - xp[i]) * RFD : 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const double yp = __shfl_sync(FULL_MASK, y6[i], 0);
+            if (fdl) sm.Hm[(12 + i) * LD + pc] = (y6[i] - yp) * RFD;
+            if (lane == 0) sm.inn[12 + i] = sm.tau[i] - y6[i];                  // innovation y - y_pred, rows 12..17
+        }
+        if (lane < 12) sm.inn[lane] = a.meas[(size_t)inst * 12 + lane] - sm.xp[lane];
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    EPROF(3);
+    // ---- P_pred = (F P) F' + Q (:529), tile row by tile row ----
+#pragma unroll
+    for (int I = 0; I < 3; I++) {
+        double2 af[3];
+        double c1[3][2], c2[3][2];
+        load_tile_row(af, sm.Fm, I, q, t);
+        zero_acc(c1);
+        tile_row_product<true, TM_ALL>(c1, af, (TM_F >> (3 * I)) & 7u, sm.Am, q, t);          // (F P)[I][*]: B fragment of X Y = column fragment of Y
+        acc_to_frag(af, c1);
+        zero_acc(c2);
+        tile_row_product<false, TM_F>(c2, af, 7u, sm.Fm, q, t);
+        const double qd = (I == 0 && q < 6) ? QP : QV;                                          // Q(r, r), r = 8 I + q
+        if (q == 2 * t) c2[I][0] += qd;
+        if (q == 2 * t + 1) c2[I][1] += qd;
+        store_tile_row(sm.Pp, c2, I, q, t);
+    }
+    __syncwarp();
+    EPROF(2);
+    // ---- S = (H P_pred) H' (+ R, added when the rows are loaded for the inverse) (:535) ----
+#pragma unroll
+    for (int I = 0; I < 3; I++) {
+        double2 af[3];
+        double c1[3][2], c2[3][2];
+        load_tile_row(af, sm.Hm, I, q, t);
+        zero_acc(c1);
+        tile_row_product<true, TM_ALL>(c1, af, (TM_H >> (3 * I)) & 7u, sm.Pp, q, t);
+        acc_to_frag(af, c1);
+        zero_acc(c2);
+        tile_row_product<false, TM_H>(c2, af, 7u, sm.Hm, q, t);
+        store_tile_row(sm.Sm, c2, I, q, t);
+    }
+    __syncwarp();
+    EPROF(4);
     {
         // In-place Gauss-Jordan with partial pivoting.  Lane i < 18 keeps one row of the working matrix in registers.  Rows are
         // never moved: `myrow` is the row's position in the eliminated matrix, and a pivot exchange swaps positions.  Pivot =
@@ -251,7 +354,11 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
         const int li = own ? lane : 0;
         double ra[EN];
 #pragma unroll
-        for (int j = 0; j < EN; j++) ra[j] = sm.T2[li * LD + j] + (j == lane ? (DT * DT * DT * DT) / 4 : 0.0);
+        for (int j = 0; j < EN; j += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(sm.Sm + li * LD + j);
+            ra[j] = v.x + (j == lane ? QP : 0.0);
+            ra[j + 1] = v.y + (j + 1 == lane ? QP : 0.0);
+        }
         int myrow = own ? lane : 99;
         __syncwarp();
 #pragma unroll
@@ -290,45 +397,73 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
             }
             __syncwarp();
         }
-        // Si -> T2: the lane at position r holds row r of the inverse; working column c is inverse column (lane at position c)
+        // S^-1 -> Sm: the lane at position r holds row r of the inverse; working column c is inverse column (lane at position c)
 #pragma unroll
         for (int c = 0; c < EN; c++) {
             const int col = __ffs(__ballot_sync(FULL_MASK, myrow == c)) - 1;
-            if (own) sm.T2[myrow * LD + col] = ra[c];
+            if (own) sm.Sm[myrow * LD + col] = ra[c];
         }
     }
     __syncwarp();
-    // ---- Kal = Pp H' Si ----
-    mm18(sm.Pp, sm.Hm, sm.T1, true, lane);
-    double* const Kal = sm.Fm;                     // F is dead: its buffer takes the gain
-    mm18(sm.T1, sm.T2, Kal, false, lane);
-    // ---- esti_x = x_pred + Kal (y - y_pred) (:536) ----
+    EPROF(5);
+    // ---- K = (P_pred H') S^-1 -> Fm (F is dead);  A = I - K H -> Am (esti_P is dead) ----
+    double* const Kal = sm.Fm;
+#pragma unroll
+    for (int I = 0; I < 3; I++) {
+        double2 af[3];
+        double c1[3][2], c2[3][2];
+        load_tile_row(af, sm.Pp, I, q, t);
+        zero_acc(c1);
+        tile_row_product<false, TM_H>(c1, af, 7u, sm.Hm, q, t);
+        acc_to_frag(af, c1);
+        zero_acc(c2);
+        tile_row_product<true, TM_ALL>(c2, af, 7u, sm.Sm, q, t);
+        store_tile_row(Kal, c2, I, q, t);
+#pragma unroll
+        for (int K = 0; K < 3; K++) af[K] = make_double2(-c2[K][0], -c2[K][1]);
+        zero_acc(c1);
+        if (q == 2 * t) c1[I][0] = 1.0;
+        if (q == 2 * t + 1) c1[I][1] = 1.0;
+        tile_row_product<true, TM_HT>(c1, af, 7u, sm.Hm, q, t);
+        store_tile_row(sm.Am, c1, I, q, t);
+    }
+    __syncwarp();
+    EPROF(6);
+    // ---- esti_x = x_pred + K (y - y_pred) (:536) ----
     double exn = 0.0;
     if (lane < EN) {
-        double s = sm.xpv[lane];
-        for (int j = 0; j < EN; j++) s += Kal[lane * LD + j] * sm.vec[j];
+        double s = sm.xp[lane];
+#pragma unroll
+        for (int j = 0; j < EN; j++) s += Kal[lane * LD + j] * sm.inn[j];
         exn = s;
         ex[lane] = s;
     }
-    // ---- Joseph form (:537): P = (I - K H) Pp (I - K H)' + K R K' ----
-    mm18(Kal, sm.Hm, sm.T1, false, lane);
-    if (lane < EN)
-        for (int j = 0; j < EN; j++) sm.T1[lane * LD + j] = (j == lane ? 1.0 : 0.0) - sm.T1[lane * LD + j];
-    __syncwarp();
-    mm18(sm.T1, sm.Pp, sm.T2, false, lane);
-    mm18(sm.T2, sm.T1, sm.Hm, true, lane);          // Hm reused (H is dead): (I-KH) Pp (I-KH)'
-    mm18(Kal, Kal, sm.T2, true, lane);              // K K'
-    for (int idx = lane; idx < EN * EN; idx += 32) {
-        const int i = idx / EN, j = idx % EN;
-        eP[idx] = sm.Hm[i * LD + j] + sm.T2[i * LD + j] * ((DT * DT * DT * DT) / 4);
+    // ---- Joseph form (:537): P = (A P_pred) A' + K R K', R = QP I, straight to global memory ----
+#pragma unroll
+    for (int I = 0; I < 3; I++) {
+        double2 af[3], kf[3];
+        double c1[3][2], c2[3][2];
+        load_tile_row(af, sm.Am, I, q, t);
+        zero_acc(c1);
+        tile_row_product<true, TM_ALL>(c1, af, 7u, sm.Pp, q, t);
+        acc_to_frag(af, c1);
+        zero_acc(c2);
+        tile_row_product<false, TM_ALL>(c2, af, 7u, sm.Am, q, t);
+        load_tile_row(kf, Kal, I, q, t);
+#pragma unroll
+        for (int K = 0; K < 3; K++) { kf[K].x *= QP; kf[K].y *= QP; }
+        tile_row_product<false, TM_ALL>(c2, kf, 7u, Kal, q, t);
+        store_tile_row(eP, c2, I, q, t);
     }
+    EPROF(7);
     // ---- world-frame disturbance (:540-545) and OCP parameters (:324-355) ----
     const double e12 = __shfl_sync(FULL_MASK, exn, 12), e13 = __shfl_sync(FULL_MASK, exn, 13), e14 = __shfl_sync(FULL_MASK, exn, 14);
     const double e15 = __shfl_sync(FULL_MASK, exn, 15), e16 = __shfl_sync(FULL_MASK, exn, 16), e17 = __shfl_sync(FULL_MASK, exn, 17);
     if (lane == 0) {
         if (a.wf_dist) {
+            const double* ms = a.meas + (size_t)inst * 12;
             double s3, c3, s4, c4, s5, c5;
-            sincos(sm.xpv[EN + 3], &s3, &c3); sincos(sm.xpv[EN + 4], &s4, &c4); sincos(sm.xpv[EN + 5], &s5, &c5);
+            sincos(ms[3], &s3, &c3); sincos(ms[4], &s4, &c4); sincos(ms[5], &s5, &c5);
             double* wf = a.wf_dist + (size_t)inst * 6;
             wf[0] = (c5 * c4) * e12 + (-s5 * c3 + c5 * s4 * s3) * e13 + (s5 * s3 + c5 * c3 * s4) * e14;
             wf[1] = (s5 * c4) * e12 + (c5 * c3 + s3 * s4 * s5) * e13 + (-c5 * s3 + s4 * s5 * c3) * e14;
@@ -348,6 +483,17 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
             p[12] = -18.18; p[13] = -21.66; p[14] = -36.99; p[15] = -1.55;
         }
     }
+    EPROF(8);
+}
+
+// profile build: cycles per phase {load, rk4 + F, P_pred, h + H, S, inverse, gain, state + Joseph, store}; zeros otherwise
+void ekf_phase_cycles(unsigned long long* out, int reset)
+{
+    for (int i = 0; i < 12; i++) out[i] = 0;
+#ifdef BR2_PROFILE
+    cudaMemcpyFromSymbol(out, g_ekf_prof, sizeof(unsigned long long) * 12);
+    if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(g_ekf_prof, z, sizeof z); }
+#endif
 }
 
 void configure_ekf()

@@ -1030,6 +1030,16 @@ extern "C" int br2_batch_phase_cycles(br2_batch_solver* s, unsigned long long* o
     return BR2_OK;
 }
 
+extern "C" int br2_batch_ekf_phase_cycles(br2_batch_solver* s, unsigned long long* out12, int reset)
+{
+    if (!s || !out12) return fail(BR2_EINVAL, "null argument");
+    ON_DEVICE(s);
+    CK(cudaDeviceSynchronize());
+    ekf_phase_cycles(out12, reset);
+    CK(cudaGetLastError());
+    return BR2_OK;
+}
+
 // ---- nominal plant (closed-loop studies on the device) ----
 extern "C" int br2_plant_step_device(int batch, double* d_x, const double* d_u, const double* d_p, const double* d_dist,
                                      const double* d_wave_amp, const double* d_wave_tau0, int tick, double h,

@@ -96,6 +96,7 @@ struct EkfArgs {
 };
 void launch_ekf(const EkfArgs& a, cudaStream_t s);
 void configure_ekf();          // per-device function attributes
+void ekf_phase_cycles(unsigned long long* out12, int reset);   // -DBR2_PROFILE builds; zeros otherwise
 
 // RLS with variable forgetting factor (rls.cu; BLUEROV2_AMPC::RLSFF, bluerov2_ampc.cpp:731-1004), one thread per
 // (instance, axis); state layout RLS_* below == oracle ORC_RLS_STRIDE layout

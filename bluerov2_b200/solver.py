@@ -70,6 +70,7 @@ def load_library(path: str | None = None):
         "br2_batch_last_kernel_times": (C.c_int, [V, _D, _D]),
         "br2_batch_ipm_iterations_total": (C.c_longlong, [V, C.c_int]),
         "br2_batch_phase_cycles": (C.c_int, [V, V, C.c_int]),
+        "br2_batch_ekf_phase_cycles": (C.c_int, [V, V, C.c_int]),
         "br2_batch_nonzero_status_total": (C.c_longlong, [V, C.c_int]),
         "br2_batch_tick_device": (C.c_int, [V, V, V]),
         "br2_batch_tick_host": (C.c_int, [V, V]),
@@ -429,6 +430,14 @@ class BatchSolver:
         out = np.zeros(16, dtype=np.uint64)
         self._check(self._L.br2_batch_phase_cycles(self._h, out.ctypes.data_as(C.c_void_p), int(reset)))
         return {n: int(out[i]) for i, n in enumerate(self.PHASES)}
+
+    EKF_PHASES = ("load", "rk4_F", "P_pred", "h_H", "S", "inverse", "gain", "state_joseph", "store")
+
+    def ekf_phase_cycles(self, reset: bool = False) -> dict:
+        """SM cycles per phase of the EKF kernel summed over warps (library built with -DBR2_PROFILE; zeros otherwise)"""
+        out = np.zeros(12, dtype=np.uint64)
+        self._check(self._L.br2_batch_ekf_phase_cycles(self._h, out.ctypes.data_as(C.c_void_p), int(reset)))
+        return {n: int(out[i]) for i, n in enumerate(self.EKF_PHASES)}
 
     # -- EKF (BLUEROV2_DOB::EKF) -----------------------------------------------------------------------
     def ekf_reset(self):

@@ -178,6 +178,9 @@ BR2_API long long br2_batch_nonzero_status_total(br2_batch_solver *s, int reset)
  * [3] primal check, [4] costate check, [5] IPM start + roll-out, [6] IPM factor sweep, [7] affine forward sweep, [8] affine step
  * length / centring, [9] corrector backward sweep, [10] corrector forward sweep, [11] step lengths / update, [12] epilogue. */
 BR2_API int br2_batch_phase_cycles(br2_batch_solver *s, unsigned long long *out16, int reset);
+/* the same for the EKF kernel: [0] load, [1] RK4 + F, [2] P_pred, [3] h + H, [4] S, [5] inverse, [6] gain, [7] state + Joseph form,
+ * [8] store */
+BR2_API int br2_batch_ekf_phase_cycles(br2_batch_solver *s, unsigned long long *out12, int reset);
 
 /* Sharding across GPUs: instances are independent, so the global batch is cut into contiguous blocks, one solver
  * (one process, one GPU) per block, and there is no data-path collective inside the solve.  What a tick exchanges is its output:
