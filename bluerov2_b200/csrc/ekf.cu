@@ -172,6 +172,15 @@ __device__ __forceinline__ void store_tile_row(double* X, const double (&c)[3][2
             *reinterpret_cast<double2*>(X + (8 * I + q) * LD + 8 * J + 2 * t) = make_double2(c[J][0], c[J][1]);
 }
 
+// 1 / x to about an ulp without the division's special-case branch: hardware seed (~20 bits) and two Newton steps
+__device__ __forceinline__ double rcp_full(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    return fma(y, fma(-x, y, 1.0), y);
+}
+
 __device__ __forceinline__ void cp16(void* smem, const void* gmem)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -195,7 +204,7 @@ struct __align__(16) EkfSmem {
     double xp[EN];               // x_pred
     double inn[EN];              // innovation
     double tau[6], acc[6];       // K * thrusts, body acceleration
-    double prow[EN + 2];         // scaled pivot row of the Gauss-Jordan inverse
+    double prow[2][EN + 2];      // pivot row of the Gauss-Jordan inverse and the reciprocal of the pivot (double-buffered)
 };
 
 __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfArgs a)
@@ -343,13 +352,12 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
     __syncwarp();
     EPROF(4);
     {
-        // In-place Gauss-Jordan with partial pivoting.  Lane i < 18 keeps one row of the working matrix in registers.  Rows are
-        // never moved: `myrow` is the row's position in the eliminated matrix, and a pivot exchange swaps positions.  Pivot =
-        // largest |entry| of column c over positions >= c, lowest position on ties (what a sequential scan finds): three warp
-        // reductions on the value's bit pattern.  Column c of the working matrix is dead once it has been eliminated, so it
-        // takes the one column of the inverse that step c creates -- the column of the identity that belongs to the pivot
-        // row, i.e. inverse column (lane id of the pivot lane): the same multiplications as on the augmented [S | I], half
-        // the registers, shared-memory traffic and FMAs.
+        // In-place Gauss-Jordan inverse of S (symmetric positive definite: H P_pred H' + R with R > 0, so the diagonal pivots
+        // are safe; the reference's partial-pivot LU differs at rounding level).  Lane i < 18 keeps row i of the working matrix
+        // in registers; step c: lane c publishes its row and 1 / pivot (formed one step ahead, as soon as that entry is final,
+        // so the reciprocal's latency hides behind the rest of the elimination), every lane eliminates with g = row[c] / pivot.  Column c of the working matrix is dead once eliminated and takes the column of
+        // the inverse that the step creates: the same multiplications as on the augmented [S | I] in half the registers.
+        // The published row is double-buffered, so one warp barrier per step.
         const bool own = lane < EN;
         const int li = own ? lane : 0;
         double ra[EN];
@@ -359,49 +367,39 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
             ra[j] = v.x + (j == lane ? QP : 0.0);
             ra[j + 1] = v.y + (j + 1 == lane ? QP : 0.0);
         }
-        int myrow = own ? lane : 99;
-        __syncwarp();
+        double dn = rcp_full(ra[0]);          // reciprocal of the NEXT pivot, formed by its owner as soon as the entry is final
 #pragma unroll
         for (int c = 0; c < EN; c++) {
-            const double v = (own && myrow >= c) ? fabs(ra[c]) : -1.0;
-            const long long bits = __double_as_longlong(v);
-            const int hi = (int)(bits >> 32);
-            const int mhi = __reduce_max_sync(FULL_MASK, hi);
-            const unsigned lo = (hi == mhi) ? (unsigned)bits : 0u;
-            const unsigned mlo = __reduce_max_sync(FULL_MASK, lo);
-            const bool cand = (hi == mhi) && ((unsigned)bits == mlo);
-            const int pr = __reduce_min_sync(FULL_MASK, cand ? myrow : 99);      // position of the pivot row
-            const bool is_piv = own && (myrow == pr);
-            // exchange positions c <-> pr
-            if (is_piv) myrow = c;
-            else if (myrow == c) myrow = pr;
-            // pivot lane: scale its row (its own identity entry 1 becomes 1/pivot) and publish it
-            const double dinv = 1.0 / ra[c];
+            double* const pb = sm.prow[c & 1];
+            const bool is_piv = lane == c;
             if (is_piv) {
 #pragma unroll
-                for (int j = 0; j < EN; j++) ra[j] = (j == c) ? dinv : ra[j] * dinv;
+                for (int j = 0; j < EN; j += 2) *reinterpret_cast<double2*>(pb + j) = make_double2(ra[j], ra[j + 1]);
+                pb[EN] = dn;
 #pragma unroll
-                for (int j = 0; j < EN; j += 2) *reinterpret_cast<double2*>(sm.prow + j) = make_double2(ra[j], ra[j + 1]);
+                for (int j = 0; j < EN; j++) ra[j] = 0.0;
             }
             __syncwarp();
-            if (!is_piv) {
-                const double f = ra[c];
-                if (f != 0.0) {
+            double pr[EN];
 #pragma unroll
-                    for (int j = 0; j < EN; j += 2) {
-                        const double2 pa = *reinterpret_cast<const double2*>(sm.prow + j);
-                        ra[j] = (j == c) ? -(f * pa.x) : ra[j] - f * pa.x;
-                        ra[j + 1] = (j + 1 == c) ? -(f * pa.y) : ra[j + 1] - f * pa.y;
-                    }
-                }
+            for (int j = 0; j < EN; j += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(pb + j);
+                pr[j] = v.x; pr[j + 1] = v.y;
             }
-            __syncwarp();
+            const double dinv = pb[EN];
+            const double g = is_piv ? -dinv : ra[c] * dinv;          // pivot lane: row <- row / pivot, entry c <- 1 / pivot
+            if (c + 1 < EN) {
+                ra[c + 1] = fma(-g, pr[c + 1], ra[c + 1]);
+                dn = rcp_full(ra[c + 1]);
+            }
+#pragma unroll
+            for (int j = 0; j < EN; j++)
+                if (j != c + 1) ra[j] = (j == c) ? -g : fma(-g, pr[j], ra[j]);
         }
-        // S^-1 -> Sm: the lane at position r holds row r of the inverse; working column c is inverse column (lane at position c)
+        __syncwarp();
+        if (own) {
 #pragma unroll
-        for (int c = 0; c < EN; c++) {
-            const int col = __ffs(__ballot_sync(FULL_MASK, myrow == c)) - 1;
-            if (own) sm.Sm[myrow * LD + col] = ra[c];
+            for (int j = 0; j < EN; j += 2) *reinterpret_cast<double2*>(sm.Sm + lane * LD + j) = make_double2(ra[j], ra[j + 1]);
         }
     }
     __syncwarp();
@@ -459,11 +457,13 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
     // ---- world-frame disturbance (:540-545) and OCP parameters (:324-355) ----
     const double e12 = __shfl_sync(FULL_MASK, exn, 12), e13 = __shfl_sync(FULL_MASK, exn, 13), e14 = __shfl_sync(FULL_MASK, exn, 14);
     const double e15 = __shfl_sync(FULL_MASK, exn, 15), e16 = __shfl_sync(FULL_MASK, exn, 16), e17 = __shfl_sync(FULL_MASK, exn, 17);
+    double sa = 0.0, ca = 1.0;               // lanes 0..2: sin / cos of the measured roll, pitch, yaw
+    if (a.wf_dist && lane < 3) sincos(a.meas[(size_t)inst * 12 + 3 + lane], &sa, &ca);
+    const double s3 = __shfl_sync(FULL_MASK, sa, 0), c3 = __shfl_sync(FULL_MASK, ca, 0);
+    const double s4 = __shfl_sync(FULL_MASK, sa, 1), c4 = __shfl_sync(FULL_MASK, ca, 1);
+    const double s5 = __shfl_sync(FULL_MASK, sa, 2), c5 = __shfl_sync(FULL_MASK, ca, 2);
     if (lane == 0) {
         if (a.wf_dist) {
-            const double* ms = a.meas + (size_t)inst * 12;
-            double s3, c3, s4, c4, s5, c5;
-            sincos(ms[3], &s3, &c3); sincos(ms[4], &s4, &c4); sincos(ms[5], &s5, &c5);
             double* wf = a.wf_dist + (size_t)inst * 6;
             wf[0] = (c5 * c4) * e12 + (-s5 * c3 + c5 * s4 * s3) * e13 + (s5 * s3 + c5 * c3 * s4) * e14;
             wf[1] = (s5 * c4) * e12 + (c5 * c3 + s3 * s4 * s5) * e13 + (-c5 * s3 + s4 * s5 * c3) * e14;
