@@ -584,6 +584,8 @@ struct IpmUpd {
     double mu_sum = 0.0, res_max = 0.0;                         // out: complementarity sum and stationarity residual of the iterate
 };
 
+enum { PC_CHANGED = 1, PC_PINNED = 2, PC_ACTIVE = 4, PC_NAN = 8 };      // primal test of a candidate, see primal_check
+
 // Forward sweep.
 //   MODE 0: roll-out of the iterate            x+ = A x + B v + b,            x_0 = x0 - X_0   (reads V_V, writes V_X)
 //   MODE 1: affine Newton step                 ddu = -kff - K ddx, ddx+ = A ddx + B ddu, ddx_0 = 0 (writes V_DV; accumulates acc.ia, s2)
@@ -591,8 +593,12 @@ struct IpmUpd {
 //   MODE 3: corrector Newton step              like MODE 1; writes V_DX, V_DV and dlam -> V_CL / V_CU; accumulates the rest of acc
 // Z = [A|B] is read row-per-quad: lane (q,t) holds Z[q][4ki+t] and Z[8+q][4ki+t]; every product is 4 (3) local
 // FMAs and a reduction over the 4 lanes of a quad.  Returns max |b| in MODE 0 / 2.
+// MODE 2 with `ptest`: the roll-out also runs the primal test of the candidate on the fly -- the tests primal_check applies to an
+// input that is not pinned (outside the box beyond the tolerance / within 1e-3 of a bound / not finite) -- and returns the PC_*
+// flags in *ptest (PC_CHANGED = some input violates its box).  On the interior fast path, where nothing is pinned, this replaces
+// the separate pass over the candidate unless an input has to be pinned.
 template <int MODE>
-__device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr)
+__device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr, int* ptest = nullptr)
 {
     const int q = I.q, t = I.t, N = I.N;
     const bool lo = q < 4;                      // quad owns a second state row 8 + q (else: no row 12..15)
@@ -602,6 +608,8 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr)
     I.template begin<PARTS, false>();     // records in flight while the start values below are fetched
     double zr[3];                               // propagated vector, row layout: x[4ki + t]
     double bmax = 0.0;
+    bool pviol = false, pact = false, pfin = true;      // MODE 2 primal test (lanes q < 4 test input q)
+    const double lbq = I.a.lbu[q & 3], ubq = I.a.ubu[q & 3];
 #pragma unroll
     for (int ki = 0; ki < 3; ki++)
         zr[ki] = AFFINE ? I.a.x0[(size_t)I.inst * NX + 4 * ki + t] - I.Xlin[4 * ki + t] : 0.0;
@@ -622,6 +630,8 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr)
             z0[ki] = Gs[o0[ki]];
             z1[ki] = lo ? Gs[o1[ki]] : 0.0;
         }
+        double ulin = 0.0;
+        if (MODE == 2) ulin = I.Ulin[k * NU + (q & 3)];        // (for the primal test below; in flight during the gain product)
         if (q == 0 && MODE != 1) {              // (the state part of the affine step is never read)
 #pragma unroll
             for (int ki = 0; ki < 3; ki++) Vk[xoff + 4 * ki + t] = zr[ki];
@@ -640,6 +650,13 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr)
             const double uq = -Fs[MODE == 2 ? f_kc(q & 3, 12) : F_KFF + (q & 3)] - part;
             if (lo && t == 0) Vk[uoff + q] = uq;
             ut = shfl(uq, 4 * t);
+            if (MODE == 2) {
+                const double lb = lbq - ulin, ub = ubq - ulin;
+                const double tolu = 1e-12 * (ub - lb);
+                pviol |= !(uq >= lb - tolu) || !(uq <= ub + tolu);     // (written so that a NaN fails)
+                pact |= fmin(uq - lb, ub - uq) < 1e-3;
+                pfin &= isfinite(uq);
+            }
             if (NEWTON) {
                 // Side computation on the lanes that own input q (off the recursion's critical path).  Lane t handles ONE bound of
                 // input q: even t the lower (s = tl, lam = ll, ds = +du), odd t the upper (s = tu, lam = lu, ds = -du) -- the two are
@@ -688,12 +705,17 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr)
 #pragma unroll
         for (int ki = 0; ki < 3; ki++) I.V[(size_t)N * SREC + xoff + 4 * ki + t] = zr[ki];
     }
+    if (MODE == 2) pfin &= isfinite(zr[0]) && isfinite(zr[1]) && isfinite(zr[2]);   // NaN / Inf anywhere in the data reaches x_N
     __syncwarp();
     constexpr double SAFE = 1.0 + 2e-6;         // covers the error of rcp_approx
     if (MODE == 1) { acc->ia = SAFE * warp_max(ia); acc->s2 = warp_sum(c1); }
     if (MODE == 3) {
         acc->ia_p = warp_max(ia); acc->ia_d = SAFE * warp_max(ia_d); acc->dgmax = warp_max(dgmax);
         acc->a1 = warp_sum(c1); acc->a2 = warp_sum(c2); acc->a3 = warp_sum(c3);
+    }
+    if (MODE == 2 && ptest) {
+        *ptest = (__any_sync(FULL_MASK, lo && pviol) ? PC_CHANGED : 0) | (__any_sync(FULL_MASK, lo && pact) ? PC_ACTIVE : 0) |
+                 (__any_sync(FULL_MASK, lo && !pfin) ? PC_NAN : 0);
     }
     return AFFINE ? warp_max(bmax) : 0.0;
 }
@@ -1198,7 +1220,6 @@ __device__ bool costate_check(Inst& I)
 // the stage codes in a.aset are stale (first attempt of an instance without a guess): they count as 0 and are rewritten.
 // Returns bit 0: a code changed, bit 1: some input is pinned, bit 2: some input ends within 1e-3 of a bound (hint for the
 // next solve), bit 3: NaN / Inf in the candidate.
-enum { PC_CHANGED = 1, PC_PINNED = 2, PC_ACTIVE = 4, PC_NAN = 8 };
 __device__ int primal_check(Inst& I, bool fresh)
 {
     const SolveArgs& a = I.a;
@@ -1353,18 +1374,20 @@ __device__ __forceinline__ void finish_instance(Inst& I, const SolveOut& r, int*
     double* Xo = a.X + (size_t)inst * (N + 1) * NX;
     double* Uo = a.U + (size_t)inst * N * NU;
     bool finite = true;
-    bool act2 = false;
+    if (!solved) {
+        // (a candidate the fast paths accepted has been tested by its roll-out: forward_sweep<2>, PC_NAN)
+        bool act2 = false;
 #pragma unroll 5
-    for (int idx = lane; idx < nb; idx += 32) {
-        const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
-        finite &= isfinite(Vk[V_V + (idx & 3)]);
-        if (!solved) act2 |= fmin(Vk[V_TL + (idx & 3)], Vk[V_TU + (idx & 3)]) < 1e-3;
+        for (int idx = lane; idx < nb; idx += 32) {
+            const double* Vk = I.V + (size_t)(idx >> 2) * SREC;
+            finite &= isfinite(Vk[V_V + (idx & 3)]);
+            act2 |= fmin(Vk[V_TL + (idx & 3)], Vk[V_TU + (idx & 3)]) < 1e-3;
+        }
+        // the states are the exact roll-out of the inputs: NaN/Inf anywhere reaches x_N
+        if (lane < 12) finite &= isfinite(I.V[(size_t)N * SREC + V_X + lane]);
+        finite = __all_sync(FULL_MASK, finite);
+        active = __any_sync(FULL_MASK, act2);
     }
-    // the states are the exact roll-out of the inputs: NaN/Inf anywhere reaches x_N
-    if (lane < 12) finite &= isfinite(I.V[(size_t)N * SREC + V_X + lane]);
-    finite = __all_sync(FULL_MASK, finite);
-    if (!solved) active = act2;
-    active = __any_sync(FULL_MASK, active);
     if (a.active_set && !solved && status == 0) {
         // the interior-point solution's active set (slack ~ mu / lam at an active bound) is the next solve's guess
         for (int base = 0; base < nb; base += 32) {
@@ -1379,13 +1402,15 @@ __device__ __forceinline__ void finish_instance(Inst& I, const SolveOut& r, int*
             if (valid && (lane & 3) == 0) a.aset[(size_t)inst * N + (idx >> 2)] = code;
         }
     }
+    int pos = 0;
     if (lane == 0) {
         const int hard = (active || status != 0) ? 1 : 0;
         a.hint[inst] = hard;
-        // position in the next solve's visiting order: hard instances from the front, easy ones from the back
-        const int pos = hard ? atomicAdd(a.ctr + CTR_HARD, 1) : a.B - 1 - atomicAdd(a.ctr + CTR_EASY, 1);
-        order_next[pos] = inst;
+        // position in the next solve's visiting order: hard instances from the front, easy ones from the back (the counter's round
+        // trip overlaps the update of the iterate; the position is stored at the end)
+        pos = hard ? atomicAdd(a.ctr + CTR_HARD, 1) : a.B - 1 - atomicAdd(a.ctr + CTR_EASY, 1);
     }
+    double unew0 = 0.0;                         // lanes 0..3: the new U_0
     if (finite) {
         // X / U were last touched by the lineariser, before ~300 MB of stage records went through L2: without care this is
         // a chain of DRAM round trips (it was 11 % of the kernel).  The lines are prefetched into L2 ahead of the forward
@@ -1404,7 +1429,11 @@ __device__ __forceinline__ void finish_instance(Inst& I, const SolveOut& r, int*
                 const int idx = base + 32 * j;
                 // (a pinned input lands on its bound up to one rounding of (bound - U) + U, an accepted free input within 1e-12
                 // of the box width: clamp)
-                if (idx < nb) Uo[idx] = fmin(fmax(u[j] + d[j], a.lbu[idx & 3]), a.ubu[idx & 3]);
+                if (idx < nb) {
+                    const double un = fmin(fmax(u[j] + d[j], a.lbu[idx & 3]), a.ubu[idx & 3]);
+                    Uo[idx] = un;
+                    if (j == 0 && base == lane) unew0 = un;
+                }
             }
         }
         const int nxs = 12 * (N + 1);
@@ -1425,10 +1454,13 @@ __device__ __forceinline__ void finish_instance(Inst& I, const SolveOut& r, int*
         }
     } else {
         status = 1;
+        if (lane < 4) unew0 = Uo[lane];
     }
-    __syncwarp();
+    const double u00 = __shfl_sync(FULL_MASK, unew0, 0), u01 = __shfl_sync(FULL_MASK, unew0, 1);
+    const double u02 = __shfl_sync(FULL_MASK, unew0, 2), u03 = __shfl_sync(FULL_MASK, unew0, 3);
     if (lane == 0) {
-        double u0[4] = {Uo[0], Uo[1], Uo[2], Uo[3]};
+        order_next[pos] = inst;
+        double u0[4] = {u00, u01, u02, u03};
         double th[6];
         thrust_alloc(u0, th);
 #pragma unroll
@@ -1443,14 +1475,13 @@ __device__ __forceinline__ void finish_instance(Inst& I, const SolveOut& r, int*
         a.info[(size_t)inst * 4 + 1] = res_stat;
         a.info[(size_t)inst * 4 + 2] = bmax;
         a.info[(size_t)inst * 4 + 3] = stat_scale;
-    }
-    if (a.shard.world > 1 && lane == 0) {
-        // sharded batch: a second copy of the thrust vector goes into this rank's block of the LOCAL gather buffer (slot = tick
-        // parity); exchange_kernel ships the block to the peers while the next tick is already linearising
-        double* dst = a.shard.buf[a.shard.rank] + ((size_t)(a.ctr[CTR_TICK] & 1) * a.shard.world * a.B + (size_t)a.shard.rank * a.B + inst) * 6;
-        const double* src = a.thrust + (size_t)inst * 6;
+        if (a.shard.world > 1) {
+            // sharded batch: a second copy of the thrust vector goes into this rank's block of the LOCAL gather buffer (slot = tick
+            // parity); exchange_kernel ships the block to the peers while the next tick is already linearising
+            double* dst = a.shard.buf[a.shard.rank] + ((size_t)(a.ctr[CTR_TICK] & 1) * a.shard.world * a.B + (size_t)a.shard.rank * a.B + inst) * 6;
 #pragma unroll
-        for (int i = 0; i < 6; i++) dst[i] = src[i];
+            for (int i = 0; i < 6; i++) dst[i] = th[i];
+        }
     }
     __syncwarp();
 }
@@ -1483,6 +1514,9 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_PDAS_MINB) pdas_kernel(con
     int reserved = blockIdx.x * IPM_WARPS + (threadIdx.x >> 5);
     if (lane == 0) reserved = inst_of(reserved);
     bool have = true;
+    // (Tried: starting every other warp of a scheduler late by 15 .. 60 us so that one half of the resident warps rolls out while
+    // the other half factorises, on the theory that the lockstep phases fight for the fp64 pipe and then idle it together.  Every
+    // delay made the kernel slower, 0.217 -> 0.222 .. 0.265 ms at B = 4096: gpurun_out r2s)
     for (;;) {
         int inst = reserved;
         if (!have && lane == 0) {
@@ -1523,10 +1557,20 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_PDAS_MINB) pdas_kernel(con
                     }
                     have = true;
                 }
-                bmax = forward_sweep<2>(I);     // leaves (dx, du) in V_X, V_V
+                const bool fresh = att == 0 && !guess;      // nothing pinned, the stage codes in a.aset are stale
+                int fl = 0;
+                bmax = forward_sweep<2>(I, nullptr, &fl);   // leaves (dx, du) in V_X, V_V
                 PROF(PF_FWD_CL);
                 it = att + 1;
-                const int fl = primal_check(I, att == 0 && !guess);
+                if (fresh && !(fl & (PC_CHANGED | PC_NAN))) {
+                    // the candidate of the unconstrained LQR lies inside the box (tested by the roll-out itself): accepted below.  Near
+                    // a bound the next solve starts from a guess (hint = 1): leave it the empty active set
+                    if (fl & PC_ACTIVE) {
+                        for (int k = lane; k < N; k += 32) a.aset[(size_t)inst * N + k] = 0;
+                    }
+                } else {
+                    fl = primal_check(I, fresh) | (fl & PC_NAN);
+                }
                 PROF(PF_PRIMAL);
                 if (fl & PC_NAN) break;
                 active = (fl & PC_ACTIVE) != 0;
