@@ -325,6 +325,20 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b)
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
+// -DBR2_PROFILE_STAGE (with -DBR2_PROFILE): cycles of the segments of ONE factor-sweep stage into slots 5..12 (the interior-point
+// phases, unused on the fast path): scripts/stage_profile.py
+#if defined(BR2_PROFILE) && defined(BR2_PROFILE_STAGE)
+#define SPROF_START() long long sprof_t0 = clock64()
+#define SPROF(i)                                                                                          \
+    do {                                                                                                  \
+        const long long sprof_t1 = clock64();                                                             \
+        if (lane == 0 && a.prof) atomicAdd(a.prof + 5 + (i), (unsigned long long)(sprof_t1 - sprof_t0));  \
+        sprof_t0 = sprof_t1;                                                                              \
+    } while (0)
+#else
+#define SPROF_START()
+#define SPROF(i)
+#endif
 // reciprocal good to ~1e-7 relative: the hardware seed (MUFU.RCP64H, ~20 bits) and one Newton step
 __device__ __forceinline__ double rcp_approx(double x)
 {
@@ -803,8 +817,10 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             }
         }
     }
+    SPROF_START();
     for (int k = N - 1, it = 0; k >= 0; k--, it++) {
         const double* Ss = I.template advance<PARTS, true>(it);
+        SPROF(0);
         const double* Gs = Ss + S_G;
         const double* Vs = Ss + S_V;
         double* Fk = I.S + (size_t)k * SREC + S_F;
@@ -865,6 +881,7 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
         const double b12 = hi2 ? hx1 : h[1][1][0];
         // FS_ABS: vin = p+ (set at the end of the previous stage); the P+ b_k part of s+ = P+ b_k + p+ is formed AFTER the first
         // product as (Z'P+) b_k, off the path that leads into the DMMAs
+        SPROF(1);
         // ---- W' = Z' [P+ | v1 | v2] ----
         double w[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
         {
@@ -877,6 +894,7 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
                 dmma(w[m][0], z[2][m], b02); dmma(w[m][1], z[2][m], b1x);
             }
         }
+        SPROF(2);
         // ---- H = W' Z ----
         const double wx0 = shfl(w[0][1][1], src2), wx1 = shfl(w[1][1][1], src2);
         const double a02 = hi2 ? wx0 : w[0][1][0];
@@ -891,6 +909,7 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             dmma(h[0][n], w[0][0][1], z[1][n]); dmma(h[1][n], w[1][0][1], z[1][n]);
             dmma(h[0][n], a02, z[2][n]);        dmma(h[1][n], a12, z[2][n]);
         }
+        SPROF(3);
         // ---- the vector products sit in columns 12, 13 of W': lane (q,2) holds ([A|B]'v1)[8m+q], ([A|B]'v2)[8m+q] ----
         double* xch = I.sm.xch;
         double yg0, yg1;                         // (K'g)[q], (K'g)[8+q]
@@ -939,6 +958,7 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
                 if (!lo && t == 2) xch[64 + e] = gval;
             }
             __syncwarp();
+            SPROF(4);
             // ---- my entry of Lam^-1: cofactor (a, t) of the 4x4 at xch[48..63], a = q & 3 ----
             const double* LM = xch + 48;
             double cof;
@@ -959,6 +979,7 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             const double hx1 = lo ? xch[32 + lane] : (q == 4 ? xch[64 + t] : 0.0);
             // (xch is rewritten by the next stage only after the warp barrier at the top of its iteration)
             // ---- K = Lam^-1 [H_ux | g]: C layout, lane (a,t) holds K[a][8n+2t+j]; K[a][12] = kff[a] ----
+            SPROF(5);
             double kc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
             dmma(kc[0], linv, hx0);
             dmma(kc[1], linv, hx1);
@@ -971,6 +992,7 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             const double k00 = shfl(kc[0][0], sl), k01 = shfl(kc[0][1], sl), k10 = shfl(kc[1][0], sl), k11 = shfl(kc[1][1], sl);
             const double kb0 = (q & 1) ? k01 : k00, kb1 = (q & 1) ? k11 : k10;
             // ---- P = Q + H_xx - H_xu K; column 12 of the right tiles (lane t == 2, register 0) collects -(H_xu kff) = -K'g ----
+            SPROF(6);
             if (t == 2) { h[0][1][0] = 0.0; h[1][1][0] = 0.0; }
             dmma(h[0][0], -hx0, kb0); dmma(h[0][1], -hx0, kb1);
             dmma(h[1][0], -hx1, kb0); dmma(h[1][1], -hx1, kb1);
@@ -1078,6 +1100,7 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             const double i0 = shfl(pq0, 8 * t + 2), i1 = shfl(pq0, 8 * t + 6), i2 = shfl(pq1, (hi2 ? 4 * (2 * t - 3) : 8 * t) + 2);
             vin[0] = (q == 4) ? i0 : 0.0; vin[1] = (q == 4) ? i1 : 0.0; vin[2] = (q == 4) ? i2 : 0.0;
         }
+        SPROF(7);
     }
     __syncwarp();
     if (KIND == FS_IPM) { upd->mu_sum = warp_sum(mu_sum); upd->res_max = warp_max(res_max); upd->pending = false; }
