@@ -347,6 +347,15 @@ __device__ __forceinline__ double rcp_approx(double x)
     return y * fma(-x, y, 2.0);
 }
 
+// 1 / x to about an ulp without the division's special-case branch: the hardware seed and two Newton steps
+__device__ __forceinline__ double rcp_newton(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    return fma(y, fma(-x, y, 1.0), y);
+}
+
 __device__ __forceinline__ double warp_min(double v)
 {
 #pragma unroll
@@ -700,9 +709,11 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr, int* ptest = nul
                 }
             }
         }
-        double p0 = z0[3] * ut, p1 = z1[3] * ut;
+        // (the state part first: it does not wait for the gain product)
+        double p0 = z0[0] * zr[0], p1 = z1[0] * zr[0];
 #pragma unroll
-        for (int ki = 0; ki < 3; ki++) { p0 = fma(z0[ki], zr[ki], p0); p1 = fma(z1[ki], zr[ki], p1); }
+        for (int ki = 1; ki < 3; ki++) { p0 = fma(z0[ki], zr[ki], p0); p1 = fma(z1[ki], zr[ki], p1); }
+        p0 = fma(z0[3], ut, p0); p1 = fma(z1[3], ut, p1);
         p0 += shfl_x(p0, 1); p1 += shfl_x(p1, 1);
         p0 += shfl_x(p0, 2); p1 += shfl_x(p1, 2);
         if (AFFINE) {
@@ -924,8 +935,34 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             //   B fragment (row t, col 8n+q)           = H_xu[8n+q][t] = xch[32 n + lane]   (column 12: g[t])
             // The same xch values are the A fragment of H_xu in the Riccati update, whose column 12 (K's column 12 = kff) returns
             // K'g for free.
-            // Z's+ = Z'p+ + (Z'P+) b_k: lane (q,t) holds columns 2t, 2t+1, 8+2t, 9+2t of rows q / 8+q of Z'P+; the p+ part is
-            // column 12 of W', a register of lane (q,2) -- the only lane that needs at0 / at1 from here on
+            // ---- exchange: lanes t >= 2 hold H[8m+q][12 + c], c = 2(t-2) + j; rows 12..15 are Lam (R~ on its diagonal) ----
+            double e0 = h[0][1][0], e1 = h[0][1][1], f0 = h[1][1][0], f1 = h[1][1][1];
+            if (!lo && t == 2 + (e >> 1)) {
+                if (e & 1) f1 += rt; else f0 += rt;
+            }
+            double pa0 = 0.0, pa1 = 0.0;
+            bool pe = false;
+            if (PIN && code != 0) {
+                // inputs F pinned at ubar_F: their columns act on the states and on the free inputs through H[:, 12+F] ubar_F
+                // (b_k <- b_k + B_F ubar_F), then row / column F leave the system (identity row, g_F = -ubar_F => u_F = ubar_F)
+                const bool p0 = (code >> (2 * pc0)) & 3, p1 = (code >> (2 * pc1)) & 3;
+                pe = (code >> (2 * e)) & 3;
+                pa0 = (p0 ? e0 * ub0 : 0.0) + (p1 ? e1 * ub1 : 0.0);
+                pa1 = (p0 ? f0 * ub0 : 0.0) + (p1 ? f1 * ub1 : 0.0);
+                pa0 += shfl_x(pa0, 1); pa1 += shfl_x(pa1, 1);        // lanes 2 <-> 3 of the quad
+                if (p0) { e0 = 0.0; f0 = lo ? 0.0 : ((e == pc0) ? 1.0 : 0.0); }
+                if (p1) { e1 = 0.0; f1 = lo ? 0.0 : ((e == pc1) ? 1.0 : 0.0); }
+                if (!lo && pe) { f0 = (e == pc0) ? 1.0 : 0.0; f1 = (e == pc1) ? 1.0 : 0.0; }
+            }
+            if (t >= 2) {
+                *reinterpret_cast<double2*>(xch + q * 4 + 2 * (t - 2)) = make_double2(e0, e1);
+                *reinterpret_cast<double2*>(xch + (8 + q) * 4 + 2 * (t - 2)) = make_double2(f0, f1);
+            }
+            __syncwarp();
+            SPROF(4);
+            // ---- Z's+ = Z'p+ + (Z'P+) b_k, behind the barrier: only g (two segments further down) and p need it.  Lane (q,t) holds
+            // columns 2t, 2t+1, 8+2t, 9+2t of rows q / 8+q of Z'P+; the p+ part is column 12 of W', a register of lane (q,2) -- the only
+            // lane that needs at0 / at1 from here on ----
             const double bb0 = Gs[G_B_OFF + row0], bb1 = Gs[G_B_OFF + row1];
             const double bb2 = hi2 ? 0.0 : Gs[G_B_OFF + 8 + 2 * t], bb3 = hi2 ? 0.0 : Gs[G_B_OFF + 9 + 2 * t];
             double s0 = w[0][0][0] * bb0 + w[0][0][1] * bb1 + w[0][1][0] * bb2 + w[0][1][1] * bb3;
@@ -934,31 +971,10 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             s0 += shfl_x(s0, 2); s1 += shfl_x(s1, 2);
             at0 = w[0][1][0] + s0; at1 = w[1][1][0] + s1;            // meaningful on lanes t == 2
             double gval = gu_loc + at1;                               // lane (4+e, 2): g_e = rlin_e + (B's+)_e
-            // ---- exchange: lanes t >= 2 hold H[8m+q][12 + c], c = 2(t-2) + j; rows 12..15 are Lam (R~ on its diagonal) ----
-            double e0 = h[0][1][0], e1 = h[0][1][1], f0 = h[1][1][0], f1 = h[1][1][1];
-            if (!lo && t == 2 + (e >> 1)) {
-                if (e & 1) f1 += rt; else f0 += rt;
-            }
             if (PIN && code != 0) {
-                // inputs F pinned at ubar_F: their columns act on the states and on the free inputs through H[:, 12+F] ubar_F
-                // (b_k <- b_k + B_F ubar_F), then row / column F leave the system (identity row, g_F = -ubar_F => u_F = ubar_F)
-                const bool p0 = (code >> (2 * pc0)) & 3, p1 = (code >> (2 * pc1)) & 3, pe = (code >> (2 * e)) & 3;
-                double pa0 = (p0 ? e0 * ub0 : 0.0) + (p1 ? e1 * ub1 : 0.0);
-                double pa1 = (p0 ? f0 * ub0 : 0.0) + (p1 ? f1 * ub1 : 0.0);
-                pa0 += shfl_x(pa0, 1); pa1 += shfl_x(pa1, 1);        // lanes 2 <-> 3 of the quad
                 at0 += pa0;
                 if (lo) at1 += pa1; else gval = pe ? -ube : gval + pa1;
-                if (p0) { e0 = 0.0; f0 = lo ? 0.0 : ((e == pc0) ? 1.0 : 0.0); }
-                if (p1) { e1 = 0.0; f1 = lo ? 0.0 : ((e == pc1) ? 1.0 : 0.0); }
-                if (!lo && pe) { f0 = (e == pc0) ? 1.0 : 0.0; f1 = (e == pc1) ? 1.0 : 0.0; }
             }
-            if (t >= 2) {
-                *reinterpret_cast<double2*>(xch + q * 4 + 2 * (t - 2)) = make_double2(e0, e1);
-                *reinterpret_cast<double2*>(xch + (8 + q) * 4 + 2 * (t - 2)) = make_double2(f0, f1);
-                if (!lo && t == 2) xch[64 + e] = gval;
-            }
-            __syncwarp();
-            SPROF(4);
             // ---- my entry of Lam^-1: cofactor (a, t) of the 4x4 at xch[48..63], a = q & 3 ----
             const double* LM = xch + 48;
             double cof;
@@ -974,9 +990,12 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             det += shfl_x(det, 1);
             det += shfl_x(det, 2);
             ok &= (det > 0.0) && ((e != t) || (cof > 0.0));           // positive definite: det and the principal 3x3 minors
-            const double linv = lo ? cof * (1.0 / det) : 0.0;
+            const double linv = lo ? cof * rcp_newton(det) : 0.0;
             const double hx0 = xch[lane];
-            const double hx1 = lo ? xch[32 + lane] : (q == 4 ? xch[64 + t] : 0.0);
+            // g reaches its place in the B fragment (lane (4,t): g[t]) by one shuffle from lane (4+t, 2): the products behind it
+            // (Z's+ with its two reduction levels) stay off the path to the exchange barrier
+            const double gsh = shfl(gval, 4 * (4 + t) + 2);
+            const double hx1 = lo ? xch[32 + lane] : (q == 4 ? gsh : 0.0);
             // (xch is rewritten by the next stage only after the warp barrier at the top of its iteration)
             // ---- K = Lam^-1 [H_ux | g]: C layout, lane (a,t) holds K[a][8n+2t+j]; K[a][12] = kff[a] ----
             SPROF(5);
