@@ -70,8 +70,8 @@ __device__ __forceinline__ void ekf_f12(const double (&ang)[3], const double (&n
 {
     using namespace ekfc;
     double s3, c3, s4, c4, s5, c5;
-    sincos(ang[0], &s3, &c3); sincos(ang[1], &s4, &c4); sincos(ang[2], &s5, &c5);
-    const double r4 = 1.0 / c4;
+    br2_sincos(ang[0], &s3, &c3); br2_sincos(ang[1], &s4, &c4); br2_sincos(ang[2], &s5, &c5);      // (branch-free: fast_trig.h)
+    const double r4 = br2_rcp(c4);
     xd[0] = (c5 * c4) * nu[0] + (-s5 * c3 + c5 * s4 * s3) * nu[1] + (s5 * s3 + c5 * c3 * s4) * nu[2];
     xd[1] = (s5 * c4) * nu[0] + (c5 * c3 + s3 * s4 * s5) * nu[1] + (-c5 * s3 + s4 * s5 * c3) * nu[2];
     xd[2] = (-s4) * nu[0] + (c4 * s3) * nu[1] + (c4 * c3) * nu[2];
@@ -92,7 +92,7 @@ __device__ __forceinline__ void ekf_h6(double a3, double a4, const double (&nu)[
 {
     using namespace ekfc;
     double s3, c3, s4, c4;
-    sincos(a3, &s3, &c3); sincos(a4, &s4, &c4);
+    br2_sincos(a3, &s3, &c3); br2_sincos(a4, &s4, &c4);
     y[0] = M0 * acc[0] - M * nu[5] * nu[1] + M * nu[4] * nu[2] + EBUOY * s4 - dd[0] - c_Dl[0] * nu[0] - c_Dnl[0] * fabs(nu[0]) * nu[0];
     y[1] = M1 * acc[1] + M * nu[5] * nu[0] - M * nu[3] * nu[2] - EBUOY * c4 * s3 - dd[1] - c_Dl[1] * nu[1] - c_Dnl[1] * fabs(nu[1]) * nu[1];
     y[2] = M2 * acc[2] - M * nu[4] * nu[0] + M * nu[3] * nu[1] - EBUOY * c4 * c3 - dd[2] - c_Dl[2] * nu[2] - c_Dnl[2] * fabs(nu[2]) * nu[2];

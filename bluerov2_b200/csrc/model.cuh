@@ -15,6 +15,7 @@
 // (dist_x dist_y dist_z dist_psi | added mass x y z n | linear damping x y z n | quadratic damping x y z n).
 #pragma once
 #include <math.h>
+#include "fast_trig.h"
 
 #if defined(__CUDACC__)
 #define BR2_HD __host__ __device__ __forceinline__
@@ -55,18 +56,38 @@ struct ModelConst {
 
 struct Trig { double sphi, cphi, sth, cth, spsi, cpsi; };
 
+// (device: branch-free sincos / reciprocal, fast_trig.h -- the library routines' slow-path branches are scheduling barriers that keep
+// the three evaluations from overlapping; host -- the CasADi-ABI exports -- : libm)
 BR2_HD void trig_of(const double* x, Trig& t)
 {
+#ifdef __CUDA_ARCH__
+    br2_sincos(x[3], &t.sphi, &t.cphi);
+    br2_sincos(x[4], &t.sth, &t.cth);
+    br2_sincos(x[5], &t.spsi, &t.cpsi);
+#else
     sincos(x[3], &t.sphi, &t.cphi);
     sincos(x[4], &t.sth, &t.cth);
     sincos(x[5], &t.spsi, &t.cpsi);
+#endif
+}
+BR2_HD double inv_of(double x)
+{
+#ifdef __CUDA_ARCH__
+    return br2_rcp(x);
+#else
+    return 1.0 / x;
+#endif
 }
 
 // f(x,u,p)
 BR2_HD void ode(const double* x, const double* u, const ModelConst& c, const Trig& t, double* f)
 {
     const double uu = x[6], v = x[7], w = x[8], pp = x[9], q = x[10], r = x[11];
+#ifdef __CUDA_ARCH__
+    const double icth = inv_of(t.cth), tth = t.sth * icth;
+#else
     const double tth = t.sth / t.cth, icth = 1.0 / t.cth;
+#endif
     f[0] = (t.cpsi * t.cth) * uu + (-t.spsi * t.cphi + t.cpsi * t.sth * t.sphi) * v + (t.spsi * t.sphi + t.cpsi * t.cphi * t.sth) * w;
     f[1] = (t.spsi * t.cth) * uu + (t.cpsi * t.cphi + t.sphi * t.sth * t.spsi) * v + (-t.cpsi * t.sphi + t.sth * t.spsi * t.cphi) * w;
     f[2] = (-t.sth) * uu + (t.cth * t.sphi) * v + (t.cth * t.cphi) * w;
@@ -100,7 +121,7 @@ struct Jac {
 BR2_HD void jac_of(const double* x, const ModelConst& c, const Trig& t, Jac& J)
 {
     const double uu = x[6], v = x[7], w = x[8], pp = x[9], q = x[10], r = x[11];
-    const double icth = 1.0 / t.cth, tth = t.sth * icth, sec2 = icth * icth;
+    const double icth = inv_of(t.cth), tth = t.sth * icth, sec2 = icth * icth;
     // rows 0..2: d(R v_b)/d(angles, v_b) with R = Rz(psi) Ry(theta) Rx(phi).  The angle columns follow from R and
     // w = R v_b:  d/dphi = v R[:,2] - w R[:,1],  d/dtheta = (cos psi, sin psi, .) * w_z,  d/dpsi = (-w_y, w_x, 0).
     const double cs = t.cpsi * t.sth, ss = t.spsi * t.sth;
