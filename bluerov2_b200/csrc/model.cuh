@@ -39,6 +39,16 @@ constexpr double KT_YAW_U2 = (2.0 * 0.167 - 2.0 * 0.175) / RC;
 constexpr double KT_YAW_U4 = (2.0 * 0.167 + 2.0 * 0.175) / RC;
 constexpr double MZG = MASS * ZG * GRAV;
 
+// reciprocal: branch-free on the device (fast_trig.h), IEEE division on the host (the CasADi-ABI exports)
+BR2_HD double inv_of(double x)
+{
+#ifdef __CUDA_ARCH__
+    return br2_rcp(x);
+#else
+    return 1.0 / x;
+#endif
+}
+
 // Parameter-only constants, hoisted out of the RK stages.
 struct ModelConst {
     double imx, imy, imz, imn;       // 1/(m + added mass), 1/(Iz + added mass n)
@@ -47,7 +57,7 @@ struct ModelConst {
     double ju_surge, ju_sway, ju_heave, ju_yaw2, ju_yaw4;   // the 5 constant non-zeros of df/du
     BR2_HD void set(const double* p)
     {
-        imx = 1.0 / (MASS + p[4]); imy = 1.0 / (MASS + p[5]); imz = 1.0 / (MASS + p[6]); imn = 1.0 / (IZ + p[7]);
+        imx = inv_of(MASS + p[4]); imy = inv_of(MASS + p[5]); imz = inv_of(MASS + p[6]); imn = inv_of(IZ + p[7]);
         for (int i = 0; i < 4; i++) { dist[i] = p[i]; dl[i] = p[8 + i]; dnl[i] = p[12 + i]; }
         ju_surge = KT_SURGE * imx; ju_sway = KT_SWAY * imy; ju_heave = KT_HEAVE * imz;
         ju_yaw2 = KT_YAW_U2 * imn; ju_yaw4 = KT_YAW_U4 * imn;
@@ -70,14 +80,7 @@ BR2_HD void trig_of(const double* x, Trig& t)
     sincos(x[5], &t.spsi, &t.cpsi);
 #endif
 }
-BR2_HD double inv_of(double x)
-{
-#ifdef __CUDA_ARCH__
-    return br2_rcp(x);
-#else
-    return 1.0 / x;
-#endif
-}
+
 
 // f(x,u,p)
 BR2_HD void ode(const double* x, const double* u, const ModelConst& c, const Trig& t, double* f)

@@ -423,7 +423,7 @@ class BatchSolver:
         return int(self._L.br2_batch_nonzero_status_total(self._h, int(reset)))
 
     PHASES = ("factor_abs", "factor_as", "fwd_closed_loop", "primal_check", "costate_check", "ipm_start", "factor_ipm", "fwd_affine",
-              "e1_centring", "bwd_corrector", "fwd_corrector", "e2_update", "epilogue")
+              "e1_centring", "bwd_corrector", "fwd_corrector", "e2_update", "epilogue", "lin_state_trajectory", "lin_jacobians", "lin_sensitivities")
 
     def phase_cycles(self, reset: bool = False) -> dict:
         """SM cycles per phase of the IPM kernel summed over warps (library built with -DBR2_PROFILE; zeros otherwise)"""
