@@ -196,11 +196,19 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
         // housekeeping for the IPM kernel that follows in the stream: reset its work-queue counters, flip the order buffers
         if (a.housekeeping) tick_housekeeping(a.ctr);
     }
+#ifdef BR2_PROFILE
+    // cycles per phase of the lineariser into slots 13..15 (state trajectory / Jacobians / sensitivities + stores)
+    long long lprof_t0 = clock64();
+#define LPROF(i) do { const long long t_ = clock64(); if (lane == 0 && a.prof) atomicAdd(a.prof + 13 + (i), (unsigned long long)(t_ - lprof_t0)); lprof_t0 = clock64(); } while (0)
+#else
+#define LPROF(i) do { } while (0)
+#endif
     if (lane < LRND) {
         const int gs = base + lane;
         lin_phase_a(a, sm, lane, gs < total ? gs : total - 1, gs < total);
     }
     __syncwarp();
+    LPROF(0);
 
     const int tm = lane >> 3, l = lane & 7;
     // my two column slots: Z column, unit seed row (or none), Su column (or none)
@@ -233,6 +241,7 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
             jac_store(J, sm.jb + (i * 4 + s) * JREC);
         }
         __syncwarp();
+        LPROF(1);
         // ---- phase B: sensitivities, 4 stages per pass ----
 #pragma unroll 1
         for (int pp = 0; pp < LSUB / 4; pp++) {
@@ -295,6 +304,7 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
             }
         }
         __syncwarp();
+        LPROF(2);
     }
 }
 
