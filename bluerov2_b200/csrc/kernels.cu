@@ -64,7 +64,10 @@ namespace br2 {
 #endif
 constexpr int LRND = BR2_LIN_RND;              // stages per warp round (16 or 32)
 constexpr int LSUB = BR2_LIN_SUB;              // stages per Jacobian sub-round (4 or 8)
-constexpr int XT_F = 15;                       // x[3..11], sphi cphi sth cth spsi cpsi
+#ifndef BR2_LIN_TRIG
+#define BR2_LIN_TRIG 1                         // 1: phase A hands its sin / cos values to the Jacobian phase; 0: recomputed there (smaller xt)
+#endif
+constexpr int XT_F = BR2_LIN_TRIG ? 15 : 9;    // x[3..11] (, sphi cphi sth cth spsi cpsi)
 constexpr int XT_SSTRIDE = XT_F * LRND + 8;    // +8: RK-stage planes land on different banks for the J-phase reads
 constexpr int CS_F = 18;                       // imx imy imz imn | dl[4] | dnl[4] | ju[5] | h
 constexpr int JREC = 50;                       // 48 + 2: 128-bit accesses of consecutive records are conflict-free
@@ -142,8 +145,10 @@ __device__ __forceinline__ void lin_phase_a(const SolveArgs& a, LinSmem& sm, int
         double* xt = sm.xt + xt_idx(s, 0, slot);
 #pragma unroll
         for (int i = 0; i < 9; i++) xt[i * LRND] = xs[3 + i];
-        xt[9 * LRND] = t.sphi; xt[10 * LRND] = t.cphi; xt[11 * LRND] = t.sth;
-        xt[12 * LRND] = t.cth; xt[13 * LRND] = t.spsi; xt[14 * LRND] = t.cpsi;
+        if (BR2_LIN_TRIG) {
+            xt[9 * LRND] = t.sphi; xt[10 * LRND] = t.cphi; xt[11 * LRND] = t.sth;
+            xt[12 * LRND] = t.cth; xt[13 * LRND] = t.spsi; xt[14 * LRND] = t.cpsi;
+        }
         const double bw = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
         const double cn = (s == 2) ? 1.0 : 0.5;     // c_{s+1} of the classical tableau
 #pragma unroll
@@ -229,8 +234,12 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
 #pragma unroll
             for (int f = 0; f < 9; f++) xs[3 + f] = xt[f * LRND];
             Trig t;
-            t.sphi = xt[9 * LRND]; t.cphi = xt[10 * LRND]; t.sth = xt[11 * LRND];
-            t.cth = xt[12 * LRND]; t.spsi = xt[13 * LRND]; t.cpsi = xt[14 * LRND];
+            if (BR2_LIN_TRIG) {
+                t.sphi = xt[9 * LRND]; t.cphi = xt[10 * LRND]; t.sth = xt[11 * LRND];
+                t.cth = xt[12 * LRND]; t.spsi = xt[13 * LRND]; t.cpsi = xt[14 * LRND];
+            } else {
+                trig_of(xs, t);
+            }
             const double* cs = sm.cs + slot;
             ModelConst mc;
             mc.imx = cs[0 * LRND]; mc.imy = cs[1 * LRND]; mc.imz = cs[2 * LRND]; mc.imn = cs[3 * LRND];
