@@ -316,18 +316,35 @@ def roofline_of(B, N, iters_mean, t_qp, kernel):
             "formula": f"B*{BYTES_PER_STAGE_ITER}*N*mean_qp_iterations / t_qp"}
 
 
-def host_loop(torch, sol, w, xs, ls, W, K, explicit_yref, N):
+def host_loop(torch, sol, w, xs, ls, W, K, explicit_yref, N, announce_next=False, write_combined=False):
     """closed-loop ticks through the host API with pinned host buffers, a distinct input buffer per tick; wall clock around K ticks.
     explicit_yref: upload the (N+1) x 16 reference window per instance like ocp_nlp_cost_model_set("yref") x (N+1) does
     (bluerov2_dob.cpp:370-372) instead of naming a trajectory row"""
+    from bluerov2_b200 import solver as S_mod
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
     B = w["x0"].shape[0]
     h_x0 = [pin(a) for a in xs[:W + K]]
     h_p = pin(w["p"])
     out = (pin(np.empty((B, 4))), pin(np.empty((B, 6))), pin(np.empty((B,), dtype=np.int32)))
     if explicit_yref:
-        h_ref = [pin(traj.window_batch(w["traj"], l.astype(np.int64), N)) for l in ls[:W + K]]
-        call = lambda t: sol.tick(h_x0[t], p=h_p, yref=h_ref[t], out=out)   # noqa: E731
+        def window(l):
+            # write-combined pinned memory when asked for: the host only writes these 21.5 MB, the copy engine reads them
+            a = traj.window_batch(w["traj"], l.astype(np.int64), N)
+            if not write_combined:
+                return pin(a)
+            b = S_mod.pinned_empty(a.shape, np.float64, write_combined=True)
+            b[...] = a
+            return b
+        h_ref = [window(l) for l in ls[:W + K]]
+        if announce_next:
+            # the reference window of tick t + 1 is known while tick t runs (the measurement is not): registered before the call, it is
+            # uploaded beside tick t's kernels (br2_batch_set_next_yref_host)
+            def call(t):
+                if t + 1 < W + K:
+                    sol.set_next_yref(h_ref[t + 1])
+                return sol.tick(h_x0[t], p=h_p, yref=h_ref[t], out=out)
+        else:
+            call = lambda t: sol.tick(h_x0[t], p=h_p, yref=h_ref[t], out=out)   # noqa: E731
         h2d = (B * 12 + B * 16 + B * (N + 1) * 16) * 8
     else:
         h_ref = [pin(l.astype(np.int32)) for l in ls[:W + K]]
@@ -538,6 +555,7 @@ def run_ours(args):
     dt_exp = None
     if world == 1 and not args.quick:
         dt_exp, exp_ok, h2d_exp, _ = host_loop(torch, sol, w, xs, ls, W, min(K, 50), True, N)
+        dt_ann, ann_ok, _, _ = host_loop(torch, sol, w, xs, ls, W, min(K, 50), True, N, announce_next=True, write_combined=True)
 
     if distributed:
         tt = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=dev)
@@ -577,7 +595,13 @@ def run_ours(args):
             line["e2e_explicit_yref"] = {"value": B * Ke / dt_exp, "unit": UNIT, "ms_per_step": 1e3 * dt_exp / Ke, "h2d_bytes_per_step": h2d_exp,
                                          "d2h_bytes_per_step": d2h, "ok": exp_ok, "fraction_of_windowed_e2e": (B * Ke / dt_exp) / (B * K / dt_e2e),
                                          "api": "br2_batch_tick_host with the explicit (N+1) x 16 reference window per instance "
-                                                "(ocp_nlp_cost_model_set \"yref\" x (N+1), bluerov2_dob.cpp:370-372)"}
+                                                "(ocp_nlp_cost_model_set \"yref\" x (N+1), bluerov2_dob.cpp:370-372)",
+                                         "announced_one_tick_ahead": {
+                                             "value": B * Ke / dt_ann, "unit": UNIT, "ms_per_step": 1e3 * dt_ann / Ke, "ok": ann_ok,
+                                             "h2d_bytes_per_step": h2d_exp, "fraction_of_windowed_e2e": (B * Ke / dt_ann) / (B * K / dt_e2e),
+                                             "api": "the same call, the NEXT tick's window registered before it (br2_batch_set_next_yref_host): "
+                                                    "uploaded beside the running tick's kernels; x0 and p still go up when the tick is called; "
+                                                    "windows in write-combined pinned memory (br2_host_alloc)"}}
         if world == 1 and not args.no_cpu:
             r = cpu_leg(N, budget_s=args.cpu_budget, ticks_wanted=3 + 2, seed=0, pos_spread=args.pos_spread)
             tcpu = float(np.sum(r["times"][2:]))

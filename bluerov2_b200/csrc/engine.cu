@@ -67,6 +67,14 @@ struct br2_batch_solver {
     unsigned long long tick_stamp;
     int graphs_built, kernel_timing, tick_graph;
     cudaEvent_t ev_fork, ev_chunk[4];
+    // host path, explicit reference known one tick ahead (br2_batch_set_next_yref_host): the next window is uploaded on a stream of
+    // its own behind this tick's small uploads, into the one of two buffers the running tick does not read
+    double* d_yref_pf[2];
+    cudaStream_t stream_pf;
+    cudaEvent_t ev_pf, ev_up_p, ev_up_x0;   // prefetch complete; this tick's p / x0 uploads complete (external events inside the tick graph)
+    const double* next_yref;               // registered for the tick after the coming one
+    const double* pf_host;                 // host buffer whose window sits (or is arriving) in d_yref_pf[pf_slot]
+    int pf_slot;
     struct Miss { br2_tick_io io; int host; int xchg; unsigned gen; bool valid; } miss[4];   // the last keys that missed the graph cache
     unsigned miss_next;
 };
@@ -126,6 +134,12 @@ extern "C" int br2_batch_free(br2_batch_solver* s)
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev_mid) cudaEventDestroy(s->ev_mid);
+    if (s->ev_pf) cudaEventDestroy(s->ev_pf);
+    if (s->ev_up_p) cudaEventDestroy(s->ev_up_p);
+    if (s->ev_up_x0) cudaEventDestroy(s->ev_up_x0);
+    if (s->stream_pf) cudaStreamDestroy(s->stream_pf);
+    for (int i = 0; i < 2; i++)
+        if (s->d_yref_pf[i]) cudaFree(s->d_yref_pf[i]);
     if (s->ev_x0) cudaEventDestroy(s->ev_x0);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     for (auto e : s->ev_chunk)
@@ -219,6 +233,10 @@ extern "C" int br2_batch_create(br2_batch_solver** out, int batch, int N, const 
     CKF(cudaStreamCreateWithFlags(&s->stream_x0, cudaStreamNonBlocking));
     CKF(cudaEventCreateWithFlags(&s->ev_x0, cudaEventDisableTiming));
     CKF(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    CKF(cudaStreamCreateWithFlags(&s->stream_pf, cudaStreamNonBlocking));
+    CKF(cudaEventCreateWithFlags(&s->ev_pf, cudaEventDisableTiming));
+    CKF(cudaEventCreateWithFlags(&s->ev_up_p, cudaEventDisableTiming));
+    CKF(cudaEventCreateWithFlags(&s->ev_up_x0, cudaEventDisableTiming));
     for (auto& e : s->ev_chunk) CKF(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : s->ev_done) CKF(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& c : s->stream_c) CKF(cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking));
@@ -639,6 +657,7 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
     const int* d_lines = io.lines;
     bool forked = false, chunked = false;
     int nchunk = 4;
+    const int pf = host >= 2 ? host - 2 : -1;        // host path variant: the reference window is resident in d_yref_pf[pf]
     if (host) {
         if (io.ekf) {
             CK(cudaMemcpyAsync(s->d_x0, io.x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, st));
@@ -648,16 +667,17 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
         } else {
             CK(cudaMemcpyAsync(s->d_p, io.p, psz, cudaMemcpyHostToDevice, st));
             d_p = s->d_p;
+            if (io.yref) CK(cudaEventRecordWithFlags(s->ev_up_p, st, evflag));      // (the prefetch of the next reference queues behind this)
         }
         // explicit reference windows are the big upload (B x (N+1) x 16 doubles: 21.5 MB at B = 4096, N = 40 -- longer on the wire
         // than the kernels of the tick): for large batches without a filter it is cut into four instance ranges and
         // pipelined, range c being linearised and solved while ranges c+1.. are still in flight (below)
         static const int kChunks = [] { const char* e = getenv("BR2_YREF_CHUNKS"); int v = e ? atoi(e) : 4; return v == 1 || v == 2 || v == 4 ? v : 4; }();
         nchunk = kChunks;
-        chunked = !io.lines && !io.ekf && B >= 1024 && nchunk > 1;
+        chunked = !io.lines && !io.ekf && B >= 1024 && nchunk > 1 && pf < 0;
         if (io.lines) { CK(cudaMemcpyAsync(s->d_lines, io.lines, sizeof(int) * B, cudaMemcpyHostToDevice, st)); d_lines = s->d_lines; }
-        else if (!chunked) { CK(cudaMemcpyAsync(s->d_yref, io.yref, sizeof(double) * B * (N + 1) * NY, cudaMemcpyHostToDevice, st)); }
-        if (!io.lines) d_yref = s->d_yref;
+        else if (!chunked && pf < 0) { CK(cudaMemcpyAsync(s->d_yref, io.yref, sizeof(double) * B * (N + 1) * NY, cudaMemcpyHostToDevice, st)); }
+        if (!io.lines) d_yref = pf >= 0 ? s->d_yref_pf[pf] : s->d_yref;
         d_x0 = s->d_x0;
         if (!io.ekf) {
             // x0 rides a second stream past the lineariser: the QP kernel is its first reader
@@ -665,6 +685,7 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
             CK(cudaEventRecord(s->ev_fork, st));
             CK(cudaStreamWaitEvent(s->stream_x0, s->ev_fork, 0));
             CK(cudaMemcpyAsync(s->d_x0, io.x0, sizeof(double) * B * NX, cudaMemcpyHostToDevice, s->stream_x0));
+            if (io.yref) CK(cudaEventRecordWithFlags(s->ev_up_x0, s->stream_x0, evflag));     // (before ev_x0: that one joins the capture)
             CK(cudaEventRecord(s->ev_x0, s->stream_x0));
             forked = true;
             if (chunked) {
@@ -978,6 +999,28 @@ extern "C" int br2_batch_tick_device(br2_batch_solver* s, const br2_tick_io* io_
     return tick_issue(s, io, 0, st, xchg);                    // the caller is capturing its own graph, or graphs are switched off
 }
 
+// Pinned host memory for the host entry points.  write_combined != 0: write-combined pages -- the CPU writes them (streaming), only the
+// copy engine reads them, without snooping the CPU caches on the way: the choice for large per-tick inputs such as reference windows.
+extern "C" int br2_host_alloc(void** out, size_t bytes, int write_combined)
+{
+    if (!out || !bytes) return fail(BR2_EINVAL, "br2_host_alloc: bad argument");
+    CK(cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped | (write_combined ? cudaHostAllocWriteCombined : 0)));
+    return BR2_OK;
+}
+extern "C" int br2_host_free(void* p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return BR2_OK;
+}
+
+extern "C" int br2_batch_set_next_yref_host(br2_batch_solver* s, const double* yref_next)
+{
+    if (!s) return fail(BR2_EINVAL, "null solver");
+    if (yref_next && !pinned_host(yref_next)) return fail(BR2_EINVAL, "br2_batch_set_next_yref_host: the buffer must be pinned host memory");
+    s->next_yref = yref_next;
+    return BR2_OK;
+}
+
 extern "C" int br2_batch_tick_host(br2_batch_solver* s, const br2_tick_io* io_in)
 {
     int rc = tick_validate(s, io_in, 1, "br2_batch_tick_host");
@@ -993,16 +1036,36 @@ extern "C" int br2_batch_tick_host(br2_batch_solver* s, const br2_tick_io* io_in
     const bool pinned = pinned_host(io.x0) && pinned_host(io.yref) && pinned_host(io.p) && pinned_host(io.thrusts) && pinned_host(io.lines) &&
                         pinned_host(io.body_acc) && pinned_host(io.u0) && pinned_host(io.thrust) && pinned_host(io.wf_dist) && pinned_host(io.status);
     const int xchg = shard_pending(s);
+    // explicit reference registered one tick ahead (br2_batch_set_next_yref_host): it is resident (or arriving) in d_yref_pf[pf_slot]
+    const int pf = (io.yref && !io.ekf && io.yref == s->pf_host) ? s->pf_slot : -1;
+    const int variant = pf >= 0 ? 2 + pf : 1;
+    if (pf >= 0) CK(cudaStreamWaitEvent(s->stream, s->ev_pf, 0));
     if (pinned) {
-        rc = tick_graph_for(s, io, 1, xchg, &exec);
+        rc = tick_graph_for(s, io, variant, xchg, &exec);
         if (rc != BR2_OK) return rc;
     }
     s->ticks_host++;
     s->xchg_host += xchg;
     if (exec) { CK(cudaGraphLaunch(exec, s->stream)); s->timed = true; }
     else {
-        rc = tick_issue(s, io, 1, s->stream, xchg);
+        rc = tick_issue(s, io, variant, s->stream, xchg);
         if (rc != BR2_OK) return rc;
+    }
+    if (s->next_yref) {
+        // upload the NEXT tick's reference window now: behind this tick's own uploads on the wire (its p and x0 copies carry external
+        // events), beside its kernels, into the buffer this tick does not read
+        const int slot = pf >= 0 ? 1 - pf : 0;
+        const size_t bytes = sizeof(double) * (size_t)s->B * (s->N + 1) * NY;
+        if (!s->d_yref_pf[slot]) CK(cudaMalloc((void**)&s->d_yref_pf[slot], bytes));
+        if (!io.ekf) {
+            CK(cudaStreamWaitEvent(s->stream_pf, s->ev_up_p, 0));
+            CK(cudaStreamWaitEvent(s->stream_pf, s->ev_up_x0, 0));
+        }
+        CK(cudaMemcpyAsync(s->d_yref_pf[slot], s->next_yref, bytes, cudaMemcpyHostToDevice, s->stream_pf));
+        CK(cudaEventRecord(s->ev_pf, s->stream_pf));
+        s->pf_host = s->next_yref; s->pf_slot = slot; s->next_yref = nullptr;
+    } else if (pf >= 0) {
+        s->pf_host = nullptr;                      // consumed
     }
     CK(cudaStreamSynchronize(s->stream));
     return BR2_OK;

@@ -69,6 +69,9 @@ def load_library(path: str | None = None):
         "br2_batch_last_solve_time": (C.c_double, [V]),
         "br2_batch_last_kernel_times": (C.c_int, [V, _D, _D]),
         "br2_batch_ipm_iterations_total": (C.c_longlong, [V, C.c_int]),
+        "br2_batch_set_next_yref_host": (C.c_int, [V, V]),
+        "br2_host_alloc": (C.c_int, [V, C.c_size_t, C.c_int]),
+        "br2_host_free": (C.c_int, [V]),
         "br2_batch_phase_cycles": (C.c_int, [V, V, C.c_int]),
         "br2_batch_ekf_phase_cycles": (C.c_int, [V, V, C.c_int]),
         "br2_batch_nonzero_status_total": (C.c_longlong, [V, C.c_int]),
@@ -353,6 +356,18 @@ class BatchSolver:
         else:
             self._check(self._L.br2_batch_tick_host(self._h, ent[2]))
         return out
+
+    def set_next_yref(self, yref_next):
+        """host path, explicit reference: register the NEXT tick's (N+1) x 16 window (a pinned numpy array that stays untouched until that
+        tick has returned) before calling tick(); it is uploaded while the current tick computes (br2_batch_set_next_yref_host)"""
+        if yref_next is None:
+            self._check(self._L.br2_batch_set_next_yref_host(self._h, None))
+            return
+        if not (isinstance(yref_next, np.ndarray) and yref_next.dtype == np.float64 and yref_next.flags.c_contiguous
+                and yref_next.shape == (self.B, self.N + 1, NY)):
+            raise ValueError(f"set_next_yref(): contiguous float64 array of shape {(self.B, self.N + 1, NY)} expected")
+        self._next_yref_keepalive = yref_next
+        self._check(self._L.br2_batch_set_next_yref_host(self._h, C.c_void_p(yref_next.ctypes.data)))
 
     def graphs_built(self) -> int:
         return int(self._L.br2_batch_graphs_built(self._h))
@@ -647,3 +662,32 @@ class BatchEskf:
 
 def device_count() -> int:
     return int(load_library().br2_device_count())
+
+
+class _HostBlock:
+    """owner of one br2_host_alloc block (freed when the last array viewing it goes away)"""
+
+    def __init__(self, ptr, lib):
+        self.ptr, self._lib = ptr, lib
+
+    def __del__(self):
+        try:
+            self._lib.br2_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64, write_combined: bool = False) -> np.ndarray:
+    """numpy array in pinned host memory (br2_host_alloc) for the buffers of the host entry points.  write_combined: for large inputs the
+    CPU only writes (reference windows): the copy engine reads them without snooping the CPU caches; reading such an array back on the
+    CPU is slow."""
+    L = load_library()
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    rc = L.br2_host_alloc(C.byref(p), C.c_size_t(max(n, 1)), int(bool(write_combined)))
+    if rc != 0:
+        raise SolverError(f"bluerov2_b200 error {rc}: {L.br2_last_error().decode()}")
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    buf._owner = _HostBlock(p.value, L)                      # the ctypes buffer (kept alive by the array) keeps the block alive
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

@@ -18,6 +18,8 @@
 #ifndef BLUEROV2_B200_H_
 #define BLUEROV2_B200_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -82,10 +84,10 @@ BR2_API int br2_batch_set_bounds(br2_batch_solver *s, const double *lbu4, const 
 BR2_API int br2_batch_set_time_steps(br2_batch_solver *s, const double *time_steps);
 /* options: "qp_iter_max" (int, default 50), "qp_tol" (double, default 1e-12), "fast_path" (int, default 1: try the
  * unconstrained Riccati solution first and accept it when it lies inside the input box -- it is then the exact QP
- * minimiser; 0 = always run the interior-point iteration), "active_set_path" (int, default 0 = off, opt-in: an instance whose previous
- * solution had active input bounds is first solved as the LQR with that active set pinned; a costate sweep checks the KKT
- * conditions -- free inputs inside the box, multipliers of the pinned inputs of the right sign --, repairs the guess and
- * retries up to twice; accepted solutions are exact, everything else falls through to the interior-point iteration),
+ * minimiser; 0 = always run the interior-point iteration), "active_set_path" (int, default 1: when the unconstrained solution leaves the
+ * box, the primal-dual active-set iteration -- inputs outside the box pinned at the violated bound, the LQR re-solved, a costate
+ * sweep checking the multiplier signs of the pinned inputs, up to six solves -- ; accepted solutions satisfy the KKT conditions of
+ * the strictly convex QP, i.e. are its minimiser; everything else falls through to the interior-point iteration; 0 = off),
  * "ekf_model" (int, 0 = DOB filter, 1 = AMPC filter), "kernel_timing" (int, default 1: an event between the lineariser and the QP
  * kernels feeds br2_batch_last_kernel_times; 0 removes it from the tick), "tick_graph" (int, default 1: br2_batch_tick_* replay
  * cached CUDA graphs; 0 = always enqueue kernel by kernel) */
@@ -139,6 +141,17 @@ typedef struct br2_tick_io {
 } br2_tick_io;
 BR2_API int br2_batch_tick_device(br2_batch_solver *s, const br2_tick_io *io, void *stream);
 BR2_API int br2_batch_tick_host(br2_batch_solver *s, const br2_tick_io *io);
+/* Host path with an explicit reference (yref != NULL): a tracking controller knows its reference window one tick ahead -- the
+ * measurement it does not.  Registering the NEXT tick's window (pinned host memory, not to be touched until that tick has returned)
+ * before calling br2_batch_tick_host lets the library upload it while the current tick computes: behind the current tick's own
+ * small uploads on the wire, beside its kernels, into the one of two device buffers the current tick does not read.  The tick whose
+ * io.yref is that pointer then uploads only x0 / p; any other pointer takes the ordinary path.  The (N+1) x 16 doubles per instance
+ * are 21.5 MB per tick at B = 4096, N = 40 -- longer on PCIe than the tick's kernels. */
+BR2_API int br2_batch_set_next_yref_host(br2_batch_solver *s, const double *yref_next);
+/* Pinned (page-locked, mapped) host memory for the buffers of the _host entry points; write_combined != 0 for buffers the CPU only
+ * writes and the copy engine reads (large per-tick inputs): no cache snooping on the way to the device. */
+BR2_API int br2_host_alloc(void **out, size_t bytes, int write_combined);
+BR2_API int br2_host_free(void *p);
 /* number of CUDA graphs instantiated so far (diagnostic: stays constant in a steady closed loop) */
 BR2_API int br2_batch_graphs_built(const br2_batch_solver *s);
 /* host path: replays of a cached graph on NEW (pinned) input buffers -- its upload nodes are re-pointed, nothing is re-instantiated */

@@ -189,3 +189,41 @@ def test_host_graph_replayed_on_new_input_buffers(solver_mod):
         lines = lines + 1
     assert a.graphs_built() == 0 and b.graphs_built() == 1 and b.graph_updates() == T - 2
     a.close(); b.close()
+
+
+def test_reference_announced_one_tick_ahead_equals_plain_host_ticks(solver_mod):
+    """br2_batch_set_next_yref_host: the next tick's explicit reference window, registered before the call, is uploaded beside the running
+    tick's kernels into the buffer that tick does not read; the tick that names it uploads only x0 / p.  Same results as plain host
+    ticks, bit for bit, over a closed loop from a saturated start -- also when an announced window ends up NOT being the one passed
+    (ordinary path) and when nothing is announced in between"""
+    N, B, T = 10, 1024 + 5, 8
+    w = wl.tracking_batch(B, N, seed=12, pos_spread=1.0)
+    a = solver_mod.BatchSolver(B, N); a.set_iterate(w["X"], w["U"])
+    b = solver_mod.BatchSolver(B, N); b.set_iterate(w["X"], w["U"])
+    hp = _pin(w["p"])
+    outa = (_pin(np.zeros((B, 4))), _pin(np.zeros((B, 6))), _pin(np.zeros(B, dtype=np.int32)))
+    outb = (_pin(np.zeros((B, 4))), _pin(np.zeros((B, 6))), _pin(np.zeros(B, dtype=np.int32)))
+    lines = w["lines"].copy()
+    def wc(a):                                          # write-combined pinned memory from the library's own allocator
+        b = solver_mod.pinned_empty(a.shape, np.float64, write_combined=True)
+        b[...] = a
+        return b
+    refs = [wc(traj.window_batch(w["traj"], lines + t, N)) for t in range(T + 1)]       # the reference is a trajectory: known ahead
+    decoy = _pin(np.zeros((B, N + 1, 16)))
+    x0 = w["x0"].copy()
+    for t in range(T):
+        hx = _pin(x0)
+        ua, tha, sta = a.tick(hx, p=hp, yref=refs[t], out=outa)
+        if t == 4:
+            b.set_next_yref(decoy)                     # announced, but the next tick passes another window: ordinary upload
+        elif t != 5:
+            b.set_next_yref(refs[t + 1])               # (t == 5: nothing announced; tick 6 takes the ordinary path)
+        ub, thb, stb = b.tick(hx, p=hp, yref=refs[t], out=outb)
+        assert np.array_equal(ua, ub) and np.array_equal(tha, thb) and np.array_equal(sta, stb), t
+        assert (sta == 0).all()
+        x0 = wl.plant_step(x0, ua.copy(), w["p"], 0.05)
+    Xa, Ua = a.get_iterate(); Xb, Ub = b.get_iterate()
+    assert np.array_equal(Xa, Xb) and np.array_equal(Ua, Ub)
+    with pytest.raises(solver_mod.SolverError):
+        b.set_next_yref(np.zeros((B, N + 1, 16)))      # pageable memory is refused
+    a.close(); b.close()
