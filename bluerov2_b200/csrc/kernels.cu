@@ -366,6 +366,10 @@ __device__ __forceinline__ double rcp_approx(double x)
     return y * fma(-x, y, 2.0);
 }
 
+// slot of entry (a, c), a <= c, of the symmetric 4x4 Lam^-1 in the interior-point F record (upper triangle, row by row: 10 doubles
+// from F_L_OFF, where round 1 kept the Cholesky factor and its inverse diagonal)
+__device__ __forceinline__ int linv_slot(int a, int c) { return 4 * a + c - (a * (a + 1)) / 2; }
+
 // 1 / x to about an ulp without the division's special-case branch: the hardware seed and two Newton steps
 __device__ __forceinline__ double rcp_newton(double x)
 {
@@ -507,85 +511,6 @@ __device__ __forceinline__ void prefetch_iterate(const Inst& I)
     for (int o = I.lane * 128; o < ubytes + 128; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ub + (o < ubytes ? o : ubytes - 8)));
 }
 
-// 4x4 Cholesky of the symmetric matrix with lower entries m (row-major lower: 00 10 11 20 21 22 30 31 32 33).
-// Outputs strictly-lower entries and reciprocal diagonal.  Returns false when a pivot is not positive.
-struct Chol4 { double l10, l20, l21, l30, l31, l32, i0, i1, i2, i3; };
-__device__ __forceinline__ bool chol4(const double* m, Chol4& L)
-{
-    bool ok = true;
-    double d = m[0];
-    ok &= d > 0.0; L.i0 = rsqrt(d);
-    L.l10 = m[1] * L.i0; L.l20 = m[3] * L.i0; L.l30 = m[6] * L.i0;
-    d = m[2] - L.l10 * L.l10;
-    ok &= d > 0.0; L.i1 = rsqrt(d);
-    L.l21 = (m[4] - L.l20 * L.l10) * L.i1; L.l31 = (m[7] - L.l30 * L.l10) * L.i1;
-    d = m[5] - L.l20 * L.l20 - L.l21 * L.l21;
-    ok &= d > 0.0; L.i2 = rsqrt(d);
-    L.l32 = (m[8] - L.l30 * L.l20 - L.l31 * L.l21) * L.i2;
-    d = m[9] - L.l30 * L.l30 - L.l31 * L.l31 - L.l32 * L.l32;
-    ok &= d > 0.0; L.i3 = rsqrt(d);
-    return ok;
-}
-// v <- L^-1 v
-__device__ __forceinline__ void chol4_fwd(const Chol4& L, double* v)
-{
-    v[0] = v[0] * L.i0;
-    v[1] = (v[1] - L.l10 * v[0]) * L.i1;
-    v[2] = (v[2] - L.l20 * v[0] - L.l21 * v[1]) * L.i2;
-    v[3] = (v[3] - L.l30 * v[0] - L.l31 * v[1] - L.l32 * v[2]) * L.i3;
-}
-// v <- L^-T v
-__device__ __forceinline__ void chol4_bwd(const Chol4& L, double* v)
-{
-    v[3] = v[3] * L.i3;
-    v[2] = (v[2] - L.l32 * v[3]) * L.i2;
-    v[1] = (v[1] - L.l21 * v[2] - L.l31 * v[3]) * L.i1;
-    v[0] = (v[0] - L.l10 * v[1] - L.l20 * v[2] - L.l30 * v[3]) * L.i0;
-}
-__device__ __forceinline__ void load_chol(const double* Fk, Chol4& L)
-{
-    L.l10 = Fk[F_L_OFF + 0]; L.l20 = Fk[F_L_OFF + 1]; L.l21 = Fk[F_L_OFF + 2];
-    L.l30 = Fk[F_L_OFF + 3]; L.l31 = Fk[F_L_OFF + 4]; L.l32 = Fk[F_L_OFF + 5];
-    L.i0 = Fk[F_ID_OFF + 0]; L.i1 = Fk[F_ID_OFF + 1]; L.i2 = Fk[F_ID_OFF + 2]; L.i3 = Fk[F_ID_OFF + 3];
-}
-
-// Explicit inverse of the symmetric positive definite 4x4 matrix with lower entries m (same packing as chol4) by
-// 2x2 sub-determinants: no dependent rsqrt/divide chain (one reciprocal), used where Lam is well conditioned (the
-// unconstrained LQR of the fast path: Lam = R + B'PB).  Returns false unless all leading minors are positive.
-struct Inv4 { double b00, b10, b11, b20, b21, b22, b30, b31, b32, b33, id; };   // adjugate (unscaled) and 1 / det
-__device__ __forceinline__ bool inv4(const double* m, Inv4& B)
-{
-    const double m00 = m[0], m10 = m[1], m11 = m[2], m20 = m[3], m21 = m[4], m22 = m[5], m30 = m[6], m31 = m[7],
-                 m32 = m[8], m33 = m[9];
-    const double s0 = m00 * m11 - m10 * m10, s1 = m00 * m21 - m10 * m20, s2 = m00 * m31 - m10 * m30;
-    const double s3 = m10 * m21 - m11 * m20, s4 = m10 * m31 - m11 * m30, s5 = m20 * m31 - m21 * m30;
-    const double c5 = m22 * m33 - m32 * m32, c4 = m21 * m33 - m31 * m32, c3 = m21 * m32 - m31 * m22;
-    const double c2 = m20 * m33 - m30 * m32, c1 = m20 * m32 - m30 * m22, c0 = m20 * m31 - m30 * m21;
-    const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
-    const double minor3 = m20 * s3 - m21 * s1 + m22 * s0;
-    const bool ok = (m00 > 0.0) && (s0 > 0.0) && (minor3 > 0.0) && (det > 0.0);
-    B.id = 1.0 / det;
-    B.b00 = m11 * c5 - m21 * c4 + m31 * c3;
-    B.b10 = -m10 * c5 + m20 * c4 - m30 * c3;
-    B.b11 = m00 * c5 - m20 * c2 + m30 * c1;
-    B.b20 = m31 * s5 - m32 * s4 + m33 * s3;
-    B.b21 = -m30 * s5 + m32 * s2 - m33 * s1;
-    B.b22 = m30 * s4 - m31 * s2 + m33 * s0;
-    B.b30 = -m21 * s5 + m22 * s4 - m32 * s3;
-    B.b31 = m20 * s5 - m22 * s2 + m32 * s1;
-    B.b32 = -m20 * s4 + m21 * s2 - m32 * s0;
-    B.b33 = minor3;
-    return ok;
-}
-// o <- (adj v) / det: the adjugate products run while the reciprocal of the determinant is still in flight
-__device__ __forceinline__ void inv4_apply(const Inv4& B, const double* v, double* o)
-{
-    o[0] = (B.b00 * v[0] + B.b10 * v[1] + B.b20 * v[2] + B.b30 * v[3]) * B.id;
-    o[1] = (B.b10 * v[0] + B.b11 * v[1] + B.b21 * v[2] + B.b31 * v[3]) * B.id;
-    o[2] = (B.b20 * v[0] + B.b21 * v[1] + B.b22 * v[2] + B.b32 * v[3]) * B.id;
-    o[3] = (B.b30 * v[0] + B.b31 * v[1] + B.b32 * v[2] + B.b33 * v[3]) * B.id;
-}
-
 // E0: cold start of the IPM iterate (qp_solver_warm_start 0): du = 0 pushed strictly inside the box, slacks
 // exactly consistent, lam = mu0 / t.
 __device__ void ipm_init(Inst& I)
@@ -712,7 +637,7 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr, int* ptest = nul
                     if (lo) ia = fmax(ia, fmax(-r, 1.0 + r));
                     if (lo && t < 2) c1 = fma(-l_b * (1.0 + r), ds, c1);                 // S2 += dlam ds
                 } else {
-                    const double is = 1.0 / s_b, c_b = Vs[V_CL + fo];
+                    const double is = rcp_newton(s_b), c_b = Vs[V_CL + fo];       // (branch-free: a division's special-case branch is a scheduling barrier)
                     const double dl = fma(fma(-l_b, ds, c_b), is, -l_b);                 // dlam = (c - lam ds) / s - lam
                     double piece = (t & 1) ? -(dl + l_b) : (dl + l_b);                     // dgu = -gu + (dll + ll) - (dlu + lu)
                     piece += shfl_x(piece, 1);
@@ -767,7 +692,7 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr, int* ptest = nul
 // Backward factor sweep: Riccati factorisation of the stage LQR plus the vector recursion(s) that share it.
 //   W' = Z' [P+ | v1 | v2]    (16 x 14, DMMA; the vectors ride in the otherwise padded columns 12, 13)
 //   H  = W'[:, 0:12] Z        (16 x 16, DMMA)  = [A|B]' P+ [A|B]
-//   Lam = H_uu + R~ = L L',  Y = L^-1 H_ux,  K = L^-T Y,  P = Q + H_xx - Y'Y (DMMA, k = 4)
+//   Lam = H_uu + R~,  Lam^-1 entry by entry (one 3x3 cofactor per lane),  K = Lam^-1 [H_ux | g] (DMMA),  P = Q + H_xx - H_xu K (DMMA, k = 4)
 // KIND = FS_IPM  (interior-point iteration, residual form around the iterate): R~ = R + lam_l/t_l + lam_u/t_u,
 //                 v1 = pi+ (costate of the iterate -> reduced gradient gu), v2 = p+ (predictor rhs gh = gu).
 // KIND = FS_ABS  (interior fast path, absolute form of the unconstrained LQR): R~ = R, v1 = s+ = P+ b_k + p+,
@@ -780,7 +705,7 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr, int* ptest = nul
 //   - the C registers of P+ (read through its symmetry, P[k][c] = P[c][k]) are the B fragments of the first product,
 //   - and ONE gather of Z, z[kt][m] = Z[row(kt,t)][8m+q], is the A fragment of Z' (first product) and the B fragment
 //     of Z (second product).
-// Returns false if a Cholesky pivot failed.
+// Returns false unless every Lam is positive definite (determinant and principal minors).
 enum { FS_IPM = 0, FS_ABS = 1, FS_AS = 2 };    // FS_AS: FS_ABS with the inputs of the guessed active set pinned at their bounds
 
 template <int KIND>
@@ -901,7 +826,7 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             // residual form around the iterate (x, v):  Q (x + X - xref) = Q x + qlin,  R (v + U - uref) = R v + rlin
             qx0 = fma(qd0, xq0, qx0);
             if (lo) qx1 = fma(qd1, xq1, qx1);
-            rt += ll_e / tl + lu_e / tu;
+            rt += ll_e * rcp_newton(tl) + lu_e * rcp_newton(tu);
             gu_loc = fma(rd, v, gu_loc);
             cmp_e = ll_e * tl + lu_e * tu;
         }
@@ -1036,87 +961,67 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
             dmma(h[1][0], -hx1, kb0); dmma(h[1][1], -hx1, kb1);
             yg0 = -h[0][1][0]; yg1 = -h[1][1][0];                     // meaningful on lanes t == 2
         } else {
+            // ================= interior-point stage: the same distributed inverse as the fast paths =================
+            // (Round 1 / early round 2 factorised Lam redundantly on every lane -- Cholesky, five triangular solves, Y'Y update: a long
+            // dependent chain of sqrt / divide per stage.)  Lane (a, t) forms one entry of Lam^-1 as a cofactor, K = Lam^-1 [H_ux | g]
+            // and the update P = Q + H_xx - H_xu K are DMMAs, K'g falls out of the update's column 12.  The F record keeps the layout
+            // the vector sweeps of the iteration read: K' at (4 ki + t) * 4 + a, kff, and -- for the corrector's second right-hand
+            // side -- the upper triangle of Lam^-1 where the Cholesky factor used to be.
             at0 = shfl(w[0][1][0], qb | 2); at1 = shfl(w[1][1][0], qb | 2);
             bt0 = shfl(w[0][1][1], qb | 2); bt1 = shfl(w[1][1][1], qb | 2);
             const double gu = gu_loc + at1;          // quads 4..7: R du + r + B'pi+
             const double gval = gu + bt1;            // predictor rhs: gh = gu
-            // ---- Lam = B'P+B + R~ : add the diagonal where the diagonal element lives, then broadcast ----
+            double e0 = h[0][1][0], e1 = h[0][1][1], f0 = h[1][1][0], f1 = h[1][1][1];
             if (!lo && t == 2 + (e >> 1)) {
-                if (e & 1) h[1][1][1] += rt; else h[1][1][0] += rt;
+                if (e & 1) f1 += rt; else f0 += rt;
             }
             if (t >= 2) {
-                *reinterpret_cast<double2*>(xch + q * 4 + 2 * (t - 2)) = make_double2(h[0][1][0], h[0][1][1]);
-                *reinterpret_cast<double2*>(xch + (8 + q) * 4 + 2 * (t - 2)) = make_double2(h[1][1][0], h[1][1][1]);
-                if (!lo && t == 2) xch[64 + e] = gval;
+                *reinterpret_cast<double2*>(xch + q * 4 + 2 * (t - 2)) = make_double2(e0, e1);
+                *reinterpret_cast<double2*>(xch + (8 + q) * 4 + 2 * (t - 2)) = make_double2(f0, f1);
             }
             __syncwarp();
-            double m10[10];
-            {
-                const double2 r1 = *reinterpret_cast<const double2*>(xch + 13 * 4);
-                const double2 r2a = *reinterpret_cast<const double2*>(xch + 14 * 4), r3a = *reinterpret_cast<const double2*>(xch + 15 * 4);
-                const double2 r3b = *reinterpret_cast<const double2*>(xch + 15 * 4 + 2);
-                m10[0] = xch[12 * 4];
-                m10[1] = r1.x; m10[2] = r1.y;
-                m10[3] = r2a.x; m10[4] = r2a.y; m10[5] = xch[14 * 4 + 2];
-                m10[6] = r3a.x; m10[7] = r3a.y; m10[8] = r3b.x; m10[9] = r3b.y;
-            }
-            // ---- rows q and 8+q of H_xu ----
-            double y0[4], y1[4], gt[4];
-            {
-                const double2 a0 = *reinterpret_cast<const double2*>(xch + q * 4), a1 = *reinterpret_cast<const double2*>(xch + q * 4 + 2);
-                const double2 b0 = *reinterpret_cast<const double2*>(xch + (8 + q) * 4), b1 = *reinterpret_cast<const double2*>(xch + (8 + q) * 4 + 2);
-                const double2 g0 = *reinterpret_cast<const double2*>(xch + 64), g1 = *reinterpret_cast<const double2*>(xch + 66);
-                y0[0] = a0.x; y0[1] = a0.y; y0[2] = a1.x; y0[3] = a1.y;
-                y1[0] = b0.x; y1[1] = b0.y; y1[2] = b1.x; y1[3] = b1.y;
-                gt[0] = g0.x; gt[1] = g0.y; gt[2] = g1.x; gt[3] = g1.y;       // g on every lane
-            }
             if (!lo && t == 2) {
                 Vk[V_GU + e] = gu;
                 mu_sum += cmp_e;
                 res_max = fmax(res_max, fabs(gu - ll_e + lu_e));
             }
-            Chol4 L;
-            ok &= chol4(m10, L);
-            chol4_fwd(L, y0);                    // Y[:, q]
-            chol4_fwd(L, y1);                    // Y[:, 8+q]   (garbage in quads 4..7, masked below)
-            // ---- feedback gain columns K[:, q], K[:, 8+q] -> F record ----
+            const double* LM = xch + 48;
+            double cof;
             {
-                double kc[4] = {y0[0], y0[1], y0[2], y0[3]};
-                chol4_bwd(L, kc);
-                if (t == 0) {
-                    *reinterpret_cast<double2*>(Fk + q * 4) = make_double2(kc[0], kc[1]);
-                    *reinterpret_cast<double2*>(Fk + q * 4 + 2) = make_double2(kc[2], kc[3]);
-                }
-                double kd[4] = {y1[0], y1[1], y1[2], y1[3]};
-                chol4_bwd(L, kd);
-                if (t == 1 && lo) {
-                    *reinterpret_cast<double2*>(Fk + (8 + q) * 4) = make_double2(kd[0], kd[1]);
-                    *reinterpret_cast<double2*>(Fk + (8 + q) * 4 + 2) = make_double2(kd[2], kd[3]);
-                }
+                const double m00 = LM[ro0 + co0], m01 = LM[ro0 + co1], m02 = LM[ro0 + co2];
+                const double m10_ = LM[ro1 + co0], m11 = LM[ro1 + co1], m12 = LM[ro1 + co2];
+                const double m20 = LM[ro2 + co0], m21 = LM[ro2 + co1], m22 = LM[ro2 + co2];
+                const double d0 = m11 * m22 - m12 * m21, d1 = m10_ * m22 - m12 * m20, d2 = m10_ * m21 - m11 * m20;
+                cof = m00 * d0 - m01 * d1 + m02 * d2;
+                if ((e + t) & 1) cof = -cof;
             }
-            if (lane == 2) {                     // the corrector's backward sweep re-solves with Lam
-                Fk[F_L_OFF + 0] = L.l10; Fk[F_L_OFF + 1] = L.l20; Fk[F_L_OFF + 2] = L.l21;
-                Fk[F_L_OFF + 3] = L.l30; Fk[F_L_OFF + 4] = L.l31; Fk[F_L_OFF + 5] = L.l32;
-                Fk[F_ID_OFF + 0] = L.i0; Fk[F_ID_OFF + 1] = L.i1; Fk[F_ID_OFF + 2] = L.i2; Fk[F_ID_OFF + 3] = L.i3;
+            double det = LM[4 * e + t] * cof;                         // expansion along row a
+            det += shfl_x(det, 1);
+            det += shfl_x(det, 2);
+            ok &= (det > 0.0) && ((e != t) || (cof > 0.0));           // positive definite: det and the principal 3x3 minors
+            const double linv = lo ? cof * rcp_newton(det) : 0.0;
+            const double hx0 = xch[lane];
+            const double gsh = shfl(gval, 4 * (4 + t) + 2);           // g[t] from lane (4+t, 2)
+            const double hx1 = lo ? xch[32 + lane] : (q == 4 ? gsh : 0.0);
+            double kc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            dmma(kc[0], linv, hx0);
+            dmma(kc[1], linv, hx1);
+            // F record (interior-point layout): K'[c][a] at c * 4 + a for c < 12, kff[a] = K[a][12], upper triangle of Lam^-1
+            if (lo) {
+                const int a4 = q;                                     // row a of K held by lanes (a, t)
+                Fk[(2 * t) * 4 + a4] = kc[0][0]; Fk[(2 * t + 1) * 4 + a4] = kc[0][1];
+                if (t < 2) { Fk[(8 + 2 * t) * 4 + a4] = kc[1][0]; Fk[(9 + 2 * t) * 4 + a4] = kc[1][1]; }
+                if (t == 2) Fk[F_KFF + a4] = kc[1][0];
+                if (t >= a4) Fk[F_L_OFF + linv_slot(a4, t)] = linv;
             }
-            // ---- kff = Lam^-1 g ----
-            chol4_fwd(L, gt);                    // L^-1 g
-            yg0 = y0[0] * gt[0] + y0[1] * gt[1] + y0[2] * gt[2] + y0[3] * gt[3];
-            yg1 = y1[0] * gt[0] + y1[1] * gt[1] + y1[2] * gt[2] + y1[3] * gt[3];
-            {
-                double kf[4] = {gt[0], gt[1], gt[2], gt[3]};
-                chol4_bwd(L, kf);
-                if (lane == 1) {
-                    *reinterpret_cast<double2*>(Fk + F_KFF) = make_double2(kf[0], kf[1]);
-                    *reinterpret_cast<double2*>(Fk + F_KFF + 2) = make_double2(kf[2], kf[3]);
-                }
-            }
-            // ---- P = Q + H_xx - Y'Y  (A fragment of Y' and B fragment of Y are the same register: Y[t][8m+q]) ----
-            const double ys0 = (t == 0) ? y0[0] : (t == 1) ? y0[1] : (t == 2) ? y0[2] : y0[3];
-            double ys1 = (t == 0) ? y1[0] : (t == 1) ? y1[1] : (t == 2) ? y1[2] : y1[3];
-            if (!lo) ys1 = 0.0;
-            dmma(h[0][0], -ys0, ys0); dmma(h[0][1], -ys0, ys1);
-            dmma(h[1][0], -ys1, ys0); dmma(h[1][1], -ys1, ys1);
+            const int sl = 4 * t + (q >> 1);
+            const double k00 = shfl(kc[0][0], sl), k01 = shfl(kc[0][1], sl), k10 = shfl(kc[1][0], sl), k11 = shfl(kc[1][1], sl);
+            const double kb0 = (q & 1) ? k01 : k00, kb1 = (q & 1) ? k11 : k10;
+            // P = Q + H_xx - H_xu K; column 12 of the right tiles (lane t == 2, register 0) collects -(H_xu kff) = -K'g
+            if (t == 2) { h[0][1][0] = 0.0; h[1][1][0] = 0.0; }
+            dmma(h[0][0], -hx0, kb0); dmma(h[0][1], -hx0, kb1);
+            dmma(h[1][0], -hx1, kb0); dmma(h[1][1], -hx1, kb1);
+            yg0 = shfl(-h[0][1][0], qb | 2); yg1 = shfl(-h[1][1][0], qb | 2);      // K'g lives on lanes t == 2: to the whole quad
         }
         if (t == (q >> 1)) {                     // diagonal element (8m+q, 8m+q) is C register q&1 of lane (q, q>>1)
             if (q & 1) { h[0][0][1] += qd0; h[1][1][1] += qd1; } else { h[0][0][0] += qd0; h[1][1][0] += qd1; }
@@ -1168,7 +1073,7 @@ __device__ void backward_vec_sweep(Inst& I, double sigmu)
             o0 = fma(Gk[((ki * 2 + 0) << 5) + lane], pr[ki], o0);
             o1 = fma(Gk[((ki * 2 + 1) << 5) + lane], pr[ki], o1);
         }
-        const double itl = 1.0 / Vs[V_TL + e], itu = 1.0 / Vs[V_TU + e];
+        const double itl = rcp_newton(Vs[V_TL + e]), itu = rcp_newton(Vs[V_TU + e]);
         const double ll = Vs[V_LL + e], lu = Vs[V_LU + e], dva = Vs[V_DV + e];
         const double cl = fma(dva, fma(ll * dva, itl, ll), sigmu);       // sigma mu - dv dll,  dll = -ll - ll dv / tl
         const double cu = fma(dva, fma(lu * dva, itu, -lu), sigmu);      // sigma mu + dv dlu,  dlu = -lu + lu dv / tu
@@ -1177,8 +1082,6 @@ __device__ void backward_vec_sweep(Inst& I, double sigmu)
         const double2 ka = *reinterpret_cast<const double2*>(Fk + q * 4), kb = *reinterpret_cast<const double2*>(Fk + q * 4 + 2);
         double2 kc = make_double2(0.0, 0.0), kd = make_double2(0.0, 0.0);
         if (lo) { kc = *reinterpret_cast<const double2*>(Fk + (8 + q) * 4); kd = *reinterpret_cast<const double2*>(Fk + (8 + q) * 4 + 2); }
-        Chol4 L;
-        load_chol(Fk, L);
         o0 += shfl_x(o0, 1); o1 += shfl_x(o1, 1);
         o0 += shfl_x(o0, 2); o1 += shfl_x(o1, 2);          // (Z'p+)[q], (Z'p+)[8+q]
         const double gval = gh + o1;                          // quads 4..7
@@ -1190,13 +1093,13 @@ __device__ void backward_vec_sweep(Inst& I, double sigmu)
         pr[0] = shfl(pv0, 4 * t);
         pr[1] = shfl(pv0, 4 * (4 + t));
         pr[2] = shfl(pv1, 4 * t);
-        // feed-forward for the forward sweep (off the recursion's critical path)
-        chol4_fwd(L, gt);
-        chol4_bwd(L, gt);
-        if (lane == 0) {
-            double* Fo = I.S + (size_t)k * SREC + S_F + F_KFF;
-            *reinterpret_cast<double2*>(Fo) = make_double2(gt[0], gt[1]);
-            *reinterpret_cast<double2*>(Fo + 2) = make_double2(gt[2], gt[3]);
+        // feed-forward for the forward sweep, kff = Lam^-1 g (off the recursion's critical path): lanes 0..3 one entry each, from the
+        // upper triangle of Lam^-1 the factor sweep left in the F record
+        if (lane < 4) {
+            double kf = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) kf = fma(Fk[F_L_OFF + linv_slot(lane < c ? lane : c, lane < c ? c : lane)], gt[c], kf);
+            I.S[(size_t)k * SREC + S_F + F_KFF + lane] = kf;
         }
     }
     __syncwarp();

@@ -31,16 +31,14 @@ __host__ __device__ constexpr int g_off(int row, int col)
 }
 
 // Factor record F_k written by the backward factorisation, read by the vector sweeps (record = 512 B).  Two layouts:
-//  (a) after an interior-point factorisation (Cholesky of Lam = R~ + B'PB):
+//  (a) after an interior-point factorisation (Lam = R~ + B'PB):
 //   [0..47]  Kt[j][a] = K[a][j]  (feedback gain transposed: column j of K is 4 contiguous doubles)
-//   [48..53] strictly-lower Cholesky entries of Lam: l10 l20 l21 l30 l31 l32
-//   [54..57] reciprocal diagonal 1/l00 .. 1/l33
+//   [48..57] upper triangle of Lam^-1, row by row (the corrector's backward sweep forms its own feed-forward with it)
 //   [58..61] feed-forward kff = Lam^-1 g of the most recent backward sweep (16-byte aligned);  [62..63] pad
 //  (b) after an absolute-form factorisation (fast paths): [K | kff] = Lam^-1 [H_ux | g] (4 x 13, padded to 4 x 16) exactly as
 //   the DMMA that forms it leaves it in registers -- C-fragment order: K[a][c] at f_kc(a, c); kff[a] = column 12
 constexpr int FREC = 64;
 constexpr int F_L_OFF = 48;
-constexpr int F_ID_OFF = 54;
 constexpr int F_KFF = 58;
 // layout (b): C register j = c & 1 of tile n = c >> 3 of lane 4 a + ((c & 7) >> 1); register (n, j) of lanes 0..15 is one 128-byte row
 __host__ __device__ constexpr int f_kc(int a, int c) { return (((c >> 3) * 2 + (c & 1)) << 4) + 4 * a + ((c & 7) >> 1); }
