@@ -72,6 +72,7 @@ struct br2_batch_solver {
     double* d_yref_pf[2];
     cudaStream_t stream_pf;
     cudaEvent_t ev_pf, ev_up_p, ev_up_x0;   // prefetch complete; this tick's p / x0 uploads complete (external events inside the tick graph)
+    int p_resident;                        // parameters of the last host call that supplied them sit in d_p: 1 = [B][16], 2 = per stage
     const double* next_yref;               // registered for the tick after the coming one
     const double* pf_host;                 // host buffer whose window sits (or is arriving) in d_yref_pf[pf_slot]
     int pf_slot;
@@ -515,6 +516,7 @@ extern "C" int br2_batch_solve_windowed_host(br2_batch_solver* s, const double* 
     const size_t B = s->B, N = s->N;
     cudaStream_t st = s->stream;
     CK(cudaMemcpyAsync(s->d_p, p, sizeof(double) * B * (p_per_stage ? (N + 1) * NP : NP), cudaMemcpyHostToDevice, st));
+    s->p_resident = p_per_stage ? 2 : 1;
     CK(cudaMemcpyAsync(s->d_lines, lines, sizeof(int) * B, cudaMemcpyHostToDevice, st));
     return solve_host_common(s, x0, nullptr, s->d_lines, p_per_stage, u0, thrust, status);
 }
@@ -545,6 +547,7 @@ extern "C" int br2_batch_solve_host(br2_batch_solver* s, const double* x0, const
     const size_t B = s->B, N = s->N;
     cudaStream_t st = s->stream;
     CK(cudaMemcpyAsync(s->d_p, p, sizeof(double) * B * (p_per_stage ? (N + 1) * NP : NP), cudaMemcpyHostToDevice, st));
+    s->p_resident = p_per_stage ? 2 : 1;
     CK(cudaMemcpyAsync(s->d_yref, yref, sizeof(double) * B * (N + 1) * NY, cudaMemcpyHostToDevice, st));
     return solve_host_common(s, x0, s->d_yref, nullptr, p_per_stage, u0, thrust, status);
 }
@@ -652,8 +655,9 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
         launch_exchange(s->shard, s->B, s->d_counter, s->stream_xchg);
         CK(cudaEventRecord(s->ev_xdone, s->stream_xchg));
     }
-    const size_t psz = sizeof(double) * B * (io.p_per_stage ? (N + 1) * NP : NP);
-    const double *d_x0 = io.x0, *d_yref = io.yref, *d_p = io.p, *d_thr = io.thrusts, *d_acc = io.body_acc;
+    const int p_per_stage = io.ekf ? 0 : (io.p ? io.p_per_stage : s->p_resident == 2);
+    const size_t psz = sizeof(double) * B * (p_per_stage ? (N + 1) * NP : NP);
+    const double *d_x0 = io.x0, *d_yref = io.yref, *d_p = io.p ? io.p : s->d_p, *d_thr = io.thrusts, *d_acc = io.body_acc;
     const int* d_lines = io.lines;
     bool forked = false, chunked = false;
     int nchunk = 4;
@@ -665,9 +669,11 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
             CK(cudaMemcpyAsync(s->d_acc, io.body_acc, sizeof(double) * B * 6, cudaMemcpyHostToDevice, st));
             d_thr = s->d_thr; d_acc = s->d_acc;
         } else {
-            CK(cudaMemcpyAsync(s->d_p, io.p, psz, cudaMemcpyHostToDevice, st));
+            // (p == NULL: the parameters of the last call that supplied them are still in d_p -- they persist like the capsule's after
+            // bluerov2_acados_update_params)
+            if (io.p) CK(cudaMemcpyAsync(s->d_p, io.p, psz, cudaMemcpyHostToDevice, st));
             d_p = s->d_p;
-            if (io.yref) CK(cudaEventRecordWithFlags(s->ev_up_p, st, evflag));      // (the prefetch of the next reference queues behind this)
+            if (io.yref && io.p) CK(cudaEventRecordWithFlags(s->ev_up_p, st, evflag));      // (the prefetch of the next reference queues behind this)
         }
         // explicit reference windows are the big upload (B x (N+1) x 16 doubles: 21.5 MB at B = 4096, N = 40 -- longer on the wire
         // than the kernels of the tick): for large batches without a filter it is cut into four instance ranges and
@@ -717,7 +723,7 @@ static int tick_issue(br2_batch_solver* s, const br2_tick_io& io, int host, cuda
         d_p = s->d_pout;
     }
     SolveArgs a;
-    fill_args(s, a, d_x0, d_yref, d_lines, d_p, io.ekf ? 0 : io.p_per_stage, o_u0, o_th, o_st);
+    fill_args(s, a, d_x0, d_yref, d_lines, d_p, p_per_stage, o_u0, o_th, o_st);
     CK(cudaEventRecordWithFlags(s->ev0, st, evflag));
     if (chunked) {
         // range c on its own stream: waits for its part of the upload (and for x0), then lineariser -> pdas_kernel; the ranges
@@ -769,7 +775,8 @@ static int tick_validate(br2_batch_solver* s, const br2_tick_io* io, int host, c
     if (io->lines && !s->d_traj) return fail(BR2_EINVAL, "%s: lines given but no trajectory set (br2_batch_set_trajectory)", who);
     if (io->ekf < 0 || io->ekf > 2) return fail(BR2_EINVAL, "%s: ekf = %d", who, io->ekf);
     if (io->ekf && (!io->thrusts || !io->body_acc)) return fail(BR2_EINVAL, "%s: ekf needs thrusts and body_acc", who);
-    if (!io->ekf && !io->p) return fail(BR2_EINVAL, "%s: p is NULL (and no filter produces it)", who);
+    if (!io->ekf && !io->p && !s->p_resident)
+        return fail(BR2_EINVAL, "%s: p is NULL, no filter produces it and no earlier host call has supplied the parameters", who);
     if (host && io->plant_h > 0) return fail(BR2_EINVAL, "%s: the plant step is a device-path option", who);
     if ((io->wave_amp == nullptr) != (io->wave_tau0 == nullptr)) return fail(BR2_EINVAL, "%s: wave_amp and wave_tau0 go together", who);
     return BR2_OK;
@@ -789,7 +796,7 @@ static int tick_inputs(const br2_batch_solver* s, const br2_tick_io& io, const v
 }
 static bool same_but_inputs(const br2_tick_io& a, const br2_tick_io& b)
 {
-    if ((a.yref == nullptr) != (b.yref == nullptr) || (a.lines == nullptr) != (b.lines == nullptr)) return false;
+    if ((a.yref == nullptr) != (b.yref == nullptr) || (a.lines == nullptr) != (b.lines == nullptr) || (a.p == nullptr) != (b.p == nullptr)) return false;
     br2_tick_io x = a, y = b;
     x.x0 = y.x0 = nullptr; x.yref = y.yref = nullptr; x.lines = y.lines = nullptr;
     if (a.ekf) { x.thrusts = y.thrusts = nullptr; x.body_acc = y.body_acc = nullptr; } else { x.p = y.p = nullptr; }
@@ -1035,6 +1042,11 @@ extern "C" int br2_batch_tick_host(br2_batch_solver* s, const br2_tick_io* io_in
     // copies from / to pageable memory are staged by the driver at enqueue time: only pinned buffers go into a graph
     const bool pinned = pinned_host(io.x0) && pinned_host(io.yref) && pinned_host(io.p) && pinned_host(io.thrusts) && pinned_host(io.lines) &&
                         pinned_host(io.body_acc) && pinned_host(io.u0) && pinned_host(io.thrust) && pinned_host(io.wf_dist) && pinned_host(io.status);
+    if (io.p && !io.ekf) {
+        const int mode = io.p_per_stage ? 2 : 1;
+        if (s->p_resident && s->p_resident != mode) s->gen++;      // (graphs that rely on the resident layout are stale)
+        s->p_resident = mode;
+    }
     const int xchg = shard_pending(s);
     // explicit reference registered one tick ahead (br2_batch_set_next_yref_host): it is resident (or arriving) in d_yref_pf[pf_slot]
     const int pf = (io.yref && !io.ekf && io.yref == s->pf_host) ? s->pf_slot : -1;

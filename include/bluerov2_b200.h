@@ -122,7 +122,9 @@ BR2_API int br2_batch_solve_host(br2_batch_solver *s, const double *x0, const do
  *   x0        [B][12]  measured state; with ekf != 0 also the filter's measurement (meas_y, bluerov2_dob.cpp:501-503)
  *   yref      [B][N+1][16] explicit reference, or NULL with lines != NULL: windowed from br2_batch_set_trajectory
  *   lines     [B] first trajectory row per instance (int)
- *   p         [B][16] ([B][N+1][16] when p_per_stage) OCP parameters; ignored when ekf != 0 (the filter writes them)
+ *   p         [B][16] ([B][N+1][16] when p_per_stage) OCP parameters; ignored when ekf != 0 (the filter writes them).  NULL (ekf == 0):
+ *             the parameters of the last _host call that supplied them -- they persist in the solver like the capsule's after
+ *             bluerov2_acados_update_params, which the reference's nodes call only when a parameter changes
  *   ekf       0: no filter.  1: BLUEROV2_DOB::EKF -> p (bluerov2_dob.cpp:324-355).  2: EKF -> RLSFF -> p (BLUEROV2_AMPC::solve,
  *             bluerov2_ampc.cpp:340-382).  thrusts[B][6], body_acc[B][6] are the filter's inputs; compensate = COMPENSATE_D
  *   u0 [B][4], thrust [B][6], status [B] outputs (any may be NULL: internal buffers); wf_dist [B][6] world-frame disturbance (or NULL)

@@ -227,3 +227,27 @@ def test_reference_announced_one_tick_ahead_equals_plain_host_ticks(solver_mod):
     with pytest.raises(solver_mod.SolverError):
         b.set_next_yref(np.zeros((B, N + 1, 16)))      # pageable memory is refused
     a.close(); b.close()
+
+
+def test_parameters_persist_between_host_ticks(solver_mod):
+    """p == NULL on the host path: the parameters of the last call that supplied them stay in the solver (bluerov2_acados_update_params
+    semantics); ticks without p equal ticks that pass the same p every time; a solver that never got parameters refuses"""
+    N, B, T = 10, 300, 5
+    w = wl.tracking_batch(B, N, seed=14, pos_spread=0.5)
+    a = solver_mod.BatchSolver(B, N); a.set_iterate(w["X"], w["U"]); a.set_trajectory(w["traj"])
+    b = solver_mod.BatchSolver(B, N); b.set_iterate(w["X"], w["U"]); b.set_trajectory(w["traj"])
+    p2 = w["p"].copy(); p2[:, 0] += 0.3                       # a second parameter set (disturbance estimate changed)
+    hp, hp2 = _pin(w["p"]), _pin(p2)
+    outa = (_pin(np.zeros((B, 4))), _pin(np.zeros((B, 6))), _pin(np.zeros(B, dtype=np.int32)))
+    outb = (_pin(np.zeros((B, 4))), _pin(np.zeros((B, 6))), _pin(np.zeros(B, dtype=np.int32)))
+    x0, lines = w["x0"].copy(), w["lines"].astype(np.int32)
+    with pytest.raises(solver_mod.SolverError):
+        b.tick(_pin(x0), lines=_pin(lines), out=outb)         # nothing resident yet
+    for t in range(T):
+        hx, hl = _pin(x0), _pin(lines + t)
+        pa = hp if t < 3 else hp2
+        ua, _, sta = a.tick(hx, p=pa, lines=hl, out=outa)
+        ub, _, stb = b.tick(hx, p=(hp if t == 0 else hp2 if t == 3 else None), lines=hl, out=outb)
+        assert np.array_equal(ua, ub) and np.array_equal(sta, stb) and (sta == 0).all(), t
+        x0 = wl.plant_step(x0, ua.copy(), pa, 0.05)
+    a.close(); b.close()
