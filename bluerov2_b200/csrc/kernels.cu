@@ -417,6 +417,11 @@ __device__ __forceinline__ void cp16(uint32_t dst, const char* src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// the same under a predicate (no branch: a divergent-branch region around a copy is a scheduling barrier at the top of every stage)
+__device__ __forceinline__ void cp16_if(bool pr, uint32_t dst, const char* src)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(src), "r"((int)pr) : "memory");
+}
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
@@ -425,18 +430,18 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 //   V = j 0,   G = j 1..3 and lanes < 16 of j 4,   F = lanes >= 16 of j 4 and lanes < 16 of j 5.
 // dst / src are the lane's own addresses (slot base / record base + 16 lane).
 template <int PARTS>
-__device__ __forceinline__ void stage_copy(uint32_t dst, const char* src, int lane)
+__device__ __forceinline__ void stage_copy(uint32_t dst, const char* src, int lane, bool on = true)
 {
-    if (PARTS & P_V) cp16(dst, src);
+    if (PARTS & P_V) cp16_if(on, dst, src);
     if (PARTS & P_G) {
-        cp16(dst + 512, src + 512);
-        cp16(dst + 1024, src + 1024);
-        cp16(dst + 1536, src + 1536);
+        cp16_if(on, dst + 512, src + 512);
+        cp16_if(on, dst + 1024, src + 1024);
+        cp16_if(on, dst + 1536, src + 1536);
     }
-    if ((PARTS & P_G) && (PARTS & P_F)) cp16(dst + 2048, src + 2048);
-    else if (PARTS & P_G) { if (lane < 16) cp16(dst + 2048, src + 2048); }
-    else if (PARTS & P_F) { if (lane >= 16) cp16(dst + 2048, src + 2048); }
-    if (PARTS & P_F) { if (lane < 16) cp16(dst + 2560, src + 2560); }
+    if ((PARTS & P_G) && (PARTS & P_F)) cp16_if(on, dst + 2048, src + 2048);
+    else if (PARTS & P_G) cp16_if(on && lane < 16, dst + 2048, src + 2048);
+    else if (PARTS & P_F) cp16_if(on && lane >= 16, dst + 2048, src + 2048);
+    if (PARTS & P_F) cp16_if(on && lane < 16, dst + 2560, src + 2560);
 }
 
 // Per-instance pointers and the sweep pipeline
@@ -450,6 +455,7 @@ struct Inst {
     const double* Ulin;
     const char* src;            // pipeline: the lane's global address inside the next record to copy
     uint32_t dst0;              // pipeline: the lane's shared address inside ring slot 0
+    int rslot;                  // pipeline: ring slot of the stage being read (the next refill goes into the one read before it)
     __device__ Inst(const SolveArgs& a_, WarpSmem& sm_, int inst_, int lane_)
         : a(a_), sm(sm_), inst(inst_), lane(lane_), q(lane_ >> 2), t(lane_ & 3), N(a_.N)
     {
@@ -469,10 +475,11 @@ struct Inst {
         src = reinterpret_cast<const char*>(S) + 16 * lane + (BACKWARD ? (size_t)(N - 1) * REC_BYTES : 0);
 #pragma unroll
         for (int j = 0; j < NSLOT - 1; j++) {
-            if (j < N) stage_copy<PARTS>(dst0 + j * REC_BYTES, src, lane);
+            stage_copy<PARTS>(dst0 + j * REC_BYTES, src, lane, j < N);
             cp_commit();
             src += BACKWARD ? -REC_BYTES : REC_BYTES;
         }
+        rslot = NSLOT - 1;      // (advance(0) steps it to slot 0 and refills slot NSLOT - 1)
     }
     // top of iteration i: wait for this iteration's records (all but the NSLOT-2 youngest groups complete), warp barrier (the
     // copies of the other lanes become visible, and every lane is past its reads of the slot consumed by iteration i-1), then
@@ -482,8 +489,10 @@ struct Inst {
     {
         cp_wait<NSLOT - 2>();
         __syncwarp();
-        const int j = i + NSLOT - 1;
-        if (j < N) stage_copy<PARTS>(dst0 + (j % NSLOT) * REC_BYTES, src, lane);
+        // stage i + NSLOT - 1 goes into the slot read by iteration i - 1 (for i = 0: the last slot, still empty); no modulo, no branch
+        const int wslot = rslot;
+        rslot = rslot + 1 == NSLOT ? 0 : rslot + 1;
+        stage_copy<PARTS>(dst0 + wslot * REC_BYTES, src, lane, i + NSLOT - 1 < N);
         cp_commit();
         if (BR2_PF_DIST > 0) {
             // experiment (off: BR2_PF_DIST = 0): the copy above runs NSLOT-1 stages ahead and 21 % of the stall samples are the wait
@@ -497,7 +506,7 @@ struct Inst {
             }
         }
         src += BACKWARD ? -REC_BYTES : REC_BYTES;
-        return sm.st[i % NSLOT];
+        return sm.st[rslot];
     }
 };
 
