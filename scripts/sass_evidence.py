@@ -15,15 +15,15 @@ for line in out.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Za-z0-9_.]+)", line)
     if m and cur:
         cnt[cur][m.group(1)] += 1
-want = ["DMMA.8x8x4", "UBLKCP.S.G", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "SYNCS.PHASECHK.TRANS64", "FENCE.VIEW.ASYNC.S",
+want = ["DMMA.8x8x4", "LDGSTS.E.BYPASS.128", "LDGDEPBAR", "UBLKCP.S.G", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "SYNCS.PHASECHK.TRANS64", "FENCE.VIEW.ASYNC.S",
         "CCTL.E.PF2", "STG.E.ENL2.256", "LDS.128", "DFMA", "SHFL.IDX", "SHFL.BFLY", "MUFU.RCP64H", "MUFU.RSQ64H", "CREDUX"]
-names = {"ipm_kernelILb0": "ipm_kernel<false> (default)", "ipm_kernelILb1": "ipm_kernel<true> (option active_set_path)",
-         "linearize_kernel": "linearize_kernel", "ekf_kernel": "ekf_kernel", "rls_kernel": "rls_kernel", "plant_kernel": "plant_kernel",
+names = {"pdas_kernel": "pdas_kernel", "ipm_kernel": "ipm_kernel", "eskf_predict": "eskf_predict_kernel", "eskf_update": "eskf_update_kernel",
+         "exchange_kernel": "exchange_kernel", "linearize_kernel": "linearize_kernel", "ekf_kernel": "ekf_kernel", "rls_kernel": "rls_kernel", "plant_kernel": "plant_kernel",
          "yaw_unwrap_kernel": "yaw_unwrap_kernel"}
 lines = ["# SASS evidence: cuobjdump -sass bluerov2_b200/lib/libacados_ocp_solver_bluerov2.so (sm_100a), selected mnemonics per kernel",
          "# DMMA.8x8x4 = mma.sync.m8n8k4.f64; UBLKCP.S.G = cp.async.bulk global->shared (TMA bulk copy); SYNCS.* = mbarrier arrive.expect_tx /",
          "# try_wait / test_wait; FENCE.VIEW.ASYNC = fence.proxy.async; CCTL.E.PF2 = prefetch.global.L2; STG.E.ENL2.256 = st.global.v4.f64;",
-         "# CREDUX = __reduce_{max,min}_sync"]
+         "# CREDUX = __reduce_{max,min}_sync; LDGSTS.E.BYPASS.128 = cp.async.cg 16 B (global -> shared, L1 bypassed); LDGDEPBAR = cp.async.commit_group"]
 for k in sorted(cnt, key=lambda n: [v for key, v in names.items() if key in n] or ["~"]):
     nm = [v for key, v in names.items() if key in k]
     if not nm:
