@@ -12,7 +12,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${T}_smoke.l
 BR2_VARIANT=prof timeout 300 python scripts/phase_profile.py > $O/${T}_phase_profile.json 2> $O/${T}_phase.err
 BR2_VARIANT=prof timeout 300 python scripts/ekf_phase_profile.py > $O/${T}_ekf_phase_profile.json 2> $O/${T}_ekf_phase.err
 timeout 300 python scripts/active_set_probe.py > $O/${T}_active_set_probe.json 2> $O/${T}_probe.err; tail -3 $O/${T}_probe.err
-timeout 300 python scripts/single_latency.py > $O/${T}_single_instance_latency.json 2> $O/${T}_single.err; cat $O/${T}_single_instance_latency.json
+timeout 300 python tests/tools/single_latency.py > $O/${T}_single_instance_latency.json 2> $O/${T}_single.err; cat $O/${T}_single_instance_latency.json
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ekf_kernel -s 6 -c 1 -f -o $O/prof_ekf_$T python scripts/ekf_phase_profile.py > $O/${T}_ncu_ekf.log 2>&1; echo "ncu ekf rc=$?"
 python - <<PY
 import json

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""scripts/parity_soak.py -- parity of the CUDA path against the CPU oracle over long closed loops at larger batch than the
+"""tests/tools/parity_soak.py -- parity of the CUDA path against the CPU oracle over long closed loops at larger batch than the
 unit tests run: every tick both sides solve the same (x0, yref, p, iterate); the oracle's iterate is carried on both sides so
 that differences do not compound.  Workloads: config 2 nominal (interior fast path), config 2 with 3 m position spread (active
 bounds: interior-point iterations), the same with the fast path disabled, horizons 10/20/80.  Prints one JSON line per case
@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from bluerov2_b200 import solver as S, traj, workloads as wl   # noqa: E402
 from oracle import Oracle                                        # noqa: E402

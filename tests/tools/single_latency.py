@@ -4,7 +4,7 @@ acados-generated C-ABI from C (tests/abi/_bin/dob_tick) -- per-tick latency as t
 the CPU oracle's single-instance latency on this host.  Prints one JSON line."""
 import json, os, struct, subprocess, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from bluerov2_b200 import traj, workloads as wl
 from oracle import Oracle, NOMINAL_P

@@ -4,7 +4,7 @@
 bounded-variable least squares as the referee, the condition number of the condensed Hessian."""
 import json, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from bluerov2_b200 import solver as S, traj, workloads as wl
 from oracle import Oracle, W_DEFAULT, WE_DEFAULT, LBU, UBU
