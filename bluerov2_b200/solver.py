@@ -313,6 +313,21 @@ class BatchSolver:
         """One control tick as ONE call (br2_batch_tick_device / _host): [EKF (-> RLS) -> p ->] RTI step [-> plant step on x0 in
         place].  All arrays torch CUDA tensors (enqueue on torch's current stream) or all numpy arrays (synchronous).  A caller
         that passes the same buffers every tick replays one cached CUDA graph.  Returns (u0, thrust, status)."""
+        if out is not None:
+            # hot path: a call seen before (same objects; the cache entry keeps them alive, so an id cannot have been recycled) is one
+            # dictionary lookup and one foreign call -- the wrapper is on the critical path of a synchronous host tick
+            w0, w1 = wave if wave is not None else (None, None)
+            ent = self._tick_cache.get((id(x0), id(p), id(yref), id(lines), id(thrusts), id(body_acc), id(out[0]), id(out[1]), id(out[2]),
+                                        id(wf_dist), id(w0), id(w1), ekf, compensate, plant_h))
+            if ent is not None:
+                if ent[3]:
+                    import torch
+                    rc = self._L.br2_batch_tick_device(self._h, ent[2], C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream))
+                else:
+                    rc = self._L.br2_batch_tick_host(self._h, ent[2])
+                if rc:
+                    self._check(rc)
+                return out
         dev = _is_torch(x0)
         if out is None:
             if dev:
@@ -323,32 +338,31 @@ class BatchSolver:
             else:
                 out = (np.empty((self.B, NU)), np.empty((self.B, NTHRUST)), np.empty((self.B,), dtype=np.int32))
         args = (x0, p, yref, lines, thrusts, body_acc, out[0], out[1], out[2], wf_dist) + (tuple(wave) if wave is not None else (None, None))
-        key = tuple(id(a) for a in args) + (int(ekf), bool(compensate), float(plant_h))
-        ent = self._tick_cache.get(key)
-        if ent is None or any(a is not b for a, b in zip(ent[1], args)):
-            per_stage = int(p is not None and len(p.shape) == 3)
-            shapes = ((self.B, NX), (self.B, self.N + 1, NP) if per_stage else (self.B, NP), (self.B, self.N + 1, NY), (self.B,),
-                      (self.B, 6), (self.B, 6), (self.B, NU), (self.B, NTHRUST), (self.B,), (self.B, 6), (self.B, 4), (self.B,))
-            ints = (3, 8)       # lines, status
-            ptrs = []
-            for i, (a, shp) in enumerate(zip(args, shapes)):
-                if a is None:
-                    ptrs.append(None)
-                    continue
-                if dev:
-                    import torch
-                    self._dev_check(a, shp, torch.int32 if i in ints else torch.float64)
-                    ptrs.append(a.data_ptr())
-                else:
-                    want = np.int32 if i in ints else np.float64
-                    if not (isinstance(a, np.ndarray) and a.dtype == want and a.flags.c_contiguous and a.shape == tuple(shp)):
-                        raise ValueError(f"tick(): argument {i} must be a contiguous {want.__name__} array of shape {tuple(shp)}")
-                    ptrs.append(a.ctypes.data)
-            io = _TickIO(ptrs[0], ptrs[2], ptrs[1], ptrs[4], ptrs[3], ptrs[5], ptrs[6], ptrs[7], ptrs[9], ptrs[8], ptrs[10], ptrs[11],
-                         float(plant_h), per_stage, int(ekf), int(bool(compensate)))
-            if len(self._tick_cache) > 32:
-                self._tick_cache.clear()
-            ent = self._tick_cache[key] = (io, args, C.byref(io))
+        key = tuple(id(a) for a in args) + (ekf, compensate, plant_h)
+        per_stage = int(p is not None and len(p.shape) == 3)
+        shapes = ((self.B, NX), (self.B, self.N + 1, NP) if per_stage else (self.B, NP), (self.B, self.N + 1, NY), (self.B,),
+                  (self.B, 6), (self.B, 6), (self.B, NU), (self.B, NTHRUST), (self.B,), (self.B, 6), (self.B, 4), (self.B,))
+        ints = (3, 8)       # lines, status
+        ptrs = []
+        for i, (a, shp) in enumerate(zip(args, shapes)):
+            if a is None:
+                ptrs.append(None)
+                continue
+            if dev:
+                import torch
+                self._dev_check(a, shp, torch.int32 if i in ints else torch.float64)
+                ptrs.append(a.data_ptr())
+            else:
+                want = np.int32 if i in ints else np.float64
+                if not (isinstance(a, np.ndarray) and a.dtype == want and a.flags.c_contiguous and a.shape == tuple(shp)):
+                    raise ValueError(f"tick(): argument {i} must be a contiguous {want.__name__} array of shape {tuple(shp)}")
+                ptrs.append(a.ctypes.data)
+        io = _TickIO(ptrs[0], ptrs[2], ptrs[1], ptrs[4], ptrs[3], ptrs[5], ptrs[6], ptrs[7], ptrs[9], ptrs[8], ptrs[10], ptrs[11],
+                     float(plant_h), per_stage, int(ekf), int(bool(compensate)))
+        if len(self._tick_cache) >= 1024:          # (a caller cycling through many buffers: forget the older half)
+            for k in list(self._tick_cache)[:512]:
+                del self._tick_cache[k]
+        ent = self._tick_cache[key] = (io, args, C.byref(io), dev)
         if dev:
             import torch
             stream = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)

@@ -50,26 +50,35 @@ def main():
     h_p = pin(w["p"])
     o = (pin(np.empty((B, 4))), pin(np.empty((B, 6))), pin(np.empty((B,), dtype=np.int32)))
     sol.set_iterate(w["X"], w["U"])
-    same = lambda t: sol.tick(h_x0[0], p=h_p, lines=h_l[0], out=o)      # noqa: E731
+    sol.tick(h_x0[0], p=h_p, lines=h_l[0], out=o)                        # parameters supplied once: resident from here on
+    same = lambda t: sol.tick(h_x0[0], lines=h_l[0], out=o)             # noqa: E731
     for t in range(W):
         same(t)
     out["C_host_same_buffers_us"] = wall(same, K)
-    dist_ = lambda t: sol.tick(h_x0[t % (W + K)], p=h_p, lines=h_l[t % (W + K)], out=o)   # noqa: E731
+    dist_ = lambda t: sol.tick(h_x0[t % (W + K)], lines=h_l[t % (W + K)], out=o)   # noqa: E731
+    for t in range(W):
+        dist_(t)
+    sol.set_iterate(w["X"], w["U"])
     for t in range(W):
         dist_(t)
     out["D_host_distinct_us"] = wall(dist_, K)
+    sol.set_iterate(w["X"], w["U"])
+    for t in range(W):
+        dist_(t)
     out["D_with_status_check_us"] = wall(lambda t: (dist_(t), bool((o[2] == 0).all())), K)
     # raw ctypes on prebuilt structs
     ios = []
     for t in range(W + K):
-        io = S._TickIO(h_x0[t].ctypes.data, None, h_p.ctypes.data, None, h_l[t].ctypes.data, None, o[0].ctypes.data, o[1].ctypes.data,
+        io = S._TickIO(h_x0[t].ctypes.data, None, None, None, h_l[t].ctypes.data, None, o[0].ctypes.data, o[1].ctypes.data,
                        None, o[2].ctypes.data, None, None, 0.0, 0, 0, 1)
         ios.append((io, C.byref(io)))
     L, h = sol._L, sol._h
     raw = lambda t: L.br2_batch_tick_host(h, ios[t % (W + K)][1])      # noqa: E731
+    sol.set_iterate(w["X"], w["U"])
     for t in range(W):
         raw(t)
     out["E_host_distinct_raw_ctypes_us"] = wall(raw, K)
+    sol.set_iterate(w["X"], w["U"])
     # python wrapper alone (no GPU work): cost of the cache lookup etc.
     t0 = time.perf_counter()
     for t in range(K):
