@@ -174,6 +174,8 @@ class BatchSolver:
         self._h = C.c_void_p()
         self._hostargs = _HostArgs()
         self._tick_cache = {}
+        self._arr_cache = {}
+        self._tick_tpl = {}
         ts = None if time_steps is None else _np(time_steps, (N,))
         self._check(self._L.br2_batch_create(C.byref(self._h), int(batch), int(N), _ptr(ts), int(device)))
         self.B, self.N, self.device = int(batch), int(N), int(device)
@@ -328,6 +330,35 @@ class BatchSolver:
                 if rc:
                     self._check(rc)
                 return out
+            # a new buffer in a call shape seen before (a caller that hands in a fresh message buffer every tick): only x0 and the
+            # reference are new -- validate those two, copy the validated struct of the sibling call and re-point it
+            tpl = self._tick_tpl.get((id(p), id(thrusts), id(body_acc), id(out[0]), id(out[1]), id(out[2]), id(wf_dist), id(w0), id(w1),
+                                      ekf, compensate, plant_h, yref is None, lines is None))
+            if tpl is not None and not tpl[3]:
+                B, N = self.B, self.N
+                ref, rshape, rtype = (lines, (B,), np.int32) if yref is None else (yref, (B, N + 1, NY), np.float64)
+                if (type(x0) is np.ndarray and x0.dtype == np.float64 and x0.flags.c_contiguous and x0.shape == (B, NX)
+                        and type(ref) is np.ndarray and ref.dtype == rtype and ref.flags.c_contiguous and ref.shape == rshape):
+                    try:
+                        px, pr = C.addressof(C.c_char.from_buffer(x0)), C.addressof(C.c_char.from_buffer(ref))
+                    except (TypeError, ValueError):
+                        px, pr = x0.ctypes.data, ref.ctypes.data
+                    io = _TickIO.from_buffer_copy(tpl[0])
+                    io.x0 = px
+                    if yref is None:
+                        io.lines = pr
+                    else:
+                        io.yref = pr
+                    if len(self._tick_cache) >= 1024:
+                        for k in list(self._tick_cache)[:512]:
+                            del self._tick_cache[k]
+                    ref_io = C.byref(io)
+                    self._tick_cache[(id(x0), id(p), id(yref), id(lines), id(thrusts), id(body_acc), id(out[0]), id(out[1]), id(out[2]),
+                                      id(wf_dist), id(w0), id(w1), ekf, compensate, plant_h)] = (io, (x0, ref), ref_io, False)
+                    rc = self._L.br2_batch_tick_host(self._h, ref_io)
+                    if rc:
+                        self._check(rc)
+                    return out
         dev = _is_torch(x0)
         if out is None:
             if dev:
@@ -353,16 +384,34 @@ class BatchSolver:
                 self._dev_check(a, shp, torch.int32 if i in ints else torch.float64)
                 ptrs.append(a.data_ptr())
             else:
+                # (validated once per array object and role; the address without numpy's ctypes helper object: this path runs on
+                # every tick of a caller that hands in a fresh message buffer each time)
+                hit = self._arr_cache.get((id(a), i))
+                if hit is not None:
+                    ptrs.append(hit[1])
+                    continue
                 want = np.int32 if i in ints else np.float64
-                if not (isinstance(a, np.ndarray) and a.dtype == want and a.flags.c_contiguous and a.shape == tuple(shp)):
+                if not (type(a) is np.ndarray and a.dtype == want and a.flags.c_contiguous and a.shape == tuple(shp)):
                     raise ValueError(f"tick(): argument {i} must be a contiguous {want.__name__} array of shape {tuple(shp)}")
-                ptrs.append(a.ctypes.data)
+                try:
+                    ptr = C.addressof(C.c_char.from_buffer(a))
+                except (TypeError, ValueError):          # read-only or empty buffer
+                    ptr = a.ctypes.data
+                if len(self._arr_cache) >= 4096:
+                    self._arr_cache.clear()
+                self._arr_cache[(id(a), i)] = (a, ptr)
+                ptrs.append(ptr)
         io = _TickIO(ptrs[0], ptrs[2], ptrs[1], ptrs[4], ptrs[3], ptrs[5], ptrs[6], ptrs[7], ptrs[9], ptrs[8], ptrs[10], ptrs[11],
                      float(plant_h), per_stage, int(ekf), int(bool(compensate)))
         if len(self._tick_cache) >= 1024:          # (a caller cycling through many buffers: forget the older half)
             for k in list(self._tick_cache)[:512]:
                 del self._tick_cache[k]
         ent = self._tick_cache[key] = (io, args, C.byref(io), dev)
+        w0, w1 = wave if wave is not None else (None, None)
+        if len(self._tick_tpl) >= 64:
+            self._tick_tpl.clear()
+        self._tick_tpl[(id(p), id(thrusts), id(body_acc), id(out[0]), id(out[1]), id(out[2]), id(wf_dist), id(w0), id(w1),
+                        ekf, compensate, plant_h, yref is None, lines is None)] = (io, args, None, dev)
         if dev:
             import torch
             stream = C.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)

@@ -86,6 +86,14 @@ def main():
         key = tuple(id(x) for x in args) + (0, True, 0.0)
         sol._tick_cache.get(key)
     out["python_key_lookup_us"] = 1e6 * (time.perf_counter() - t0) / K
+    dtb, okb, _, _ = bench.host_loop(torch, sol, w, xs, ls, 5, K, False, a.N)
+    out["G_bench_host_loop_us"] = 1e6 * dtb / K
+    dtb, okb, _, _ = bench.host_loop(torch, sol, w, xs, ls, 5, K, False, a.N)
+    out["G_bench_host_loop_again_us"] = 1e6 * dtb / K
+    sol.set_iterate(w["X"], w["U"])
+    for t in range(W):
+        dist_(t)
+    out["D_again_us"] = wall(lambda t: (dist_(t), bool((o[2] == 0).all())), K)
     sol.set_option("tick_graph", 0)
     for t in range(W):
         dist_(t)
