@@ -316,10 +316,12 @@ def roofline_of(B, N, iters_mean, t_qp, kernel):
             "formula": f"B*{BYTES_PER_STAGE_ITER}*N*mean_qp_iterations / t_qp"}
 
 
-def host_loop(torch, sol, w, xs, ls, W, K, explicit_yref, N, announce_next=False, write_combined=False):
+def host_loop(torch, sol, w, xs, ls, W, K, explicit_yref, N, announce_next=False, write_combined=False, c_abi=False):
     """closed-loop ticks through the host API with pinned host buffers, a distinct input buffer per tick; wall clock around K ticks.
     explicit_yref: upload the (N+1) x 16 reference window per instance like ocp_nlp_cost_model_set("yref") x (N+1) does
-    (bluerov2_dob.cpp:370-372) instead of naming a trajectory row"""
+    (bluerov2_dob.cpp:370-372) instead of naming a trajectory row.
+    c_abi: the ticks go through the C-ABI entry point itself -- br2_batch_tick_host(solver, &io) on br2_tick_io structs filled before
+    the loop, what a C / C++ caller such as the reference's nodes does -- instead of through the Python wrapper around it"""
     from bluerov2_b200 import solver as S_mod
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
     B = w["x0"].shape[0]
@@ -353,6 +355,17 @@ def host_loop(torch, sol, w, xs, ls, W, K, explicit_yref, N, announce_next=False
         # measured state and the trajectory row index
         call = lambda t: sol.tick(h_x0[t], p=h_p if t == 0 else None, lines=h_ref[t], out=out)  # noqa: E731
         h2d = B * 12 * 8 + B * 4                 # x0 (fp64) and one trajectory row index per instance (int32)
+        if c_abi:
+            import ctypes as C
+            ios = [S_mod._TickIO(h_x0[t].ctypes.data, None, h_p.ctypes.data if t == 0 else None, None, h_ref[t].ctypes.data, None,
+                                 out[0].ctypes.data, out[1].ctypes.data, None, out[2].ctypes.data, None, None, 0.0, 0, 0, 1) for t in range(W + K)]
+            refs = [C.byref(io) for io in ios]
+            tick_host, handle = sol._L.br2_batch_tick_host, sol._h
+
+            def call(t):                        # noqa: F811
+                rc = tick_host(handle, refs[t])
+                if rc:
+                    sol._check(rc)
     sol.set_iterate(w["X"], w["U"])
     ok = True
     for t in range(W):
@@ -568,25 +581,33 @@ def run_ours(args):
     graphs = sol.graphs_built()
 
     # ---- e2e: the same closed-loop ticks through the host API ----
-    xs, ls = record_states(torch, loop, W + K, dev)
-    dt_e2e, e2e_ok, h2d, d2h = host_loop(torch, sol, w, xs, ls, W, K, False, N)
+    # the host loops warm up for at least 20 ticks (W is the contract's minimum): a synchronous host tick is sensitive to cold code paths
+    # and page-locked buffers in a way the enqueue-only device loop is not, and K can be as small as 20
+    Wh = max(W, 20)
+    xs, ls = record_states(torch, loop, Wh + K, dev)
+    # e2e = the C-ABI call with host buffers (what the reference's C++ nodes would make); the same ticks through the Python wrapper beside it
+    # throw-away pass of the same length: host graphs built, code paths warm, and the pinned input buffers of the timed passes come out of
+    # torch's pinned-memory cache instead of fresh cudaHostAlloc calls (first-use page-locking shows up as ~2 % on the tick)
+    host_loop(torch, sol, w, xs, ls, Wh, K, False, N, c_abi=True)
+    dt_e2e, e2e_ok, h2d, d2h = host_loop(torch, sol, w, xs, ls, Wh, K, False, N, c_abi=True)
+    dt_py, py_ok, _, _ = host_loop(torch, sol, w, xs, ls, Wh, K, False, N)
     dt_exp = dt_ann = None
     extra_errors = {}
     if world == 1 and not args.quick:
         # the secondary host-path legs must not take the headline line down with them (pinned-memory limits of the box, ...)
         try:
-            dt_exp, exp_ok, h2d_exp, _ = host_loop(torch, sol, w, xs, ls, W, min(K, 50), True, N)
+            dt_exp, exp_ok, h2d_exp, _ = host_loop(torch, sol, w, xs, ls, Wh, min(K, 50), True, N)
         except Exception as e:       # noqa: BLE001
             extra_errors["e2e_explicit_yref"] = repr(e)[:300]
         try:
-            dt_ann, ann_ok, _, _ = host_loop(torch, sol, w, xs, ls, W, min(K, 50), True, N, announce_next=True, write_combined=True)
+            dt_ann, ann_ok, _, _ = host_loop(torch, sol, w, xs, ls, Wh, min(K, 50), True, N, announce_next=True, write_combined=True)
         except Exception as e:       # noqa: BLE001
             extra_errors["announced_one_tick_ahead"] = repr(e)[:300]
 
     if distributed:
-        tt = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=dev)
+        tt = torch.tensor([dt, dt_e2e, dt_py], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt, dt_e2e = float(tt[0]), float(tt[1])
+        dt, dt_e2e, dt_py = float(tt[0]), float(tt[1]), float(tt[2])
         cnt = torch.tensor([float(iters_mean), float(n_bad)], dtype=torch.float64, device=dev)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         iters_mean, n_bad = float(cnt[0]) / world, int(cnt[1])
@@ -606,9 +627,14 @@ def run_ours(args):
                                                               ", one NCCL all-gather of the thrust vectors per tick (double-buffered: it overlaps the next "
                                                               "tick's lineariser)"),
             "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ok": e2e_ok,
-                    "ms_per_step": 1e3 * dt_e2e / K, "api": "br2_batch_tick_host (windowed reference: one trajectory row index per instance; parameters supplied once, "
-                                                                 "resident in the solver)",
-                    "overhead_over_device_time": dt_e2e / dt - 1.0},
+                    "ms_per_step": 1e3 * dt_e2e / K, "api": "br2_batch_tick_host(solver, &io) -- the C-ABI entry point on br2_tick_io structs filled before "
+                                                                 "the loop, as a C / C++ caller holds them (windowed reference: one trajectory row index per "
+                                                                 "instance; parameters supplied once, resident in the solver); status words read on the host "
+                                                                 "every tick",
+                    "overhead_over_device_time": dt_e2e / dt - 1.0,
+                    "through_python_wrapper": {"value": world * B * K / dt_py, "unit": UNIT, "ms_per_step": 1e3 * dt_py / K, "ok": py_ok,
+                                               "overhead_over_device_time": dt_py / dt - 1.0,
+                                               "api": "BatchSolver.tick(...) with a fresh pinned input buffer per tick"}},
             "gpu_launches": 4 * K,
             "gpu_launches_per_tick": {"count": 4, "kernels": ["linearize_kernel", "pdas_kernel", "ipm_kernel (fallback list, normally empty)",
                                                               "plant_kernel"], "graphs_instantiated": graphs,
@@ -620,14 +646,14 @@ def run_ours(args):
         if dt_exp is not None:
             Ke = min(K, 50)
             line["e2e_explicit_yref"] = {"value": B * Ke / dt_exp, "unit": UNIT, "ms_per_step": 1e3 * dt_exp / Ke, "h2d_bytes_per_step": h2d_exp,
-                                         "d2h_bytes_per_step": d2h, "ok": exp_ok, "fraction_of_windowed_e2e": (B * Ke / dt_exp) / (B * K / dt_e2e),
+                                         "d2h_bytes_per_step": d2h, "ok": exp_ok, "fraction_of_windowed_e2e": (B * Ke / dt_exp) / (B * K / dt_py),
                                          "api": "br2_batch_tick_host with the explicit (N+1) x 16 reference window per instance "
                                                 "(ocp_nlp_cost_model_set \"yref\" x (N+1), bluerov2_dob.cpp:370-372)",
                                          }
             if dt_ann is not None:
                 line["e2e_explicit_yref"]["announced_one_tick_ahead"] = {
                     "value": B * Ke / dt_ann, "unit": UNIT, "ms_per_step": 1e3 * dt_ann / Ke, "ok": ann_ok,
-                    "h2d_bytes_per_step": h2d_exp, "fraction_of_windowed_e2e": (B * Ke / dt_ann) / (B * K / dt_e2e),
+                    "h2d_bytes_per_step": h2d_exp, "fraction_of_windowed_e2e": (B * Ke / dt_ann) / (B * K / dt_py),
                     "api": "the same call, the NEXT tick's window registered before it (br2_batch_set_next_yref_host): "
                            "uploaded beside the running tick's kernels; x0 and p still go up when the tick is called; "
                            "windows in write-combined pinned memory (br2_host_alloc)"}
