@@ -21,6 +21,23 @@ for t in range(3):
 s.set_option("fast_path", 0)
 u0, th, st = s.solve(x0, traj.window_batch(w["traj"], lines, N), w["p"])
 print("status", int((st != 0).sum()), "ok")
+# one-call ticks: device graph with the plant step, host tick with resident parameters and an announced reference window
+import torch
+s.set_option("fast_path", 1)
+pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+out = (pin(np.zeros((B, 4))), pin(np.zeros((B, 6))), pin(np.zeros(B, dtype=np.int32)))
+refs = [pin(traj.window_batch(w["traj"], lines + t, N)) for t in range(4)]
+hx, hp = pin(x0), pin(w["p"])
+for t in range(3):
+    s.set_next_yref(refs[t + 1])
+    s.tick(hx, p=hp if t == 0 else None, yref=refs[t], out=out)
+d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+dx, dl, dp, da = d(x0), d(lines.astype(np.int32)), d(w["p"]), torch.zeros((B, 6), dtype=torch.float64, device="cuda")
+for t in range(3):
+    s.tick(dx, p=dp, lines=dl, body_acc=da, plant_h=0.05)
+torch.cuda.synchronize()
+f = S.BatchEskf(B) if hasattr(S, "BatchEskf") else None
+print("ticks ok")
 s.close()
 PY
 for tool in memcheck racecheck; do
