@@ -35,6 +35,9 @@
 #ifndef BR2_PF_DIST
 #define BR2_PF_DIST 0
 #endif
+#ifndef BR2_PDL
+#define BR2_PDL 0                   // programmatic dependent launch of the QP kernel behind the lineariser (experiment, see launch_pdas)
+#endif
 #ifndef BR2_LIN_MINB
 #define BR2_LIN_MINB 12
 #endif
@@ -201,6 +204,11 @@ __global__ void __launch_bounds__(32, BR2_LIN_MINB) linearize_kernel(SolveArgs a
         // housekeeping for the IPM kernel that follows in the stream: reset its work-queue counters, flip the order buffers
         if (a.housekeeping) tick_housekeeping(a.ctr);
     }
+#if BR2_PDL
+    // programmatic dependent launch: the QP kernel behind this one may be scheduled as soon as every block of this grid has got here
+    // (its blocks then wait in griddepcontrol.wait for this grid to finish and flush); hides the launch gap behind the last wave
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
 #ifdef BR2_PROFILE
     // cycles per phase of the lineariser into slots 13..15 (state trajectory / Jacobians / sensitivities + stores)
     long long lprof_t0 = clock64();
@@ -1476,6 +1484,9 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_PDAS_MINB) pdas_kernel(con
     // a warp's first position is its global warp index, later ones come from an atomic counter that starts behind the statically
     // assigned block and is reserved one instance ahead (the atomic's round trip was ~4 % of the kernel).  Only lane 0 holds the
     // reservation.  The epilogue appends the instance to order_next (hard ones from the front, easy ones from the back).
+#if BR2_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // (launched early: the lineariser's records and counters are complete from here on)
+#endif
     const int par = a.ctr[CTR_PARITY] & 1;
     const int* order_cur = a.order + (size_t)par * a.B;
     int* order_next = a.order + (size_t)(par ^ 1) * a.B;
@@ -1667,7 +1678,17 @@ void launch_pdas(const SolveArgs& a, int sm_count, cudaStream_t s)
     // number of resident warps and the queue already evens out the tail; profiles/r01h_ipm_variants.txt.)
     const int need = (a.hi - a.lo + IPM_WARPS - 1) / IPM_WARPS;
     const int blocks = need < sm_count * BR2_PDAS_MINB ? need : sm_count * BR2_PDAS_MINB;
+#if BR2_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(IPM_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, pdas_kernel, a);
+#else
     pdas_kernel<<<blocks, IPM_WARPS * 32, 0, s>>>(a);
+#endif
 }
 
 void launch_ipm_fallback(const SolveArgs& a, int sm_count, cudaStream_t s)
