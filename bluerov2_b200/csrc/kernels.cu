@@ -817,11 +817,14 @@ __device__ bool factor_sweep(Inst& I, IpmUpd* upd = nullptr)
         z[2][0] = Gs[zo2]; z[2][1] = Gs[zo2 + 32];
         const double tsk = Gs[G_TS];
         // state rows q and 8+q
-        const double qd0 = tsk * a.W[q];
-        const double qd1 = lo ? tsk * a.W[8 + e] : 0.0;
+        // (stage weights from the warp's copy in shared memory: a.W sits in the constant bank, and a lane-dependent index there is replayed
+        // once per distinct address -- three such loads per stage at the top of the dependent chain)
+        const double* Wsm = I.sm.xch + 64;
+        const double qd0 = tsk * Wsm[q];
+        const double qd1 = lo ? tsk * Wsm[8 + e] : 0.0;
         double qx0 = Gs[G_QLIN + q], qx1 = lo ? Gs[G_QLIN + 8 + e] : 0.0;
         // input row e (meaningful in quads 4..7)
-        const double rd = tsk * a.W[12 + e];
+        const double rd = tsk * Wsm[12 + e];
         double rt = rd;
         double gu_loc = Gs[G_RLIN + e];
         double ll_e = 0.0, lu_e = 0.0, cmp_e = 0.0;     // FS_IPM: multipliers and complementarity products of input e
@@ -1478,6 +1481,8 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_PDAS_MINB) pdas_kernel(con
     const int lane = threadIdx.x & 31;
     const int N = a.N, nb = 4 * N;
     WarpSmem& sm = smem[threadIdx.x >> 5];
+    if (lane < 16) sm.xch[64 + lane] = a.W[lane];           // the warp's copy of the stage weights (factor_sweep)
+    __syncwarp();
     // Work distribution.  Instances are visited in the order the PREVIOUS solve left behind: those that ended with active bounds
     // (hint = 1: several factorisations, possibly interior-point iterations) first, so that the long jobs start at t = 0 and the
     // one-factorisation instances fill the tail (longest-processing-time-first).  queue position -> instance through order_cur;
@@ -1587,6 +1592,8 @@ __global__ void __launch_bounds__(IPM_WARPS * 32, BR2_IPM_MINB) ipm_kernel(const
     __shared__ WarpSmem smem[IPM_WARPS];
     const int lane = threadIdx.x & 31;
     WarpSmem& sm = smem[threadIdx.x >> 5];
+    if (lane < 16) sm.xch[64 + lane] = a.W[lane];           // the warp's copy of the stage weights (factor_sweep)
+    __syncwarp();
     const int nfb = a.ctr[CTR_FB];
     int* order_next = a.order + (size_t)((a.ctr[CTR_PARITY] & 1) ^ 1) * a.B;
     int pos = blockIdx.x * IPM_WARPS + (threadIdx.x >> 5);
