@@ -4,18 +4,25 @@
 //                      in three phases (state trajectory / Jacobians / sensitivities); replaces acados' ERK integrator
 //                      driving bluerov2_expl_vde_forw (acados_solver_bluerov2.c:310-318,633-639) -> stage records
 //                      G_k = [A_k | B_k], b_k, cost gradients in HBM.
-//   ipm_kernel       : one warp per OCP instance, persistent over the batch.  Mehrotra predictor-corrector
-//                      primal-dual IPM on the box-constrained OCP-QP of the RTI step; every Newton system is an
-//                      LQR solved by a Riccati recursion over the horizon (replaces acados full condensing + HPIPM
-//                      dense IPM, acados_solver_bluerov2.c:146,664-668).  The two 12x16 stage products of the
-//                      factorisation run on the fp64 tensor-core instruction (DMMA, mma.sync.m8n8k4.f64): on B200 it
-//                      has the same 64 FMA/clk/SM as DFMA but reaches it from 4 warps/SM with 8x fewer issue slots,
-//                      no redundant lanes and fragment-resident operands (profiles/r01_fp64_probe.txt).
-//                      Epilogue: full SQP step on (X,U), u0 and the 4->6 thrust allocation (bluerov2_dob.cpp:388-395).
+//   pdas_kernel      : the QP of the RTI step, one warp per OCP instance, persistent over the batch (atomic work queue in
+//                      longest-first order).  Primal-dual active-set iteration on Riccati solves: the unconstrained LQR first (one
+//                      backward factor sweep + one closed-loop roll-out that tests its own candidate against the box), inputs
+//                      outside the box pinned and the LQR re-solved, a costate sweep checking the multiplier signs; a candidate
+//                      that passes satisfies the KKT conditions of the strictly convex QP, i.e. is the minimiser HPIPM converges
+//                      to (replaces acados full condensing + HPIPM dense IPM, acados_solver_bluerov2.c:146,664-668).
+//   ipm_kernel       : the fallback list of pdas_kernel (normally empty): Mehrotra predictor-corrector primal-dual IPM, every
+//                      Newton system an LQR solved by the same Riccati sweeps.
+//                      Both: the two 12x16 stage products of the factorisation, the gain K = Lam^-1 [H_ux | g] and the Riccati
+//                      update run on the fp64 tensor-core instruction (DMMA, mma.sync.m8n8k4.f64; on B200 the same 64 FMA/clk/SM
+//                      as DFMA, reached from 4 warps/SM with 8x fewer issue slots and fragment-resident operands,
+//                      profiles/r01_fp64_probe.txt); Lam^-1 is formed entry by entry, one 3x3 cofactor per lane; stage records
+//                      are staged HBM -> shared memory by cp.async two stages ahead.  Epilogue: full SQP step on (X, U), u0 and
+//                      the 4->6 thrust allocation (bluerov2_dob.cpp:388-395), hint and place in the next solve's visiting order.
+//   exchange_kernel, shard_wait_kernel : sharded batches, peer-to-peer exchange of the thrust vectors.
 //
-// Arithmetic: fp64 throughout (casadi_real = double in the reference).  The algorithm is the one restated
+// Arithmetic: fp64 throughout (casadi_real = double in the reference).  The interior-point iteration is the one restated
 // in oracle/bluerov2_oracle.c (feasible-start, residual-form Newton steps, split primal/dual step lengths);
-// see DESIGN.md for the lane mapping and the per-stage byte/flop budget.
+// see DESIGN.md for the lane mapping, the per-stage byte/flop budget and what bounds each kernel.
 #include "engine.h"
 #include <stdint.h>
 
