@@ -13,8 +13,11 @@ reference, N = 40, fp64), closed loop with the nominal ERK4 plant at 0.05 s, ite
 
   value : whole-job steps/s, device-resident closed loop: one br2_batch_tick_device per tick (lineariser -> QP kernels -> plant
           step on the device state, replayed as one CUDA graph), CUDA events on the launching stream, max over ranks.
-  e2e   : the same closed-loop ticks through the host API (BatchSolver.tick -> br2_batch_tick_host) with pinned HOST buffers:
-          H2D of x0 / row indices / p and D2H of u0 / thrust / status inside the timed region, a distinct input buffer per tick.
+  e2e   : the same closed-loop ticks through the C-ABI entry point br2_batch_tick_host(solver, &io) with pinned HOST buffers (what a
+          C / C++ caller such as the reference's nodes does; br2_tick_io structs filled before the loop): H2D of x0 / row indices and
+          D2H of u0 / thrust / status inside the timed region, a distinct input buffer per tick, the status words read on the host
+          every tick; the OCP parameters of config 2 do not change and are supplied once (update_params semantics).  The same ticks
+          through the Python wrapper (BatchSolver.tick) are reported beside it (e2e.through_python_wrapper).
   roofline / cpu_baseline / sub-records (forced interior-point iteration, saturated start, config 3, config 5, explicit-yref
   host path): see DESIGN.md "Measurement".
 
