@@ -619,8 +619,8 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr, int* ptest = nul
 #pragma unroll
         for (int ki = 0; ki < 4; ki++) {
             z0[ki] = Gs[o0[ki]];
-            z1[ki] = lo ? Gs[o1[ki]] : 0.0;
-        }
+            z1[ki] = Gs[o1[ki]];                // (quads 4..7 read a valid row too: their p1 / uq are never consumed -- every
+        }                                       // shuffle below reads from a lane of quads 0..3 -- and a select per load costs more)
         double ulin = 0.0;
         if (MODE == 2) ulin = I.Ulin[k * NU + (q & 3)];        // (for the primal test below; in flight during the gain product)
         if (q == 0 && MODE != 1) {              // (the state part of the affine step is never read)
@@ -635,7 +635,7 @@ __device__ double forward_sweep(Inst& I, IpmAcc* acc = nullptr, int* ptest = nul
             // absolute-form factorisation): K in C-fragment order, kff = its column 12
             double part = 0.0;
 #pragma unroll
-            for (int ki = 0; ki < 3; ki++) part = fma(lo ? Fs[MODE == 2 ? f_kc(q & 3, 4 * ki + t) : (4 * ki + t) * 4 + q] : 0.0, zr[ki], part);
+            for (int ki = 0; ki < 3; ki++) part = fma(Fs[MODE == 2 ? f_kc(q & 3, 4 * ki + t) : (4 * ki + t) * 4 + (q & 3)], zr[ki], part);
             part += shfl_x(part, 1);
             part += shfl_x(part, 2);
             const double uq = -Fs[MODE == 2 ? f_kc(q & 3, 12) : F_KFF + (q & 3)] - part;
