@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
     const double e12 = __shfl_sync(FULL_MASK, exn, 12), e13 = __shfl_sync(FULL_MASK, exn, 13), e14 = __shfl_sync(FULL_MASK, exn, 14);
     const double e15 = __shfl_sync(FULL_MASK, exn, 15), e16 = __shfl_sync(FULL_MASK, exn, 16), e17 = __shfl_sync(FULL_MASK, exn, 17);
     double sa = 0.0, ca = 1.0;               // lanes 0..2: sin / cos of the measured roll, pitch, yaw
-    if (a.wf_dist && lane < 3) sincos(a.meas[(size_t)inst * 12 + 3 + lane], &sa, &ca);
+    if (a.wf_dist && lane < 3) br2_sincos(a.meas[(size_t)inst * 12 + 3 + lane], &sa, &ca);
     const double s3 = __shfl_sync(FULL_MASK, sa, 0), c3 = __shfl_sync(FULL_MASK, ca, 0);
     const double s4 = __shfl_sync(FULL_MASK, sa, 1), c4 = __shfl_sync(FULL_MASK, ca, 1);
     const double s5 = __shfl_sync(FULL_MASK, sa, 2), c5 = __shfl_sync(FULL_MASK, ca, 2);
@@ -468,16 +468,17 @@ __global__ void __launch_bounds__(EKF_WARPS * 32, BR2_EKF_MINB) ekf_kernel(EkfAr
             wf[0] = (c5 * c4) * e12 + (-s5 * c3 + c5 * s4 * s3) * e13 + (s5 * s3 + c5 * c3 * s4) * e14;
             wf[1] = (s5 * c4) * e12 + (c5 * c3 + s3 * s4 * s5) * e13 + (-c5 * s3 + s4 * s5 * c3) * e14;
             wf[2] = (-s4) * e12 + (c4 * s3) * e13 + (c4 * c3) * e14;
-            wf[3] = e15 + (s5 * s4 / c4) * e16 + c3 * s4 / c4 * e17;
+            const double r4 = br2_rcp(c4);          // (branch-free reciprocals: no out-of-line division code in this kernel)
+            wf[3] = e15 + (s5 * s4 * r4) * e16 + c3 * s4 * r4 * e17;
             wf[4] = (c3) * e16 + (s3) * e17;
-            wf[5] = (s3 / c4) * e16 + (c3 / c4) * e17;
+            wf[5] = (s3 * r4) * e16 + (c3 * r4) * e17;
         }
         if (a.p_out) {
             double* p = a.p_out + (size_t)inst * NP;
-            p[0] = a.compensate ? e12 / COMP : 0.0;
-            p[1] = a.compensate ? e13 / COMP : 0.0;
-            p[2] = a.compensate ? e14 / RCK : 0.0;
-            p[3] = a.compensate ? e17 / RCK : 0.0;
+            p[0] = a.compensate ? e12 * (1.0 / COMP) : 0.0;
+            p[1] = a.compensate ? e13 * (1.0 / COMP) : 0.0;
+            p[2] = a.compensate ? e14 * (1.0 / RCK) : 0.0;
+            p[3] = a.compensate ? e17 * (1.0 / RCK) : 0.0;
             p[4] = 1.7182; p[5] = 0; p[6] = 5.468; p[7] = 0.4006;
             p[8] = -11.7391; p[9] = -20; p[10] = -31.8678; p[11] = -5;
             p[12] = -18.18; p[13] = -21.66; p[14] = -36.99; p[15] = -1.55;
