@@ -248,12 +248,23 @@ BR2_HD void ju_add(const ModelConst& c, int a, double* o)
 // 4 -> 6 thrust allocation, bluerov2_dob.cpp:390-395 (== bluerov2_ctrl.cpp:256-266)
 BR2_HD void thrust_alloc(const double* u, double* t)
 {
+#ifdef __CUDA_ARCH__
+    // (device: times the reciprocal -- a division brings its out-of-line special-case code into the QP kernels' epilogue)
+    constexpr double IRC = 1.0 / RC;
+    t[0] = (-u[0] + u[1] + u[3]) * IRC;
+    t[1] = (-u[0] - u[1] - u[3]) * IRC;
+    t[2] = (u[0] + u[1] - u[3]) * IRC;
+    t[3] = (u[0] - u[1] + u[3]) * IRC;
+    t[4] = (-u[2]) * IRC;
+    t[5] = (-u[2]) * IRC;
+#else
     t[0] = (-u[0] + u[1] + u[3]) / RC;
     t[1] = (-u[0] - u[1] - u[3]) / RC;
     t[2] = (u[0] + u[1] - u[3]) / RC;
     t[3] = (u[0] - u[1] + u[3]) / RC;
     t[4] = (-u[2]) / RC;
     t[5] = (-u[2]) / RC;
+#endif
 }
 
 }  // namespace br2
