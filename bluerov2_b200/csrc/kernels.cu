@@ -550,7 +550,7 @@ __device__ void ipm_init(Inst& I)
         const double tl = v - lb, tu = ub - v;
         double* Vk = I.V + (size_t)k * SREC;
         Vk[V_V + e] = v; Vk[V_TL + e] = tl; Vk[V_TU + e] = tu;
-        Vk[V_LL + e] = mu0 / tl; Vk[V_LU + e] = mu0 / tu;
+        Vk[V_LL + e] = mu0 * rcp_newton(tl); Vk[V_LU + e] = mu0 * rcp_newton(tu);
     }
     __syncwarp();
 }
@@ -1290,7 +1290,7 @@ __device__ __forceinline__ void ipm_solve(Inst& I, IpmOut& out)
     ipm_init(I);
     bmax = forward_sweep<0>(I);
     PROF(PF_IPM_INIT);
-    const double inv2nb = 1.0 / (2.0 * nb);
+    const double inv2nb = rcp_newton(2.0 * nb);
     for (it = 0; it < a.max_iter; it++) {
         // ---------- B1: (pending update,) factorisation, predictor rhs, mu and residual of the iterate ----------
         const bool okf = factor_sweep<FS_IPM>(I, &upd);
@@ -1303,9 +1303,9 @@ __device__ __forceinline__ void ipm_solve(Inst& I, IpmOut& out)
         // ---------- F1: affine step, its step length and complementarity -> sigma ----------
         forward_sweep<1>(I, &acc);
         PROF(PF_FWD_AFF);
-        const double a_aff = acc.ia > 1.0 ? 1.0 / acc.ia : 1.0;
+        const double a_aff = acc.ia > 1.0 ? rcp_newton(acc.ia) : 1.0;       // (branch-free reciprocals: no out-of-line division code)
         const double mu_aff = ((1.0 - a_aff) * upd.mu_sum + a_aff * a_aff * acc.s2) * inv2nb;
-        double sigma = mu_aff / mu;
+        double sigma = mu_aff * rcp_newton(mu);
         sigma = sigma * sigma * sigma;
         // ---------- B2 / F2: corrector ----------
         prefetch_iterate(I);            // this may be the last iteration: have X, U in L2 for the epilogue
@@ -1314,7 +1314,7 @@ __device__ __forceinline__ void ipm_solve(Inst& I, IpmOut& out)
         forward_sweep<3>(I, &acc);
         PROF(PF_FWD_COR);
         // ---------- step lengths; the update itself is left to the next factor sweep / the epilogue ----------
-        double ap = acc.ia_p > 1.0 ? 1.0 / acc.ia_p : 1.0, ad = acc.ia_d > 1.0 ? 1.0 / acc.ia_d : 1.0;
+        double ap = acc.ia_p > 1.0 ? rcp_newton(acc.ia_p) : 1.0, ad = acc.ia_d > 1.0 ? rcp_newton(acc.ia_d) : 1.0;
         const double tau = fmin(fmax(0.995, 1.0 - mu), 1.0 - 1e-8);
         ap = fmin(1.0, tau * ap);
         ad = fmin(1.0, tau * ad);
