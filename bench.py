@@ -124,12 +124,16 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_leg(N: int, budget_s: float, ticks_wanted: int, threads: int = 0, seed: int = 0, pos_spread: float = 0.5):
-    """the oracle port timed on the host cores over a bounded closed-loop sample of the same workload"""
+def cpu_leg(N: int, budget_s: float, ticks_wanted: int, threads: int = 0, seed: int = 0, pos_spread: float = 0.5, dense: bool = False):
+    """the oracle port timed on the host cores over a bounded closed-loop sample of the same workload.
+    dense: the QP by full condensing + a dense interior-point iteration instead of the Riccati recursion -- the cost profile of the
+    reference's FULL_CONDENSING_HPIPM (plain C loops, so reported beside the Riccati arm, never instead of it)"""
     from oracle import Oracle, CasadiRef
     from oracle.oracle import REF_SO
     o = Oracle()
-    kind_note = "oracle port (oracle/bluerov2_oracle.c, Riccati IPM)"
+    o.set_qp_mode(1 if dense else 0)
+    kind_note = ("oracle port (oracle/bluerov2_oracle.c, full condensing + dense IPM)" if dense
+                 else "oracle port (oracle/bluerov2_oracle.c, Riccati IPM)")
     if os.path.exists(REF_SO):
         o.use_casadi(CasadiRef())
         kind_note += " with the ERK driven by the reference's CasADi-generated bluerov2_expl_vde_forw (oracle/_ref)"
@@ -159,6 +163,7 @@ def cpu_leg(N: int, budget_s: float, ticks_wanted: int, threads: int = 0, seed: 
         iters.append(float(info[:, 0].mean()))
         x0 = wl.plant_step(x0, U[:, 0].copy(), w["p"], 0.05)
         lines = lines + 1
+    o.set_qp_mode(0)
     return dict(batch=Bs, times=times, iters=iters, cores=int(used), note=kind_note)
 
 
@@ -668,6 +673,16 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": r["batch"] * 3 / tcpu, "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": f"{r['batch']} instances x 3 closed-loop ticks (after 2 warm-up ticks) of the same workload; {r['note']}",
                                     "mean_ipm_iterations": float(np.mean(r["iters"][2:]))}
+            try:
+                rd = cpu_leg(N, budget_s=args.cpu_budget / 3, ticks_wanted=2 + 1, seed=0, pos_spread=args.pos_spread, dense=True)
+                td = float(np.sum(rd["times"][1:]))
+                line["cpu_baseline"]["dense_condensed"] = {
+                    "value": rd["batch"] * 2 / td, "unit": UNIT, "cores": rd["cores"],
+                    "sample": f"{rd['batch']} instances x 2 closed-loop ticks (after 1 warm-up tick); {rd['note']}",
+                    "what": "the same RTI step with the QP solved the way the reference's configuration does (FULL_CONDENSING_HPIPM: states "
+                            "eliminated, dense interior-point iteration on the N*nu inputs), in plain C without BLASFEO-class kernels"}
+            except Exception as e:       # noqa: BLE001
+                line["cpu_baseline"]["dense_condensed"] = {"error": repr(e)[:200]}
         if world == 1 and not args.quick:
             sol.close()
             try:

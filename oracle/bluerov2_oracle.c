@@ -598,6 +598,197 @@ int orc_qp_solve(const orc_qp *qp, int max_iter, double tol, double *dx, double 
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * The same QP by FULL CONDENSING + a dense interior-point iteration -- the cost profile of the reference's own QP path
+ * (qp_solver FULL_CONDENSING_HPIPM, acados_solver_bluerov2.c:146,664-668: acados eliminates the states, HPIPM runs its dense
+ * Mehrotra IPM on the N*nu = 160 remaining variables).  States eliminated through dx_k = c_k + sum_j Gam[k][j] du_j
+ * (Gam[j+1][j] = B_j, Gam[k+1][j] = A_k Gam[k][j]; c_0 = dx0, c_{k+1} = A_k c_k + b_k), condensed Hessian
+ * H = sum_k Gam_k' Q_k Gam_k + R, gradient g = sum_k Gam_k' (Q_k c_k + q_k) + r; the iteration is the one of orc_qp_solve
+ * (same cold start, same predictor-corrector, same step rule) with every LQR solve replaced by a dense Cholesky solve of
+ * H + diag(lam_l / t_l + lam_u / t_u).  Plain C loops: a BLASFEO-class implementation would run the same flops several times
+ * faster, so this arm is reported beside the Riccati arm, never instead of it.  Selected by orc_set_qp_mode(1).
+ * ---------------------------------------------------------------------------------------------- */
+static int g_qp_mode = 0;
+void orc_set_qp_mode(int mode) { g_qp_mode = mode; }
+int orc_get_qp_mode(void) { return g_qp_mode; }
+
+static int chol_dense(int n, double *M)            /* in place, lower triangle; returns non-zero on a non-positive pivot */
+{
+    for (int j = 0; j < n; j++) {
+        double d = M[(size_t)j * n + j];
+        for (int k = 0; k < j; k++) d -= M[(size_t)j * n + k] * M[(size_t)j * n + k];
+        if (!(d > 0.0)) return 1;
+        d = sqrt(d);
+        M[(size_t)j * n + j] = d;
+        for (int i = j + 1; i < n; i++) {
+            double sacc = M[(size_t)i * n + j];
+            for (int k = 0; k < j; k++) sacc -= M[(size_t)i * n + k] * M[(size_t)j * n + k];
+            M[(size_t)i * n + j] = sacc / d;
+        }
+    }
+    return 0;
+}
+static void chol_dense_solve(int n, const double *L, double *v)   /* v <- (L L')^-1 v */
+{
+    for (int i = 0; i < n; i++) {
+        double sacc = v[i];
+        for (int k = 0; k < i; k++) sacc -= L[(size_t)i * n + k] * v[k];
+        v[i] = sacc / L[(size_t)i * n + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double sacc = v[i];
+        for (int k = i + 1; k < n; k++) sacc -= L[(size_t)k * n + i] * v[k];
+        v[i] = sacc / L[(size_t)i * n + i];
+    }
+}
+
+int orc_qp_solve_dense(const orc_qp *qp, int max_iter, double tol, double *dx, double *du, double *pi, double *lam_l,
+                       double *lam_u, orc_qp_stats *st)
+{
+    const int N = qp->N, n = N * NU;
+    const size_t nn = (size_t)n * n;
+    /* Gam: for every stage k = 1..N the 12 x (4k) block row, stored with row length n */
+    double *mem = (double *)malloc(sizeof(double) * ((size_t)(N + 1) * NX * n + (size_t)(N + 1) * NX + 2 * nn + 19 * (size_t)n));
+    if (!mem) return 4;
+    double *Gam = mem, *c = Gam + (size_t)(N + 1) * NX * n, *H = c + (size_t)(N + 1) * NX, *Mw = H + nn, *g = Mw + nn;
+    double *tl = g + n, *tu = tl + n, *ll = tu + n, *lu = ll + n, *rh = lu + n, *dtl = rh + n, *dtu = dtl + n, *dll = dtu + n;
+    double *dlu = dll + n, *v = dlu + n, *vt = v + n, *cl = vt + n, *cu = cl + n, *gu = cu + n, *w1 = gu + n, *w2 = w1 + n;
+    (void)w1; (void)w2;
+    memset(Gam, 0, sizeof(double) * (size_t)(N + 1) * NX * n);
+    memcpy(c, qp->dx0, sizeof(double) * NX);
+    for (int k = 0; k < N; k++) {
+        const double *A = qp->A + (size_t)k * 144, *B = qp->B + (size_t)k * 48, *b = qp->b + (size_t)k * 12;
+        double *Gk = Gam + (size_t)k * NX * n, *Gn = Gam + (size_t)(k + 1) * NX * n;
+        for (int i = 0; i < NX; i++) {
+            double sacc = b[i];
+            for (int j = 0; j < NX; j++) sacc += A[i * NX + j] * c[k * NX + j];
+            c[(k + 1) * NX + i] = sacc;
+            for (int col = 0; col < k * NU; col++) {
+                double t = 0.0;
+                for (int j = 0; j < NX; j++) t += A[i * NX + j] * Gk[(size_t)j * n + col];
+                Gn[(size_t)i * n + col] = t;
+            }
+            for (int a = 0; a < NU; a++) Gn[(size_t)i * n + k * NU + a] = B[i * NU + a];
+        }
+    }
+    memset(H, 0, sizeof(double) * nn);
+    memset(g, 0, sizeof(double) * n);
+    for (int k = 1; k <= N; k++) {
+        const double *Gk = Gam + (size_t)k * NX * n;
+        const int nc = k * NU;
+        for (int i = 0; i < NX; i++) {
+            const double qd = qp->Qd[k * NX + i], ge = qd * c[k * NX + i] + qp->q[k * NX + i];
+            const double *row = Gk + (size_t)i * n;
+            for (int a = 0; a < nc; a++) {
+                const double ra = row[a];
+                if (ra == 0.0) continue;
+                g[a] += ra * ge;
+                const double qa = qd * ra;
+                for (int bb = 0; bb <= a; bb++) H[(size_t)a * n + bb] += qa * row[bb];
+            }
+        }
+    }
+    for (int a = 0; a < n; a++) {
+        H[(size_t)a * n + a] += qp->Rd[a];
+        g[a] += qp->r[a];
+        for (int bb = 0; bb < a; bb++) H[(size_t)bb * n + a] = H[(size_t)a * n + bb];
+    }
+    int status = 2, it = 0;
+    double mu = 0, res_stat = 0, stat_scale = 1.0;
+    const double thr = 1e-1, mu0 = 1.0;
+    for (int i = 0; i < n; i++) {
+        v[i] = fmin(fmax(0.0, qp->lb[i] + thr), qp->ub[i] - thr);
+        if (qp->ub[i] - qp->lb[i] < 2 * thr) v[i] = 0.5 * (qp->lb[i] + qp->ub[i]);
+        tl[i] = v[i] - qp->lb[i];
+        tu[i] = qp->ub[i] - v[i];
+        ll[i] = mu0 / tl[i];
+        lu[i] = mu0 / tu[i];
+    }
+    for (it = 0; it < max_iter; it++) {
+        mu = 0;
+        for (int i = 0; i < n; i++) mu += ll[i] * tl[i] + lu[i] * tu[i];
+        mu /= (2.0 * n);
+        res_stat = 0;
+        for (int a = 0; a < n; a++) {
+            double sacc = g[a];
+            for (int bb = 0; bb < n; bb++) sacc += H[(size_t)a * n + bb] * v[bb];
+            gu[a] = sacc;
+            res_stat = fmax(res_stat, fabs(sacc - ll[a] + lu[a]));
+        }
+        if (it == 0) stat_scale = fmax(1.0, res_stat);
+        if (mu < tol && res_stat < tol * stat_scale) { status = 0; break; }
+        memcpy(Mw, H, sizeof(double) * nn);
+        for (int i = 0; i < n; i++) Mw[(size_t)i * n + i] += ll[i] / tl[i] + lu[i] / tu[i];
+        if (chol_dense(n, Mw)) { status = 4; break; }
+        for (int i = 0; i < n; i++) vt[i] = -gu[i];
+        chol_dense_solve(n, Mw, vt);
+        for (int i = 0; i < n; i++) {
+            dtl[i] = vt[i];
+            dtu[i] = -vt[i];
+            dll[i] = -ll[i] - ll[i] * dtl[i] / tl[i];
+            dlu[i] = -lu[i] - lu[i] * dtu[i] / tu[i];
+        }
+        double a_aff = fmin(fmin(max_step(n, tl, dtl), max_step(n, tu, dtu)), fmin(max_step(n, ll, dll), max_step(n, lu, dlu)));
+        double mu_aff = 0;
+        for (int i = 0; i < n; i++)
+            mu_aff += (ll[i] + a_aff * dll[i]) * (tl[i] + a_aff * dtl[i]) + (lu[i] + a_aff * dlu[i]) * (tu[i] + a_aff * dtu[i]);
+        mu_aff /= (2.0 * n);
+        double sigma = mu_aff / mu;
+        sigma = sigma * sigma * sigma;
+        for (int i = 0; i < n; i++) {
+            cl[i] = sigma * mu - dtl[i] * dll[i];
+            cu[i] = sigma * mu - dtu[i] * dlu[i];
+            rh[i] = gu[i] - cl[i] / tl[i] + cu[i] / tu[i];
+            vt[i] = -rh[i];
+        }
+        chol_dense_solve(n, Mw, vt);
+        for (int i = 0; i < n; i++) {
+            dtl[i] = vt[i];
+            dtu[i] = -vt[i];
+            dll[i] = cl[i] / tl[i] - ll[i] - ll[i] * dtl[i] / tl[i];
+            dlu[i] = cu[i] / tu[i] - lu[i] - lu[i] * dtu[i] / tu[i];
+        }
+        double ap = fmin(max_step(n, tl, dtl), max_step(n, tu, dtu));
+        double ad = fmin(max_step(n, ll, dll), max_step(n, lu, dlu));
+        const double tau = fmin(fmax(0.995, 1.0 - mu), 1.0 - 1e-8);
+        ap = fmin(1.0, tau * ap);
+        ad = fmin(1.0, tau * ad);
+        for (int i = 0; i < n; i++) {
+            v[i] += ap * dtl[i];
+            tl[i] += ap * dtl[i];
+            tu[i] += ap * dtu[i];
+            ll[i] += ad * dll[i];
+            lu[i] += ad * dlu[i];
+        }
+    }
+    memcpy(du, v, sizeof(double) * n);
+    /* states by the exact roll-out of the inputs, costates by the adjoint recursion (as orc_qp_solve) */
+    memcpy(dx, qp->dx0, sizeof(double) * NX);
+    for (int k = 0; k < N; k++) {
+        const double *A = qp->A + (size_t)k * 144, *B = qp->B + (size_t)k * 48, *b = qp->b + (size_t)k * 12;
+        for (int i = 0; i < NX; i++) {
+            double sacc = b[i];
+            for (int j = 0; j < NX; j++) sacc += A[i * NX + j] * dx[k * NX + j];
+            for (int a = 0; a < NU; a++) sacc += B[i * NU + a] * du[k * NU + a];
+            dx[(k + 1) * NX + i] = sacc;
+        }
+    }
+    for (int i = 0; i < NX; i++) pi[N * NX + i] = qp->Qd[N * NX + i] * dx[N * NX + i] + qp->q[N * NX + i];
+    for (int k = N - 1; k >= 0; k--) {
+        const double *A = qp->A + (size_t)k * 144;
+        for (int i = 0; i < NX; i++) {
+            double sacc = qp->Qd[k * NX + i] * dx[k * NX + i] + qp->q[k * NX + i];
+            for (int l = 0; l < NX; l++) sacc += A[l * NX + i] * pi[(k + 1) * NX + l];
+            pi[k * NX + i] = sacc;
+        }
+    }
+    memcpy(lam_l, ll, sizeof(double) * n);
+    memcpy(lam_u, lu, sizeof(double) * n);
+    if (st) { st->iters = it; st->status = status; st->mu = mu; st->res_stat = res_stat; st->res_ineq = 0; st->res_comp = mu; }
+    free(mem);
+    return status;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * One SQP-RTI step (preparation + feedback, rti_phase 0).  Follows acados_solver_bluerov2.c:
  *   cost NONLINEAR_LS with y=[x;u], scaling = Ts on stages 0..N-1, terminal unscaled (:389-394,:424-479);
  *   Gauss-Newton Hessian (cost Hessian structurally empty, bluerov2_cost_y_hess.c:60);
@@ -648,7 +839,8 @@ int orc_rti_step(int N, const double *Ts, const double *W, const double *We, con
     }
     orc_qp qp = {N, A, B, b, Qd, Rd, q, r, lb, ub, dx0};
     orc_qp_stats st;
-    int status = orc_qp_solve(&qp, max_iter, tol, dx, du, pi, ll, lu, &st);
+    int status = g_qp_mode == 1 ? orc_qp_solve_dense(&qp, max_iter, tol, dx, du, pi, ll, lu, &st)
+                                : orc_qp_solve(&qp, max_iter, tol, dx, du, pi, ll, lu, &st);
     int nan = 0;
     for (int i = 0; i < N * NU; i++) nan |= !(du[i] == du[i]);
     if (!nan) {

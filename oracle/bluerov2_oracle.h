@@ -76,6 +76,12 @@ typedef struct {
  * Riccati recursion.  Outputs dx ((N+1)x12), du (Nx4), pi ((N+1)x12 costates), lam_l/lam_u (Nx4). */
 int orc_qp_solve(const orc_qp *qp, int max_iter, double tol,
                  double *dx, double *du, double *pi, double *lam_l, double *lam_u, orc_qp_stats *st);
+/* the same QP by full condensing + a dense interior-point iteration (the cost profile of FULL_CONDENSING_HPIPM); orc_rti_step uses
+ * it when orc_set_qp_mode(1) */
+int orc_qp_solve_dense(const orc_qp *qp, int max_iter, double tol,
+                       double *dx, double *du, double *pi, double *lam_l, double *lam_u, orc_qp_stats *st);
+void orc_set_qp_mode(int mode);    /* 0 = Riccati IPM (default), 1 = full condensing + dense IPM; process-wide */
+int orc_get_qp_mode(void);
 /* KKT residuals of a candidate (dx,du,pi,lam) -- the solver-independent certificate used by the tests.
  * res[0]=stationarity, res[1]=dynamics, res[2]=bound violation, res[3]=complementarity, res[4]=min(lam) */
 void orc_qp_kkt(const orc_qp *qp, const double *dx, const double *du, const double *pi,

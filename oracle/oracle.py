@@ -110,6 +110,8 @@ class Oracle:
         L.orc_ekf_step.argtypes = [D, D, D, D, D, D]
         L.orc_ekf_step_batch.argtypes = [C.c_int, D, D, D, D, D, D, C.c_int]
         L.orc_ekf_set_model.argtypes = [C.c_int]
+        L.orc_set_qp_mode.argtypes = [C.c_int]
+        L.orc_get_qp_mode.restype = C.c_int
         L.orc_yaw_unwrap.argtypes = [C.POINTER(C.c_float), C.c_double]
         L.orc_yaw_unwrap.restype = C.c_double
         L.orc_rls_init.argtypes = [D]
@@ -235,6 +237,11 @@ class Oracle:
         wf = np.zeros((nb, 6))
         self.lib.orc_ekf_step_batch(nb, _p(esti_x), _p(esti_P), _p(thrusts), _p(meas12), _p(body_acc), _p(wf), int(nthreads))
         return wf
+
+    def set_qp_mode(self, mode: int):
+        """0 = Riccati interior-point iteration (default), 1 = full condensing + dense interior-point iteration (the cost profile of the
+        reference's FULL_CONDENSING_HPIPM); process-wide, read by rti_step / rti_step_batch"""
+        self.lib.orc_set_qp_mode(int(mode))
 
     def ekf_set_model(self, model: int):
         """0 = BLUEROV2_DOB filter (default), 1 = BLUEROV2_AMPC filter (Dl = 0, no quadratic damping). Process-wide."""

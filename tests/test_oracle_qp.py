@@ -134,3 +134,25 @@ def test_rti_step_matches_scipy_bvls(oracle, N, spread, seed):
             X, U = Xn, Un
     if spread >= 3.0 and N == 40:
         assert n_active > 0, "active-bound set did not activate any bound"
+
+
+@pytest.mark.parametrize("N,spread,seed", [(40, 0.5, 0), (40, 3.0, 1), (10, 3.0, 2), (80, 1.0, 3)])
+def test_dense_condensed_variant_matches_riccati(oracle, N, spread, seed):
+    """orc_set_qp_mode(1): the same RTI step with the QP solved by full condensing + a dense interior-point iteration (the cost profile of
+    the reference's FULL_CONDENSING_HPIPM; bench.py's cpu_baseline.dense_condensed) lands on the iterate of the Riccati variant"""
+    B = 6
+    w = wl.tracking_batch(B, N, seed=seed, pos_spread=spread)
+    Ts = wl.time_steps(N)
+    yref = traj.window_batch(w["traj"], w["lines"], N)
+    Xa, Ua = w["X"].copy(), w["U"].copy()
+    Xb, Ub = w["X"].copy(), w["U"].copy()
+    try:
+        oracle.set_qp_mode(0)
+        sa, ia, _ = oracle.rti_step_batch(Ts, w["x0"], yref, w["p"], Xa, Ua, nthreads=1)
+        oracle.set_qp_mode(1)
+        sb, ib, _ = oracle.rti_step_batch(Ts, w["x0"], yref, w["p"], Xb, Ub, nthreads=1)
+    finally:
+        oracle.set_qp_mode(0)
+    assert (sa == 0).all() and (sb == 0).all()
+    assert np.abs(Ua - Ub).max() < 1e-9 and np.abs(Xa - Xb).max() < 1e-9
+    assert np.array_equal(ia[:, 0], ib[:, 0])            # the same iteration, solve for solve
