@@ -219,10 +219,13 @@ class DeviceLoop:
         self.mode = os.environ.get("BR2_GATHER", "peer") if self.distributed else "none"
         self.gather = PipelinedThrustGather(world * B, dev, depth=int(os.environ.get("BR2_GATHER_DEPTH", "2")))
         self.thr = torch.empty((B, 6), dtype=torch.float64, device=dev)
-        self.peer = None
+        self.peer, self.gather_note = None, None
         if self.mode == "peer":
-            from bluerov2_b200.sharding import PeerThrustExchange
-            self.peer = PeerThrustExchange(sol, B)
+            from bluerov2_b200.sharding import PeerThrustExchange, PeerExchangeUnavailable
+            try:
+                self.peer = PeerThrustExchange(sol, B)
+            except PeerExchangeUnavailable as e:        # raised on every rank together: all of them run the NCCL all-gather instead
+                self.mode, self.gather_note = "nccl", str(e)
         sol.set_trajectory(w["traj"])
 
     def restart(self):
@@ -633,7 +636,8 @@ def run_ours(args):
                                                               ", thrust vectors exchanged peer-to-peer from the QP epilogue (stores into every rank's gather "
                                                               "buffer over NVLink, one flag per rank and tick; no collective kernel)" if loop.mode == "peer" else
                                                               ", one NCCL all-gather of the thrust vectors per tick (double-buffered: it overlaps the next "
-                                                              "tick's lineariser)"),
+                                                              "tick's lineariser)") +
+                           (f" [{loop.gather_note}]" if loop.gather_note else ""),
             "e2e": {"value": world * B * K / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ok": e2e_ok,
                     "ms_per_step": 1e3 * dt_e2e / K, "api": "br2_batch_tick_host(solver, &io) -- the C-ABI entry point on br2_tick_io structs filled before "
                                                                  "the loop, as a C / C++ caller holds them (windowed reference: one trajectory row index per "

@@ -103,6 +103,9 @@ class PipelinedThrustGather:
             self._wait(i)
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """raised on EVERY rank when any rank could not set the peer-to-peer exchange up (the caller may then run the NCCL all-gather)"""
+
 
 class PeerThrustExchange:
     """The per-tick exchange of the thrust vectors without a collective (include/bluerov2_b200.h "Sharding"): every
@@ -121,19 +124,38 @@ class PeerThrustExchange:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.B = int(batch_per_rank)
         self.bounds = [(r * self.B, (r + 1) * self.B) for r in range(self.world)]
-        solver.shard_init(self.rank, self.world)
-        mine = solver.shard_handle()
-        handles = [None] * self.world
-        if self.world > 1:
-            dist.all_gather_object(handles, mine, group=group)
-        else:
-            handles[0] = mine
-        self.handles = handles
-        for r, h in enumerate(handles):
-            if r != self.rank:
-                solver.shard_connect(r, h)
-        if self.world > 1:
-            dist.barrier(group=group)          # nobody ticks before everybody is mapped
+        # Every step that can fail on ONE rank (no IPC in this container, no peer access between two devices) is followed by an
+        # exchange of the outcome, so that all ranks raise PeerExchangeUnavailable together instead of one raising while the
+        # others wait in a collective.  A solver left half connected never ships anything (engine.cu shard_pending).
+        mine, err = None, None
+        try:
+            solver.shard_init(self.rank, self.world)
+            mine = solver.shard_handle()
+        except Exception as e:                          # noqa: BLE001 -- reported to every rank below
+            err = f"rank {self.rank}: {type(e).__name__}: {e}"
+        got = self._all_gather((mine, err))
+        self._raise_if_any([g[1] for g in got], "shard_init / shard_handle")
+        self.handles = [g[0] for g in got]
+        try:
+            for r, h in enumerate(self.handles):
+                if r != self.rank:
+                    solver.shard_connect(r, h)
+        except Exception as e:                          # noqa: BLE001
+            err = f"rank {self.rank}: {type(e).__name__}: {e}"
+        self._raise_if_any(self._all_gather(err), "shard_connect")     # also the barrier: nobody ticks before everybody is mapped
+
+    def _all_gather(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    @staticmethod
+    def _raise_if_any(errors, step):
+        bad = [e for e in errors if e]
+        if bad:
+            raise PeerExchangeUnavailable(f"peer-to-peer thrust exchange unavailable ({step}): " + "; ".join(bad))
 
     def wait(self, stream=None):
         self.solver.shard_wait(stream)

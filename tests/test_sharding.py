@@ -145,6 +145,47 @@ def test_peer_exchange_rendezvous_gloo():
         assert bounds == [(0, 5), (5, 10)] and handles == [0, 1]
 
 
+class _FailingSolver(_RecordingSolver):
+    """rank 1 cannot map its peer (what a box without IPC / peer access looks like)"""
+
+    def shard_connect(self, peer, handle):
+        if self.rank == 1:
+            raise RuntimeError("cudaIpcOpenMemHandle: invalid device context")
+        super().shard_connect(peer, handle)
+
+
+def _peer_fail_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bluerov2_b200.sharding import PeerThrustExchange, PeerExchangeUnavailable
+        try:
+            PeerThrustExchange(_FailingSolver(rank), batch_per_rank=5)
+            q.put((rank, None))
+        except PeerExchangeUnavailable as e:
+            q.put((rank, str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_failure_on_one_rank_raises_on_all_gloo():
+    """one rank failing to connect must not leave the others waiting in a collective: every rank gets the same exception"""
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_fail_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r for r, _ in res] == [0, 1]
+    for _, msg in res:
+        assert msg is not None and "shard_connect" in msg and "rank 1" in msg and "cudaIpcOpenMemHandle" in msg
+
+
 def test_peer_exchange_single_rank_needs_no_process_group():
     from bluerov2_b200.sharding import PeerThrustExchange
     s = _RecordingSolver(0)
