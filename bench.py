@@ -615,7 +615,13 @@ def run_ours(args):
         except Exception as e:       # noqa: BLE001
             extra_errors["announced_one_tick_ahead"] = repr(e)[:300]
 
+    by_rank = None
     if distributed:
+        # every rank's own device time beside the max: names what the slowest rank is (chip-to-chip variation or the exchange)
+        mine = torch.tensor([1e3 * dt / K, 1e3 * t_lin, 1e3 * t_qp], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        by_rank = {k: [round(float(a[i]), 5) for a in allr] for i, k in enumerate(("ms_per_step", "lineariser_ms", "qp_ms"))}
         tt = torch.tensor([dt, dt_e2e, dt_py], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt, dt_e2e, dt_py = float(tt[0]), float(tt[1]), float(tt[2])
@@ -635,6 +641,7 @@ def run_ours(args):
             "parallelism": f"{world} x independent shards" + ("" if not distributed else
                                                               ", thrust vectors exchanged peer-to-peer from the QP epilogue (stores into every rank's gather "
                                                               "buffer over NVLink, one flag per rank and tick; no collective kernel)" if loop.mode == "peer" else
+                                                              ", NO exchange of the thrust vectors (BR2_GATHER=none: diagnostic)" if loop.mode == "none" else
                                                               ", one NCCL all-gather of the thrust vectors per tick (double-buffered: it overlaps the next "
                                                               "tick's lineariser)") +
                            (f" [{loop.gather_note}]" if loop.gather_note else ""),
@@ -652,6 +659,7 @@ def run_ours(args):
                                                               "plant_kernel"], "graphs_instantiated": graphs,
                                       "how": "one cudaGraphLaunch per tick (br2_batch_tick_device)"},
             "kernels": {"linearize_ms": 1e3 * t_lin, "qp_ms": 1e3 * t_qp, "qp_share_of_step": t_qp / (dt / K)},
+            "by_rank": by_rank,
             "roofline": roofline_of(B, N, iters_mean, t_qp, "ipm_kernel" if args.no_fast_path else "pdas_kernel"),
             "clocks": clocks,
         }
